@@ -1,0 +1,34 @@
+# Top-level build: the product library + CLI (sm_100a only) and the test-only oracle.
+#   make            -> phfpfac_b200/_build/libpfac_b200.so, phfpfac_b200/_build/gphf, oracle
+#   make lib | cli | oracle
+NVCC ?= /usr/local/cuda/bin/nvcc
+HOSTCXX := g++
+ARCH := -gencode arch=compute_100a,code=sm_100a
+B := phfpfac_b200/_build
+SRC := phfpfac_b200/csrc
+NVFLAGS := $(ARCH) -lineinfo -O3 -std=c++17 -ccbin $(HOSTCXX) -Iinclude -I$(SRC) \
+           -Xcompiler -fPIC,-Wall,-Wextra,-pthread -Xptxas -v
+HOST_SRCS := $(SRC)/pfac_tables.cc $(SRC)/pfac_writer.cc $(SRC)/pfac_job.cc $(SRC)/pfac_synth.cc
+CUDA_SRCS := $(SRC)/pfac_device.cu
+HDRS := include/pfac_b200.h include/pfac_synth.h $(SRC)/pfac_internal.h $(SRC)/pfac_kernel.cuh
+
+.PHONY: all lib cli oracle clean
+all: lib cli oracle
+
+lib: $(B)/libpfac_b200.so
+cli: $(B)/gphf
+
+$(B)/libpfac_b200.so: $(HOST_SRCS) $(CUDA_SRCS) $(HDRS)
+	@mkdir -p $(B)
+	$(NVCC) $(NVFLAGS) -shared -cudart static -o $@ $(CUDA_SRCS) $(HOST_SRCS) 2> $(B)/ptxas.log || (cat $(B)/ptxas.log; false)
+	@grep -E "registers|spill|error" $(B)/ptxas.log | head -20 || true
+
+$(B)/gphf: $(SRC)/gphf_main.cc $(B)/libpfac_b200.so
+	$(HOSTCXX) -O2 -std=c++17 -Wall -Wextra -Iinclude -o $@ $(SRC)/gphf_main.cc -L$(B) -lpfac_b200 -Wl,-rpath,'$$ORIGIN'
+
+oracle:
+	$(MAKE) -C oracle all
+
+clean:
+	rm -rf $(B)
+	$(MAKE) -C oracle clean

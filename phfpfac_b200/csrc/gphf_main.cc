@@ -1,0 +1,104 @@
+// gphf -- command-line driver with the reference's surface (regex_GPU_PHF/main.cc:45-352):
+//
+//     gphf <pattern file name> <stream number per GPU> <Hash table width> <input file name>
+//
+// writes GPU_match_result.txt in the current directory (main.cc:335), byte-identical to the
+// reference.  argv[2] keeps its place but means "pipeline streams per GPU" (input sub-chunks
+// in flight); the result does not depend on it.  Exits 1 with a message on any failure, 255
+// on a usage error (the reference's exit(-1), main.cc:95).
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "pfac_b200.h"
+
+static double now()
+{
+    return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+static int fail(const char *what)
+{
+    fprintf(stderr, "%s: %s\n", what, pfac_last_error());
+    return 1;
+}
+
+int main(int argc, char **argv)
+{
+    if (argc != 5) {   // main.cc:93-96
+        fprintf(stderr, "usage: %s <pattern file name> <streamnum> <PHF width> <input file name>\n", argv[0]);
+        return 255;
+    }
+    const int streamnum = atoi(argv[2]);   // main.cc:48
+    const int width = atoi(argv[3]);       // main.cc:120
+    if (streamnum < 1) {
+        fprintf(stderr, "stream number per GPU must be >= 1\n");
+        return 1;
+    }
+    const char *out_name = getenv("GPHF_OUTPUT") ? getenv("GPHF_OUTPUT") : "GPU_match_result.txt";   // main.cc:335
+
+    double t0 = now();
+    pfac_tables *tables = nullptr;
+    if (pfac_tables_build_file(argv[1], 1, width, &tables)) return fail("create PFAC/PHF tables");
+    double t1 = now();
+    int32_t info[9];
+    pfac_tables_part_info(tables, 0, info);
+    printf("state num : %d\nfinal state num : %d\nmax pattern length : %d\nhash table size : %d\n", info[0],
+           info[1], info[2], info[3]);
+
+    FILE *fpin = fopen(argv[4], "rb");   // main.cc:131
+    if (!fpin) {
+        perror("Open input file failed.");
+        return 1;
+    }
+    fseek(fpin, 0, SEEK_END);
+    long long fsize = ftell(fpin);
+    rewind(fpin);
+    const uint64_t input_size = fsize > 0 ? (uint64_t)fsize - 1 : 0;   // main.cc:138 (drops the last byte)
+    printf("input size is %llu char\n", (unsigned long long)input_size);
+
+    int n_gpu = 0;
+    if (pfac_device_count(&n_gpu) || n_gpu < 1) return fail("no CUDA device");   // main.cc:50
+    if (getenv("GPHF_GPUS")) n_gpu = std::max(1, std::min(n_gpu, atoi(getenv("GPHF_GPUS"))));
+
+    void *input = nullptr;
+    if (pfac_host_alloc(&input, (size_t)input_size + 1)) return fail("cudaHostAlloc input");   // main.cc:147
+    if (input_size && fread(input, 1, (size_t)input_size, fpin) != (size_t)input_size) {         // main.cc:154
+        fprintf(stderr, "short read on %s\n", argv[4]);
+        return 1;
+    }
+    fclose(fpin);
+
+    pfac_job *job = nullptr;
+    if (pfac_job_create(tables, nullptr, n_gpu, streamnum, 0, &job)) return fail("create GPU contexts");
+    double t2 = now();
+    uint64_t n_matches = 0;
+    if (pfac_job_run(job, input, input_size, &n_matches)) return fail("scan");
+    double t3 = now();
+
+    void *w = nullptr;
+    if (pfac_write_begin(out_name, &w)) return fail("open output");
+    for (int i = 0; i < pfac_job_n_segments(job); i++) {
+        uint64_t base, cnt;
+        const pfac_match *rec;
+        pfac_job_segment(job, i, &base, &rec, &cnt);
+        if (pfac_write_records(w, base, rec, cnt)) return fail("write output");
+    }
+    if (pfac_write_end(w)) return fail("close output");
+    double t4 = now();
+
+    printf("/////////////////////////////////////////////\n");
+    printf("1.Time for  create PFAC + Hashtable : %lf seconds\n", t1 - t0);
+    printf("2.Time for  %d GPU setup: %lf mseconds\n", n_gpu, (t2 - t1) * 1000);
+    printf("3.Time for  %d GPU match progress: %lf mseconds (%.3f GB/s end to end)\n", n_gpu, (t3 - t2) * 1000,
+           input_size / (t3 - t2) / 1e9);
+    printf("4.Time for  writing %llu matches: %lf mseconds\n", (unsigned long long)n_matches, (t4 - t3) * 1000);
+    printf("matching process finshed\n");
+    printf("/////////////////////////////////////////////\n");
+    pfac_job_destroy(job);
+    pfac_host_free(input);
+    pfac_tables_destroy(tables);
+    return 0;
+}

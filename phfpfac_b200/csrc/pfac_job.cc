@@ -1,0 +1,150 @@
+// Multi-GPU job: the GPU x stream scan loop of the reference (main.cc:171-272), re-cut for
+// input sharding.  GPU g scans the contiguous chunk [start_g, end_g) plus a halo of
+// max_pat_len-1 bytes and reports only matches that START inside its chunk, so concatenating
+// the per-GPU record lists in GPU order is already globally position-ordered.  One host thread
+// per GPU (the reference uses one OpenMP thread per GPU x stream, main.cc:225-241); streams
+// inside a GPU are driven asynchronously by pfac_scan_host.  No inter-GPU traffic, no NCCL.
+#include <algorithm>
+#include <chrono>
+#include <memory>
+#include <thread>
+
+#include "pfac_internal.h"
+
+namespace {
+
+struct Segment {
+    uint64_t base = 0;       // global position of record pos 0
+    uint64_t n_starts = 0;
+    pfac_match *rec = nullptr;   // pinned
+    uint64_t cap = 0;
+    uint64_t count = 0;
+};
+
+// one pfac_scan_host call covers < 4 GiB; keep segments at 1 GiB of start positions
+constexpr uint64_t kSegmentBytes = 1ull << 30;
+
+}  // namespace
+
+struct pfac_job {
+    std::vector<pfac_ctx *> ctxs;
+    std::vector<std::vector<Segment>> segs;   // per GPU
+    std::vector<const Segment *> flat;
+    int max_pat_len = 0;
+    double secs[4] = {0, 0, 0, 0};
+};
+
+extern "C" {
+
+int pfac_job_create(const pfac_tables *t, const int *devices, int n_devices, int streams_per_gpu,
+                    size_t chunk_bytes, pfac_job **out)
+{
+    if (!t || !out || n_devices < 1 || streams_per_gpu < 1) return pfac::set_error(PFAC_ERR_ARG, "bad arguments to pfac_job_create");
+    if (pfac_tables_n_parts(t) != 1)
+        return pfac::set_error(PFAC_ERR_ARG, "the scanner takes a single-partition table set (got %d)", pfac_tables_n_parts(t));
+    std::unique_ptr<pfac_job> job(new pfac_job);
+    job->max_pat_len = pfac_tables_max_pat_len(t);
+    for (int i = 0; i < n_devices; i++) {
+        pfac_ctx *ctx = nullptr;
+        int rc = pfac_ctx_create(devices ? devices[i] : i, t, 0, streams_per_gpu, chunk_bytes, &ctx);
+        if (rc) {
+            for (pfac_ctx *c : job->ctxs) pfac_ctx_destroy(c);
+            return rc;
+        }
+        job->ctxs.push_back(ctx);
+    }
+    job->segs.resize((size_t)n_devices);
+    *out = job.release();
+    return PFAC_OK;
+}
+
+void pfac_job_destroy(pfac_job *job)
+{
+    if (!job) return;
+    for (auto &v : job->segs)
+        for (auto &s : v) pfac_host_free(s.rec);
+    for (pfac_ctx *c : job->ctxs) pfac_ctx_destroy(c);
+    delete job;
+}
+
+int pfac_job_run(pfac_job *job, const void *h_in, uint64_t n, uint64_t *n_matches)
+{
+    if (!job || (!h_in && n) || !n_matches) return pfac::set_error(PFAC_ERR_ARG, "bad arguments to pfac_job_run");
+    const int G = (int)job->ctxs.size();
+    const uint64_t halo = job->max_pat_len > 0 ? (uint64_t)job->max_pat_len - 1 : 0;
+    // contiguous chunk per GPU, 64 KiB granularity so sub-chunks stay tile aligned
+    uint64_t per = (n + (uint64_t)G - 1) / (uint64_t)G;
+    per = (per + 65535) & ~65535ull;
+    std::vector<int> rcs((size_t)G, PFAC_OK);
+    std::vector<std::string> errs((size_t)G);
+    const auto t0 = std::chrono::steady_clock::now();
+    auto work = [&](int g) {
+        const uint64_t lo = std::min<uint64_t>(n, (uint64_t)g * per), hi = std::min<uint64_t>(n, lo + per);
+        std::vector<Segment> &segs = job->segs[(size_t)g];
+        const size_t n_seg = (size_t)((hi - lo + kSegmentBytes - 1) / kSegmentBytes);
+        for (size_t i = n_seg; i < segs.size(); i++) { pfac_host_free(segs[i].rec); }
+        segs.resize(n_seg);
+        for (size_t i = 0; i < n_seg; i++) {
+            Segment &s = segs[i];
+            s.base = lo + (uint64_t)i * kSegmentBytes;
+            s.n_starts = std::min<uint64_t>(kSegmentBytes, hi - s.base);
+            s.count = 0;
+            const uint64_t nv = std::min<uint64_t>(s.n_starts + halo, n - s.base);
+            for (int attempt = 0; attempt < 2; attempt++) {
+                if (!s.rec) {
+                    s.cap = std::max<uint64_t>(s.cap, std::max<uint64_t>(s.n_starts / 8, 65536));
+                    int rc = pfac_host_alloc((void **)&s.rec, (size_t)s.cap * sizeof(pfac_match));
+                    if (rc) { rcs[(size_t)g] = rc; errs[(size_t)g] = pfac_last_error(); return; }
+                }
+                int rc = pfac_scan_host(job->ctxs[(size_t)g], (const uint8_t *)h_in + s.base, s.n_starts, nv,
+                                        s.base, s.rec, s.cap, &s.count);
+                if (rc == PFAC_ERR_OUTPUT_FULL && attempt == 0) {   // dense matches: exact-size retry
+                    pfac_host_free(s.rec);
+                    s.rec = nullptr;
+                    s.cap = s.count;
+                    continue;
+                }
+                if (rc) { rcs[(size_t)g] = rc; errs[(size_t)g] = pfac_last_error(); return; }
+                break;
+            }
+        }
+    };
+    std::vector<std::thread> th;
+    for (int g = 1; g < G; g++) th.emplace_back(work, g);
+    work(0);
+    for (auto &t : th) t.join();
+    job->secs[0] = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    job->flat.clear();
+    uint64_t total = 0;
+    for (int g = 0; g < G; g++) {
+        if (rcs[(size_t)g]) return pfac::set_error(rcs[(size_t)g], "GPU %d: %s", pfac_ctx_device(job->ctxs[(size_t)g]), errs[(size_t)g].c_str());
+        for (const Segment &s : job->segs[(size_t)g]) {
+            job->flat.push_back(&s);
+            total += s.count;
+        }
+    }
+    *n_matches = total;
+    return PFAC_OK;
+}
+
+int pfac_job_n_segments(const pfac_job *job) { return job ? (int)job->flat.size() : 0; }
+
+int pfac_job_segment(const pfac_job *job, int i, uint64_t *base_pos, const pfac_match **records, uint64_t *count)
+{
+    if (!job || i < 0 || i >= (int)job->flat.size() || !base_pos || !records || !count)
+        return pfac::set_error(PFAC_ERR_ARG, "bad segment index");
+    const Segment *s = job->flat[(size_t)i];
+    *base_pos = s->base;
+    *records = s->rec;
+    *count = s->count;
+    return PFAC_OK;
+}
+
+int pfac_job_last_timing(const pfac_job *job, double secs[4])
+{
+    if (!job || !secs) return pfac::set_error(PFAC_ERR_ARG, "bad arguments");
+    for (int i = 0; i < 4; i++) secs[i] = job->secs[i];
+    return PFAC_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,474 @@
+// Host-side table construction: pattern file -> sorted patterns -> PFAC trie -> PHF arrays.
+//
+// Produces, bit for bit, what the reference's create_PFAC_table_reorder()
+// (CreateTable/create_table_reorder.c:201-378) and FFDM() (PHF/phf.c:151-291) produce, but
+// with dynamic limits and near-linear time:
+//   * the trie is built from the sorted list with a longest-common-prefix walk instead of a
+//     dense state x 256 array (the reference pre-allocates 4,000,000 x 1 KiB rows,
+//     create_table_reorder.c:10,306-311);
+//   * SortRows' O(R^2) exchange sort (phf.c:126-139), whose tie order decides the packing, is
+//     reproduced exactly by moving elements along the chain of strict running maxima with a
+//     max-segment-tree (O(R log R));
+//   * the first-fit search (phf.c:188-195) walks free slots through a hierarchical bitmap
+//     instead of every offset.
+// tests/test_tables_*.py pin this against the reference's own code (oracle/_ref) and the
+// plain-C restatement (oracle/pfac_oracle.c).
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+
+#include "pfac_internal.h"
+
+namespace pfac {
+
+static thread_local std::string g_last_error;
+
+int set_error(int code, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    return code;
+}
+
+int width_bits(int width)
+{
+    if (width < 1 || width > 4096 || (width & (width - 1))) return -1;   // phf.c:161
+    int b = 0;
+    while ((width >> b) != 1) b++;                                        // master_kernel.cu:398
+    return b;
+}
+
+// master_kernel.cu:52-64
+int32_t Partition::lookup(int32_t state, int32_t byte) const
+{
+    int wb = width_bits(width);
+    int32_t key = (int32_t)(((uint32_t)state << 8) + (uint32_t)byte);
+    int32_t row = key >> wb;
+    int32_t col = key & ((1 << wb) - 1);
+    if (row < 0 || row >= (int32_t)r.size()) return -1;
+    int32_t index = r[row] + col;
+    if (index < 0 || index >= ht_size) return -1;
+    return HT[index] == row ? val[index] : -1;
+}
+
+namespace {
+
+struct Pattern {
+    const unsigned char *p;
+    int len;
+    int id;   // 1-based line number, create_table_reorder.c:100
+};
+
+// create_table_reorder.c:21-45 (comp_pat): memcmp over the common length, then shorter first.
+inline int comp_pat(const Pattern &a, const Pattern &b)
+{
+    int m = a.len < b.len ? a.len : b.len;
+    int res = memcmp(a.p, b.p, (size_t)m);
+    if (res) return res;
+    return a.len < b.len ? -1 : (a.len > b.len ? 1 : 0);
+}
+
+// create_table_reorder.c:53-122 (read_pattern) over a memory image of the file.
+int read_patterns(const unsigned char *buf, size_t len, std::vector<Pattern> &out)
+{
+    if (len == 0) return set_error(PFAC_ERR_PATTERN_TOO_LONG, "pattern file is empty");
+    size_t i = 0;
+    while (i < len) {
+        const unsigned char *nl = (const unsigned char *)memchr(buf + i, '\n', len - i);
+        if (!nl)   // the reference spins on EOF until the 1024 limit trips (:71-77)
+            return set_error(PFAC_ERR_PATTERN_TOO_LONG,
+                             "pattern %zu: file does not end with a newline", out.size() + 1);
+        size_t plen = (size_t)(nl - (buf + i));
+        if (plen > (size_t)kMaxPatternBytes)
+            return set_error(PFAC_ERR_PATTERN_TOO_LONG, "Pattern %zu length over 1024.", out.size() + 1);
+        if (plen == 0)
+            return set_error(PFAC_ERR_EMPTY_PATTERN, "pattern %zu is empty", out.size() + 1);
+        out.push_back(Pattern{buf + i, (int)plen, (int)out.size() + 1});
+        i += plen + 1;
+    }
+    // qsort(&all_pattern[1], ...) (:116).  glibc's qsort is a stable merge sort, so equal
+    // patterns keep file order and the LAST duplicate wins its final state (:366).
+    std::stable_sort(out.begin(), out.end(),
+                     [](const Pattern &a, const Pattern &b) { return comp_pat(a, b) < 0; });
+    return PFAC_OK;
+}
+
+// create_table_reorder.c:277-378 (patternsToPFAC) for an already sorted slice.
+// State numbering: finals 0..n-1 = index in the slice (:366), n unused, initial n+1 (:288),
+// interior states from n+2 in creation order (:292,331-333).
+// Because the slice is sorted (prefix before extension), the edges pattern i can follow are
+// exactly those on the path of pattern i-1 up to their common prefix.
+void build_trie(const Pattern *pats, int n, Partition &P)
+{
+    const int initial = n + 1;
+    int state_count = n + 2;
+    P.n_final = n;
+    P.max_len = 0;
+    P.min_len = 0;
+    P.idmap.resize((size_t)n);
+    std::vector<int32_t> &keys = P.keys, &next = P.next;
+    std::vector<int32_t> path(1, initial);   // path[d] = state after d bytes of the previous pattern
+    std::vector<size_t> edge;                // edge[d] = index of the transition path[d] -> path[d+1]
+    const Pattern *prev = nullptr;
+    for (int i = 0; i < n; i++) {
+        const Pattern &cur = pats[i];
+        P.idmap[(size_t)i] = cur.id;                                  // :318
+        if (cur.len > P.max_len) P.max_len = cur.len;                 // :319-321
+        if (P.min_len == 0 || cur.len < P.min_len) P.min_len = cur.len;
+        int l = 0;
+        if (prev) {
+            int m = prev->len < cur.len ? prev->len : cur.len;
+            while (l < m && prev->p[l] == cur.p[l]) l++;
+        }
+        path.resize((size_t)cur.len + 1);
+        edge.resize((size_t)cur.len);
+        for (int j = (l < cur.len - 1 ? l : cur.len - 1); j < cur.len - 1; j++) {   // :325-359
+            int s = state_count++;
+            keys.push_back(path[(size_t)j] * kCharSet + cur.p[j]);
+            next.push_back(s);
+            edge[(size_t)j] = keys.size() - 1;
+            path[(size_t)j + 1] = s;
+        }
+        const int last = cur.len - 1;                                 // :362-366
+        if (l == cur.len) {
+            next[edge[(size_t)last]] = i;   // duplicate pattern: PFAC[state][ch] is overwritten
+        } else {
+            keys.push_back(path[(size_t)last] * kCharSet + cur.p[last]);
+            next.push_back(i);
+            edge[(size_t)last] = keys.size() - 1;
+        }
+        path[(size_t)cur.len] = i;
+        prev = &cur;
+    }
+    P.state_num = state_count;                                        // :376
+    // ReadKey (phf.c:98) visits keys in ascending order
+    std::vector<size_t> order(keys.size());
+    for (size_t k = 0; k < order.size(); k++) order[k] = k;
+    std::sort(order.begin(), order.end(), [&](size_t a, size_t b) { return keys[a] < keys[b]; });
+    std::vector<int32_t> k2(keys.size()), n2(keys.size());
+    for (size_t k = 0; k < order.size(); k++) { k2[k] = keys[order[k]]; n2[k] = next[order[k]]; }
+    keys.swap(k2);
+    next.swap(n2);
+    P.s0.assign(kCharSet, -1);                                        // main.cc:200
+    for (size_t k = 0; k < keys.size(); k++)
+        if (keys[k] / kCharSet == initial) P.s0[(size_t)(keys[k] % kCharSet)] = next[k];
+}
+
+// max-segment-tree over positions: first index >= from whose value is > thr
+struct MaxTree {
+    int N = 1;
+    std::vector<int32_t> t;
+    explicit MaxTree(const std::vector<int32_t> &leaf)
+    {
+        while (N < (int)leaf.size()) N <<= 1;
+        t.assign((size_t)2 * N, -1);
+        for (size_t i = 0; i < leaf.size(); i++) t[(size_t)N + i] = leaf[i];
+        for (int i = N - 1; i >= 1; i--) t[(size_t)i] = std::max(t[(size_t)2 * i], t[(size_t)2 * i + 1]);
+    }
+    void set(int pos, int32_t v)
+    {
+        int i = pos + N;
+        t[(size_t)i] = v;
+        for (i >>= 1; i >= 1; i >>= 1) {
+            int32_t m = std::max(t[(size_t)2 * i], t[(size_t)2 * i + 1]);
+            if (t[(size_t)i] == m) break;
+            t[(size_t)i] = m;
+        }
+    }
+    int32_t top() const { return t[1]; }
+    int first_greater(int from, int32_t thr) const
+    {
+        if (from >= N) return -1;
+        int i = from + N;
+        while (true) {
+            if (t[(size_t)i] > thr) {
+                while (i < N) {
+                    i <<= 1;
+                    if (t[(size_t)i] <= thr) i++;
+                }
+                return i - N;
+            }
+            while (i & 1) i >>= 1;
+            i++;
+            if ((i & (i - 1)) == 0) return -1;
+        }
+    }
+};
+
+// occupancy bitmap with two summary levels: next free slot >= s, growable
+struct SlotMap {
+    std::vector<uint64_t> l0, l1, l2;   // l1 bit = l0 word full, l2 bit = l1 word full
+    void ensure(size_t slot)
+    {
+        size_t w0 = slot / 64 + 1;
+        if (w0 <= l0.size()) return;
+        w0 = std::max(w0, l0.size() * 2);
+        l0.resize(w0, 0);
+        l1.resize(w0 / 64 + 1, 0);
+        l2.resize(l1.size() / 64 + 1, 0);
+    }
+    bool used(size_t s)
+    {
+        ensure(s);
+        return (l0[s >> 6] >> (s & 63)) & 1;
+    }
+    void mark(size_t s)
+    {
+        ensure(s);
+        size_t w = s >> 6;
+        l0[w] |= 1ULL << (s & 63);
+        if (l0[w] == ~0ULL) {
+            size_t w1 = w >> 6;
+            l1[w1] |= 1ULL << (w & 63);
+            if (l1[w1] == ~0ULL) l2[w1 >> 6] |= 1ULL << (w1 & 63);
+        }
+    }
+    size_t next_free(size_t s)
+    {
+        ensure(s);
+        size_t w = s >> 6;
+        uint64_t freebits = ~l0[w] & (~0ULL << (s & 63));
+        if (freebits) return (w << 6) + (size_t)__builtin_ctzll(freebits);
+        w++;
+        while (true) {   // skip full words, 64 or 4096 at a time through the summaries
+            ensure(w << 6);
+            if ((w & 63) == 0) {
+                size_t w1 = w >> 6;
+                if ((w1 & 63) == 0 && l2[w1 >> 6] == ~0ULL) { w += 64 * 64; continue; }
+                if (l1[w1] == ~0ULL) { w += 64; continue; }
+            }
+            if (l0[w] == ~0ULL) { w++; continue; }
+            return (w << 6) + (size_t)__builtin_ctzll(~l0[w]);
+        }
+    }
+};
+
+// phf.c:151-291 (FFDM) on the sorted key list.
+int ffdm(Partition &P, int width)
+{
+    P.width = width;
+    const size_t nk = P.keys.size();
+    const int64_t n_r = ((int64_t)P.state_num * kCharSet) / width + 1;   // master_kernel.cu:221
+    P.r.assign((size_t)n_r, -1);                                          // phf.c:67
+    P.n_keys = (int32_t)nk;
+    P.max_key = nk ? P.keys[nk - 1] : 0;                                  // phf.c:111-113
+    const int MaxRow = P.max_key / width + 1;                             // phf.c:174
+    P.max_row = MaxRow;
+    // ReadKey (phf.c:90-117): per row, its columns in ascending order
+    std::vector<int32_t> cnt((size_t)MaxRow, 0);
+    std::vector<size_t> row_begin((size_t)MaxRow + 1, 0);
+    for (size_t k = 0; k < nk; k++) cnt[(size_t)(P.keys[k] / width)]++;
+    for (int rr = 0; rr < MaxRow; rr++) row_begin[(size_t)rr + 1] = row_begin[(size_t)rr] + (size_t)cnt[(size_t)rr];
+
+    // SortRows (phf.c:126-139): for i ascending, a[i] is exchanged with every later element that
+    // is strictly fuller than what a[i] currently holds.  Equivalent: carry a[i] to the nearest
+    // later position q holding a strictly greater count, drop it there, pick up a[q], repeat;
+    // what is carried at the end lands in a[i].
+    std::vector<int32_t> a((size_t)MaxRow);
+    for (int i = 0; i < MaxRow; i++) a[(size_t)i] = i;
+    {
+        MaxTree tree(cnt);
+        for (int i = 0; i < MaxRow - 1; i++) {
+            int32_t carry = a[(size_t)i];
+            int32_t cc = cnt[(size_t)carry];
+            tree.set(i, -1);
+            if (tree.top() <= cc) continue;
+            int p = i, q;
+            while ((q = tree.first_greater(p + 1, cc)) != -1) {
+                int32_t picked = a[(size_t)q];
+                a[(size_t)q] = carry;
+                tree.set(q, cc);
+                carry = picked;
+                cc = cnt[(size_t)carry];
+                p = q;
+            }
+            a[(size_t)i] = carry;
+        }
+    }
+
+    // first fit, fullest rows first (phf.c:184-229)
+    SlotMap slots;
+    std::vector<int32_t> HT, val;
+    int32_t MaxOffset = 0;
+    for (int ndx = 0; ndx < MaxRow; ndx++) {
+        const int32_t row = a[(size_t)ndx];
+        const int32_t c = cnt[(size_t)row];
+        if (c <= 0) break;                                                // phf.c:184
+        const size_t kb = row_begin[(size_t)row];
+        const int32_t col0 = P.keys[kb] % width;
+        size_t s = slots.next_free(0);
+        int64_t offset;
+        while (true) {                                                    // phf.c:188-195
+            offset = (int64_t)s - col0;
+            int i = 1;
+            for (; i < c; i++)
+                if (slots.used((size_t)(offset + P.keys[kb + (size_t)i] % width))) break;
+            if (i == c) break;
+            s = slots.next_free(s + 1);
+        }
+        if (offset > INT32_MAX - width)
+            return set_error(PFAC_ERR_LIMIT, "hash table offset exceeds 32 bits");
+        P.r[(size_t)row] = (int32_t)offset;                               // phf.c:197
+        if (offset > MaxOffset) MaxOffset = (int32_t)offset;
+        const size_t hi = (size_t)(offset + P.keys[kb + (size_t)c - 1] % width);
+        if (hi >= HT.size()) {
+            size_t ns = std::max(hi + 1, HT.size() * 2);
+            HT.resize(ns, -1);
+            val.resize(ns, -1);
+        }
+        for (int i = 0; i < c; i++) {
+            const size_t slot = (size_t)(offset + P.keys[kb + (size_t)i] % width);
+            HT[slot] = row;                                               // phf.c:211
+            val[slot] = P.next[kb + (size_t)i];                           // phf.c:216
+            slots.mark(slot);
+        }
+    }
+    int32_t HTSize = 0;                                                   // phf.c:232-236
+    for (int64_t i = MaxOffset; i < (int64_t)MaxOffset + width && i < (int64_t)HT.size(); i++)
+        if (HT[(size_t)i] >= 0 || val[(size_t)i] >= 0) HTSize = (int32_t)i + 1;
+    HT.resize((size_t)HTSize, -1);
+    val.resize((size_t)HTSize, -1);
+    P.HT.swap(HT);
+    P.val.swap(val);
+    P.max_offset = MaxOffset;
+    P.ht_size = HTSize;
+    return PFAC_OK;
+}
+
+int build(const unsigned char *buf, size_t len, int n_parts, int width, pfac_tables **out)
+{
+    if (!out || n_parts < 1) return set_error(PFAC_ERR_ARG, "bad arguments");
+    if (width_bits(width) < 0)
+        return set_error(PFAC_ERR_WIDTH, "width must be a power of two in [1,4096], got %d", width);
+    std::vector<Pattern> pats;
+    int e = read_patterns(buf, len, pats);
+    if (e) return e;
+    std::unique_ptr<pfac_tables> t(new pfac_tables);
+    t->n_patterns = (int)pats.size();
+    t->width = width;
+    t->parts.resize((size_t)n_parts);
+    const int n = (int)pats.size();
+    const int k = n / n_parts;            // create_table_reorder.c:220
+    const int l = k + n % n_parts;        // create_table_reorder.c:222
+    for (int g = 0; g < n_parts; g++) {
+        const int cnt = (g == n_parts - 1) ? l : k;   // divide_patterns, :260-272
+        Partition &P = t->parts[(size_t)g];
+        if ((int64_t)cnt + 2 + (int64_t)len > (int64_t)(INT32_MAX / kCharSet))
+            return set_error(PFAC_ERR_LIMIT, "automaton too large for 32-bit keys");
+        build_trie(pats.data() + (size_t)g * (size_t)k, cnt, P);
+        if (P.max_len > t->max_pat_len) t->max_pat_len = P.max_len;   // :238
+        e = ffdm(P, width);
+        if (e) return e;
+    }
+    *out = t.release();
+    return PFAC_OK;
+}
+
+}  // namespace
+}  // namespace pfac
+
+using namespace pfac;
+
+extern "C" {
+
+const char *pfac_last_error(void) { return g_last_error.c_str(); }
+int pfac_abi_version(void) { return PFAC_B200_ABI_VERSION; }
+
+int pfac_tables_build_mem(const void *pattern_bytes, size_t len, int n_parts, int width, pfac_tables **out)
+{
+    if (!pattern_bytes && len) return set_error(PFAC_ERR_ARG, "null pattern buffer");
+    try {
+        return build((const unsigned char *)pattern_bytes, len, n_parts, width, out);
+    } catch (const std::bad_alloc &) {
+        return set_error(PFAC_ERR_NOMEM, "out of memory building tables");
+    }
+}
+
+int pfac_tables_build_file(const char *pattern_file, int n_parts, int width, pfac_tables **out)
+{
+    FILE *f = pattern_file ? fopen(pattern_file, "rb") : nullptr;
+    if (!f) return set_error(PFAC_ERR_IO, "Open input file failed: %s", pattern_file ? pattern_file : "(null)");
+    std::vector<unsigned char> buf;
+    unsigned char tmp[1 << 16];
+    size_t got;
+    while ((got = fread(tmp, 1, sizeof tmp, f)) > 0) buf.insert(buf.end(), tmp, tmp + got);
+    fclose(f);
+    return pfac_tables_build_mem(buf.data(), buf.size(), n_parts, width, out);
+}
+
+int pfac_tables_from_arrays(const int32_t *s0, const int32_t *r, int32_t n_r, const int32_t *HT,
+                            const int32_t *val, int32_t ht_size, int32_t width, int32_t state_num,
+                            int32_t n_final, const int32_t *idmap, int32_t max_pat_len, pfac_tables **out)
+{
+    if (!out || !s0 || !r || n_r < 1 || ht_size < 0 || (ht_size && (!HT || !val)) || n_final < 0 ||
+        (n_final && !idmap) || max_pat_len < 0)
+        return set_error(PFAC_ERR_ARG, "bad arguments");
+    if (width_bits(width) < 0) return set_error(PFAC_ERR_WIDTH, "width must be a power of two in [1,4096]");
+    try {
+        std::unique_ptr<pfac_tables> t(new pfac_tables);
+        t->n_patterns = n_final;
+        t->max_pat_len = max_pat_len;
+        t->width = width;
+        t->parts.resize(1);
+        Partition &P = t->parts[0];
+        P.state_num = state_num;
+        P.n_final = n_final;
+        P.max_len = max_pat_len;
+        P.min_len = 1;
+        P.width = width;
+        P.ht_size = ht_size;
+        P.s0.assign(s0, s0 + kCharSet);
+        P.r.assign(r, r + n_r);
+        P.HT.assign(HT, HT + ht_size);
+        P.val.assign(val, val + ht_size);
+        P.idmap.assign(idmap, idmap + n_final);
+        for (int32_t i = 0; i < ht_size; i++)
+            if (P.HT[(size_t)i] >= 0) P.n_keys++;
+        *out = t.release();
+        return PFAC_OK;
+    } catch (const std::bad_alloc &) {
+        return set_error(PFAC_ERR_NOMEM, "out of memory");
+    }
+}
+
+void pfac_tables_destroy(pfac_tables *t) { delete t; }
+int pfac_tables_n_parts(const pfac_tables *t) { return t ? (int)t->parts.size() : 0; }
+int pfac_tables_n_patterns(const pfac_tables *t) { return t ? t->n_patterns : 0; }
+int pfac_tables_max_pat_len(const pfac_tables *t) { return t ? t->max_pat_len : 0; }
+int pfac_tables_width(const pfac_tables *t) { return t ? t->width : 0; }
+
+static const Partition *part_of(const pfac_tables *t, int part)
+{
+    if (!t || part < 0 || part >= (int)t->parts.size()) return nullptr;
+    return &t->parts[(size_t)part];
+}
+
+int pfac_tables_part_info(const pfac_tables *t, int part, int32_t info[9])
+{
+    const Partition *P = part_of(t, part);
+    if (!P || !info) return set_error(PFAC_ERR_ARG, "bad partition index");
+    info[0] = P->state_num; info[1] = P->n_final; info[2] = P->max_len; info[3] = P->ht_size;
+    info[4] = (int32_t)P->r.size(); info[5] = P->n_keys; info[6] = P->max_key; info[7] = P->max_offset;
+    info[8] = P->min_len;
+    return PFAC_OK;
+}
+
+const int32_t *pfac_tables_s0(const pfac_tables *t, int part) { const Partition *P = part_of(t, part); return P ? P->s0.data() : nullptr; }
+const int32_t *pfac_tables_r(const pfac_tables *t, int part) { const Partition *P = part_of(t, part); return P ? P->r.data() : nullptr; }
+const int32_t *pfac_tables_HT(const pfac_tables *t, int part) { const Partition *P = part_of(t, part); return P ? P->HT.data() : nullptr; }
+const int32_t *pfac_tables_val(const pfac_tables *t, int part) { const Partition *P = part_of(t, part); return P ? P->val.data() : nullptr; }
+const int32_t *pfac_tables_idmap(const pfac_tables *t, int part) { const Partition *P = part_of(t, part); return P ? P->idmap.data() : nullptr; }
+
+int32_t pfac_tables_lookup(const pfac_tables *t, int part, int32_t state, int32_t byte)
+{
+    const Partition *P = part_of(t, part);
+    if (!P || state < 0 || byte < 0 || byte > 255) return -1;
+    return P->lookup(state, byte);
+}
+
+}  // extern "C"
