@@ -1,0 +1,340 @@
+#!/usr/bin/env python
+"""bench.py -- input GB/s matched by the PFAC scan (BASELINE.json metric) on N B200s.
+
+    python bench.py --gpus N --steps K --warmup W            (N>1: launched by torchrun, one rank per GPU)
+    python bench.py --impl reference ...                      (CPU port of the reference's scan, rank 0 only)
+
+A "step" is one pass of the hot path over one rank's shard of synthetic input:
+  * `value`  : device-resident -- input already in HBM, one pfac_scan_device launch per step,
+               timed with CUDA events on the launching stream, max over ranks;
+  * `e2e`    : the same shard through pfac_scan_host (pinned host buffer -> H2D -> kernel -> D2H of
+               the compact records), host<->device copies inside the timed region.
+Workload at N=1 = BASELINE.json configs[2] (the config the metric is quoted on): 10,000 synthetic
+Snort-like patterns over 1 GiB of HTTP-like text, 4 streams per GPU.  For N>1 every rank scans its
+own 1 GiB shard (+ halo from the next shard): weak scaling, no data-path collective.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (pattern kind, count, seed, min_len, max_len, text kind, text seed, default bytes, description)
+    "config2": (0, 1000, 1, 8, 32, 0, 2, 256 << 20,
+                "config2: 1,000 synthetic patterns (len 8-32) over 256 MiB printable text with planted matches"),
+    "config3": (1, 10000, 3, 4, 64, 1, 4, 1 << 30,
+                "config3: 10,000 synthetic Snort-like patterns over 1 GiB HTTP-like text per GPU"),
+    "config4": (0, 100000, 5, 8, 32, 0, 6, 512 << 20,
+                "config4: 100,000 synthetic patterns (len 8-32) over 512 MiB printable text per GPU"),
+}
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="config3", choices=sorted(WORKLOADS))
+    ap.add_argument("--bytes", type=int, default=0, help="bytes per rank (default: the workload's size)")
+    ap.add_argument("--streams", type=int, default=4)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=0, help="steps of the end-to-end leg (default min(steps, 10))")
+    return ap.parse_args()
+
+
+def make_workload(args, rank):
+    import phfpfac_b200 as pf
+    pk, cnt, pseed, lo, hi, tk, tseed, nbytes, desc = WORKLOADS[args.workload]
+    n = args.bytes or nbytes
+    pats = pf.synth_patterns(pk, cnt, pseed, lo, hi)
+    tables = pf.Tables.from_bytes(pats, n_parts=1, width=256)
+    return pf, pats, tables, n, tk, tseed, desc
+
+
+def make_shard(pf, pats, mpl, tk, tseed, n, rank, world, out=None):
+    """Rank `rank`'s shard of the job's input: n bytes of its own seeded text followed by the halo =
+    the first max_pat_len-1 bytes of the next rank's text (nothing after the last rank).  The job's
+    whole input is the concatenation of all ranks' n bytes; rank r owns start positions
+    [r*n, (r+1)*n).  Returns (buffer of n + halo bytes, n_valid)."""
+    halo = max(mpl - 1, 0)
+    buf = np.empty(n + halo, dtype=np.uint8) if out is None else out
+    pf.synth_text(tk, tseed + 1000 * rank, n, patterns=pats, out=buf[:n])
+    if rank + 1 < world and halo:
+        buf[n:] = pf.synth_text(tk, tseed + 1000 * (rank + 1), min(n, 65536), patterns=pats)[:halo]
+        return buf, n + halo
+    buf[n:] = 0
+    return buf, n
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons through NVML while the timed regions run."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self.active = threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if not self.nv:
+            return
+        nv = self.nv
+        names = {
+            nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+            nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+            nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+            nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap",
+            nv.nvmlClocksThrottleReasonHwPowerBrakeSlowdown: "hw_power_brake",
+        }
+        while not self._stop.is_set():
+            if self.active.is_set():
+                try:
+                    self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                    for bit, name in names.items():
+                        if r & bit:
+                            self.reasons.add(name)
+                except Exception:
+                    pass
+            time.sleep(0.001)
+
+    def stop(self):
+        self._stop.set()
+
+    def summary(self):
+        return {"sm_mhz": float(np.median(self.samples)) if self.samples else None,
+                "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def cpu_baseline(tables, text, nthreads=None, budget_s=12.0):
+    """The oracle's port of SUBSEG_MATCH over the SAME PHF arrays on host threads (the reference
+    ships no CPU matcher, main.cc:239).  Bounded sample: calibrate on 4 MiB, then ~budget_s of work."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from _oracle import oracle_lib, scan_tables_cpu
+    lib = oracle_lib()
+    cores = nthreads or lib.oracle_max_threads()
+    part = tables.part(0)
+    cal = min(len(text), 4 << 20)
+    t0 = time.perf_counter()
+    scan_tables_cpu(part, part.idmap, tables.max_pat_len, text[:cal], nthreads=cores, count_only=True)
+    dt = max(time.perf_counter() - t0, 1e-6)
+    sample = int(min(len(text), max(cal, (cal / dt) * budget_s)))
+    sample = max(1 << 20, sample & ~0xFFFFF)
+    sample = min(sample, len(text))
+    best = None
+    for _ in range(2):
+        t0 = time.perf_counter()
+        cnt = scan_tables_cpu(part, part.idmap, tables.max_pat_len, text[:sample], nthreads=cores, count_only=True)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    return {"value": sample / best / 1e9, "unit": "GB/s", "cores": cores, "kind": "port",
+            "sample": f"first {sample >> 20} MiB of the rank-0 shard, best of 2, {cnt} matches counted"}, sample
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    pf, pats, tables, n, tk, tseed, desc = make_workload(args, 0)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from _oracle import oracle_lib, scan_tables_cpu
+    cores = oracle_lib().oracle_max_threads()
+    part = tables.part(0)
+    # bounded sample per step so K+W steps end within a few minutes
+    cal_n = 4 << 20
+    text = pf.synth_text(tk, tseed, min(n, 256 << 20), patterns=pats)
+    t0 = time.perf_counter()
+    scan_tables_cpu(part, part.idmap, tables.max_pat_len, text[:cal_n], nthreads=cores, count_only=True)
+    rate = cal_n / max(time.perf_counter() - t0, 1e-6)
+    total_steps = args.steps + args.warmup
+    sample = int(min(len(text), max(1 << 20, rate * 120.0 / max(total_steps, 1))))
+    sample &= ~0xFFFFF
+    sample = max(sample, 1 << 20)
+    for _ in range(args.warmup):
+        scan_tables_cpu(part, part.idmap, tables.max_pat_len, text[:sample], nthreads=cores, count_only=True)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        scan_tables_cpu(part, part.idmap, tables.max_pat_len, text[:sample], nthreads=cores, count_only=True)
+    dt = time.perf_counter() - t0
+    v = sample * args.steps / dt / 1e9
+    line = {
+        "impl": "reference", "metric": "input GB/s matched", "value": v, "unit": "GB/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": desc, "bytes_per_gpu": n, "streams_per_gpu": args.streams,
+                   "note": "reference ships no CPU matcher and its kernel does not compile on CUDA 12; "
+                           "this arm is the oracle's OpenMP port of SUBSEG_MATCH over the same PHF tables"},
+        "cpu_baseline": {"value": v, "unit": "GB/s", "cores": cores, "kind": "port",
+                         "sample": f"{sample >> 20} MiB of the rank-0 shard per step"},
+        "e2e": {"value": v, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a GPU: the PFAC scan has no CPU path")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    pf, pats, tables, n, tk, tseed, desc = make_workload(args, rank)
+    mpl = tables.max_pat_len
+    halo = mpl - 1
+    # the rank's shard in pinned host memory, followed by the halo = first bytes of the next shard
+    h_text = torch.empty(n + halo, dtype=torch.uint8, pin_memory=True)
+    text = h_text.numpy()
+    _, n_valid = make_shard(pf, pats, mpl, tk, tseed, n, rank, world, out=text)
+    d_text = h_text.cuda()
+    m = pf.Matcher(tables, device=local_rank, n_streams=args.streams, chunk_bytes=0)
+    cap = max(n // 8, 1 << 16)
+    d_out = torch.empty((cap, 2), dtype=torch.int32, device="cuda")
+    d_cnt = torch.zeros(1, dtype=torch.int64, device="cuda")
+    # a real (non-default) stream: handle 0 would mean "the library's own stream" to the C ABI, and
+    # torch.cuda.Event must be recorded on the stream the kernel runs on
+    tstream = torch.cuda.Stream()
+    torch.cuda.set_stream(tstream)
+    stream = tstream.cuda_stream
+    assert stream != 0
+
+    def step_dev():
+        m.scan_device_raw(d_text.data_ptr(), n, n_valid, rank * n, d_out.data_ptr(), cap, d_cnt.data_ptr(), stream)
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    step_dev()
+    torch.cuda.synchronize()
+    n_matches = int(d_cnt.item())
+    if n_matches > cap:      # dense workload: size the record buffer to what the scan reports
+        cap = n_matches
+        d_out = torch.empty((cap, 2), dtype=torch.int32, device="cuda")
+    for _ in range(max(args.warmup, 3)):
+        step_dev()
+    torch.cuda.synchronize()
+    n_matches = int(d_cnt.item())
+    if dist:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler.active.set()
+    ev0.record()
+    for _ in range(args.steps):
+        step_dev()
+    ev1.record()
+    torch.cuda.synchronize()
+    sampler.active.clear()
+    ms = ev0.elapsed_time(ev1)
+    if dist:
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.barrier()
+        ms_max = float(t.item())
+    else:
+        ms_max = ms
+    torch.cuda.synchronize()
+    launches = m.last_info()["launches"] * args.steps
+
+    # ---- end to end through the public host API: pinned input -> H2D -> scan -> D2H records
+    e2e_steps = args.e2e_steps or min(args.steps, 10)
+    h_out = torch.empty((cap, 2), dtype=torch.int32, pin_memory=True)
+    cnt = C.c_uint64(0)
+
+    def step_e2e():
+        pf.check(pf.lib.pfac_scan_host(m._h, h_text.data_ptr(), n, n_valid, rank * n, h_out.data_ptr(), cap,
+                                       C.byref(cnt)))
+
+    for _ in range(2):
+        step_e2e()
+    assert cnt.value == n_matches, (cnt.value, n_matches)
+    if dist:
+        dist.barrier()
+    sampler.active.set()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        step_e2e()
+    e2e_s = time.perf_counter() - t0
+    sampler.active.clear()
+    info = m.last_info()
+    if dist:
+        t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+        tm = torch.tensor([n_matches], dtype=torch.int64, device="cuda")
+        dist.all_reduce(tm)
+        total_matches = int(tm.item())
+    else:
+        total_matches = n_matches
+    sampler.stop()
+    launches_e2e = info["launches"] * e2e_steps
+
+    if rank == 0:
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(peaks_path):
+            peak, peak_src = json.load(open(peaks_path))["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)"
+        else:
+            peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+        if os.path.exists(tpath):
+            traffic = json.load(open(tpath)).get(args.workload if not args.bytes else "", None)
+        ms_step = ms_max / args.steps
+        alg_bytes = n + 8 * n_matches           # per launch: input bytes + 8 B per match record
+        achieved = alg_bytes / (ms / args.steps * 1e-3) / 1e9
+        line = {
+            "metric": "input GB/s matched (device-resident)", "value": world * n * args.steps / (ms_max * 1e-3) / 1e9,
+            "unit": "GB/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u8", "data": "synthetic",
+            "config": {"workload": desc, "bytes_per_gpu": n, "streams_per_gpu": args.streams, "phf_width": 256,
+                       "matches_per_gpu_step": n_matches, "total_matches": total_matches,
+                       "l2": "input per step (>= 256 MiB) exceeds the 126 MB L2; no flush needed",
+                       "parallelism": f"input sharded x{world}, no collective"},
+            "clocks": sampler.summary(),
+            "e2e": {"value": world * n * e2e_steps / e2e_s / 1e9, "unit": "GB/s", "steps": e2e_steps,
+                    "h2d_bytes_per_step": int(info["h2d_bytes"]), "d2h_bytes_per_step": int(info["d2h_bytes"]),
+                    "launches_per_step": int(info["launches"])},
+            "gpu_launches": int(world * (launches + launches_e2e)),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                         "kernel": "pfac_scan_kernel", "algorithmic_bytes_per_launch": alg_bytes},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"], _ = cpu_baseline(tables, text[:n])
+        print(json.dumps(line))
+    if dist:
+        dist.barrier()
+        dist.destroy_process_group()
+    m.close()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

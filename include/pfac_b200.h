@@ -147,6 +147,13 @@ int pfac_job_n_segments(const pfac_job *job);
 /* Segment i: records[count] with positions relative to *base_pos; segments are in position order. */
 int pfac_job_segment(const pfac_job *job, int i, uint64_t *base_pos, const pfac_match **records,
                      uint64_t *count);
+/* The sharding rule pfac_job_run applies, as a pure function (also used by bench.py to cut one
+ * shard per rank): shard `i` of `n_shards` over an input of `n` bytes owns the start positions
+ * [*start, *start + *n_starts) and may read *n_valid >= *n_starts bytes from *start (its halo =
+ * the first max_pat_len-1 bytes of the next shard, clipped to n).  Shard sizes are multiples of
+ * 64 KiB except the last; trailing shards may be empty. */
+int pfac_job_plan(uint64_t n, int n_shards, int max_pat_len, int i, uint64_t *start, uint64_t *n_starts,
+                  uint64_t *n_valid);
 /* wall-clock seconds of the last run: [0] total scan (H2D+kernel+D2H, all GPUs) */
 int pfac_job_last_timing(const pfac_job *job, double secs[4]);
 

@@ -24,7 +24,7 @@ from ._lib import PFAC_ERR_OUTPUT_FULL, PfacError, check, lib
 MATCH_DTYPE = np.dtype([("pos", "<u4"), ("id", "<u4")])   # struct pfac_match
 
 __all__ = ["Tables", "Matcher", "Job", "PfacError", "MATCH_DTYPE", "format_records", "write_result",
-           "synth_patterns", "synth_text", "device_count"]
+           "synth_patterns", "synth_text", "device_count", "plan_shard"]
 
 
 def _arr(ptr, n):
@@ -88,9 +88,9 @@ class Tables:
         return lib.pfac_tables_lookup(self._h, g, state, byte)
 
     def close(self):
-        if self._h:
+        if self._h and lib is not None:
             lib.pfac_tables_destroy(self._h)
-            self._h = None
+        self._h = None
 
     def __del__(self):
         self.close()
@@ -114,9 +114,9 @@ class Matcher:
         self.device = device
 
     def close(self):
-        if self._h:
+        if self._h and lib is not None:
             lib.pfac_ctx_destroy(self._h)
-            self._h = None
+        self._h = None
 
     def __del__(self):
         self.close()
@@ -199,12 +199,19 @@ class Job:
         return n.value, segs
 
     def close(self):
-        if self._h:
+        if self._h and lib is not None:
             lib.pfac_job_destroy(self._h)
-            self._h = None
+        self._h = None
 
     def __del__(self):
         self.close()
+
+
+def plan_shard(n, n_shards, max_pat_len, i):
+    """pfac_job_plan: (start, n_starts, n_valid) of shard i -- contiguous chunk + halo of max_pat_len-1."""
+    a, b, c = C.c_uint64(0), C.c_uint64(0), C.c_uint64(0)
+    check(lib.pfac_job_plan(n, n_shards, max_pat_len, i, C.byref(a), C.byref(b), C.byref(c)))
+    return a.value, b.value, c.value
 
 
 def format_records(records, base_pos=0):

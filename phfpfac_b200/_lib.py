@@ -21,7 +21,7 @@ ABI_SYMBOLS = [
     "pfac_scan_device", "pfac_scan_device_sync", "pfac_scan_host", "pfac_host_alloc", "pfac_host_free",
     "pfac_ctx_last_scan_info",
     "pfac_job_create", "pfac_job_destroy", "pfac_job_run", "pfac_job_n_segments", "pfac_job_segment",
-    "pfac_job_last_timing",
+    "pfac_job_last_timing", "pfac_job_plan",
     "pfac_write_begin", "pfac_write_records", "pfac_write_end", "pfac_format_records",
     "pfac_synth_patterns", "pfac_synth_text",
 ]
@@ -82,6 +82,8 @@ def _load():
     lib.pfac_job_run.argtypes = [_vp, _vp, C.c_uint64, C.POINTER(C.c_uint64)]
     lib.pfac_job_n_segments.argtypes = [_vp]
     lib.pfac_job_segment.argtypes = [_vp, C.c_int, C.POINTER(C.c_uint64), C.POINTER(_vp), C.POINTER(C.c_uint64)]
+    lib.pfac_job_plan.argtypes = [C.c_uint64, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64),
+                                  C.POINTER(C.c_uint64)]
     lib.pfac_job_last_timing.argtypes = [_vp, C.POINTER(C.c_double)]
     lib.pfac_write_begin.argtypes = [C.c_char_p, C.POINTER(_vp)]
     lib.pfac_write_records.argtypes = [_vp, C.c_uint64, _vp, C.c_uint64]

@@ -65,6 +65,7 @@ struct pfac_ctx {
     size_t tile_cap = 0;
     std::vector<Stage> stages;
     uint64_t info[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    uint32_t debug = 0;   // PFAC_DEBUG env (timing experiments only)
     std::mutex mu;
 };
 
@@ -138,6 +139,7 @@ int launch_scan(pfac_ctx *ctx, const void *d_in, uint64_t n_starts, uint64_t n_v
     p.tile_state = *tile_state;
     p.ticket = &d_ctrl->ticket;
     p.error_flag = &d_ctrl->error_flag;
+    p.debug = ctx->debug;
     CU_TRY(cudaMemsetAsync(*tile_state, 0, (size_t)p.n_tiles * sizeof(unsigned long long), stream));
     const uint32_t grid = (uint32_t)std::min<uint64_t>(p.n_tiles, (uint64_t)ctx->sm_count * ctx->blocks_per_sm);
     pfac_scan_kernel<<<grid, kThreads, ctx->smem_bytes, stream>>>(p);
@@ -204,6 +206,7 @@ int pfac_ctx_create(int device, const pfac_tables *t, int part, int n_streams, s
     ctx->max_pat_len = P.max_len;
     ctx->halo = (uint32_t)std::max(16, ((P.max_len > 0 ? P.max_len - 1 : 0) + 15) / 16 * 16);
     ctx->smem_bytes = scan_smem_bytes(ctx->halo);
+    if (const char *dbg = getenv("PFAC_DEBUG")) ctx->debug = (uint32_t)atoi(dbg);
 
     // canonical arrays -> device (r, {HT,val} interleaved, idmap, s0) + the 2-byte prefix bitmap
     const size_t n_r = std::max<size_t>(P.r.size(), 1), n_ht = std::max<size_t>((size_t)P.ht_size, 1);

@@ -67,19 +67,34 @@ void pfac_job_destroy(pfac_job *job)
     delete job;
 }
 
+int pfac_job_plan(uint64_t n, int n_shards, int max_pat_len, int i, uint64_t *start, uint64_t *n_starts,
+                  uint64_t *n_valid)
+{
+    if (n_shards < 1 || i < 0 || i >= n_shards || !start || !n_starts || !n_valid)
+        return pfac::set_error(PFAC_ERR_ARG, "bad arguments to pfac_job_plan");
+    const uint64_t halo = max_pat_len > 0 ? (uint64_t)max_pat_len - 1 : 0;
+    // contiguous shard per GPU, 64 KiB granularity so sub-chunks stay tile aligned
+    uint64_t per = (n + (uint64_t)n_shards - 1) / (uint64_t)n_shards;
+    per = (per + 65535) & ~65535ull;
+    const uint64_t lo = std::min<uint64_t>(n, (uint64_t)i * per), hi = std::min<uint64_t>(n, lo + per);
+    *start = lo;
+    *n_starts = hi - lo;
+    *n_valid = std::min<uint64_t>(hi - lo + halo, n - lo);
+    return PFAC_OK;
+}
+
 int pfac_job_run(pfac_job *job, const void *h_in, uint64_t n, uint64_t *n_matches)
 {
     if (!job || (!h_in && n) || !n_matches) return pfac::set_error(PFAC_ERR_ARG, "bad arguments to pfac_job_run");
     const int G = (int)job->ctxs.size();
     const uint64_t halo = job->max_pat_len > 0 ? (uint64_t)job->max_pat_len - 1 : 0;
-    // contiguous chunk per GPU, 64 KiB granularity so sub-chunks stay tile aligned
-    uint64_t per = (n + (uint64_t)G - 1) / (uint64_t)G;
-    per = (per + 65535) & ~65535ull;
     std::vector<int> rcs((size_t)G, PFAC_OK);
     std::vector<std::string> errs((size_t)G);
     const auto t0 = std::chrono::steady_clock::now();
     auto work = [&](int g) {
-        const uint64_t lo = std::min<uint64_t>(n, (uint64_t)g * per), hi = std::min<uint64_t>(n, lo + per);
+        uint64_t lo = 0, ns = 0, nvld = 0;
+        pfac_job_plan(n, G, job->max_pat_len, g, &lo, &ns, &nvld);
+        const uint64_t hi = lo + ns;
         std::vector<Segment> &segs = job->segs[(size_t)g];
         const size_t n_seg = (size_t)((hi - lo + kSegmentBytes - 1) / kSegmentBytes);
         for (size_t i = n_seg; i < segs.size(); i++) { pfac_host_free(segs[i].rec); }

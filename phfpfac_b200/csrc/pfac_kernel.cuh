@@ -44,6 +44,7 @@ struct ScanParams {
     unsigned long long *tile_state;   // decoupled look-back: [63:62] status, [61:0] value
     unsigned int *ticket;
     unsigned int *error_flag;
+    uint32_t debug;           // PFAC_DEBUG bits (timing experiments only): 1 no walk, 2 no look-back, 4 no filter
 };
 
 constexpr int kThreads = 512;          // 16 warps per CTA
@@ -294,7 +295,7 @@ __global__ void __launch_bounds__(kThreads, 2) pfac_scan_kernel(const ScanParams
             const uint4 v = *reinterpret_cast<const uint4 *>(buf + off);
             uint32_t nx = __shfl_down_sync(0xffffffffu, v.x, 1);
             if (lane == 31) nx = *reinterpret_cast<const uint32_t *>(buf + off + 16);
-            uint32_t mask = filter16(v, nx, s_bitmap);
+            uint32_t mask = (p.debug & 4u) ? 0u : filter16(v, nx, s_bitmap);
             if (edge) {   // start positions are [mis, a_start_end) in aligned coordinates
                 const uint32_t a = a0 + off;
                 const uint32_t lo = p.mis > a ? p.mis - a : 0u;
@@ -324,6 +325,7 @@ __global__ void __launch_bounds__(kThreads, 2) pfac_scan_kernel(const ScanParams
         const uint32_t qb = lane * per;
         const uint32_t qe = (qb + per < nq) ? qb + per : nq;
         uint32_t csum = 0;
+        if (!(p.debug & 1u))
         for (uint32_t e = qb; e < qe; e++) {
             const uint32_t tpos = wq[e];
             csum += walk_start<false>(p, buf, s_s0, tpos, walk_limit(p, a0, tpos), 0u, 0ull);
@@ -355,7 +357,7 @@ __global__ void __launch_bounds__(kThreads, 2) pfac_scan_kernel(const ScanParams
                 s_tile[b] = t;
                 if (t < p.n_tiles) issue_tile(p, t, buf, &s_mbar[b]);
             }
-            if (warp == 0) {
+            if (warp == 0 && !(p.debug & 2u)) {
                 const unsigned long long excl = tile_lookback(p.tile_state, tile, 0ull, lane, p.error_flag);
                 if (lane == 0 && tile == p.n_tiles - 1) *p.count_out = excl;
             }

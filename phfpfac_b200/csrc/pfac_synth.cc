@@ -198,10 +198,13 @@ long long pfac_synth_patterns(int kind, int count, uint64_t seed, int min_len, i
         } else {                                   // config 3: Snort-like literals
             int L = lognormal_len(g, 12.0, 0.6, min_len, max_len);
             if (g.below(100) < 60) {
+                // vocabulary prefix (shared with the text) + a distinctive tail of >= 4 random
+                // characters: prefixes are walked often, full matches stay rare (IDS-like)
                 p = kPrefixTok[g.below((uint32_t)kNumPrefixTok)];
                 if (g.below(4) == 0) p += kPrefixTok[g.below((uint32_t)kNumPrefixTok)];
-                if ((int)p.size() > L) p.resize((size_t)L);
-                while ((int)p.size() < L) p += kAlnum[g.below((uint32_t)kNumAlnum)];
+                int tail = std::max(4, L - (int)p.size());
+                if ((int)p.size() + tail > max_len) tail = max_len - (int)p.size();
+                for (int i = 0; i < tail; i++) p += kAlnum[g.below((uint32_t)kNumAlnum)];
             } else {
                 for (int i = 0; i < L; i++) {
                     uint32_t b = g.below(255);

@@ -1,0 +1,150 @@
+"""The product's table builder (phfpfac_b200/csrc/pfac_tables.cc) is bit-compatible with
+create_PFAC_table_reorder + FFDM: compared with the reference-generated goldens, with the oracle
+on random sets, and (where oracle/_ref exists) with the reference builder itself."""
+import os
+
+import numpy as np
+import pytest
+
+import phfpfac_b200 as pf
+from _oracle import Oracle, RefBuild, ref_available
+from conftest import digest, parse_key
+
+
+def same(a, b):
+    return (a.state_num == b.state_num and a.n_final == b.n_final and a.max_len == b.max_len
+            and a.ht_size == b.ht_size and np.array_equal(a.s0, b.s0) and np.array_equal(a.r, b.r)
+            and np.array_equal(a.HT, b.HT) and np.array_equal(a.val, b.val) and np.array_equal(a.idmap, b.idmap))
+
+
+def test_tables_match_reference_goldens(fixtures, golden):
+    for key, g in golden["ref_tables"].items():
+        name, parts, width = parse_key(key)
+        t = pf.Tables.from_bytes(fixtures[name], n_parts=parts, width=width)
+        assert t.n_parts == parts and t.max_pat_len == g["max_pat_len"], key
+        for i, want in enumerate(g["parts"]):
+            assert digest(t.part(i)) == want, (key, i)
+
+
+def test_kat_counts(fixtures, golden):
+    for name, k in golden["kat_counts"].items():
+        p = pf.Tables.from_bytes(fixtures[name], n_parts=1, width=k["width"]).part(0)
+        assert (p.state_num, p.n_final, p.n_keys, p.max_key) == (k["state_num"], k["n_final"], k["n_keys"], k["max_key"])
+
+
+def random_patterns(rng, n, alpha, max_len, base=97):
+    pats = set()
+    while len(pats) < n:
+        L = int(rng.integers(1, max_len + 1))
+        pats.add(bytes((rng.integers(0, alpha, L) + base).astype(np.uint8)))
+    pats = list(pats)
+    rng.shuffle(pats)
+    return b"".join(p + b"\n" for p in pats)
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_tables_equal_oracle_random(seed):
+    rng = np.random.default_rng(100 + seed)
+    n = int(rng.integers(1, 1500))
+    blob = random_patterns(rng, n, int(rng.integers(1, 200)) if seed % 2 else int(rng.integers(2, 6)),
+                           int(rng.integers(1, 40)), base=11 if seed % 2 else 97)
+    width = int(2 ** rng.integers(5, 13))
+    parts = int(rng.integers(1, 9))
+    if parts > n:
+        parts = 1
+    o = Oracle(blob, n_parts=parts, width=width)
+    t = pf.Tables.from_bytes(blob, n_parts=parts, width=width)
+    assert t.n_patterns == o.n_patterns and t.max_pat_len == o.max_pat_len
+    for g in range(parts):
+        a, b = t.part(g), o.part(g)
+        assert same(a, b), (seed, g)
+        assert a.n_keys == b.extra["n_keys"] and a.max_key == b.extra["max_key"] and a.max_offset == b.extra["max_offset"]
+
+
+def test_duplicate_and_prefix_patterns():
+    """Duplicates: the last in sort order owns the final state (create_table_reorder.c:366);
+    prefixes: the shorter pattern's final state becomes an interior node (:116)."""
+    blob = b"abc\nab\nabc\nabcd\na\nabc\nb\n"
+    for parts in (1, 2):
+        o = Oracle(blob, n_parts=parts, width=64)
+        t = pf.Tables.from_bytes(blob, n_parts=parts, width=64)
+        for g in range(parts):
+            assert same(t.part(g), o.part(g))
+
+
+def test_lookup_equals_transition_rule(fixtures):
+    """pfac_tables_lookup == master_kernel.cu:52-64 over the canonical arrays == the trie edge."""
+    o = Oracle(fixtures["xad"], n_parts=1, width=256)
+    t = pf.Tables.from_bytes(fixtures["xad"], n_parts=1, width=256)
+    p = t.part(0)
+    rng = np.random.default_rng(3)
+    for s in rng.integers(0, p.state_num, 64):
+        row = o.pfac_row(0, int(s))
+        for b in rng.integers(0, 256, 32):
+            assert t.lookup(int(s), int(b)) == row[int(b)]
+        for b in np.nonzero(row >= 0)[0]:
+            assert t.lookup(int(s), int(b)) == row[int(b)]
+    assert t.lookup(p.state_num + 5, 0) == -1 and t.lookup(-1, 3) == -1
+
+
+def test_from_arrays_roundtrip(fixtures):
+    t = pf.Tables.from_bytes(fixtures["xad"], n_parts=1, width=128)
+    p = t.part(0)
+    t2 = pf.Tables.from_arrays(p.s0, p.r, p.HT, p.val, 128, p.state_num, p.n_final, p.idmap, p.max_len)
+    q = t2.part(0)
+    assert same(p, q) and t2.max_pat_len == t.max_pat_len and t2.n_parts == 1
+
+
+def test_error_behaviour(tmp_path):
+    """Library errors instead of the reference's exit()/UB (create_table_reorder.c:71-77,:362; phf.c:161)."""
+    cases = [(b"abc\n\nabd\n", 256, -3), (b"abc\nabd", 256, -2), (b"x" * 1023 + b"\n", 256, -2),
+             (b"abc\n", 100, -4), (b"abc\n", 8192, -4), (b"abc\n", 0, -4), (b"", 256, -2)]
+    for blob, width, code in cases:
+        with pytest.raises(pf.PfacError) as e:
+            pf.Tables.from_bytes(blob, n_parts=1, width=width)
+        assert e.value.code == code, (blob[:10], width)
+    with pytest.raises(pf.PfacError) as e:
+        pf.Tables.from_file(str(tmp_path / "missing"), 1, 256)
+    assert e.value.code == -1
+    f = tmp_path / "pats"
+    f.write_bytes(b"x" * 1022 + b"\nhello\n")
+    t = pf.Tables.from_file(str(f), 1, 4096)
+    assert t.n_patterns == 2 and t.max_pat_len == 1022
+
+
+def test_large_set_beyond_reference_limits():
+    """100k patterns at width 256 exceed ROW_MAX (phf.c:7): the builder has dynamic limits; the PHF
+    must still be a perfect hash of the trie (every edge found, nothing else)."""
+    blob = pf.synth_patterns(0, 30000, 5, 8, 32)
+    t = pf.Tables.from_bytes(blob, n_parts=1, width=256)
+    p = t.part(0)
+    assert p.n_final == 30000 and p.n_r == p.state_num * 256 // 256 + 1
+    occupied = p.HT >= 0
+    assert int(occupied.sum()) == p.n_keys
+    # every pattern walks to its own final state through the PHF
+    lines = blob.split(b"\n")[:-1]
+    order = sorted(range(len(lines)), key=lambda i: lines[i])
+    for rank in (0, 1, 777, 29999):
+        pat = lines[order[rank]]
+        s = int(p.s0[pat[0]])
+        for b in pat[1:]:
+            s = t.lookup(s, b)
+            assert s >= 0
+        assert s == rank and p.idmap[s] == order[rank] + 1
+
+
+@pytest.mark.skipif(not ref_available() or not os.path.isdir("/root/reference"),
+                    reason="oracle/_ref not built or reference tree absent (GPU box)")
+def test_tables_equal_live_reference_builder(tmp_path):
+    rng = np.random.default_rng(17)
+    for trial in range(4):
+        blob = random_patterns(rng, int(rng.integers(10, 600)), int(rng.integers(2, 60)), 14)
+        f = tmp_path / f"p{trial}"
+        f.write_bytes(blob)
+        width = int(2 ** rng.integers(3, 13))
+        rb = RefBuild(str(f), streamnum=1, width=width)
+        t = pf.Tables.from_bytes(blob, n_parts=4, width=width)
+        for g in range(4):
+            assert same(t.part(g), rb.part(g)), (trial, g)
+        rb1 = RefBuild(str(f), width=width, single=True)
+        assert same(pf.Tables.from_bytes(blob, n_parts=1, width=width).part(0), rb1.part(0))
