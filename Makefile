@@ -8,9 +8,9 @@ B := phfpfac_b200/_build
 SRC := phfpfac_b200/csrc
 NVFLAGS := $(ARCH) -lineinfo -O3 -std=c++17 -ccbin $(HOSTCXX) -Iinclude -I$(SRC) \
            -Xcompiler -fPIC,-Wall,-Wextra,-pthread -Xptxas -v
-HOST_SRCS := $(SRC)/pfac_tables.cc $(SRC)/pfac_writer.cc $(SRC)/pfac_job.cc $(SRC)/pfac_synth.cc
+HOST_SRCS := $(SRC)/pfac_tables.cc $(SRC)/pfac_writer.cc $(SRC)/pfac_job.cc $(SRC)/pfac_synth.cc $(SRC)/pfac_derive.cc
 CUDA_SRCS := $(SRC)/pfac_device.cu
-HDRS := include/pfac_b200.h include/pfac_synth.h $(SRC)/pfac_internal.h $(SRC)/pfac_kernel.cuh
+HDRS := include/pfac_b200.h include/pfac_synth.h $(SRC)/pfac_internal.h $(SRC)/pfac_kernel.cuh $(SRC)/pfac_derive.h
 
 .PHONY: all lib cli oracle clean
 all: lib cli oracle

@@ -87,6 +87,13 @@ const int32_t *pfac_tables_r(const pfac_tables *t, int part);     /* n_r entries
 const int32_t *pfac_tables_HT(const pfac_tables *t, int part);    /* ht_size entries */
 const int32_t *pfac_tables_val(const pfac_tables *t, int part);   /* ht_size entries */
 const int32_t *pfac_tables_idmap(const pfac_tables *t, int part); /* n_final entries */
+/* Builds the scan kernel's shared-memory accelerators for this partition on the host (the same
+ * code pfac_ctx_create runs) and verifies them against the canonical PHF: prefix filters are
+ * supersets, hot rows answer like master_kernel.cu:52-64.  stats[0..7] = image bytes, T1 pairs,
+ * T2 bits set, 4-byte prefixes, short patterns present, hot rows, hot transitions, longest probe.
+ * Needs no GPU. */
+int pfac_tables_derive_check(const pfac_tables *t, int part, uint32_t t2_bytes, uint32_t hot_bytes,
+                             uint64_t stats[8]);
 /* One transition through the PHF exactly as master_kernel.cu:52-64 does it; -1 = none. */
 int32_t pfac_tables_lookup(const pfac_tables *t, int part, int32_t state, int32_t byte);
 
@@ -107,7 +114,8 @@ int pfac_ctx_device(const pfac_ctx *ctx);
  * `base_pos` = global position of d_in[0] (only used to reproduce the reference's 4096+512
  * tile walk bound for patterns longer than 513 bytes, master_kernel.cu:141-144).
  * d_out: device array of `cap` pfac_match; d_count: device uint64 receiving the number of
- * matches found (may exceed cap: records beyond cap are dropped, never written).
+ * matches found.  If it exceeds cap nothing is written past d_out[cap) and the contents
+ * of d_out are unspecified: size the buffer from the count and scan again.
  * Asynchronous on `stream`. */
 int pfac_scan_device(pfac_ctx *ctx, const void *d_in, uint64_t n_starts, uint64_t n_valid,
                      uint64_t base_pos, void *d_out, uint64_t cap, void *d_count, void *stream);
@@ -131,6 +139,12 @@ void pfac_host_free(void *ptr);
  * info[0] = kernel launches, info[1] = tiles, info[2] = CTAs, info[3] = dynamic smem bytes,
  * info[4] = h2d bytes, info[5] = d2h bytes, info[6] = sub-chunks, info[7] = reserved */
 int pfac_ctx_last_scan_info(const pfac_ctx *ctx, uint64_t info[8]);
+
+/* Derived (shared-memory) table statistics of this context, for DESIGN.md / bench.py:
+ * info[0] = image bytes, [1] = T1 pairs set, [2] = T2 bits, [3] = T2 bits set, [4] = 4-byte prefixes,
+ * [5] = short patterns (<= 3 bytes) present, [6] = hot-table slots, [7] = hot rows, [8] = hot
+ * transitions, [9] = longest probe, [10] = dynamic smem bytes, [11] = table bytes in HBM */
+int pfac_ctx_derived_info(const pfac_ctx *ctx, uint64_t info[12]);
 
 /* ------------------------------------------------------------------------------ multi-GPU job
  * Replaces the GPU x stream loop of main.cc:171-272.  The INPUT is sharded (the reference

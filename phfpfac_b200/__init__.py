@@ -84,6 +84,13 @@ class Tables:
     def part(self, g=0):
         return PartView(self, g)
 
+    def derive_check(self, g=0, t2_bytes=16384, hot_bytes=32768):
+        """Host-side build + verification of the kernel's shared-memory tables (no GPU needed)."""
+        st = (C.c_uint64 * 8)()
+        check(lib.pfac_tables_derive_check(self._h, g, t2_bytes, hot_bytes, st))
+        keys = ("image_bytes", "t1_pairs", "t2_set", "prefixes4", "has_short", "hot_rows", "hot_entries", "hot_probe")
+        return dict(zip(keys, list(st)))
+
     def lookup(self, state, byte, g=0):
         return lib.pfac_tables_lookup(self._h, g, state, byte)
 
@@ -125,6 +132,13 @@ class Matcher:
         info = (C.c_uint64 * 8)()
         check(lib.pfac_ctx_last_scan_info(self._h, info))
         keys = ("launches", "tiles", "ctas", "smem_bytes", "h2d_bytes", "d2h_bytes", "chunks", "reserved")
+        return dict(zip(keys, list(info)))
+
+    def derived_info(self):
+        info = (C.c_uint64 * 12)()
+        check(lib.pfac_ctx_derived_info(self._h, info))
+        keys = ("image_bytes", "t1_pairs", "t2_bits", "t2_set", "prefixes4", "has_short", "hot_slots", "hot_rows",
+                "hot_entries", "hot_probe", "smem_bytes", "table_bytes")
         return dict(zip(keys, list(info)))
 
     # -- device-resident input (raw pointers; torch tensors are accepted for convenience)

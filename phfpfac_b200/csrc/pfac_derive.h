@@ -1,0 +1,56 @@
+// Device-side derived layouts of one partition's canonical tables (host code, no CUDA).
+//
+// The canonical PHF arrays r/HT/val (bit-compatible with CreateTable/FFDM, reference phf.c:151)
+// stay the authoritative transition function and are uploaded unchanged (HT and val interleaved).
+// What is derived here are the shared-memory resident ACCELERATORS the scan kernel consults
+// first; every one of them is a superset filter or an exact copy of PHF rows, so lookups stay
+// equivalent to master_kernel.cu:52-64:
+//   T1    65,536 x u8 : byte 1 iff a walk that starts with bytes (c0,c1) matches a 1-byte pattern
+//                       or has a second edge  (root fan-out, s0Table of main.cc:200, folded in)
+//   T1s   65,536 bits : pair (c0,c1) can complete a pattern of length <= 3 (bypasses T2)
+//   T2    2^k2 bits   : multiplicative hash of every 4-byte pattern prefix
+//   s0f   256 x u32   : root row with the "row is hot" flag
+//   hot   open-addressing hash of COMPLETE PHF rows of the hottest states
+//                       (key = state<<8|byte -> next state | flag); a miss in a hot row means
+//                       "no transition", exactly like HT[idx] != row in the PHF
+#pragma once
+#include <cstdint>
+#include <vector>
+
+#include "pfac_internal.h"
+
+namespace pfac {
+
+constexpr uint32_t kHotFlag = 1u << 30;      // on a state word: its PHF row lives in the smem hot table
+constexpr uint32_t kStateMask = kHotFlag - 1;
+constexpr uint32_t kNoState = 0xFFFFFFFFu;
+constexpr uint32_t kHotEmpty = 0xFFFFFFFFu;
+constexpr uint32_t kHash4Mul = 0x9E3779B1u;
+
+struct Derived {
+    // shared-memory image, copied verbatim by the kernel (sections 128-byte aligned)
+    std::vector<uint8_t> image;
+    uint32_t off_t1 = 0, off_s0f = 0, off_t2 = 0, off_t1s = 0, off_hot = 0;
+    uint32_t t2_shift = 32;      // index = (w * kHash4Mul) >> t2_shift
+    uint32_t has_short = 0;      // patterns of length <= 3 exist (T1s present)
+    uint32_t hot_mask = 0;       // entries - 1 (0: no hot table)
+    uint32_t hot_shift = 32;     // slot = (key * hot_mul) >> hot_shift
+    uint32_t hot_mul = 0;
+    uint32_t hot_probe = 0;      // longest probe sequence needed
+    uint32_t n_hot_rows = 0, n_hot_entries = 0;
+    // global-memory copy of val with the hot flag (HT interleaved by the uploader)
+    std::vector<int32_t> val_flagged;
+    // statistics (pfac_ctx_derived_info)
+    uint32_t t1_set = 0, t2_set = 0, n_depth4 = 0;
+};
+
+// rotl2 of every byte: the kernel indexes T1 with text bytes rotated left by 2 so that the low,
+// high-entropy bits of ASCII text select the shared-memory bank
+inline uint32_t rot2(uint32_t c) { return ((c << 2) | (c >> 6)) & 0xFFu; }
+
+// t2_bytes / hot_bytes: shared-memory budget of the two variable sections (powers of two; 0 = none)
+void derive_tables(const Partition &P, uint32_t t2_bytes, uint32_t hot_bytes, Derived &out);
+
+int derive_selfcheck(const Partition &P, const Derived &d);
+
+}  // namespace pfac

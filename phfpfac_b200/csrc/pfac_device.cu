@@ -8,6 +8,7 @@
 #include <memory>
 #include <mutex>
 
+#include "pfac_derive.h"
 #include "pfac_internal.h"
 #include "pfac_kernel.cuh"
 
@@ -23,10 +24,18 @@ using namespace pfac;
 
 namespace {
 
-struct Ctrl {   // device-side control block, zeroed before every launch
-    unsigned int ticket;
-    unsigned int error_flag;
-    unsigned long long count;
+// Everything one in-flight scan needs besides the tables: control block, result block, tile
+// directory and the arrival-order scratch.  One per user of a stream (the context's own slot for
+// pfac_scan_device, one per pipeline stage for pfac_scan_host).
+struct Slot {
+    Ctrl *d_ctrl = nullptr;
+    Result *d_result = nullptr;
+    Result *h_result = nullptr;   // pinned
+    unsigned int *d_tile_cnt = nullptr, *d_tile_mask = nullptr;
+    uint4 *d_slice_ent = nullptr;
+    size_t tile_cap = 0;
+    uint2 *d_scratch = nullptr;
+    size_t scratch_cap = 0;   // records
 };
 
 struct Stage {   // one pipeline stage of pfac_scan_host
@@ -35,10 +44,7 @@ struct Stage {   // one pipeline stage of pfac_scan_host
     size_t d_in_cap = 0;
     pfac_match *d_out = nullptr;
     size_t d_out_cap = 0;   // records
-    Ctrl *d_ctrl = nullptr;
-    unsigned long long *d_tile_state = nullptr;
-    size_t tile_cap = 0;
-    Ctrl *h_ctrl = nullptr;   // pinned
+    Slot slot;
     cudaEvent_t done = nullptr;
 };
 
@@ -47,22 +53,21 @@ struct Stage {   // one pipeline stage of pfac_scan_host
 struct pfac_ctx {
     int device = 0;
     int sm_count = 0;
-    int blocks_per_sm = 0;
     int n_streams = 1;
     size_t chunk_bytes = 0;
-    // tables (device)
-    int32_t *d_r = nullptr, *d_idmap = nullptr, *d_s0 = nullptr;
+    // tables (device): canonical r, {HT, val|flag}, idmap + the shared-memory image
+    int32_t *d_r = nullptr, *d_idmap = nullptr;
     int2 *d_htval = nullptr;
-    uint32_t *d_bitmap2 = nullptr;
+    uint4 *d_image = nullptr;
+    Derived dv;   // image layout and hash parameters (the image bytes are dropped after the upload)
+    uint32_t image_bytes = 0;
     int32_t ht_size = 0, width_bit = 0, n_final = 0, max_pat_len = 0;
     uint32_t halo = 16;
     size_t smem_bytes = 0;
-    // scan_device scratch (own stream use)
+    size_t table_bytes = 0;
+    // pfac_scan_device: own stream and slot
     cudaStream_t own_stream = nullptr;
-    Ctrl *d_ctrl = nullptr;
-    Ctrl *h_ctrl = nullptr;
-    unsigned long long *d_tile_state = nullptr;
-    size_t tile_cap = 0;
+    Slot own;
     std::vector<Stage> stages;
     uint64_t info[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     uint32_t debug = 0;   // PFAC_DEBUG env (timing experiments only)
@@ -85,22 +90,63 @@ struct DeviceGuard {
     }
 };
 
-int ensure_tiles(unsigned long long **buf, size_t *cap, size_t need)
+int slot_init(Slot &s)
 {
-    if (need <= *cap) return PFAC_OK;
-    if (*buf) cudaFree(*buf);
-    *buf = nullptr;
-    *cap = 0;
-    size_t n = std::max<size_t>(need, 4096);
-    CU_TRY(cudaMalloc(buf, n * sizeof(unsigned long long)));
-    *cap = n;
+    if (s.d_ctrl) return PFAC_OK;
+    CU_TRY(cudaMalloc(&s.d_ctrl, sizeof(Ctrl)));
+    CU_TRY(cudaMemset(s.d_ctrl, 0, sizeof(Ctrl)));
+    CU_TRY(cudaMalloc(&s.d_result, sizeof(Result)));
+    CU_TRY(cudaHostAlloc(&s.h_result, sizeof(Result), cudaHostAllocPortable));
     return PFAC_OK;
 }
 
-// Enqueue one scan on `stream`.  d_ctrl / tile_state belong to that stream's user.
-int launch_scan(pfac_ctx *ctx, const void *d_in, uint64_t n_starts, uint64_t n_valid, uint64_t base_pos,
-                uint32_t pos_bias, void *d_out, uint64_t cap, Ctrl *d_ctrl, unsigned long long **tile_state, size_t *tile_cap,
-                cudaStream_t stream, uint64_t *tiles_out, uint64_t *ctas_out)
+void slot_free(Slot &s)
+{
+    if (s.d_ctrl) cudaFree(s.d_ctrl);
+    if (s.d_result) cudaFree(s.d_result);
+    if (s.h_result) cudaFreeHost(s.h_result);
+    if (s.d_tile_cnt) cudaFree(s.d_tile_cnt);
+    if (s.d_tile_mask) cudaFree(s.d_tile_mask);
+    if (s.d_slice_ent) cudaFree(s.d_slice_ent);
+    if (s.d_scratch) cudaFree(s.d_scratch);
+    s = Slot();
+}
+
+// Grow the tile directory / scratch of a slot.  Growing synchronises the stream first (the old
+// buffers may still be in use); steady-state calls never get here.
+int slot_reserve(Slot &s, size_t n_tiles, size_t records, cudaStream_t stream)
+{
+    if (n_tiles > s.tile_cap) {
+        CU_TRY(cudaStreamSynchronize(stream));
+        if (s.d_tile_cnt) cudaFree(s.d_tile_cnt);
+        if (s.d_tile_mask) cudaFree(s.d_tile_mask);
+        if (s.d_slice_ent) cudaFree(s.d_slice_ent);
+        s.d_tile_cnt = s.d_tile_mask = nullptr;
+        s.d_slice_ent = nullptr;
+        s.tile_cap = 0;
+        const size_t n = std::max<size_t>(n_tiles, 1024);
+        CU_TRY(cudaMalloc(&s.d_tile_cnt, n * sizeof(unsigned int)));
+        CU_TRY(cudaMalloc(&s.d_tile_mask, n * sizeof(unsigned int)));
+        CU_TRY(cudaMalloc(&s.d_slice_ent, n * kSlicesPerTile * sizeof(uint4)));
+        s.tile_cap = n;
+    }
+    if (records > s.scratch_cap) {
+        CU_TRY(cudaStreamSynchronize(stream));
+        if (s.d_scratch) cudaFree(s.d_scratch);
+        s.d_scratch = nullptr;
+        s.scratch_cap = 0;
+        const size_t n = std::max<size_t>(records, 4096);
+        CU_TRY(cudaMalloc(&s.d_scratch, n * sizeof(uint2)));
+        s.scratch_cap = n;
+    }
+    return PFAC_OK;
+}
+
+// Enqueue one scan (scan kernel + ordering pass) on `stream`.  On completion slot.d_result holds
+// {count, error}; d_count (optional, device) receives the count as well.
+int launch_scan(pfac_ctx *ctx, Slot &slot, const void *d_in, uint64_t n_starts, uint64_t n_valid, uint64_t base_pos,
+                uint32_t pos_bias, void *d_out, uint64_t cap, void *d_count, cudaStream_t stream,
+                uint64_t *tiles_out, uint64_t *ctas_out, uint64_t *launches_out)
 {
     if (n_valid < n_starts) return set_error(PFAC_ERR_ARG, "n_valid < n_starts");
     const uint64_t useful = n_starts + (uint64_t)(ctx->max_pat_len > 0 ? ctx->max_pat_len - 1 : 0);
@@ -108,11 +154,18 @@ int launch_scan(pfac_ctx *ctx, const void *d_in, uint64_t n_starts, uint64_t n_v
     const uint32_t mis = (uint32_t)((uintptr_t)d_in & 15u);
     if (n_valid + mis + (uint64_t)kTile + 4096 >= (1ull << 32))
         return set_error(PFAC_ERR_LIMIT, "one scan call covers less than 4 GiB; split the input");
-    CU_TRY(cudaMemsetAsync(d_ctrl, 0, sizeof(Ctrl), stream));
     if (tiles_out) *tiles_out = 0;
     if (ctas_out) *ctas_out = 0;
-    if (n_starts == 0 || ctx->max_pat_len == 0) return PFAC_OK;
+    if (launches_out) *launches_out = 0;
+    int e = slot_init(slot);
+    if (e) return e;
+    if (n_starts == 0 || ctx->max_pat_len == 0) {
+        CU_TRY(cudaMemsetAsync(slot.d_result, 0, sizeof(Result), stream));
+        if (d_count) CU_TRY(cudaMemsetAsync(d_count, 0, sizeof(unsigned long long), stream));
+        return PFAC_OK;
+    }
     ScanParams p;
+    memset(&p, 0, sizeof p);
     p.in_al = (const uint8_t *)d_in - mis;
     p.mis = mis;
     p.a_start_end = (uint32_t)(mis + n_starts);
@@ -126,26 +179,53 @@ int launch_scan(pfac_ctx *ctx, const void *d_in, uint64_t n_starts, uint64_t n_v
     p.r = ctx->d_r;
     p.htval = ctx->d_htval;
     p.idmap = ctx->d_idmap;
-    p.s0 = ctx->d_s0;
-    p.bitmap2 = ctx->d_bitmap2;
     p.ht_size = ctx->ht_size;
     p.width_bit = ctx->width_bit;
     p.n_final = ctx->n_final;
-    p.out = (uint2 *)d_out;
-    p.cap = cap;
-    p.count_out = &d_ctrl->count;
-    int e = ensure_tiles(tile_state, tile_cap, p.n_tiles);
+    p.image = ctx->d_image;
+    p.image_bytes = ctx->image_bytes;
+    p.off_t1 = ctx->dv.off_t1;
+    p.off_s0f = ctx->dv.off_s0f;
+    p.off_t2 = ctx->dv.off_t2;
+    p.off_t1s = ctx->dv.off_t1s;
+    p.off_hot = ctx->dv.off_hot;
+    p.t2_shift = ctx->dv.t2_shift;
+    p.has_short = ctx->dv.has_short;
+    p.hot_mask = ctx->dv.hot_mask;
+    p.hot_shift = ctx->dv.hot_shift;
+    p.hot_mul = ctx->dv.hot_mul;
+    p.hot_probe = ctx->dv.hot_probe;
+    e = slot_reserve(slot, p.n_tiles, (size_t)std::max<uint64_t>(cap, 4096), stream);
     if (e) return e;
-    p.tile_state = *tile_state;
-    p.ticket = &d_ctrl->ticket;
-    p.error_flag = &d_ctrl->error_flag;
+    p.scratch = slot.d_scratch;
+    p.scratch_cap = slot.scratch_cap;
+    p.tile_cnt = slot.d_tile_cnt;
+    p.tile_mask = slot.d_tile_mask;
+    p.slice_ent = slot.d_slice_ent;
+    p.ctrl = slot.d_ctrl;
     p.debug = ctx->debug;
-    CU_TRY(cudaMemsetAsync(*tile_state, 0, (size_t)p.n_tiles * sizeof(unsigned long long), stream));
-    const uint32_t grid = (uint32_t)std::min<uint64_t>(p.n_tiles, (uint64_t)ctx->sm_count * ctx->blocks_per_sm);
+    const uint32_t grid = (uint32_t)std::min<uint64_t>(p.n_tiles, (uint64_t)ctx->sm_count);
     pfac_scan_kernel<<<grid, kThreads, ctx->smem_bytes, stream>>>(p);
+    CU_TRY(cudaGetLastError());
+
+    FinalizeParams f;
+    f.tile_cnt = slot.d_tile_cnt;
+    f.tile_mask = slot.d_tile_mask;
+    f.slice_ent = slot.d_slice_ent;
+    f.scratch = slot.d_scratch;
+    f.scratch_cap = slot.scratch_cap;
+    f.out = (uint2 *)d_out;
+    f.cap = cap;
+    f.n_tiles = p.n_tiles;
+    f.ctrl = slot.d_ctrl;
+    f.result = slot.d_result;
+    f.count_out = (unsigned long long *)d_count;
+    const uint32_t fgrid = (uint32_t)std::min<uint64_t>((p.n_tiles + kFinThreads - 1) / kFinThreads, (uint64_t)ctx->sm_count);
+    pfac_finalize_kernel<<<fgrid, kFinThreads, 0, stream>>>(f);
     CU_TRY(cudaGetLastError());
     if (tiles_out) *tiles_out = p.n_tiles;
     if (ctas_out) *ctas_out = grid;
+    if (launches_out) *launches_out = 2;
     return PFAC_OK;
 }
 
@@ -153,9 +233,7 @@ void free_stage(Stage &s)
 {
     if (s.d_in) cudaFree(s.d_in);
     if (s.d_out) cudaFree(s.d_out);
-    if (s.d_ctrl) cudaFree(s.d_ctrl);
-    if (s.d_tile_state) cudaFree(s.d_tile_state);
-    if (s.h_ctrl) cudaFreeHost(s.h_ctrl);
+    slot_free(s.slot);
     if (s.done) cudaEventDestroy(s.done);
     if (s.stream) cudaStreamDestroy(s.stream);
     s = Stage();
@@ -205,50 +283,56 @@ int pfac_ctx_create(int device, const pfac_tables *t, int part, int n_streams, s
     ctx->n_final = P.n_final;
     ctx->max_pat_len = P.max_len;
     ctx->halo = (uint32_t)std::max(16, ((P.max_len > 0 ? P.max_len - 1 : 0) + 15) / 16 * 16);
-    ctx->smem_bytes = scan_smem_bytes(ctx->halo);
     if (const char *dbg = getenv("PFAC_DEBUG")) ctx->debug = (uint32_t)atoi(dbg);
 
-    // canonical arrays -> device (r, {HT,val} interleaved, idmap, s0) + the 2-byte prefix bitmap
+    // shared-memory budget: the fixed parts first, then as much T2 / hot table as fits
+    const size_t smem_max = (size_t)prop.sharedMemPerBlockOptin;
+    uint32_t t2_bytes = 16384, hot_bytes = 32768;
+    if (const char *v = getenv("PFAC_T2_BYTES")) t2_bytes = (uint32_t)atoi(v);
+    if (const char *v = getenv("PFAC_HOT_BYTES")) hot_bytes = (uint32_t)atoi(v);
+    while (true) {
+        derive_tables(P, t2_bytes, hot_bytes, ctx->dv);
+        ctx->image_bytes = (uint32_t)ctx->dv.image.size();
+        ctx->smem_bytes = scan_smem_bytes(ctx->image_bytes, ctx->halo);
+        if (ctx->smem_bytes <= smem_max) break;
+        if (hot_bytes >= 2048) hot_bytes /= 2;
+        else if (hot_bytes) hot_bytes = 0;
+        else if (t2_bytes >= 2048) t2_bytes /= 2;
+        else
+            return set_error(PFAC_ERR_CUDA, "scan kernel needs %zu B of shared memory, device offers %zu",
+                             ctx->smem_bytes, smem_max);
+    }
+
+    // canonical arrays -> device: r, {HT, val|hot flag} interleaved, idmap; + the shared-memory image
     const size_t n_r = std::max<size_t>(P.r.size(), 1), n_ht = std::max<size_t>((size_t)P.ht_size, 1);
     const size_t n_id = std::max<size_t>((size_t)P.n_final, 1);
     std::vector<int2> htval(n_ht, make_int2(-1, -1));
-    for (int32_t i = 0; i < P.ht_size; i++) htval[(size_t)i] = make_int2(P.HT[(size_t)i], P.val[(size_t)i]);
-    std::vector<uint32_t> bitmap(2048, 0);
-    for (int b0 = 0; b0 < 256; b0++) {
-        const int32_t s = P.s0.empty() ? -1 : P.s0[(size_t)b0];
-        if (s < 0) continue;
-        for (int b1 = 0; b1 < 256; b1++) {
-            // a 1-byte pattern matches whatever follows; otherwise the walk must have a 2nd edge
-            if (s < P.n_final || P.lookup(s, b1) >= 0) {
-                const uint32_t win = (uint32_t)b0 | ((uint32_t)b1 << 8);
-                bitmap[win >> 5] |= 1u << (win & 31u);
-            }
-        }
-    }
+    for (int32_t i = 0; i < P.ht_size; i++) htval[(size_t)i] = make_int2(P.HT[(size_t)i], ctx->dv.val_flagged[(size_t)i]);
     CU_TRY(cudaMalloc(&ctx->d_r, n_r * sizeof(int32_t)));
     CU_TRY(cudaMalloc(&ctx->d_htval, n_ht * sizeof(int2)));
     CU_TRY(cudaMalloc(&ctx->d_idmap, n_id * sizeof(int32_t)));
-    CU_TRY(cudaMalloc(&ctx->d_s0, 256 * sizeof(int32_t)));
-    CU_TRY(cudaMalloc(&ctx->d_bitmap2, 2048 * sizeof(uint32_t)));
+    CU_TRY(cudaMalloc(&ctx->d_image, ctx->image_bytes));
     CU_TRY(cudaMemset(ctx->d_r, 0xFF, n_r * sizeof(int32_t)));
     CU_TRY(cudaMemset(ctx->d_idmap, 0, n_id * sizeof(int32_t)));
     if (!P.r.empty()) CU_TRY(cudaMemcpy(ctx->d_r, P.r.data(), P.r.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
     CU_TRY(cudaMemcpy(ctx->d_htval, htval.data(), n_ht * sizeof(int2), cudaMemcpyHostToDevice));
     if (P.n_final) CU_TRY(cudaMemcpy(ctx->d_idmap, P.idmap.data(), (size_t)P.n_final * sizeof(int32_t), cudaMemcpyHostToDevice));
-    std::vector<int32_t> s0(256, -1);
-    if (!P.s0.empty()) s0 = P.s0;
-    CU_TRY(cudaMemcpy(ctx->d_s0, s0.data(), 256 * sizeof(int32_t), cudaMemcpyHostToDevice));
-    CU_TRY(cudaMemcpy(ctx->d_bitmap2, bitmap.data(), 2048 * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    CU_TRY(cudaMemcpy(ctx->d_image, ctx->dv.image.data(), ctx->image_bytes, cudaMemcpyHostToDevice));
+    ctx->table_bytes = n_r * 4 + n_ht * 8 + n_id * 4 + ctx->image_bytes;
+    ctx->dv.image.clear();
+    ctx->dv.image.shrink_to_fit();
+    ctx->dv.val_flagged.clear();
+    ctx->dv.val_flagged.shrink_to_fit();
 
-    CU_TRY(cudaFuncSetAttribute(pfac_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_bytes));
+    // the attribute is per function and device, not per context: always allow the device maximum
+    CU_TRY(cudaFuncSetAttribute(pfac_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
     int bps = 0;
     CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, pfac_scan_kernel, kThreads, ctx->smem_bytes));
     if (bps < 1) return set_error(PFAC_ERR_CUDA, "scan kernel does not fit on an SM (smem %zu B)", ctx->smem_bytes);
-    ctx->blocks_per_sm = bps;
 
     CU_TRY(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
-    CU_TRY(cudaMalloc(&ctx->d_ctrl, sizeof(Ctrl)));
-    CU_TRY(cudaHostAlloc(&ctx->h_ctrl, sizeof(Ctrl), cudaHostAllocPortable));
+    int e = slot_init(ctx->own);
+    if (e) return e;
     *out = ctx.release();
     return PFAC_OK;
 }
@@ -259,19 +343,27 @@ void pfac_ctx_destroy(pfac_ctx *ctx)
     DeviceGuard g(ctx->device);
     cudaDeviceSynchronize();
     for (auto &s : ctx->stages) free_stage(s);
+    slot_free(ctx->own);
     if (ctx->d_r) cudaFree(ctx->d_r);
     if (ctx->d_htval) cudaFree(ctx->d_htval);
     if (ctx->d_idmap) cudaFree(ctx->d_idmap);
-    if (ctx->d_s0) cudaFree(ctx->d_s0);
-    if (ctx->d_bitmap2) cudaFree(ctx->d_bitmap2);
-    if (ctx->d_ctrl) cudaFree(ctx->d_ctrl);
-    if (ctx->h_ctrl) cudaFreeHost(ctx->h_ctrl);
-    if (ctx->d_tile_state) cudaFree(ctx->d_tile_state);
+    if (ctx->d_image) cudaFree(ctx->d_image);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
 }
 
 int pfac_ctx_device(const pfac_ctx *ctx) { return ctx ? ctx->device : -1; }
+
+int pfac_ctx_derived_info(const pfac_ctx *ctx, uint64_t info[12])
+{
+    if (!ctx || !info) return set_error(PFAC_ERR_ARG, "bad arguments");
+    const Derived &d = ctx->dv;
+    const uint64_t v[12] = {ctx->image_bytes, d.t1_set, d.t2_shift >= 32 ? 0 : (1ull << (32 - d.t2_shift)), d.t2_set,
+                            d.n_depth4, d.has_short, d.hot_mask ? (uint64_t)d.hot_mask + 1 : 0, d.n_hot_rows,
+                            d.n_hot_entries, d.hot_probe, ctx->smem_bytes, ctx->table_bytes};
+    memcpy(info, v, sizeof v);
+    return PFAC_OK;
+}
 
 int pfac_scan_device(pfac_ctx *ctx, const void *d_in, uint64_t n_starts, uint64_t n_valid, uint64_t base_pos,
                      void *d_out, uint64_t cap, void *d_count, void *stream)
@@ -280,12 +372,10 @@ int pfac_scan_device(pfac_ctx *ctx, const void *d_in, uint64_t n_starts, uint64_
     std::lock_guard<std::mutex> lk(ctx->mu);
     DeviceGuard g(ctx->device);
     cudaStream_t st = stream ? (cudaStream_t)stream : ctx->own_stream;
-    uint64_t tiles = 0, ctas = 0;
-    int e = launch_scan(ctx, d_in, n_starts, n_valid, base_pos, 0u, d_out, cap, ctx->d_ctrl, &ctx->d_tile_state,
-                        &ctx->tile_cap, st, &tiles, &ctas);
+    uint64_t tiles = 0, ctas = 0, launches = 0;
+    int e = launch_scan(ctx, ctx->own, d_in, n_starts, n_valid, base_pos, 0u, d_out, cap, d_count, st, &tiles, &ctas, &launches);
     if (e) return e;
-    CU_TRY(cudaMemcpyAsync(d_count, &ctx->d_ctrl->count, sizeof(unsigned long long), cudaMemcpyDeviceToDevice, st));
-    ctx->info[0] = tiles ? 1 : 0;
+    ctx->info[0] = launches;
     ctx->info[1] = tiles;
     ctx->info[2] = ctas;
     ctx->info[3] = ctx->smem_bytes;
@@ -297,26 +387,25 @@ int pfac_scan_device(pfac_ctx *ctx, const void *d_in, uint64_t n_starts, uint64_
 int pfac_scan_device_sync(pfac_ctx *ctx, const void *d_in, uint64_t n_starts, uint64_t n_valid, uint64_t base_pos,
                           void *d_out, uint64_t cap, uint64_t *count, void *stream)
 {
-    if (!ctx || !count) return set_error(PFAC_ERR_ARG, "bad arguments to pfac_scan_device_sync");
+    if (!ctx || !count || (!d_in && n_starts) || (!d_out && cap)) return set_error(PFAC_ERR_ARG, "bad arguments to pfac_scan_device_sync");
     cudaStream_t st = stream ? (cudaStream_t)stream : ctx->own_stream;
     {
         std::lock_guard<std::mutex> lk(ctx->mu);
         DeviceGuard g(ctx->device);
-        uint64_t tiles = 0, ctas = 0;
-        int e = launch_scan(ctx, d_in, n_starts, n_valid, base_pos, 0u, d_out, cap, ctx->d_ctrl, &ctx->d_tile_state,
-                            &ctx->tile_cap, st, &tiles, &ctas);
+        uint64_t tiles = 0, ctas = 0, launches = 0;
+        int e = launch_scan(ctx, ctx->own, d_in, n_starts, n_valid, base_pos, 0u, d_out, cap, nullptr, st, &tiles, &ctas, &launches);
         if (e) return e;
-        CU_TRY(cudaMemcpyAsync(ctx->h_ctrl, ctx->d_ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, st));
+        CU_TRY(cudaMemcpyAsync(ctx->own.h_result, ctx->own.d_result, sizeof(Result), cudaMemcpyDeviceToHost, st));
         CU_TRY(cudaStreamSynchronize(st));
-        ctx->info[0] = tiles ? 1 : 0;
+        ctx->info[0] = launches;
         ctx->info[1] = tiles;
         ctx->info[2] = ctas;
         ctx->info[3] = ctx->smem_bytes;
         ctx->info[4] = ctx->info[5] = 0;
         ctx->info[6] = 1;
-        if (ctx->h_ctrl->error_flag)
-            return set_error(PFAC_ERR_INTERNAL, "device watchdog tripped (code %u)", ctx->h_ctrl->error_flag);
-        *count = ctx->h_ctrl->count;
+        if (ctx->own.h_result->error_flag)
+            return set_error(PFAC_ERR_INTERNAL, "device watchdog tripped (code %u)", ctx->own.h_result->error_flag);
+        *count = ctx->own.h_result->count;
     }
     if (*count > cap) return set_error(PFAC_ERR_OUTPUT_FULL, "%llu matches exceed the capacity of %llu records",
                                        (unsigned long long)*count, (unsigned long long)cap);
@@ -363,8 +452,8 @@ int pfac_scan_host(pfac_ctx *ctx, const void *h_in, uint64_t n_starts, uint64_t 
         if (!st.stream) {
             CU_TRY(cudaStreamCreateWithFlags(&st.stream, cudaStreamNonBlocking));
             CU_TRY(cudaEventCreateWithFlags(&st.done, cudaEventDisableTiming));
-            CU_TRY(cudaMalloc(&st.d_ctrl, sizeof(Ctrl)));
-            CU_TRY(cudaHostAlloc(&st.h_ctrl, sizeof(Ctrl), cudaHostAllocPortable));
+            int e = slot_init(st.slot);
+            if (e) return e;
         }
         const size_t need_in = (size_t)(std::min<uint64_t>(chunk, n_starts) + halo + 64);
         if (st.d_in_cap < need_in) {
@@ -391,15 +480,15 @@ int pfac_scan_host(pfac_ctx *ctx, const void *h_in, uint64_t n_starts, uint64_t 
         const uint64_t nv = std::min<uint64_t>(ns + halo, n_valid - off);
         CU_TRY(cudaMemcpyAsync(st.d_in, (const uint8_t *)h_in + off, (size_t)nv, cudaMemcpyHostToDevice, st.stream));
         h2d += nv;
-        uint64_t tiles = 0, ctas = 0;
-        int e = launch_scan(ctx, st.d_in, ns, nv, base_pos + off, (uint32_t)off, st.d_out, st.d_out_cap, st.d_ctrl,
-                            &st.d_tile_state, &st.tile_cap, st.stream, &tiles, &ctas);
+        uint64_t tiles = 0, ctas = 0, nl = 0;
+        int e = launch_scan(ctx, st.slot, st.d_in, ns, nv, base_pos + off, (uint32_t)off, st.d_out, st.d_out_cap, nullptr,
+                            st.stream, &tiles, &ctas, &nl);
         if (e) return e;
-        launches += tiles ? 1 : 0;
+        launches += nl;
         tiles_total += tiles;
         ctas_max = std::max(ctas_max, ctas);
-        CU_TRY(cudaMemcpyAsync(st.h_ctrl, st.d_ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, st.stream));
-        d2h += sizeof(Ctrl);
+        CU_TRY(cudaMemcpyAsync(st.slot.h_result, st.slot.d_result, sizeof(Result), cudaMemcpyDeviceToHost, st.stream));
+        d2h += sizeof(Result);
         CU_TRY(cudaEventRecord(st.done, st.stream));
         return PFAC_OK;
     };
@@ -410,9 +499,9 @@ int pfac_scan_host(pfac_ctx *ctx, const void *h_in, uint64_t n_starts, uint64_t 
     for (uint64_t c = 0; c < n_chunks; c++) {
         Stage &st = ctx->stages[(size_t)(c % (uint64_t)S)];
         CU_TRY(cudaEventSynchronize(st.done));
-        if (st.h_ctrl->error_flag)
-            return set_error(PFAC_ERR_INTERNAL, "device watchdog tripped (code %u)", st.h_ctrl->error_flag);
-        uint64_t m = st.h_ctrl->count;
+        if (st.slot.h_result->error_flag)
+            return set_error(PFAC_ERR_INTERNAL, "device watchdog tripped (code %u)", st.slot.h_result->error_flag);
+        uint64_t m = st.slot.h_result->count;
         if (m > st.d_out_cap) {
             // dense matches: grow this stage's record buffer and scan the sub-chunk again
             CU_TRY(cudaStreamSynchronize(st.stream));
@@ -423,7 +512,7 @@ int pfac_scan_host(pfac_ctx *ctx, const void *h_in, uint64_t n_starts, uint64_t 
             st.d_out_cap = (size_t)m;
             if ((rc = enqueue(c)) != PFAC_OK) return rc;
             CU_TRY(cudaEventSynchronize(st.done));
-            m = st.h_ctrl->count;
+            m = st.slot.h_result->count;
         }
         // records already carry positions relative to h_in[0] (pos_bias = sub-chunk offset)
         const uint64_t room = total < cap ? cap - total : 0;

@@ -1,25 +1,39 @@
-// PFAC scan kernel for sm_100a (B200).  Replaces TraceTable_kernel + SUBSEG_MATCH
-// (reference master_kernel.cu:37-180).
+// PFAC scan kernels for sm_100a (B200).  Replace TraceTable_kernel + SUBSEG_MATCH
+// (reference master_kernel.cu:37-180).  Design notes: DESIGN.md section 3.
 //
-// Design:
-//   * persistent CTAs pull tile tickets from an atomic counter; every tile (start positions
-//     plus a halo of max_pat_len-1 bytes) is staged into shared memory by one
-//     cp.async.bulk (TMA bulk copy, SASS UBLKCP) per tile, double buffered on mbarriers;
-//   * phase 1 (filter): every lane tests 16 start positions against a shared-memory bitmap of
-//     all 2-byte pattern prefixes (root fan-out folded in); survivors are compacted, in
-//     position order, into a per-warp queue (prefix-popc);
-//   * phase 2 (walk): full warps walk the queued starts through the PHF (r[] then the
-//     interleaved {HT,val} slot, read-only L2/L1-resident loads) and count matches;
-//   * phase 3 (emit): tile totals go through a decoupled look-back over tile tickets, so the
-//     (pos,id) records land in global memory ordered by position without a second pass over
-//     the input; only starts that matched are walked again to write their records.
-// Output order within a start position is walk depth = pattern length ascending, the order
-// main.cc:341-349 prints.
+//   pfac_scan_kernel      persistent, one CTA per SM, warp specialised:
+//     * producer warp: claims tile tickets and streams 16 KiB tiles (+ halo of max_pat_len-1
+//       bytes) into a shared-memory ring with cp.async.bulk (TMA bulk copy, SASS UBLKCP),
+//       full/empty mbarriers per stage, L2 evict-first hint on the streamed input;
+//     * consumer warps: claim 512-byte slices of the current tile.  Per slice
+//         stage 1  16 start positions per lane against T1 (64 KiB byte table over the first
+//                  two bytes, root fan-out folded in), survivors compacted in position order;
+//         stage 2  survivors against T2 (hashed 4-byte prefixes), compacted again;
+//         walk     the remaining starts walk the automaton: hot PHF rows from the shared-memory
+//                  hash, everything else through r[] / {HT,val} (read-only, L2-resident); lanes
+//                  refill from the warp queue as their walks end;
+//         emit     only slices that matched: one atomic reservation in the arrival-order
+//                  scratch, records written in (position, pattern length) order.
+//   pfac_finalize_kernel  scans the per-tile counts and moves the records from arrival order to
+//                         position order (tile, slice, start, depth) -- the order main.cc:341-349
+//                         prints.  Output is deterministic run to run.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
 
 namespace pfac {
+
+struct Ctrl {   // device-side control block; the finalize kernel resets it for the next launch
+    unsigned int ticket;
+    unsigned int error_flag;
+    unsigned long long alloc;   // records reserved in the arrival-order scratch
+};
+
+struct Result {   // written by the finalize kernel, copied to the host
+    unsigned long long count;
+    unsigned int error_flag;
+    unsigned int pad;
+};
 
 struct ScanParams {
     const uint8_t *in_al;     // 16-byte aligned base: caller's pointer rounded down
@@ -32,35 +46,61 @@ struct ScanParams {
     int32_t use_ref_bound;    // reproduce the 4096+512 walk bound (master_kernel.cu:141-144)
     uint64_t base_pos;        // global position of the first start position
     uint32_t pos_bias;        // added to every record position (sub-chunk offset inside a host call)
-    const int32_t *r;         // canonical r[]                      (phf.c:197)
-    const int2 *htval;        // {HT[i], val[i]} interleaved        (phf.c:211,216)
-    const int32_t *idmap;     // final state -> pattern id          (create_table_reorder.c:318)
-    const int32_t *s0;        // root row                           (main.cc:200)
-    const uint32_t *bitmap2;  // 65536 bits: bit (b0 | b1<<8) set iff a walk from b0,b1 can go on or match
+    // canonical PHF in global memory (L2-resident)
+    const int32_t *r;         // r[]                                 (phf.c:197)
+    const int2 *htval;        // {HT[i], val[i] | hot flag}          (phf.c:211,216)
+    const int32_t *idmap;     // final state -> pattern id           (create_table_reorder.c:318)
     int32_t ht_size, width_bit, n_final;
-    uint2 *out;               // pfac_match records
-    unsigned long long cap;
-    unsigned long long *count_out;
-    unsigned long long *tile_state;   // decoupled look-back: [63:62] status, [61:0] value
-    unsigned int *ticket;
-    unsigned int *error_flag;
-    uint32_t debug;           // PFAC_DEBUG bits (timing experiments only): 1 no walk, 2 no look-back, 4 no filter
+    // shared-memory image (pfac_derive.h)
+    const uint4 *image;
+    uint32_t image_bytes, off_t1, off_s0f, off_t2, off_t1s, off_hot;
+    uint32_t t2_shift, has_short, hot_mask, hot_shift, hot_mul, hot_probe;
+    // output
+    uint2 *scratch;                   // arrival-order records
+    unsigned long long scratch_cap;
+    unsigned int *tile_cnt;           // [n_tiles] matches per tile
+    unsigned int *tile_mask;          // [n_tiles] bit s set iff slice s of the tile matched
+    uint4 *slice_ent;                 // [n_tiles*32] {count, scratch offset lo, hi, -} of matching slices
+    Ctrl *ctrl;
+    uint32_t debug;           // PFAC_DEBUG bits (timing experiments only): 1 no walk, 4 no filter, 8 no T2
 };
 
-constexpr int kThreads = 512;          // 16 warps per CTA
-constexpr int kWarpRange = 1024;       // start positions per warp per tile (2 steps of 32 lanes x 16 B)
-constexpr int kWarps = kThreads / 32;
-constexpr int kTile = kWarps * kWarpRange;   // 16 KiB of start positions per tile
-constexpr int kSmemFixed = 9472;       // bitmap 8192 + s0 1024 + control 256
-constexpr unsigned kSpinLimit = 1u << 26;
+struct FinalizeParams {
+    const unsigned int *tile_cnt;
+    const unsigned int *tile_mask;
+    const uint4 *slice_ent;
+    const uint2 *scratch;
+    unsigned long long scratch_cap;
+    uint2 *out;
+    unsigned long long cap;
+    uint32_t n_tiles;
+    Ctrl *ctrl;
+    Result *result;
+    unsigned long long *count_out;    // caller's device counter (may be null)
+};
+
+constexpr int kConsumerWarps = 24;
+constexpr int kThreads = (kConsumerWarps + 1) * 32;   // + the producer warp
+constexpr int kTile = 16384;          // start positions per tile
+constexpr int kSlice = 512;           // start positions per warp step (32 lanes x 16 B)
+constexpr int kSlicesPerTile = kTile / kSlice;
+constexpr int kStages = 3;
+constexpr int kQCap = 640;            // queue entries per warp (a batch stops growing at kBatchMin)
+constexpr int kBatchMin = 48;
+constexpr int kCtrlBytes = 256;
+constexpr unsigned kSpinLimit = 1u << 24;
 
 __host__ __device__ inline uint32_t scan_buf_stride(uint32_t halo) { return (kTile + halo + 32 + 127) & ~127u; }
-__host__ inline size_t scan_smem_bytes(uint32_t halo)
+__host__ inline size_t scan_smem_bytes(uint32_t image_bytes, uint32_t halo)
 {
-    return (size_t)kSmemFixed + (size_t)kWarps * kWarpRange * 2 + 2 * (size_t)scan_buf_stride(halo);
+    return (size_t)image_bytes + kCtrlBytes + (size_t)kConsumerWarps * (kQCap * 4 + 128) +
+           (size_t)kStages * scan_buf_stride(halo);
 }
 
 #ifdef __CUDACC__
+
+constexpr uint32_t kHotFlagD = 1u << 30;
+constexpr uint32_t kStateMaskD = kHotFlagD - 1;
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -72,6 +112,10 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
 {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity)
 {
     uint32_t ok;
@@ -82,125 +126,92 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity)
         : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
     return ok != 0;
 }
-// TMA bulk copy global -> shared, completion counted in bytes on the mbarrier (SASS: UBLKCP)
-__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+// returns false if the watchdog tripped (never expected)
+__device__ __forceinline__ bool mbar_wait(uint64_t *bar, uint32_t parity, unsigned int *error_flag, unsigned code)
 {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ unsigned long long ld_relaxed_gpu(const unsigned long long *p)
-{
-    unsigned long long v;
-    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_relaxed_gpu(unsigned long long *p, unsigned long long v)
-{
-    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-
-constexpr unsigned long long kStA = 1ull << 62;   // tile aggregate published
-constexpr unsigned long long kStP = 2ull << 62;   // inclusive prefix published
-constexpr unsigned long long kStMask = (1ull << 62) - 1;
-
-// Decoupled look-back over tile tickets (one warp).  Returns the number of matches in all
-// tiles before `tile`; publishes this tile's aggregate first and its inclusive prefix last.
-// Tickets are handed out in order, so every predecessor is held by a running CTA.
-__device__ __forceinline__ unsigned long long tile_lookback(unsigned long long *st, uint32_t tile,
-                                                            unsigned long long T, int lane,
-                                                            unsigned int *error_flag)
-{
-    if (tile == 0) {
-        if (lane == 0) st_relaxed_gpu(&st[0], kStP | T);
-        return 0;
-    }
-    if (lane == 0) st_relaxed_gpu(&st[tile], kStA | T);
-    unsigned long long excl = 0;
-    long long j = (long long)tile - 1;
     unsigned spins = 0;
-    while (true) {
-        long long idx = j - lane;
-        unsigned long long s = idx >= 0 ? ld_relaxed_gpu(&st[idx]) : kStP;
-        unsigned status = (unsigned)(s >> 62);
-        unsigned inval = __ballot_sync(0xffffffffu, status == 0);
-        unsigned pm = __ballot_sync(0xffffffffu, status == 2);
-        int firstP = pm ? (__ffs(pm) - 1) : 32;
-        unsigned need = firstP >= 31 ? 0xffffffffu : ((2u << firstP) - 1u);
-        if (inval & need) {
-            if (++spins > kSpinLimit) {   // watchdog: never expected
-                if (lane == 0) atomicExch(error_flag, 1u);
-                break;
-            }
-            __nanosleep(64);
-            continue;
+    while (!mbar_try_wait(bar, parity)) {
+        if (++spins > kSpinLimit) {
+            atomicExch(error_flag, code);
+            return false;
         }
-        unsigned long long v = (lane <= firstP) ? (s & kStMask) : 0ull;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        excl += v;
-        if (firstP < 32) break;
-        j -= 32;
     }
-    if (lane == 0) st_relaxed_gpu(&st[tile], kStP | ((excl + T) & kStMask));
-    return excl;
+    return true;
+}
+// TMA bulk copy global -> shared with an L2 evict-first policy: the input is streamed once and
+// must not push the PHF tables out of L2.  Completion is counted in bytes on the mbarrier.
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar, uint64_t policy)
+{
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+        ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy) : "memory");
+}
+__device__ __forceinline__ uint64_t policy_evict_first()
+{
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
 }
 
-// 16 start positions per lane: bit i of the result is set iff the 2-byte window at byte i
-// is in the prefix bitmap.
-__device__ __forceinline__ uint32_t filter16(const uint4 v, const uint32_t nx, const uint32_t *__restrict__ bm)
+// rotl2 of each of the 4 bytes (pfac_derive.h rot2): bank-spreads the T1 index for ASCII text
+__device__ __forceinline__ uint32_t rot2x4(uint32_t w)
 {
-    const uint32_t w[5] = {v.x, v.y, v.z, v.w, nx};
+    return ((w << 2) & 0xFCFCFCFCu) | ((w >> 6) & 0x03030303u);
+}
+
+// The kernel's dynamic shared memory.  T1 sits at offset 0 (pfac_derive.cc) so that its lookups
+// are LDS.U8 [index + constant] with no address arithmetic.
+extern __shared__ __align__(128) uint8_t smem[];
+
+// 16 start positions per lane: bit i of the result is set iff T1 passes the 2-byte window at byte i
+__device__ __forceinline__ uint32_t filter16(const uint4 v, const uint32_t nx)
+{
+    const uint8_t *t1 = smem;
+    const uint32_t w[5] = {rot2x4(v.x), rot2x4(v.y), rot2x4(v.z), rot2x4(v.w), rot2x4(nx)};
     uint32_t mask = 0;
 #pragma unroll
     for (int k = 0; k < 4; k++) {
-#pragma unroll
-        for (int i = 0; i < 4; i++) {
-            uint32_t win;
-            if (i == 0) win = w[k] & 0xffffu;
-            else if (i == 1) win = (w[k] >> 8) & 0xffffu;
-            else if (i == 2) win = w[k] >> 16;
-            else win = __funnelshift_r(w[k], w[k + 1], 24) & 0xffffu;
-            uint32_t bit = (bm[win >> 5] >> (win & 31u)) & 1u;
-            mask |= bit << (4 * k + i);
-        }
+        const uint32_t i0 = w[k] & 0xffffu;
+        const uint32_t i1 = __byte_perm(w[k], 0u, 0x4421);
+        const uint32_t i2 = w[k] >> 16;
+        const uint32_t i3 = __funnelshift_r(w[k], w[k + 1], 24) & 0xffffu;
+        mask += (uint32_t)t1[i0] << (4 * k);
+        mask += (uint32_t)t1[i1] << (4 * k + 1);
+        mask += (uint32_t)t1[i2] << (4 * k + 2);
+        mask += (uint32_t)t1[i3] << (4 * k + 3);
     }
     return mask;
 }
 
-// One start position: the walk of SUBSEG_MATCH (master_kernel.cu:39-73).  tpos = tile-relative
-// byte index of the start, lim_t = tile-relative exclusive bound of readable bytes.
-// WRITE == false: returns the number of final states visited.
-// WRITE == true : also stores one record per final state at out[obase + k].
-template <bool WRITE>
-__device__ __forceinline__ uint32_t walk_start(const ScanParams &p, const uint8_t *__restrict__ buf,
-                                               const int32_t *__restrict__ s_s0, uint32_t tpos,
-                                               uint32_t lim_t, uint32_t rec_pos,
-                                               unsigned long long obase)
+struct WalkCtx {
+    const int32_t *__restrict__ r;
+    const int2 *__restrict__ htval;
+    const uint2 *__restrict__ hot;   // shared
+    const uint32_t *__restrict__ s0f;   // shared
+    int32_t ht_size, width_bit, colmask, n_final;
+    uint32_t hot_mask, hot_shift, hot_mul, hot_probe;
+};
+
+// One transition (master_kernel.cu:52-64).  sw = state | hot flag; returns the next state word
+// or 0xFFFFFFFF.  A hot row is complete in the shared-memory hash: a miss there is final.
+__device__ __forceinline__ uint32_t step_state(const WalkCtx &c, uint32_t sw, uint32_t byte)
 {
-    int32_t state = s_s0[buf[tpos]];                       // :41
-    if (state < 0) return 0;                               // :43
-    uint32_t c = 0;
-    const int32_t colmask = (1 << p.width_bit) - 1;
-    if (state < p.n_final) {                               // :44-47
-        if (WRITE && obase + c < p.cap) p.out[obase + c] = make_uint2(rec_pos, (uint32_t)__ldg(&p.idmap[state]));
-        c++;
-    }
-    uint32_t q = tpos + 1;
-    while (q < lim_t) {                                    // :50
-        const int32_t key = (state << 8) + buf[q];         // :52
-        const int32_t row = key >> p.width_bit;            // :53
-        const int32_t idx = __ldg(&p.r[row]) + (key & colmask);   // :54-55
-        if (idx < 0 || idx >= p.ht_size) break;            // :56-57
-        const int2 hv = __ldg(&p.htval[idx]);              // :59-61
-        if (hv.x != row) break;
-        state = hv.y;
-        if (state < p.n_final) {                           // :67-70
-            if (WRITE && obase + c < p.cap) p.out[obase + c] = make_uint2(rec_pos, (uint32_t)__ldg(&p.idmap[state]));
-            c++;
+    const uint32_t key = (sw << 8) | byte;   // the flag bit shifts out
+    if (sw & kHotFlagD) {
+        uint32_t slot = (key * c.hot_mul) >> c.hot_shift;
+        for (uint32_t pr = 0; pr < c.hot_probe; pr++) {
+            const uint2 e = c.hot[slot];
+            if (e.x == key) return e.y;
+            if (e.x == 0xFFFFFFFFu) break;
+            slot = (slot + 1) & c.hot_mask;
         }
-        q++;
+        return 0xFFFFFFFFu;
     }
-    return c;
+    const int32_t row = (int32_t)key >> c.width_bit;                 // :53
+    const int32_t idx = __ldg(&c.r[row]) + ((int32_t)key & c.colmask);   // :54-55
+    if (idx < 0 || idx >= c.ht_size) return 0xFFFFFFFFu;            // :56-57
+    const int2 hv = __ldg(&c.htval[idx]);                            // :59-61
+    return hv.x == row ? (uint32_t)hv.y : 0xFFFFFFFFu;
 }
 
 // tile-relative walk bound of a start at tile-relative tpos
@@ -219,171 +230,383 @@ __device__ __forceinline__ uint32_t walk_limit(const ScanParams &p, uint32_t a0,
     return lim_t < depth ? lim_t : depth;
 }
 
-__device__ __forceinline__ void issue_tile(const ScanParams &p, uint32_t tile, uint8_t *buf, uint64_t *bar)
+// The walk of SUBSEG_MATCH (master_kernel.cu:39-73) for one start, writing one record per final
+// state visited, in visiting order = pattern length ascending.
+__device__ __forceinline__ void walk_emit(const ScanParams &p, const WalkCtx &c, const uint8_t *__restrict__ buf,
+                                          uint32_t tpos, uint32_t lim_t, uint32_t rec_pos, unsigned long long o)
 {
-    const uint32_t a0 = tile * (uint32_t)kTile;
-    uint32_t nbytes = p.a_valid_end - a0;
-    const uint32_t want = (uint32_t)kTile + p.halo;
-    if (nbytes > want) nbytes = want;
-    const uint32_t nb16 = nbytes & ~15u;
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    mbar_expect_tx(bar, nb16);
-    if (nb16) bulk_g2s(buf, p.in_al + a0, nb16, bar);
+    uint32_t sw = c.s0f[buf[tpos]];                                  // :41
+    uint32_t q = tpos + 1;
+    while (sw != 0xFFFFFFFFu) {
+        const uint32_t st = sw & kStateMaskD;
+        if ((int32_t)st < c.n_final) {                               // :44-47, :67-70
+            if (o < p.scratch_cap) p.scratch[o] = make_uint2(rec_pos, (uint32_t)__ldg(&p.idmap[st]));
+            o++;
+        }
+        if (q >= lim_t) break;                                       // :50
+        sw = step_state(c, sw, buf[q]);
+        q++;
+    }
 }
 
-__global__ void __launch_bounds__(kThreads, 2) pfac_scan_kernel(const ScanParams p)
+__global__ void __launch_bounds__(kThreads, 1) pfac_scan_kernel(const ScanParams p)
 {
-    extern __shared__ __align__(128) uint8_t smem[];
-    uint32_t *s_bitmap = reinterpret_cast<uint32_t *>(smem);
-    int32_t *s_s0 = reinterpret_cast<int32_t *>(smem + 8192);
-    uint64_t *s_mbar = reinterpret_cast<uint64_t *>(smem + 9216);                    // [2]
-    uint32_t *s_tile = reinterpret_cast<uint32_t *>(smem + 9232);                    // [2]
-    unsigned long long *s_base = reinterpret_cast<unsigned long long *>(smem + 9240);   // [1]
-    uint32_t *s_wtot = reinterpret_cast<uint32_t *>(smem + 9248);                    // [2][kWarps]
-    uint16_t *s_queue = reinterpret_cast<uint16_t *>(smem + kSmemFixed);
-    uint8_t *s_in = smem + kSmemFixed + kWarps * kWarpRange * 2;
+    const uint32_t *s_s0f = reinterpret_cast<const uint32_t *>(smem + p.off_s0f);
+    const uint32_t *s_t2 = reinterpret_cast<const uint32_t *>(smem + p.off_t2);
+    const uint32_t *s_t1s = reinterpret_cast<const uint32_t *>(smem + p.off_t1s);
+    const uint2 *s_hot = reinterpret_cast<const uint2 *>(smem + p.off_hot);
+    uint8_t *ctl = smem + p.image_bytes;
+    uint64_t *s_full = reinterpret_cast<uint64_t *>(ctl);              // [kStages]
+    uint64_t *s_empty = reinterpret_cast<uint64_t *>(ctl + 32);        // [kStages]
+    uint32_t *s_tile = reinterpret_cast<uint32_t *>(ctl + 64);         // [kStages] tile id of the stage
+    uint32_t *s_ticket = reinterpret_cast<uint32_t *>(ctl + 80);       // [kStages] slice tickets
+    uint32_t *s_done = reinterpret_cast<uint32_t *>(ctl + 96);         // [kStages] warps finished
+    uint32_t *s_tcnt = reinterpret_cast<uint32_t *>(ctl + 112);        // [kStages] matches in the tile
+    uint32_t *s_tmask = reinterpret_cast<uint32_t *>(ctl + 128);       // [kStages] matching slices
+    uint8_t *qbase = ctl + kCtrlBytes;
+    uint8_t *s_in = qbase + kConsumerWarps * (kQCap * 4 + 128);
     const uint32_t stride = scan_buf_stride(p.halo);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
-    for (int i = tid; i < 2048; i += kThreads) s_bitmap[i] = __ldg(&p.bitmap2[i]);
-    if (tid < 256) s_s0[tid] = __ldg(&p.s0[tid]);
+    {   // shared-memory image: T1, root row, T2, T1s, hot rows
+        uint4 *dst = reinterpret_cast<uint4 *>(smem);
+        const uint32_t n16 = p.image_bytes >> 4;
+        for (uint32_t i = tid; i < n16; i += kThreads) dst[i] = __ldg(&p.image[i]);
+    }
     if (tid == 0) {
-        mbar_init(&s_mbar[0], 1);
-        mbar_init(&s_mbar[1], 1);
+        for (int s = 0; s < kStages; s++) {
+            mbar_init(&s_full[s], 1);
+            mbar_init(&s_empty[s], kConsumerWarps);
+            s_ticket[s] = 0;
+            s_done[s] = 0;
+            s_tcnt[s] = 0;
+            s_tmask[s] = 0;
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    if (tid == 0) {
-        for (int b = 0; b < 2; b++) {
-            const uint32_t t = atomicAdd(p.ticket, 1u);
-            s_tile[b] = t;
-            if (t < p.n_tiles) issue_tile(p, t, s_in + b * stride, &s_mbar[b]);
+
+    if (warp == kConsumerWarps) {
+        // ------------------------------------------------------------------ producer
+        if (lane == 0) {
+            const uint64_t policy = policy_evict_first();
+            for (uint32_t it = 0;; it++) {
+                const int s = it % kStages;
+                const uint32_t t = atomicAdd(&p.ctrl->ticket, 1u);
+                if (it >= (uint32_t)kStages)
+                    if (!mbar_wait(&s_empty[s], ((it / kStages) - 1) & 1u, &p.ctrl->error_flag, 3u)) break;
+                s_tile[s] = t;
+                if (t >= p.n_tiles) {   // sentinel: consumers leave when they see it
+                    mbar_arrive(&s_full[s]);
+                    break;
+                }
+                uint8_t *buf = s_in + s * stride;
+                const uint32_t a0 = t * (uint32_t)kTile;
+                uint32_t nbytes = p.a_valid_end - a0;
+                const uint32_t want = (uint32_t)kTile + p.halo;
+                if (nbytes > want) nbytes = want;
+                const uint32_t nb16 = nbytes & ~15u;
+                // last bytes of the input: not a whole 16-byte block, copied by hand
+                for (uint32_t i = nb16; i < nbytes; i++) buf[i] = p.in_al[(size_t)a0 + i];
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                mbar_expect_tx(&s_full[s], nb16);
+                if (nb16) bulk_g2s(buf, p.in_al + a0, nb16, &s_full[s], policy);
+            }
         }
+        return;
+    }
+
+    // ---------------------------------------------------------------------- consumers
+    uint16_t *wq = reinterpret_cast<uint16_t *>(qbase + warp * (kQCap * 4 + 128));   // start positions
+    uint16_t *wc = wq + kQCap;                                                         // matches per start
+    uint16_t *w_sid = wc + kQCap;       // [32] slice ids of the batch
+    uint16_t *w_send = w_sid + 32;      // [32] queue end of each slice of the batch
+    WalkCtx wk;
+    wk.r = p.r;
+    wk.htval = p.htval;
+    wk.hot = s_hot;
+    wk.s0f = s_s0f;
+    wk.ht_size = p.ht_size;
+    wk.width_bit = p.width_bit;
+    wk.colmask = (1 << p.width_bit) - 1;
+    wk.n_final = p.n_final;
+    wk.hot_mask = p.hot_mask;
+    wk.hot_shift = p.hot_shift;
+    wk.hot_mul = p.hot_mul;
+    wk.hot_probe = p.hot_probe;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+
+    for (uint32_t it = 0;; it++) {
+        const int s = it % kStages;
+        if (!mbar_wait(&s_full[s], (it / kStages) & 1u, &p.ctrl->error_flag, 2u)) break;
+        const uint32_t tile = s_tile[s];
+        if (tile >= p.n_tiles) break;
+        const uint8_t *buf = s_in + s * stride;
+        const uint32_t a0 = tile * (uint32_t)kTile;
+        const bool edge = (a0 < p.mis) || (a0 + (uint32_t)kTile > p.a_start_end);
+        uint32_t tile_starts = p.a_start_end - a0;
+        if (tile_starts > (uint32_t)kTile) tile_starts = kTile;
+        const uint32_t n_slices = (tile_starts + kSlice - 1) / kSlice;
+        const uint32_t valid_t = p.a_valid_end - a0;   // tile-relative end of readable input (may exceed the buffer)
+
+        while (true) {
+            // ---- build a batch: filter slices until enough starts survive (or the tile is out of slices)
+            uint32_t nq = 0, nb = 0;
+            while (nq < (uint32_t)kBatchMin) {
+                uint32_t slice = 0;
+                if (lane == 0) slice = atomicAdd(&s_ticket[s], 1u);
+                slice = __shfl_sync(0xffffffffu, slice, 0);
+                if (slice >= n_slices) break;
+                const uint32_t q0 = nq;
+                // stage 1: T1 over 16 positions per lane, ordered compaction
+                const uint32_t off = slice * kSlice + lane * 16;
+                const uint4 v = *reinterpret_cast<const uint4 *>(buf + off);
+                const uint32_t nx = *reinterpret_cast<const uint32_t *>(buf + off + 16);
+                uint32_t mask = (p.debug & 4u) ? 0u : filter16(v, nx);
+                if (edge) {   // start positions are [mis, a_start_end) in aligned coordinates
+                    const uint32_t a = a0 + off;
+                    const uint32_t lo = p.mis > a ? p.mis - a : 0u;
+                    const uint32_t hi = p.a_start_end > a ? p.a_start_end - a : 0u;
+                    uint32_t keep = hi >= 16u ? 0xffffu : ((1u << hi) - 1u);
+                    keep &= lo >= 16u ? 0u : (0xffffu << lo);
+                    mask &= keep;
+                }
+                uint32_t incl = __popc(mask);
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t n = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= o) incl += n;
+                }
+                uint32_t q = nq + incl - __popc(mask);
+                nq += __shfl_sync(0xffffffffu, incl, 31);
+                while (mask) {
+                    const uint32_t bit = __ffs(mask) - 1;
+                    wq[q++] = (uint16_t)(off + bit);
+                    mask &= mask - 1;
+                }
+                __syncwarp();
+                // stage 2: T2 over the 4-byte prefix, in-place ordered compaction
+                if (!(p.debug & 8u)) {
+                    uint32_t wr = q0;
+                    for (uint32_t e0 = q0; e0 < nq; e0 += 32) {
+                        const uint32_t e = e0 + lane;
+                        bool keep = false;
+                        uint32_t tpos = 0;
+                        if (e < nq) {
+                            tpos = wq[e];
+                            const uint32_t *wp = reinterpret_cast<const uint32_t *>(buf + (tpos & ~3u));
+                            const uint32_t w4 = __funnelshift_r(wp[0], wp[1], (tpos & 3u) * 8u);
+                            keep = tpos + 4u > valid_t;                      // fewer than 4 readable bytes
+                            if (p.has_short) {
+                                const uint32_t pair = w4 & 0xffffu;
+                                keep |= (s_t1s[pair >> 5] >> (pair & 31u)) & 1u;
+                            }
+                            const uint32_t h = (w4 * 0x9E3779B1u) >> p.t2_shift;
+                            keep |= (s_t2[h >> 5] >> (h & 31u)) & 1u;
+                        }
+                        const uint32_t bal = __ballot_sync(0xffffffffu, keep);
+                        if (keep) wq[wr + __popc(bal & lt_mask)] = (uint16_t)tpos;
+                        wr += __popc(bal);
+                    }
+                    nq = wr;
+                    __syncwarp();
+                }
+                if (lane == 0) {
+                    w_sid[nb] = (uint16_t)slice;
+                    w_send[nb] = (uint16_t)nq;
+                }
+                nb++;
+                if (nq + (uint32_t)kSlice > (uint32_t)kQCap) break;
+            }
+            if (nb == 0) break;   // the tile has no slices left
+            __syncwarp();
+
+            // ---- walk the batch: lanes refill from the queue as their walks end; count matches
+            uint32_t total = 0;
+            if (!(p.debug & 1u) && nq) {
+                uint32_t head = 0, my_e = 0, q = 0, lim = 0, cnt = 0, sw = 0xFFFFFFFFu;
+                bool active = false;
+                while (true) {
+                    const uint32_t need = __ballot_sync(0xffffffffu, !active);
+                    if (need) {
+                        if (!active) {
+                            const uint32_t e = head + __popc(need & lt_mask);
+                            if (e < nq) {
+                                my_e = e;
+                                const uint32_t tpos = wq[e];
+                                sw = s_s0f[buf[tpos]];
+                                q = tpos + 1;
+                                lim = walk_limit(p, a0, tpos);
+                                cnt = 0;
+                                active = true;
+                            }
+                        }
+                        head += __popc(need);
+                    }
+                    if (!__any_sync(0xffffffffu, active)) break;
+                    if (active) {
+                        bool fin = (sw == 0xFFFFFFFFu);
+                        if (!fin) {
+                            cnt += ((int32_t)(sw & kStateMaskD) < wk.n_final) ? 1u : 0u;
+                            if (q >= lim) fin = true;
+                            else {
+                                sw = step_state(wk, sw, buf[q]);
+                                q++;
+                            }
+                        }
+                        if (fin) {
+                            wc[my_e] = (uint16_t)cnt;
+                            total += cnt;
+                            active = false;
+                        }
+                    }
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
+            }
+            __syncwarp();
+
+            // ---- emit (rare): reserve scratch space, write records in position order
+            if (total) {
+                unsigned long long base = 0;
+                if (lane == 0) base = atomicAdd(&p.ctrl->alloc, (unsigned long long)total);
+                base = __shfl_sync(0xffffffffu, base, 0);
+                // per-slice counts and scratch offsets (slices of a batch are in position order)
+                uint32_t run = 0, smask = 0, qs = 0;
+                for (uint32_t sl = 0; sl < nb; sl++) {
+                    const uint32_t qe = w_send[sl];
+                    uint32_t c = 0;
+                    for (uint32_t e = qs + lane; e < qe; e += 32) c += wc[e];
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+                    if (c) {
+                        const unsigned long long so = base + run;
+                        if (lane == 0)
+                            p.slice_ent[(size_t)tile * kSlicesPerTile + w_sid[sl]] =
+                                make_uint4(c, (uint32_t)so, (uint32_t)(so >> 32), 0u);
+                        smask |= 1u << w_sid[sl];
+                    }
+                    run += c;
+                    qs = qe;
+                }
+                // records: exclusive scan of the per-start counts, then re-walk the starts that matched
+                run = 0;
+                for (uint32_t e0 = 0; e0 < nq; e0 += 32) {
+                    const uint32_t e = e0 + lane;
+                    const uint32_t c = e < nq ? wc[e] : 0u;
+                    uint32_t incl = c;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const uint32_t n = __shfl_up_sync(0xffffffffu, incl, o);
+                        if (lane >= o) incl += n;
+                    }
+                    if (c) {
+                        const uint32_t tpos = wq[e];
+                        walk_emit(p, wk, buf, tpos, walk_limit(p, a0, tpos), a0 + tpos - p.mis + p.pos_bias,
+                                  base + run + incl - c);
+                    }
+                    run += __shfl_sync(0xffffffffu, incl, 31);
+                }
+                if (lane == 0) {
+                    atomicAdd(&s_tcnt[s], total);
+                    atomicOr(&s_tmask[s], smask);
+                }
+            }
+        }
+
+        // ---- this warp is done with the tile; the last one publishes the tile's totals
+        __syncwarp();
+        if (lane == 0) {
+            __threadfence_block();
+            const uint32_t old = atomicAdd(&s_done[s], 1u);
+            if (old == (uint32_t)kConsumerWarps - 1u) {
+                __threadfence_block();
+                p.tile_cnt[tile] = s_tcnt[s];
+                p.tile_mask[tile] = s_tmask[s];
+                s_tcnt[s] = 0;
+                s_tmask[s] = 0;
+                s_done[s] = 0;
+                s_ticket[s] = 0;
+                __threadfence_block();
+            }
+            mbar_arrive(&s_empty[s]);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Position-ordering pass: exclusive scan of the per-tile counts, then every matching slice's
+// records move from the arrival-order scratch to their final place.  Grid-stride by tile range;
+// each CTA sums the counts before its range itself (n_tiles * 4 bytes, L2-resident).
+constexpr int kFinThreads = 256;
+
+__global__ void __launch_bounds__(kFinThreads) pfac_finalize_kernel(const FinalizeParams f)
+{
+    __shared__ unsigned long long s_red[kFinThreads / 32];
+    __shared__ unsigned long long s_base[kFinThreads];
+    __shared__ unsigned int s_cnt[kFinThreads];
+    __shared__ unsigned long long s_run;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t per = (f.n_tiles + gridDim.x - 1) / gridDim.x;
+    const uint32_t lo = min(f.n_tiles, blockIdx.x * per), hi = min(f.n_tiles, lo + per);
+
+    unsigned long long sum = 0;
+    for (uint32_t i = tid; i < lo; i += kFinThreads) sum += f.tile_cnt[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    if (lane == 0) s_red[warp] = sum;
+    __syncthreads();
+    if (tid == 0) {
+        unsigned long long t = 0;
+        for (int w = 0; w < kFinThreads / 32; w++) t += s_red[w];
+        s_run = t;
     }
     __syncthreads();
 
-    uint16_t *wq = s_queue + warp * kWarpRange;
-    for (uint32_t it = 0;; it++) {
-        const int b = it & 1;
-        const uint32_t tile = s_tile[b];
-        if (tile >= p.n_tiles) break;
-        uint8_t *buf = s_in + b * stride;
-        const uint32_t a0 = tile * (uint32_t)kTile;
-        {   // wait for the bulk copy of this tile
-            const uint32_t parity = (it >> 1) & 1u;
-            unsigned spins = 0;
-            while (!mbar_try_wait(&s_mbar[b], parity)) {
-                if (++spins > kSpinLimit) { atomicExch(p.error_flag, 2u); break; }
-            }
-        }
-        uint32_t avail = p.a_valid_end - a0;
-        const uint32_t want = (uint32_t)kTile + p.halo;
-        if (avail > want) avail = want;
-        if (avail & 15u) {   // last bytes of the input: not a whole 16-byte block, copied by hand
-            const uint32_t nb16 = avail & ~15u;
-            if ((uint32_t)tid < (avail & 15u)) buf[nb16 + tid] = p.in_al[(size_t)a0 + nb16 + tid];
-            __syncthreads();
-        }
-        const bool edge = (a0 < p.mis) || (a0 + (uint32_t)kTile > p.a_start_end);
-
-        // ---- phase 1: filter + ordered compaction into the warp queue
-        uint32_t nq = 0;
-#pragma unroll
-        for (int st = 0; st < kWarpRange / 512; st++) {
-            const uint32_t off = (uint32_t)warp * kWarpRange + st * 512 + lane * 16;
-            const uint4 v = *reinterpret_cast<const uint4 *>(buf + off);
-            uint32_t nx = __shfl_down_sync(0xffffffffu, v.x, 1);
-            if (lane == 31) nx = *reinterpret_cast<const uint32_t *>(buf + off + 16);
-            uint32_t mask = (p.debug & 4u) ? 0u : filter16(v, nx, s_bitmap);
-            if (edge) {   // start positions are [mis, a_start_end) in aligned coordinates
-                const uint32_t a = a0 + off;
-                const uint32_t lo = p.mis > a ? p.mis - a : 0u;
-                const uint32_t hi = p.a_start_end > a ? p.a_start_end - a : 0u;
-                uint32_t keep = hi >= 16u ? 0xffffu : ((1u << hi) - 1u);
-                keep &= lo >= 16u ? 0u : (0xffffu << lo);
-                mask &= keep;
-            }
-            uint32_t incl = __popc(mask);
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const uint32_t n = __shfl_up_sync(0xffffffffu, incl, o);
-                if (lane >= o) incl += n;
-            }
-            uint32_t q = nq + incl - __popc(mask);
-            nq += __shfl_sync(0xffffffffu, incl, 31);
-            while (mask) {
-                const uint32_t bit = __ffs(mask) - 1;
-                wq[q++] = (uint16_t)(off + bit);
-                mask &= mask - 1;
-            }
-        }
-        __syncwarp();
-
-        // ---- phase 2: walk the queue, count matches (lane owns a contiguous run of entries)
-        const uint32_t per = (nq + 31u) >> 5;
-        const uint32_t qb = lane * per;
-        const uint32_t qe = (qb + per < nq) ? qb + per : nq;
-        uint32_t csum = 0;
-        if (!(p.debug & 1u))
-        for (uint32_t e = qb; e < qe; e++) {
-            const uint32_t tpos = wq[e];
-            csum += walk_start<false>(p, buf, s_s0, tpos, walk_limit(p, a0, tpos), 0u, 0ull);
-        }
-        uint32_t incl = csum;
+    for (uint32_t c0 = lo; c0 < hi; c0 += kFinThreads) {
+        const uint32_t i = c0 + tid;
+        const unsigned int c = i < hi ? f.tile_cnt[i] : 0u;
+        unsigned long long incl = c;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t n = __shfl_up_sync(0xffffffffu, incl, o);
+            const unsigned long long n = __shfl_up_sync(0xffffffffu, incl, o);
             if (lane >= o) incl += n;
         }
-        const uint32_t lane_off = incl - csum;
-        if (lane == 31) s_wtot[b * kWarps + warp] = incl;
-        __syncthreads();   // S1: every warp is done reading this tile for phase 2
-
-        // ---- phase 3: tile total, look-back, ordered emit
-        uint32_t wv = lane < kWarps ? s_wtot[b * kWarps + lane] : 0u;
-        uint32_t winc = wv;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t n = __shfl_up_sync(0xffffffffu, winc, o);
-            if (lane >= o) winc += n;
-        }
-        const uint32_t T = __shfl_sync(0xffffffffu, winc, 31);
-        const uint32_t woff = __shfl_sync(0xffffffffu, winc - wv, warp);
-
-        if (T == 0) {
-            if (tid == 0) {   // nobody reads this buffer again: refill it before the look-back
-                const uint32_t t = atomicAdd(p.ticket, 1u);
-                s_tile[b] = t;
-                if (t < p.n_tiles) issue_tile(p, t, buf, &s_mbar[b]);
-            }
-            if (warp == 0 && !(p.debug & 2u)) {
-                const unsigned long long excl = tile_lookback(p.tile_state, tile, 0ull, lane, p.error_flag);
-                if (lane == 0 && tile == p.n_tiles - 1) *p.count_out = excl;
-            }
-        } else {
-            if (warp == 0) {
-                const unsigned long long excl = tile_lookback(p.tile_state, tile, (unsigned long long)T, lane, p.error_flag);
-                if (lane == 0) {
-                    *s_base = excl;
-                    if (tile == p.n_tiles - 1) *p.count_out = excl + T;
-                }
-            }
-            __syncthreads();   // S2: tile base visible
-            if (csum) {
-                unsigned long long o = *s_base + woff + lane_off;
-                for (uint32_t e = qb; e < qe; e++) {
-                    const uint32_t tpos = wq[e];
-                    o += walk_start<true>(p, buf, s_s0, tpos, walk_limit(p, a0, tpos), a0 + tpos - p.mis + p.pos_bias, o);
-                }
-            }
-            __syncthreads();   // S3: buffer and queue free
-            if (tid == 0) {
-                const uint32_t t = atomicAdd(p.ticket, 1u);
-                s_tile[b] = t;
-                if (t < p.n_tiles) issue_tile(p, t, buf, &s_mbar[b]);
+        if (lane == 31) s_red[warp] = incl;
+        __syncthreads();
+        unsigned long long wbase = 0;
+        for (int w = 0; w < warp; w++) wbase += s_red[w];
+        s_base[tid] = s_run + wbase + incl - c;
+        s_cnt[tid] = c;
+        __syncthreads();
+        // one warp per matching tile
+        for (int j = warp; j < kFinThreads; j += kFinThreads / 32) {
+            if (!s_cnt[j]) continue;
+            const uint32_t tile = c0 + j;
+            unsigned long long dst = s_base[j];
+            unsigned int m = f.tile_mask[tile];
+            while (m) {
+                const int sl = __ffs(m) - 1;
+                m &= m - 1;
+                const uint4 ent = f.slice_ent[(size_t)tile * kSlicesPerTile + sl];
+                const unsigned long long src = (unsigned long long)ent.y | ((unsigned long long)ent.z << 32);
+                for (uint32_t k = lane; k < ent.x; k += 32)
+                    if (src + k < f.scratch_cap && dst + k < f.cap) f.out[dst + k] = f.scratch[src + k];
+                dst += ent.x;
             }
         }
+        __syncthreads();
+        if (tid == kFinThreads - 1) s_run = s_base[tid] + s_cnt[tid];
+        __syncthreads();
+    }
+    if (tid == 0 && lo < hi && hi == f.n_tiles) {   // the CTA whose range ends the input owns the total
+        f.result->count = s_run;
+        f.result->error_flag = f.ctrl->error_flag;
+        if (f.count_out) *f.count_out = s_run;
+        f.ctrl->ticket = 0;
+        f.ctrl->error_flag = 0;
+        f.ctrl->alloc = 0;
     }
 }
 

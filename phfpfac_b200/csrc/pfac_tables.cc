@@ -18,6 +18,7 @@
 #include <cstring>
 #include <memory>
 
+#include "pfac_derive.h"
 #include "pfac_internal.h"
 
 namespace pfac {
@@ -463,6 +464,26 @@ const int32_t *pfac_tables_r(const pfac_tables *t, int part) { const Partition *
 const int32_t *pfac_tables_HT(const pfac_tables *t, int part) { const Partition *P = part_of(t, part); return P ? P->HT.data() : nullptr; }
 const int32_t *pfac_tables_val(const pfac_tables *t, int part) { const Partition *P = part_of(t, part); return P ? P->val.data() : nullptr; }
 const int32_t *pfac_tables_idmap(const pfac_tables *t, int part) { const Partition *P = part_of(t, part); return P ? P->idmap.data() : nullptr; }
+
+int pfac_tables_derive_check(const pfac_tables *t, int part, uint32_t t2_bytes, uint32_t hot_bytes, uint64_t stats[8])
+{
+    const Partition *P = part_of(t, part);
+    if (!P) return set_error(PFAC_ERR_ARG, "bad partition index");
+    try {
+        Derived d;
+        derive_tables(*P, t2_bytes, hot_bytes, d);
+        if (stats) {
+            const uint64_t v[8] = {d.image.size(), d.t1_set, d.t2_set, d.n_depth4, d.has_short, d.n_hot_rows,
+                                   d.n_hot_entries, d.hot_probe};
+            memcpy(stats, v, sizeof v);
+        }
+        const int bad = derive_selfcheck(*P, d);
+        if (bad) return set_error(PFAC_ERR_INTERNAL, "derived tables violate invariant %d", bad);
+        return PFAC_OK;
+    } catch (const std::bad_alloc &) {
+        return set_error(PFAC_ERR_NOMEM, "out of memory");
+    }
+}
 
 int32_t pfac_tables_lookup(const pfac_tables *t, int part, int32_t state, int32_t byte)
 {

@@ -148,3 +148,23 @@ def test_tables_equal_live_reference_builder(tmp_path):
             assert same(t.part(g), rb.part(g)), (trial, g)
         rb1 = RefBuild(str(f), width=width, single=True)
         assert same(pf.Tables.from_bytes(blob, n_parts=1, width=width).part(0), rb1.part(0))
+
+
+@pytest.mark.parametrize("case", ["experimentpattern", "xad", "dictionary", "short", "config3", "binary"])
+def test_derived_device_tables_selfcheck(fixtures, case):
+    """The kernel's shared-memory accelerators (pfac_derive.cc), built and verified on the host:
+    T1 exact over 2-byte prefixes, T1s/T2 supersets, hot rows == master_kernel.cu:52-64 lookups."""
+    blob = {"short": b"a\nab\nabc\nabcd\nb\nbcdef\nxyzxyzxyz\n",
+            "config3": pf.synth_patterns(1, 3000, 3, 4, 64),
+            "binary": b"".join(bytes([i, (i * 7) % 256 or 1, 200, 201, 202]).replace(b"\n", b"\x0b") + b"\n" for i in range(256) if i != 10),
+            }.get(case) or fixtures[case]
+    for width in (256, 64, 4096):
+        t = pf.Tables.from_bytes(blob, 1, width)
+        for t2b, hotb in ((16384, 32768), (1024, 2048), (0, 0), (65536, 1024)):
+            st = t.derive_check(0, t2b, hotb)
+            assert st["t1_pairs"] > 0
+            if hotb == 0:
+                assert st["hot_rows"] == 0
+    p = pf.Tables.from_bytes(blob, 1, 256).part(0)
+    t2 = pf.Tables.from_arrays(p.s0, p.r, p.HT, p.val, 256, p.state_num, p.n_final, p.idmap, p.max_len)
+    assert t2.derive_check() == pf.Tables.from_bytes(blob, 1, 256).derive_check()
