@@ -84,7 +84,12 @@ void derive_tables(const Partition &P, uint32_t t2_bytes, uint32_t hot_bytes, De
     uint32_t hot_entries = 0;
     std::vector<uint8_t> is_hot((size_t)n_states, 0);
     std::vector<int32_t> hot_rows;
-    const bool key_fits = n_states < (1 << 22);   // key = state<<8|byte and the flag bit must fit 32 bits
+    const bool key_fits = n_states < (1 << kStateBits);   // room for the flags above the state number
+    if (key_fits) {
+        out.state_mask = kStateMask;
+        out.hot_bit = kHotFlag;
+        out.single_bit = kSingleFlag;
+    }
     uint32_t hot_cap = 0;
     if (hot_bytes >= 1024 && key_fits && !order.empty()) {
         hot_cap = 1;
@@ -108,7 +113,11 @@ void derive_tables(const Partition &P, uint32_t t2_bytes, uint32_t hot_bytes, De
     }
     auto flagged = [&](int32_t s) -> uint32_t {
         if (s < 0) return kNoState;
-        return (uint32_t)s | ((s < n_states && is_hot[(size_t)s]) ? kHotFlag : 0u);
+        if (!key_fits || s >= n_states) return (uint32_t)s;
+        const uint32_t n = row_end(s) - row_begin(s);
+        if (n == 0 || is_hot[(size_t)s]) return (uint32_t)s | kHotFlag;   // a leaf is a complete (empty) hot row
+        if (n == 1) return (uint32_t)s | kSingleFlag | ((uint32_t)edges[row_begin(s)].byte << 24);
+        return (uint32_t)s;
     };
 
     // ---- image layout
@@ -238,7 +247,7 @@ void derive_tables(const Partition &P, uint32_t t2_bytes, uint32_t hot_bytes, De
     out.val_flagged.resize((size_t)std::max(P.ht_size, 0));
     for (int32_t i = 0; i < P.ht_size; i++) {
         const int32_t v = P.val[(size_t)i];
-        out.val_flagged[(size_t)i] = v < 0 ? v : (int32_t)flagged(v);
+        out.val_flagged[(size_t)i] = v < 0 ? -1 : (int32_t)flagged(v);
     }
     for (uint8_t b : t1) out.t1_set += b;
     for (uint32_t w : t2) out.t2_set += (uint32_t)__builtin_popcount(w);
@@ -258,8 +267,8 @@ int derive_selfcheck(const Partition &P, const Derived &d)
     const uint32_t *t1s = reinterpret_cast<const uint32_t *>(img + d.off_t1s);
     const uint32_t *hot = reinterpret_cast<const uint32_t *>(img + d.off_hot);
     auto hot_lookup = [&](uint32_t sw, uint32_t byte) -> uint32_t {
-        const uint32_t key = (sw << 8) | byte;
-        uint32_t slot = (key * d.hot_mul) >> d.hot_shift;
+        const uint32_t key = ((sw & d.state_mask) << 8) | byte;
+        uint32_t slot = d.hot_probe ? (key * d.hot_mul) >> d.hot_shift : 0;
         for (uint32_t pr = 0; pr < d.hot_probe; pr++) {
             if (hot[slot * 2] == key) return hot[slot * 2 + 1];
             if (hot[slot * 2] == kHotEmpty) break;
@@ -268,13 +277,13 @@ int derive_selfcheck(const Partition &P, const Derived &d)
         return kNoState;
     };
     auto is_final = [&](int32_t s) { return s >= 0 && s < P.n_final; };
-    std::vector<uint32_t> hot_states;
+    std::vector<uint32_t> all_words;   // every state word the kernel can hold
     for (int b0 = 0; b0 < kCharSet; b0++) {
         const int32_t s1 = P.s0.empty() ? -1 : P.s0[(size_t)b0];
         if ((s1 < 0) != (s0f[b0] == kNoState)) return 1;
         if (s1 < 0) continue;
-        if ((s0f[b0] & kStateMask) != (uint32_t)s1) return 2;
-        if (s0f[b0] & kHotFlag) hot_states.push_back(s0f[b0]);
+        if ((s0f[b0] & d.state_mask) != (uint32_t)s1) return 2;
+        all_words.push_back(s0f[b0]);
         for (int b1 = 0; b1 < kCharSet; b1++) {
             const int32_t s2 = P.lookup(s1, b1);
             const uint32_t pair = (uint32_t)b0 | ((uint32_t)b1 << 8);
@@ -299,29 +308,37 @@ int derive_selfcheck(const Partition &P, const Derived &d)
             if (shortp && !(d.has_short && ((t1s[pair >> 5] >> (pair & 31)) & 1u))) return 7;
         }
     }
-    // hot rows: breadth-first over flagged state words reachable through the hot table / val flags
+    // every state word must describe its state's row truthfully (hot rows complete, single-edge
+    // byte right, leaves flagged hot); words come from s0f, the hot values and the flagged val[]
     std::vector<uint8_t> seen((size_t)std::max(P.state_num, 1), 0);
     for (int32_t i = 0; i < P.ht_size; i++) {
         const int32_t v = d.val_flagged[(size_t)i];
-        if (v >= 0 && ((uint32_t)v & kHotFlag)) hot_states.push_back((uint32_t)v);
-        if (v >= 0 && ((uint32_t)v & kStateMask) != (uint32_t)P.val[(size_t)i]) return 8;
-        if ((v < 0) != (P.val[(size_t)i] < 0)) return 9;
+        if ((v == -1) != (P.val[(size_t)i] < 0)) return 9;
+        if (P.val[(size_t)i] < 0) continue;
+        if (((uint32_t)v & d.state_mask) != (uint32_t)P.val[(size_t)i]) return 8;
+        all_words.push_back((uint32_t)v);
     }
     uint32_t rows = 0;
-    for (size_t i = 0; i < hot_states.size(); i++) {
-        const uint32_t sw = hot_states[i];
-        const int32_t s = (int32_t)(sw & kStateMask);
-        if (s >= P.state_num) return 10;
-        if (seen[(size_t)s]) continue;
+    for (size_t i = 0; i < all_words.size(); i++) {
+        const uint32_t sw = all_words[i];
+        const int32_t s = (int32_t)(sw & d.state_mask);
+        if (s >= P.state_num) { if (sw != (uint32_t)s) return 10; continue; }
+        int n_edges = 0, only = -1;
+        if (sw & (d.hot_bit | d.single_bit))
+            for (int b = 0; b < kCharSet; b++)
+                if (P.lookup(s, b) >= 0) { n_edges++; only = b; }
+        if (sw & d.single_bit) {
+            if ((sw & d.hot_bit) || n_edges != 1 || (int)(sw >> 24) != only) return 15;
+        }
+        if (!(sw & d.hot_bit) || seen[(size_t)s]) continue;
         seen[(size_t)s] = 1;
-        rows++;
-        if (!d.hot_mask) return 11;
+        if (n_edges) rows++;
         for (int b = 0; b < kCharSet; b++) {
             const int32_t want = P.lookup(s, b);
             const uint32_t got = hot_lookup(sw, (uint32_t)b);
             if ((want < 0) != (got == kNoState)) return 12;
-            if (want >= 0 && (got & kStateMask) != (uint32_t)want) return 13;
-            if (want >= 0 && (got & kHotFlag)) hot_states.push_back(got);
+            if (want >= 0 && (got & d.state_mask) != (uint32_t)want) return 13;
+            if (want >= 0) all_words.push_back(got);
         }
     }
     if (rows > d.n_hot_rows) return 14;

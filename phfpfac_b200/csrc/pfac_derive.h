@@ -9,10 +9,18 @@
 //                       or has a second edge  (root fan-out, s0Table of main.cc:200, folded in)
 //   T1s   65,536 bits : pair (c0,c1) can complete a pattern of length <= 3 (bypasses T2)
 //   T2    2^k2 bits   : multiplicative hash of every 4-byte pattern prefix
-//   s0f   256 x u32   : root row with the "row is hot" flag
+//   s0f   256 x u32   : root row as state words
 //   hot   open-addressing hash of COMPLETE PHF rows of the hottest states
-//                       (key = state<<8|byte -> next state | flag); a miss in a hot row means
+//                       (key = state<<8|byte -> next state word); a miss in a hot row means
 //                       "no transition", exactly like HT[idx] != row in the PHF
+// State words (s0f, hot values, the val half of the global {HT,val} array) carry a look-ahead on
+// the TARGET state's own row, so most walks end without touching L2:
+//   bits 0..21  state number
+//   bit  22     hot: the state's row is answered by the shared-memory hash (a leaf, i.e. a row
+//               with no transition at all, is hot by definition and needs no table entry)
+//   bit  23     single: the row has exactly one transition, on the byte in bits 24..31 -- any other
+//               byte ends the walk without a lookup
+// Automata with 2^22 states or more get plain words (no flags, no hot table).
 #pragma once
 #include <cstdint>
 #include <vector>
@@ -21,8 +29,10 @@
 
 namespace pfac {
 
-constexpr uint32_t kHotFlag = 1u << 30;      // on a state word: its PHF row lives in the smem hot table
-constexpr uint32_t kStateMask = kHotFlag - 1;
+constexpr uint32_t kStateBits = 22;
+constexpr uint32_t kHotFlag = 1u << 22;
+constexpr uint32_t kSingleFlag = 1u << 23;
+constexpr uint32_t kStateMask = (1u << kStateBits) - 1;
 constexpr uint32_t kNoState = 0xFFFFFFFFu;
 constexpr uint32_t kHotEmpty = 0xFFFFFFFFu;
 constexpr uint32_t kHash4Mul = 0x9E3779B1u;
@@ -33,6 +43,7 @@ struct Derived {
     uint32_t off_t1 = 0, off_s0f = 0, off_t2 = 0, off_t1s = 0, off_hot = 0;
     uint32_t t2_shift = 32;      // index = (w * kHash4Mul) >> t2_shift
     uint32_t has_short = 0;      // patterns of length <= 3 exist (T1s present)
+    uint32_t state_mask = 0x7FFFFFFFu, hot_bit = 0, single_bit = 0;   // plain words unless flags fit
     uint32_t hot_mask = 0;       // entries - 1 (0: no hot table)
     uint32_t hot_shift = 32;     // slot = (key * hot_mul) >> hot_shift
     uint32_t hot_mul = 0;

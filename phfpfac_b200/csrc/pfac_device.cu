@@ -63,6 +63,7 @@ struct pfac_ctx {
     uint32_t image_bytes = 0;
     int32_t ht_size = 0, width_bit = 0, n_final = 0, max_pat_len = 0;
     uint32_t halo = 16;
+    uint32_t n_stages = 0;
     size_t smem_bytes = 0;
     size_t table_bytes = 0;
     // pfac_scan_device: own stream and slot
@@ -195,6 +196,10 @@ int launch_scan(pfac_ctx *ctx, Slot &slot, const void *d_in, uint64_t n_starts, 
     p.hot_shift = ctx->dv.hot_shift;
     p.hot_mul = ctx->dv.hot_mul;
     p.hot_probe = ctx->dv.hot_probe;
+    p.state_mask = ctx->dv.state_mask;
+    p.hot_bit = ctx->dv.hot_bit;
+    p.single_bit = ctx->dv.single_bit;
+    p.n_stages = ctx->n_stages;
     e = slot_reserve(slot, p.n_tiles, (size_t)std::max<uint64_t>(cap, 4096), stream);
     if (e) return e;
     p.scratch = slot.d_scratch;
@@ -293,14 +298,20 @@ int pfac_ctx_create(int device, const pfac_tables *t, int part, int n_streams, s
     while (true) {
         derive_tables(P, t2_bytes, hot_bytes, ctx->dv);
         ctx->image_bytes = (uint32_t)ctx->dv.image.size();
-        ctx->smem_bytes = scan_smem_bytes(ctx->image_bytes, ctx->halo);
-        if (ctx->smem_bytes <= smem_max) break;
+        const size_t fixed = scan_smem_bytes(ctx->image_bytes, ctx->halo, 0);
+        const size_t stride = scan_buf_stride(ctx->halo);
+        const size_t fit = smem_max > fixed ? (smem_max - fixed) / stride : 0;
+        if (fit >= 4 || (fit >= 2 && hot_bytes == 0 && t2_bytes < 2048)) {
+            ctx->n_stages = (uint32_t)std::min<size_t>(fit, kMaxStages);
+            ctx->smem_bytes = scan_smem_bytes(ctx->image_bytes, ctx->halo, ctx->n_stages);
+            break;
+        }
         if (hot_bytes >= 2048) hot_bytes /= 2;
         else if (hot_bytes) hot_bytes = 0;
         else if (t2_bytes >= 2048) t2_bytes /= 2;
         else
-            return set_error(PFAC_ERR_CUDA, "scan kernel needs %zu B of shared memory, device offers %zu",
-                             ctx->smem_bytes, smem_max);
+            return set_error(PFAC_ERR_CUDA, "scan kernel needs more than the %zu B of shared memory the device offers",
+                             smem_max);
     }
 
     // canonical arrays -> device: r, {HT, val|hot flag} interleaved, idmap; + the shared-memory image
@@ -360,7 +371,7 @@ int pfac_ctx_derived_info(const pfac_ctx *ctx, uint64_t info[12])
     const Derived &d = ctx->dv;
     const uint64_t v[12] = {ctx->image_bytes, d.t1_set, d.t2_shift >= 32 ? 0 : (1ull << (32 - d.t2_shift)), d.t2_set,
                             d.n_depth4, d.has_short, d.hot_mask ? (uint64_t)d.hot_mask + 1 : 0, d.n_hot_rows,
-                            d.n_hot_entries, d.hot_probe, ctx->smem_bytes, ctx->table_bytes};
+                            d.n_hot_entries, d.hot_probe | ((uint64_t)ctx->n_stages << 32), ctx->smem_bytes, ctx->table_bytes};
     memcpy(info, v, sizeof v);
     return PFAC_OK;
 }

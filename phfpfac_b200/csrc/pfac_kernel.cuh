@@ -55,6 +55,8 @@ struct ScanParams {
     const uint4 *image;
     uint32_t image_bytes, off_t1, off_s0f, off_t2, off_t1s, off_hot;
     uint32_t t2_shift, has_short, hot_mask, hot_shift, hot_mul, hot_probe;
+    uint32_t state_mask, hot_bit, single_bit;   // state-word layout (pfac_derive.h)
+    uint32_t n_stages;                          // depth of the input ring (as many as shared memory holds)
     // output
     uint2 *scratch;                   // arrival-order records
     unsigned long long scratch_cap;
@@ -84,23 +86,22 @@ constexpr int kThreads = (kConsumerWarps + 1) * 32;   // + the producer warp
 constexpr int kTile = 16384;          // start positions per tile
 constexpr int kSlice = 512;           // start positions per warp step (32 lanes x 16 B)
 constexpr int kSlicesPerTile = kTile / kSlice;
-constexpr int kStages = 3;
+constexpr int kMaxStages = 8;
 constexpr int kQCap = 640;            // queue entries per warp (a batch stops growing at kBatchMin)
 constexpr int kBatchMin = 48;
-constexpr int kCtrlBytes = 256;
+constexpr int kQueueBytes = kQCap * 2 + 128;   // u16 start positions + the batch's slice directory
+constexpr int kCtrlBytes = 512;
+constexpr uint32_t kMatchedBit = 0x8000u;      // on a queue entry: this start reported at least one match
 constexpr unsigned kSpinLimit = 1u << 24;
 
 __host__ __device__ inline uint32_t scan_buf_stride(uint32_t halo) { return (kTile + halo + 32 + 127) & ~127u; }
-__host__ inline size_t scan_smem_bytes(uint32_t image_bytes, uint32_t halo)
+__host__ inline size_t scan_smem_bytes(uint32_t image_bytes, uint32_t halo, uint32_t n_stages)
 {
-    return (size_t)image_bytes + kCtrlBytes + (size_t)kConsumerWarps * (kQCap * 4 + 128) +
-           (size_t)kStages * scan_buf_stride(halo);
+    return (size_t)image_bytes + kCtrlBytes + (size_t)kConsumerWarps * kQueueBytes +
+           (size_t)n_stages * scan_buf_stride(halo);
 }
 
 #ifdef __CUDACC__
-
-constexpr uint32_t kHotFlagD = 1u << 30;
-constexpr uint32_t kStateMaskD = kHotFlagD - 1;
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -190,14 +191,16 @@ struct WalkCtx {
     const uint32_t *__restrict__ s0f;   // shared
     int32_t ht_size, width_bit, colmask, n_final;
     uint32_t hot_mask, hot_shift, hot_mul, hot_probe;
+    uint32_t state_mask, hot_bit, single_bit;
 };
 
-// One transition (master_kernel.cu:52-64).  sw = state | hot flag; returns the next state word
-// or 0xFFFFFFFF.  A hot row is complete in the shared-memory hash: a miss there is final.
+// One transition (master_kernel.cu:52-64).  sw = state word (pfac_derive.h); returns the next
+// state word or 0xFFFFFFFF.  A hot row is complete in the shared-memory hash, so a miss there is
+// final; a single-edge row ends the walk on any other byte without touching L2.
 __device__ __forceinline__ uint32_t step_state(const WalkCtx &c, uint32_t sw, uint32_t byte)
 {
-    const uint32_t key = (sw << 8) | byte;   // the flag bit shifts out
-    if (sw & kHotFlagD) {
+    const uint32_t key = ((sw & c.state_mask) << 8) | byte;
+    if (sw & c.hot_bit) {
         uint32_t slot = (key * c.hot_mul) >> c.hot_shift;
         for (uint32_t pr = 0; pr < c.hot_probe; pr++) {
             const uint2 e = c.hot[slot];
@@ -207,6 +210,7 @@ __device__ __forceinline__ uint32_t step_state(const WalkCtx &c, uint32_t sw, ui
         }
         return 0xFFFFFFFFu;
     }
+    if ((sw & c.single_bit) && (sw >> 24) != byte) return 0xFFFFFFFFu;
     const int32_t row = (int32_t)key >> c.width_bit;                 // :53
     const int32_t idx = __ldg(&c.r[row]) + ((int32_t)key & c.colmask);   // :54-55
     if (idx < 0 || idx >= c.ht_size) return 0xFFFFFFFFu;            // :56-57
@@ -230,23 +234,26 @@ __device__ __forceinline__ uint32_t walk_limit(const ScanParams &p, uint32_t a0,
     return lim_t < depth ? lim_t : depth;
 }
 
-// The walk of SUBSEG_MATCH (master_kernel.cu:39-73) for one start, writing one record per final
-// state visited, in visiting order = pattern length ascending.
-__device__ __forceinline__ void walk_emit(const ScanParams &p, const WalkCtx &c, const uint8_t *__restrict__ buf,
-                                          uint32_t tpos, uint32_t lim_t, uint32_t rec_pos, unsigned long long o)
+// The walk of SUBSEG_MATCH (master_kernel.cu:39-73) for one start, start to end.  Returns the
+// number of final states visited; WRITE also stores one record per final state at scratch[o..],
+// in visiting order = pattern length ascending.
+template <bool WRITE>
+__device__ __forceinline__ uint32_t walk_full(const ScanParams &p, const WalkCtx &c, const uint8_t *__restrict__ buf,
+                                              uint32_t tpos, uint32_t lim_t, uint32_t rec_pos, unsigned long long o)
 {
     uint32_t sw = c.s0f[buf[tpos]];                                  // :41
-    uint32_t q = tpos + 1;
+    uint32_t q = tpos + 1, n = 0;
     while (sw != 0xFFFFFFFFu) {
-        const uint32_t st = sw & kStateMaskD;
+        const uint32_t st = sw & c.state_mask;
         if ((int32_t)st < c.n_final) {                               // :44-47, :67-70
-            if (o < p.scratch_cap) p.scratch[o] = make_uint2(rec_pos, (uint32_t)__ldg(&p.idmap[st]));
-            o++;
+            if (WRITE && o + n < p.scratch_cap) p.scratch[o + n] = make_uint2(rec_pos, (uint32_t)__ldg(&p.idmap[st]));
+            n++;
         }
         if (q >= lim_t) break;                                       // :50
         sw = step_state(c, sw, buf[q]);
         q++;
     }
+    return n;
 }
 
 __global__ void __launch_bounds__(kThreads, 1) pfac_scan_kernel(const ScanParams p)
@@ -256,16 +263,17 @@ __global__ void __launch_bounds__(kThreads, 1) pfac_scan_kernel(const ScanParams
     const uint32_t *s_t1s = reinterpret_cast<const uint32_t *>(smem + p.off_t1s);
     const uint2 *s_hot = reinterpret_cast<const uint2 *>(smem + p.off_hot);
     uint8_t *ctl = smem + p.image_bytes;
-    uint64_t *s_full = reinterpret_cast<uint64_t *>(ctl);              // [kStages]
-    uint64_t *s_empty = reinterpret_cast<uint64_t *>(ctl + 32);        // [kStages]
-    uint32_t *s_tile = reinterpret_cast<uint32_t *>(ctl + 64);         // [kStages] tile id of the stage
-    uint32_t *s_ticket = reinterpret_cast<uint32_t *>(ctl + 80);       // [kStages] slice tickets
-    uint32_t *s_done = reinterpret_cast<uint32_t *>(ctl + 96);         // [kStages] warps finished
-    uint32_t *s_tcnt = reinterpret_cast<uint32_t *>(ctl + 112);        // [kStages] matches in the tile
-    uint32_t *s_tmask = reinterpret_cast<uint32_t *>(ctl + 128);       // [kStages] matching slices
+    uint64_t *s_full = reinterpret_cast<uint64_t *>(ctl);               // [kMaxStages]
+    uint64_t *s_empty = reinterpret_cast<uint64_t *>(ctl + 64);         // [kMaxStages]
+    uint32_t *s_tile = reinterpret_cast<uint32_t *>(ctl + 128);         // [kMaxStages] tile id of the stage
+    uint32_t *s_ticket = reinterpret_cast<uint32_t *>(ctl + 160);       // [kMaxStages] slice tickets
+    uint32_t *s_done = reinterpret_cast<uint32_t *>(ctl + 192);         // [kMaxStages] warps finished
+    uint32_t *s_tcnt = reinterpret_cast<uint32_t *>(ctl + 224);         // [kMaxStages] matches in the tile
+    uint32_t *s_tmask = reinterpret_cast<uint32_t *>(ctl + 256);        // [kMaxStages] matching slices
     uint8_t *qbase = ctl + kCtrlBytes;
-    uint8_t *s_in = qbase + kConsumerWarps * (kQCap * 4 + 128);
+    uint8_t *s_in = qbase + kConsumerWarps * kQueueBytes;
     const uint32_t stride = scan_buf_stride(p.halo);
+    const uint32_t n_stages = p.n_stages;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
@@ -275,7 +283,7 @@ __global__ void __launch_bounds__(kThreads, 1) pfac_scan_kernel(const ScanParams
         for (uint32_t i = tid; i < n16; i += kThreads) dst[i] = __ldg(&p.image[i]);
     }
     if (tid == 0) {
-        for (int s = 0; s < kStages; s++) {
+        for (uint32_t s = 0; s < n_stages; s++) {
             mbar_init(&s_full[s], 1);
             mbar_init(&s_empty[s], kConsumerWarps);
             s_ticket[s] = 0;
@@ -291,11 +299,13 @@ __global__ void __launch_bounds__(kThreads, 1) pfac_scan_kernel(const ScanParams
         // ------------------------------------------------------------------ producer
         if (lane == 0) {
             const uint64_t policy = policy_evict_first();
-            for (uint32_t it = 0;; it++) {
-                const int s = it % kStages;
-                const uint32_t t = atomicAdd(&p.ctrl->ticket, 1u);
-                if (it >= (uint32_t)kStages)
-                    if (!mbar_wait(&s_empty[s], ((it / kStages) - 1) & 1u, &p.ctrl->error_flag, 3u)) break;
+            uint32_t s = 0, round = 0;
+            uint32_t t = atomicAdd(&p.ctrl->ticket, 1u);
+            while (true) {
+                // the next ticket is claimed before this stage is waited for: its latency hides there
+                const uint32_t t_next = t < p.n_tiles ? atomicAdd(&p.ctrl->ticket, 1u) : t;
+                if (round)
+                    if (!mbar_wait(&s_empty[s], (round - 1) & 1u, &p.ctrl->error_flag, 3u)) break;
                 s_tile[s] = t;
                 if (t >= p.n_tiles) {   // sentinel: consumers leave when they see it
                     mbar_arrive(&s_full[s]);
@@ -312,15 +322,16 @@ __global__ void __launch_bounds__(kThreads, 1) pfac_scan_kernel(const ScanParams
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 mbar_expect_tx(&s_full[s], nb16);
                 if (nb16) bulk_g2s(buf, p.in_al + a0, nb16, &s_full[s], policy);
+                t = t_next;
+                if (++s == n_stages) { s = 0; round++; }
             }
         }
         return;
     }
 
     // ---------------------------------------------------------------------- consumers
-    uint16_t *wq = reinterpret_cast<uint16_t *>(qbase + warp * (kQCap * 4 + 128));   // start positions
-    uint16_t *wc = wq + kQCap;                                                         // matches per start
-    uint16_t *w_sid = wc + kQCap;       // [32] slice ids of the batch
+    uint16_t *wq = reinterpret_cast<uint16_t *>(qbase + warp * kQueueBytes);   // start positions (+ kMatchedBit)
+    uint16_t *w_sid = wq + kQCap;       // [32] slice ids of the batch
     uint16_t *w_send = w_sid + 32;      // [32] queue end of each slice of the batch
     WalkCtx wk;
     wk.r = p.r;
@@ -335,11 +346,14 @@ __global__ void __launch_bounds__(kThreads, 1) pfac_scan_kernel(const ScanParams
     wk.hot_shift = p.hot_shift;
     wk.hot_mul = p.hot_mul;
     wk.hot_probe = p.hot_probe;
+    wk.state_mask = p.state_mask;
+    wk.hot_bit = p.hot_bit;
+    wk.single_bit = p.single_bit;
     const uint32_t lt_mask = (1u << lane) - 1u;
 
-    for (uint32_t it = 0;; it++) {
-        const int s = it % kStages;
-        if (!mbar_wait(&s_full[s], (it / kStages) & 1u, &p.ctrl->error_flag, 2u)) break;
+    uint32_t s = 0, round = 0;
+    for (;; s = (s + 1 == n_stages) ? 0 : s + 1, round += (s == 0) ? 1u : 0u) {
+        if (!mbar_wait(&s_full[s], round & 1u, &p.ctrl->error_flag, 2u)) break;
         const uint32_t tile = s_tile[s];
         if (tile >= p.n_tiles) break;
         const uint8_t *buf = s_in + s * stride;
@@ -422,8 +436,9 @@ __global__ void __launch_bounds__(kThreads, 1) pfac_scan_kernel(const ScanParams
             if (nb == 0) break;   // the tile has no slices left
             __syncwarp();
 
-            // ---- walk the batch: lanes refill from the queue as their walks end; count matches
-            uint32_t total = 0;
+            // ---- walk the batch: lanes refill from the queue as their walks end; starts that
+            //      matched get kMatchedBit on their queue entry
+            uint32_t any_match = 0;
             if (!(p.debug & 1u) && nq) {
                 uint32_t head = 0, my_e = 0, q = 0, lim = 0, cnt = 0, sw = 0xFFFFFFFFu;
                 bool active = false;
@@ -448,7 +463,7 @@ __global__ void __launch_bounds__(kThreads, 1) pfac_scan_kernel(const ScanParams
                     if (active) {
                         bool fin = (sw == 0xFFFFFFFFu);
                         if (!fin) {
-                            cnt += ((int32_t)(sw & kStateMaskD) < wk.n_final) ? 1u : 0u;
+                            cnt += ((int32_t)(sw & wk.state_mask) < wk.n_final) ? 1u : 0u;
                             if (q >= lim) fin = true;
                             else {
                                 sw = step_state(wk, sw, buf[q]);
@@ -456,55 +471,61 @@ __global__ void __launch_bounds__(kThreads, 1) pfac_scan_kernel(const ScanParams
                             }
                         }
                         if (fin) {
-                            wc[my_e] = (uint16_t)cnt;
-                            total += cnt;
+                            if (cnt) {
+                                wq[my_e] |= (uint16_t)kMatchedBit;
+                                any_match = 1;
+                            }
                             active = false;
                         }
                     }
                 }
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
+                any_match = __any_sync(0xffffffffu, any_match);
             }
             __syncwarp();
 
-            // ---- emit (rare): reserve scratch space, write records in position order
-            if (total) {
+            // ---- emit (rare): walk the matched starts again to count, reserve scratch space,
+            //      and a third time to write the records in (position, length) order
+            if (any_match) {
+                uint32_t total = 0;
+                for (uint32_t e = lane; e < nq; e += 32) {
+                    const uint32_t ent = wq[e];
+                    if (ent & kMatchedBit) {
+                        const uint32_t tpos = ent & (kMatchedBit - 1u);
+                        total += walk_full<false>(p, wk, buf, tpos, walk_limit(p, a0, tpos), 0u, 0ull);
+                    }
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
                 unsigned long long base = 0;
                 if (lane == 0) base = atomicAdd(&p.ctrl->alloc, (unsigned long long)total);
                 base = __shfl_sync(0xffffffffu, base, 0);
-                // per-slice counts and scratch offsets (slices of a batch are in position order)
-                uint32_t run = 0, smask = 0, qs = 0;
-                for (uint32_t sl = 0; sl < nb; sl++) {
-                    const uint32_t qe = w_send[sl];
-                    uint32_t c = 0;
-                    for (uint32_t e = qs + lane; e < qe; e += 32) c += wc[e];
-#pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
-                    if (c) {
-                        const unsigned long long so = base + run;
-                        if (lane == 0)
-                            p.slice_ent[(size_t)tile * kSlicesPerTile + w_sid[sl]] =
-                                make_uint4(c, (uint32_t)so, (uint32_t)(so >> 32), 0u);
-                        smask |= 1u << w_sid[sl];
-                    }
-                    run += c;
-                    qs = qe;
-                }
-                // records: exclusive scan of the per-start counts, then re-walk the starts that matched
-                run = 0;
+                uint32_t run = 0, smask = 0, sl = 0, sl_run0 = 0;   // records so far; current slice; records before it
                 for (uint32_t e0 = 0; e0 < nq; e0 += 32) {
                     const uint32_t e = e0 + lane;
-                    const uint32_t c = e < nq ? wc[e] : 0u;
+                    const uint32_t ent = e < nq ? wq[e] : 0u;
+                    const uint32_t tpos = ent & (kMatchedBit - 1u);
+                    const uint32_t lim = walk_limit(p, a0, tpos);
+                    const uint32_t c = (ent & kMatchedBit) ? walk_full<false>(p, wk, buf, tpos, lim, 0u, 0ull) : 0u;
                     uint32_t incl = c;
 #pragma unroll
                     for (int o = 1; o < 32; o <<= 1) {
                         const uint32_t n = __shfl_up_sync(0xffffffffu, incl, o);
                         if (lane >= o) incl += n;
                     }
-                    if (c) {
-                        const uint32_t tpos = wq[e];
-                        walk_emit(p, wk, buf, tpos, walk_limit(p, a0, tpos), a0 + tpos - p.mis + p.pos_bias,
-                                  base + run + incl - c);
+                    if (c) walk_full<true>(p, wk, buf, tpos, lim, a0 + tpos - p.mis + p.pos_bias, base + run + incl - c);
+                    // close every slice of the batch that ends inside this chunk of 32 entries
+                    while (sl < nb && (uint32_t)w_send[sl] <= e0 + 32u) {
+                        const uint32_t li = (uint32_t)w_send[sl] - e0;   // entries of this chunk that belong to slices <= sl
+                        const uint32_t upto = run + (li ? __shfl_sync(0xffffffffu, incl, (int)li - 1) : 0u);
+                        if (upto != sl_run0) {
+                            const unsigned long long so = base + sl_run0;
+                            if (lane == 0)
+                                p.slice_ent[(size_t)tile * kSlicesPerTile + w_sid[sl]] =
+                                    make_uint4(upto - sl_run0, (uint32_t)so, (uint32_t)(so >> 32), 0u);
+                            smask |= 1u << w_sid[sl];
+                        }
+                        sl_run0 = upto;
+                        sl++;
                     }
                     run += __shfl_sync(0xffffffffu, incl, 31);
                 }

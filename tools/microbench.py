@@ -20,6 +20,7 @@ sizes = [int(s) << 20 for s in a.sizes.split(",")]
 text = pf.synth_text(tk, tseed, max(sizes), patterns=pats)
 d = torch.from_numpy(text).cuda()
 m = pf.Matcher(tables, device=0)
+print("derived:", m.derived_info(), flush=True)
 st = torch.cuda.Stream(); torch.cuda.set_stream(st)
 cap = max(sizes) // 8
 out = torch.empty((cap, 2), dtype=torch.int32, device="cuda"); cntd = torch.zeros(1, dtype=torch.int64, device="cuda")
