@@ -89,11 +89,17 @@ const int32_t *pfac_tables_val(const pfac_tables *t, int part);   /* ht_size ent
 const int32_t *pfac_tables_idmap(const pfac_tables *t, int part); /* n_final entries */
 /* Builds the scan kernel's shared-memory accelerators for this partition on the host (the same
  * code pfac_ctx_create runs) and verifies them against the canonical PHF: prefix filters are
- * supersets, hot rows answer like master_kernel.cu:52-64.  stats[0..7] = image bytes, T1 pairs,
- * T2 bits set, 4-byte prefixes, short patterns present, hot rows, hot transitions, longest probe.
- * Needs no GPU. */
-int pfac_tables_derive_check(const pfac_tables *t, int part, uint32_t t2_bytes, uint32_t hot_bytes,
-                             uint64_t stats[8]);
+ * supersets, hot rows answer like master_kernel.cu:52-64.  stats[0..9] = image bytes, T1 pairs,
+ * T2 bits set, 4-byte prefixes, short patterns present, hot rows, hot transitions, longest probe,
+ * T3 present, T3 bits set.  t2/t3/hot_bytes = shared-memory budget of those sections.  Needs no GPU. */
+int pfac_tables_derive_check(const pfac_tables *t, int part, uint32_t t2_bytes, uint32_t t3_bytes,
+                             uint32_t hot_bytes, uint64_t stats[10]);
+/* Diagnostics: how many start positions of `text` survive each stage of the kernel's shared-memory
+ * filter cascade and how many walk steps remain (a host model that COUNTS; it reports no matches).
+ * counts[0..11] = positions, T1 pass, T2 pass, unknown at level 1, level-1 window pass, unknown at
+ * level 2, level-2 window pass, starts that walk, hot steps, look-ahead ends, L2 steps, hot probes. */
+int pfac_tables_filter_profile(const pfac_tables *t, int part, uint32_t t2_bytes, uint32_t t3_bytes,
+                               uint32_t hot_bytes, const void *text, uint64_t n, uint64_t counts[12]);
 /* One transition through the PHF exactly as master_kernel.cu:52-64 does it; -1 = none. */
 int32_t pfac_tables_lookup(const pfac_tables *t, int part, int32_t state, int32_t byte);
 
@@ -143,8 +149,9 @@ int pfac_ctx_last_scan_info(const pfac_ctx *ctx, uint64_t info[8]);
 /* Derived (shared-memory) table statistics of this context, for DESIGN.md / bench.py:
  * info[0] = image bytes, [1] = T1 pairs set, [2] = T2 bits, [3] = T2 bits set, [4] = 4-byte prefixes,
  * [5] = short patterns (<= 3 bytes) present, [6] = hot-table slots, [7] = hot rows, [8] = hot
- * transitions, [9] = longest probe, [10] = dynamic smem bytes, [11] = table bytes in HBM */
-int pfac_ctx_derived_info(const pfac_ctx *ctx, uint64_t info[12]);
+ * transitions, [9] = longest probe, [10] = dynamic smem bytes, [11] = table bytes in HBM,
+ * [12] = input ring stages, [13] = T3 bits, [14] = T3 bits set, [15] = reserved */
+int pfac_ctx_derived_info(const pfac_ctx *ctx, uint64_t info[16]);
 
 /* ------------------------------------------------------------------------------ multi-GPU job
  * Replaces the GPU x stream loop of main.cc:171-272.  The INPUT is sharded (the reference

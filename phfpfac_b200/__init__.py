@@ -84,12 +84,25 @@ class Tables:
     def part(self, g=0):
         return PartView(self, g)
 
-    def derive_check(self, g=0, t2_bytes=16384, hot_bytes=32768):
+    def derive_check(self, g=0, t2_bytes=8192, t3_bytes=16384, hot_bytes=8192):
         """Host-side build + verification of the kernel's shared-memory tables (no GPU needed)."""
-        st = (C.c_uint64 * 8)()
-        check(lib.pfac_tables_derive_check(self._h, g, t2_bytes, hot_bytes, st))
-        keys = ("image_bytes", "t1_pairs", "t2_set", "prefixes4", "has_short", "hot_rows", "hot_entries", "hot_probe")
-        return dict(zip(keys, list(st)))
+        st = (C.c_uint64 * 10)()
+        check(lib.pfac_tables_derive_check(self._h, g, t2_bytes, t3_bytes, hot_bytes, st))
+        keys = ("image_bytes", "t1_pairs", "t2_set", "prefixes4", "has_short", "hot_rows", "hot_entries", "hot_probe",
+                "tm_keys", "t3_set")
+        d = dict(zip(keys, list(st)))
+        d["tm2_keys"] = d["tm_keys"] >> 32
+        d["tm_keys"] &= 0xFFFFFFFF
+        return d
+
+    def filter_profile(self, text, g=0, t2_bytes=8192, t3_bytes=16384, hot_bytes=8192):
+        """Diagnostics: survivors per stage of the kernel's filter cascade over `text` (host model, counts only)."""
+        buf = np.ascontiguousarray(text, dtype=np.uint8)
+        c = (C.c_uint64 * 12)()
+        check(lib.pfac_tables_filter_profile(self._h, g, t2_bytes, t3_bytes, hot_bytes, buf.ctypes.data, len(buf), c))
+        keys = ("positions", "t1_pass", "t2_pass", "unknown1", "window1_pass", "unknown2", "window2_pass", "walks",
+                "hot_steps", "lookahead_ends", "l2_steps", "hot_probes")
+        return dict(zip(keys, list(c)))
 
     def lookup(self, state, byte, g=0):
         return lib.pfac_tables_lookup(self._h, g, state, byte)
@@ -135,11 +148,14 @@ class Matcher:
         return dict(zip(keys, list(info)))
 
     def derived_info(self):
-        info = (C.c_uint64 * 12)()
+        info = (C.c_uint64 * 16)()
         check(lib.pfac_ctx_derived_info(self._h, info))
         keys = ("image_bytes", "t1_pairs", "t2_bits", "t2_set", "prefixes4", "has_short", "hot_slots", "hot_rows",
-                "hot_entries", "hot_probe", "smem_bytes", "table_bytes")
-        return dict(zip(keys, list(info)))
+                "hot_entries", "hot_probe", "smem_bytes", "table_bytes", "ring_stages", "t3_bits", "t3_set", "tm_keys")
+        d = dict(zip(keys, list(info)))
+        d["tm2_keys"] = d["tm_keys"] >> 32
+        d["tm_keys"] &= 0xFFFFFFFF
+        return d
 
     # -- device-resident input (raw pointers; torch tensors are accepted for convenience)
     def scan_device_raw(self, d_in, n_starts, n_valid, base_pos, d_out, cap, d_count, stream=0):

@@ -16,7 +16,7 @@ ABI_SYMBOLS = [
     "pfac_tables_build_file", "pfac_tables_build_mem", "pfac_tables_from_arrays", "pfac_tables_destroy",
     "pfac_tables_n_parts", "pfac_tables_n_patterns", "pfac_tables_max_pat_len", "pfac_tables_width",
     "pfac_tables_part_info", "pfac_tables_s0", "pfac_tables_r", "pfac_tables_HT", "pfac_tables_val",
-    "pfac_tables_idmap", "pfac_tables_lookup", "pfac_tables_derive_check",
+    "pfac_tables_idmap", "pfac_tables_lookup", "pfac_tables_derive_check", "pfac_tables_filter_profile",
     "pfac_device_count", "pfac_ctx_create", "pfac_ctx_destroy", "pfac_ctx_device",
     "pfac_scan_device", "pfac_scan_device_sync", "pfac_scan_host", "pfac_host_alloc", "pfac_host_free",
     "pfac_ctx_last_scan_info", "pfac_ctx_derived_info",
@@ -60,7 +60,9 @@ def _load():
     for n in ("pfac_tables_s0", "pfac_tables_r", "pfac_tables_HT", "pfac_tables_val", "pfac_tables_idmap"):
         getattr(lib, n).argtypes = [_vp, C.c_int]
         getattr(lib, n).restype = _i32p
-    lib.pfac_tables_derive_check.argtypes = [_vp, C.c_int, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint64)]
+    lib.pfac_tables_derive_check.argtypes = [_vp, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint64)]
+    lib.pfac_tables_filter_profile.argtypes = [_vp, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, _vp, C.c_uint64,
+                                               C.POINTER(C.c_uint64)]
     lib.pfac_tables_lookup.argtypes = [_vp, C.c_int, C.c_int32, C.c_int32]
     lib.pfac_tables_lookup.restype = C.c_int32
     lib.pfac_device_count.argtypes = [C.POINTER(C.c_int)]

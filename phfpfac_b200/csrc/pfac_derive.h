@@ -9,6 +9,15 @@
 //                       or has a second edge  (root fan-out, s0Table of main.cc:200, folded in)
 //   T1s   65,536 bits : pair (c0,c1) can complete a pattern of length <= 3 (bypasses T2)
 //   T2    2^k2 bits   : multiplicative hash of every 4-byte pattern prefix
+//   Tm    8192 x u16  : COMPLETE cuckoo table (2 buckets x 2 tagged slots) of every 4-byte prefix
+//                       -> m1 = shortest pattern length below it; a miss rejects the start, so Tm
+//                       stands in for T2 (sets with too many prefixes keep T2 and get no Tm/T3)
+//   Tm2   4096 x u16  : same, (prefix, level-1 window) group -> m2 = shortest length in the group
+//   T3    2^k3 bits   : hash of (key, pattern bytes [m-4, m)) for every pattern below a stored key:
+//                       a start whose text at offset m-4 is not in T3 cannot complete any pattern
+//                       under that key (Wu-Manber style two-point checks; they end the walks along
+//                       prefixes the text shares with many patterns).  Keys that are not stored
+//                       are "unknown": the start simply walks.
 //   s0f   256 x u32   : root row as state words
 //   hot   open-addressing hash of COMPLETE PHF rows of the hottest states
 //                       (key = state<<8|byte -> next state word); a miss in a hot row means
@@ -36,11 +45,60 @@ constexpr uint32_t kStateMask = (1u << kStateBits) - 1;
 constexpr uint32_t kNoState = 0xFFFFFFFFu;
 constexpr uint32_t kHotEmpty = 0xFFFFFFFFu;
 constexpr uint32_t kHash4Mul = 0x9E3779B1u;
+constexpr uint32_t kTmSlotBits = 12;
+constexpr uint32_t kTmSlots = 1u << kTmSlotBits;   // u16 entries: tag << 8 | m, 0 = empty; two choices per key
+constexpr uint32_t kTm1Slots = 2 * kTmSlots;       // level 1: 4096 buckets x 2 slots, cuckoo, complete
+constexpr uint32_t kT3Seed2 = 0x5bd1e995u;
+
+#if defined(__CUDACC__)
+#define PFAC_HD __host__ __device__
+#else
+#define PFAC_HD
+#endif
+// T3 index (before the final shift) of a key and the 4 window bytes (little-endian word)
+PFAC_HD inline uint32_t hash_t3(uint32_t key, uint32_t window)
+{
+    uint32_t x = key * 0x9E3779B1u + window * 0x85EBCA6Bu;
+    x ^= x >> 15;
+    return x * 0x2C1B3C6Du;
+}
+// level-2 key of a (4-byte prefix, level-1 window) group
+PFAC_HD inline uint32_t hash_key2(uint32_t prefix, uint32_t window)
+{
+    uint32_t x = prefix * 0xC2B2AE35u ^ window * 0x27D4EB2Fu;
+    x ^= x >> 16;
+    return x * 0x165667B1u + 0x9E3779B9u;
+}
+PFAC_HD inline uint32_t tm_slot1(uint32_t key) { return (key * 0xC2B2AE35u) >> (32 - kTmSlotBits); }
+PFAC_HD inline uint32_t tm_slot2(uint32_t key) { return (key * 0x27D4EB2Fu + 0x7F4A7C15u) >> (32 - kTmSlotBits); }
+PFAC_HD inline uint32_t tm_tag(uint32_t key) { return (key * 0xFD7046C5u) >> 24; }
+// level 1 (complete table, 2 buckets x 2 slots): m of `key`, 0 = no pattern has this 4-byte prefix
+PFAC_HD inline uint32_t tm1_lookup(const uint16_t *tab, uint32_t key)
+{
+    const uint32_t tag = tm_tag(key);
+    const uint32_t *t32 = reinterpret_cast<const uint32_t *>(tab);
+    const uint32_t a = t32[tm_slot1(key)], b = t32[tm_slot2(key)];
+    if ((a & 0xffffu) && ((a >> 8) & 0xffu) == tag) return a & 255u;
+    if ((a >> 16) && (a >> 24) == tag) return (a >> 16) & 255u;
+    if ((b & 0xffffu) && ((b >> 8) & 0xffu) == tag) return b & 255u;
+    if ((b >> 16) && (b >> 24) == tag) return (b >> 16) & 255u;
+    return 0;
+}
+// the entry the kernel uses for `key` (0 = unknown): slot 1 if its tag matches, else slot 2
+PFAC_HD inline uint32_t tm_lookup(const uint16_t *tab, uint32_t key)
+{
+    const uint32_t tag = tm_tag(key);
+    const uint32_t e1 = tab[tm_slot1(key)], e2 = tab[tm_slot2(key)];
+    if (e1 && (e1 >> 8) == tag) return e1 & 255u;
+    if (e2 && (e2 >> 8) == tag) return e2 & 255u;
+    return 0;
+}
 
 struct Derived {
     // shared-memory image, copied verbatim by the kernel (sections 128-byte aligned)
     std::vector<uint8_t> image;
-    uint32_t off_t1 = 0, off_s0f = 0, off_t2 = 0, off_t1s = 0, off_hot = 0;
+    uint32_t off_t1 = 0, off_s0f = 0, off_t2 = 0, off_t1s = 0, off_tm = 0, off_tm2 = 0, off_t3 = 0, off_hot = 0;
+    uint32_t has_t3 = 0, t3_shift = 32, t3_set = 0, tm_set = 0, tm2_set = 0, tm_complete = 0;
     uint32_t t2_shift = 32;      // index = (w * kHash4Mul) >> t2_shift
     uint32_t has_short = 0;      // patterns of length <= 3 exist (T1s present)
     uint32_t state_mask = 0x7FFFFFFFu, hot_bit = 0, single_bit = 0;   // plain words unless flags fit
@@ -60,8 +118,9 @@ struct Derived {
 inline uint32_t rot2(uint32_t c) { return ((c << 2) | (c >> 6)) & 0xFFu; }
 
 // t2_bytes / hot_bytes: shared-memory budget of the two variable sections (powers of two; 0 = none)
-void derive_tables(const Partition &P, uint32_t t2_bytes, uint32_t hot_bytes, Derived &out);
+void derive_tables(const Partition &P, uint32_t t2_bytes, uint32_t t3_bytes, uint32_t hot_bytes, Derived &out);
 
 int derive_selfcheck(const Partition &P, const Derived &d);
+void derive_profile(const Partition &P, const Derived &d, const uint8_t *text, size_t n, uint64_t out[12]);
 
 }  // namespace pfac

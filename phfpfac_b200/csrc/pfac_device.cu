@@ -189,6 +189,11 @@ int launch_scan(pfac_ctx *ctx, Slot &slot, const void *d_in, uint64_t n_starts, 
     p.off_s0f = ctx->dv.off_s0f;
     p.off_t2 = ctx->dv.off_t2;
     p.off_t1s = ctx->dv.off_t1s;
+    p.off_tm = ctx->dv.off_tm;
+    p.off_tm2 = ctx->dv.off_tm2;
+    p.off_t3 = ctx->dv.off_t3;
+    p.has_t3 = ctx->dv.has_t3;
+    p.t3_shift = ctx->dv.t3_shift;
     p.off_hot = ctx->dv.off_hot;
     p.t2_shift = ctx->dv.t2_shift;
     p.has_short = ctx->dv.has_short;
@@ -292,11 +297,12 @@ int pfac_ctx_create(int device, const pfac_tables *t, int part, int n_streams, s
 
     // shared-memory budget: the fixed parts first, then as much T2 / hot table as fits
     const size_t smem_max = (size_t)prop.sharedMemPerBlockOptin;
-    uint32_t t2_bytes = 16384, hot_bytes = 32768;
+    uint32_t t2_bytes = 16384, t3_bytes = 16384, hot_bytes = 16384;   // T2 only exists when the complete Tm does not
     if (const char *v = getenv("PFAC_T2_BYTES")) t2_bytes = (uint32_t)atoi(v);
+    if (const char *v = getenv("PFAC_T3_BYTES")) t3_bytes = (uint32_t)atoi(v);
     if (const char *v = getenv("PFAC_HOT_BYTES")) hot_bytes = (uint32_t)atoi(v);
     while (true) {
-        derive_tables(P, t2_bytes, hot_bytes, ctx->dv);
+        derive_tables(P, t2_bytes, t3_bytes, hot_bytes, ctx->dv);
         ctx->image_bytes = (uint32_t)ctx->dv.image.size();
         const size_t fixed = scan_smem_bytes(ctx->image_bytes, ctx->halo, 0);
         const size_t stride = scan_buf_stride(ctx->halo);
@@ -308,6 +314,8 @@ int pfac_ctx_create(int device, const pfac_tables *t, int part, int n_streams, s
         }
         if (hot_bytes >= 2048) hot_bytes /= 2;
         else if (hot_bytes) hot_bytes = 0;
+        else if (t3_bytes >= 2048) t3_bytes /= 2;
+        else if (t3_bytes) t3_bytes = 0;
         else if (t2_bytes >= 2048) t2_bytes /= 2;
         else
             return set_error(PFAC_ERR_CUDA, "scan kernel needs more than the %zu B of shared memory the device offers",
@@ -365,13 +373,14 @@ void pfac_ctx_destroy(pfac_ctx *ctx)
 
 int pfac_ctx_device(const pfac_ctx *ctx) { return ctx ? ctx->device : -1; }
 
-int pfac_ctx_derived_info(const pfac_ctx *ctx, uint64_t info[12])
+int pfac_ctx_derived_info(const pfac_ctx *ctx, uint64_t info[16])
 {
     if (!ctx || !info) return set_error(PFAC_ERR_ARG, "bad arguments");
     const Derived &d = ctx->dv;
-    const uint64_t v[12] = {ctx->image_bytes, d.t1_set, d.t2_shift >= 32 ? 0 : (1ull << (32 - d.t2_shift)), d.t2_set,
+    const uint64_t v[16] = {ctx->image_bytes, d.t1_set, d.t2_shift >= 32 ? 0 : (1ull << (32 - d.t2_shift)), d.t2_set,
                             d.n_depth4, d.has_short, d.hot_mask ? (uint64_t)d.hot_mask + 1 : 0, d.n_hot_rows,
-                            d.n_hot_entries, d.hot_probe | ((uint64_t)ctx->n_stages << 32), ctx->smem_bytes, ctx->table_bytes};
+                            d.n_hot_entries, d.hot_probe, ctx->smem_bytes, ctx->table_bytes, ctx->n_stages,
+                            d.t3_shift >= 32 ? 0 : (1ull << (32 - d.t3_shift)), d.t3_set, d.tm_set | ((uint64_t)d.tm2_set << 32)};
     memcpy(info, v, sizeof v);
     return PFAC_OK;
 }

@@ -21,6 +21,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "pfac_derive.h"
+
 namespace pfac {
 
 struct Ctrl {   // device-side control block; the finalize kernel resets it for the next launch
@@ -53,7 +55,8 @@ struct ScanParams {
     int32_t ht_size, width_bit, n_final;
     // shared-memory image (pfac_derive.h)
     const uint4 *image;
-    uint32_t image_bytes, off_t1, off_s0f, off_t2, off_t1s, off_hot;
+    uint32_t image_bytes, off_t1, off_s0f, off_t2, off_t1s, off_tm, off_tm2, off_t3, off_hot;
+    uint32_t has_t3, t3_shift;
     uint32_t t2_shift, has_short, hot_mask, hot_shift, hot_mul, hot_probe;
     uint32_t state_mask, hot_bit, single_bit;   // state-word layout (pfac_derive.h)
     uint32_t n_stages;                          // depth of the input ring (as many as shared memory holds)
@@ -64,7 +67,7 @@ struct ScanParams {
     unsigned int *tile_mask;          // [n_tiles] bit s set iff slice s of the tile matched
     uint4 *slice_ent;                 // [n_tiles*32] {count, scratch offset lo, hi, -} of matching slices
     Ctrl *ctrl;
-    uint32_t debug;           // PFAC_DEBUG bits (timing experiments only): 1 no walk, 4 no filter, 8 no T2
+    uint32_t debug;           // PFAC_DEBUG bits (timing experiments only): 1 no walk, 4 no T1, 8 no T2/T3, 16 no T3
 };
 
 struct FinalizeParams {
@@ -122,9 +125,9 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity)
     uint32_t ok;
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"   // %3: suspend-time hint (ns)
         "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity), "r"(4000u) : "memory");
     return ok != 0;
 }
 // returns false if the watchdog tripped (never expected)
@@ -261,6 +264,9 @@ __global__ void __launch_bounds__(kThreads, 1) pfac_scan_kernel(const ScanParams
     const uint32_t *s_s0f = reinterpret_cast<const uint32_t *>(smem + p.off_s0f);
     const uint32_t *s_t2 = reinterpret_cast<const uint32_t *>(smem + p.off_t2);
     const uint32_t *s_t1s = reinterpret_cast<const uint32_t *>(smem + p.off_t1s);
+    const uint16_t *s_tm = reinterpret_cast<const uint16_t *>(smem + p.off_tm);
+    const uint16_t *s_tm2 = reinterpret_cast<const uint16_t *>(smem + p.off_tm2);
+    const uint32_t *s_t3 = reinterpret_cast<const uint32_t *>(smem + p.off_t3);
     const uint2 *s_hot = reinterpret_cast<const uint2 *>(smem + p.off_hot);
     uint8_t *ctl = smem + p.image_bytes;
     uint64_t *s_full = reinterpret_cast<uint64_t *>(ctl);               // [kMaxStages]
@@ -400,7 +406,8 @@ __global__ void __launch_bounds__(kThreads, 1) pfac_scan_kernel(const ScanParams
                     mask &= mask - 1;
                 }
                 __syncwarp();
-                // stage 2: T2 over the 4-byte prefix, in-place ordered compaction
+                // stage 2: T2 over the 4-byte prefix, then T3 over the bytes [m-4, m) of the shortest
+                // pattern below that prefix; in-place ordered compaction
                 if (!(p.debug & 8u)) {
                     uint32_t wr = q0;
                     for (uint32_t e0 = q0; e0 < nq; e0 += 32) {
@@ -416,8 +423,41 @@ __global__ void __launch_bounds__(kThreads, 1) pfac_scan_kernel(const ScanParams
                                 const uint32_t pair = w4 & 0xffffu;
                                 keep |= (s_t1s[pair >> 5] >> (pair & 31u)) & 1u;
                             }
-                            const uint32_t h = (w4 * 0x9E3779B1u) >> p.t2_shift;
-                            keep |= (s_t2[h >> 5] >> (h & 31u)) & 1u;
+                            bool pass = true;
+                            if (!p.has_t3) {
+                                const uint32_t h = (w4 * kHash4Mul) >> p.t2_shift;
+                                pass = (s_t2[h >> 5] >> (h & 31u)) & 1u;
+                            } else {
+                                // two-point checks: every pattern under a stored key is at least m bytes
+                                // long and has its bytes [m-4, m) in T3; unknown keys (m == 0) just walk
+                                const uint32_t lim = walk_limit(p, a0, tpos);
+                                const uint32_t m1 = tm1_lookup(s_tm, w4);   // complete: 0 = no such prefix
+                                {
+                                    pass = m1 != 0 && tpos + m1 <= lim;
+                                    if (pass) {
+                                        const uint32_t wo = tpos + m1 - 4u;
+                                        const uint32_t *we = reinterpret_cast<const uint32_t *>(buf + (wo & ~3u));
+                                        const uint32_t w1 = __funnelshift_r(we[0], we[1], (wo & 3u) * 8u);
+                                        const uint32_t h3 = hash_t3(w4, w1) >> p.t3_shift;
+                                        pass = (s_t3[h3 >> 5] >> (h3 & 31u)) & 1u;
+                                        if (pass) {
+                                            const uint32_t key2 = hash_key2(w4, w1);
+                                            const uint32_t m2 = tm_lookup(s_tm2, key2);
+                                            if (m2) {
+                                                pass = tpos + m2 <= lim;
+                                                if (pass) {
+                                                    const uint32_t wo2 = tpos + m2 - 4u;
+                                                    const uint32_t *wf = reinterpret_cast<const uint32_t *>(buf + (wo2 & ~3u));
+                                                    const uint32_t w2 = __funnelshift_r(wf[0], wf[1], (wo2 & 3u) * 8u);
+                                                    const uint32_t h4 = hash_t3(key2 ^ kT3Seed2, w2) >> p.t3_shift;
+                                                    pass = (s_t3[h4 >> 5] >> (h4 & 31u)) & 1u;
+                                                }
+                                            }
+                                        }
+                                    }
+                                }
+                            }
+                            keep |= pass;
                         }
                         const uint32_t bal = __ballot_sync(0xffffffffu, keep);
                         if (keep) wq[wr + __popc(bal & lt_mask)] = (uint16_t)tpos;

@@ -160,8 +160,8 @@ def test_derived_device_tables_selfcheck(fixtures, case):
             }.get(case) or fixtures[case]
     for width in (256, 64, 4096):
         t = pf.Tables.from_bytes(blob, 1, width)
-        for t2b, hotb in ((16384, 32768), (1024, 2048), (0, 0), (65536, 1024)):
-            st = t.derive_check(0, t2b, hotb)
+        for t2b, t3b, hotb in ((8192, 16384, 16384), (1024, 1024, 2048), (0, 0, 0), (65536, 0, 1024), (4096, 65536, 0)):
+            st = t.derive_check(0, t2b, t3b, hotb)
             assert st["t1_pairs"] > 0
             if hotb == 0:
                 assert st["hot_rows"] == 0
