@@ -87,19 +87,19 @@ const int32_t *pfac_tables_r(const pfac_tables *t, int part);     /* n_r entries
 const int32_t *pfac_tables_HT(const pfac_tables *t, int part);    /* ht_size entries */
 const int32_t *pfac_tables_val(const pfac_tables *t, int part);   /* ht_size entries */
 const int32_t *pfac_tables_idmap(const pfac_tables *t, int part); /* n_final entries */
-/* Builds the scan kernel's shared-memory accelerators for this partition on the host (the same
- * code pfac_ctx_create runs) and verifies them against the canonical PHF: prefix filters are
- * supersets, hot rows answer like master_kernel.cu:52-64.  stats[0..9] = image bytes, T1 pairs,
- * T2 bits set, 4-byte prefixes, short patterns present, hot rows, hot transitions, longest probe,
- * T3 present, T3 bits set.  t2/t3/hot_bytes = shared-memory budget of those sections.  Needs no GPU. */
+/* Builds the detector kernel's shared-memory filters for this partition on the host (the same
+ * code pfac_ctx_create runs) and verifies them against the canonical PHF: T1 is exact over the
+ * first two bytes, every pattern's own bytes pass T1s / T2 / Tm / Tm2 / T3.  stats[0..9] = image
+ * bytes, T1 pairs, T2 bits set, 4-byte prefixes, short patterns present, Tm/T3 present, Tm keys,
+ * Tm2 keys, T3 bits set, log2 Tm2 buckets.  t2/t3/tm2_bytes = shared-memory budget.  Needs no GPU. */
 int pfac_tables_derive_check(const pfac_tables *t, int part, uint32_t t2_bytes, uint32_t t3_bytes,
-                             uint32_t hot_bytes, uint64_t stats[10]);
-/* Diagnostics: how many start positions of `text` survive each stage of the kernel's shared-memory
- * filter cascade and how many walk steps remain (a host model that COUNTS; it reports no matches).
- * counts[0..11] = positions, T1 pass, T2 pass, unknown at level 1, level-1 window pass, unknown at
- * level 2, level-2 window pass, starts that walk, hot steps, look-ahead ends, L2 steps, hot probes. */
+                             uint32_t tm2_bytes, uint64_t stats[10]);
+/* Diagnostics: how many start positions of `text` survive each stage of the detector's filter
+ * cascade (a host model that COUNTS; it reports no matches).  counts[0..8] = positions, T1 pass,
+ * prefix found (T2/Tm), level-1 window pass, level-2 window pass, bypass, starts left for the
+ * emit kernel, 512-byte slices flagged, slices. */
 int pfac_tables_filter_profile(const pfac_tables *t, int part, uint32_t t2_bytes, uint32_t t3_bytes,
-                               uint32_t hot_bytes, const void *text, uint64_t n, uint64_t counts[12]);
+                               uint32_t tm2_bytes, const void *text, uint64_t n, uint64_t counts[12]);
 /* One transition through the PHF exactly as master_kernel.cu:52-64 does it; -1 = none. */
 int32_t pfac_tables_lookup(const pfac_tables *t, int part, int32_t state, int32_t byte);
 
@@ -143,14 +143,15 @@ void pfac_host_free(void *ptr);
 
 /* Counters of the last scan on this context (for bench.py's gpu_launches / roofline):
  * info[0] = kernel launches, info[1] = tiles, info[2] = CTAs, info[3] = dynamic smem bytes,
- * info[4] = h2d bytes, info[5] = d2h bytes, info[6] = sub-chunks, info[7] = reserved */
+ * info[4] = h2d bytes, info[5] = d2h bytes, info[6] = sub-chunks, info[7] = tiles the detector
+ * flagged for the emit kernel (pfac_scan_device_sync only) */
 int pfac_ctx_last_scan_info(const pfac_ctx *ctx, uint64_t info[8]);
 
 /* Derived (shared-memory) table statistics of this context, for DESIGN.md / bench.py:
  * info[0] = image bytes, [1] = T1 pairs set, [2] = T2 bits, [3] = T2 bits set, [4] = 4-byte prefixes,
- * [5] = short patterns (<= 3 bytes) present, [6] = hot-table slots, [7] = hot rows, [8] = hot
- * transitions, [9] = longest probe, [10] = dynamic smem bytes, [11] = table bytes in HBM,
- * [12] = input ring stages, [13] = T3 bits, [14] = T3 bits set, [15] = reserved */
+ * [5] = short patterns (<= 3 bytes) present, [6] = Tm keys, [7] = Tm2 keys, [8] = T3 bits,
+ * [9] = T3 bits set, [10] = dynamic smem bytes, [11] = table bytes in HBM, [12] = input ring stages,
+ * [13] = log2 Tm2 buckets, [14..15] = reserved */
 int pfac_ctx_derived_info(const pfac_ctx *ctx, uint64_t info[16]);
 
 /* ------------------------------------------------------------------------------ multi-GPU job

@@ -84,24 +84,21 @@ class Tables:
     def part(self, g=0):
         return PartView(self, g)
 
-    def derive_check(self, g=0, t2_bytes=8192, t3_bytes=16384, hot_bytes=8192):
-        """Host-side build + verification of the kernel's shared-memory tables (no GPU needed)."""
+    def derive_check(self, g=0, t2_bytes=32768, t3_bytes=32768, tm2_bytes=32768):
+        """Host-side build + verification of the detector's shared-memory filters (no GPU needed)."""
         st = (C.c_uint64 * 10)()
-        check(lib.pfac_tables_derive_check(self._h, g, t2_bytes, t3_bytes, hot_bytes, st))
-        keys = ("image_bytes", "t1_pairs", "t2_set", "prefixes4", "has_short", "hot_rows", "hot_entries", "hot_probe",
-                "tm_keys", "t3_set")
-        d = dict(zip(keys, list(st)))
-        d["tm2_keys"] = d["tm_keys"] >> 32
-        d["tm_keys"] &= 0xFFFFFFFF
-        return d
+        check(lib.pfac_tables_derive_check(self._h, g, t2_bytes, t3_bytes, tm2_bytes, st))
+        keys = ("image_bytes", "t1_pairs", "t2_set", "prefixes4", "has_short", "has_t3", "tm_keys", "tm2_keys",
+                "t3_set", "tm2_bits")
+        return dict(zip(keys, list(st)))
 
-    def filter_profile(self, text, g=0, t2_bytes=8192, t3_bytes=16384, hot_bytes=8192):
-        """Diagnostics: survivors per stage of the kernel's filter cascade over `text` (host model, counts only)."""
+    def filter_profile(self, text, g=0, t2_bytes=32768, t3_bytes=32768, tm2_bytes=32768):
+        """Diagnostics: survivors per stage of the detector's filter cascade over `text` (host model, counts only)."""
         buf = np.ascontiguousarray(text, dtype=np.uint8)
         c = (C.c_uint64 * 12)()
-        check(lib.pfac_tables_filter_profile(self._h, g, t2_bytes, t3_bytes, hot_bytes, buf.ctypes.data, len(buf), c))
-        keys = ("positions", "t1_pass", "t2_pass", "unknown1", "window1_pass", "unknown2", "window2_pass", "walks",
-                "hot_steps", "lookahead_ends", "l2_steps", "hot_probes")
+        check(lib.pfac_tables_filter_profile(self._h, g, t2_bytes, t3_bytes, tm2_bytes, buf.ctypes.data, len(buf), c))
+        keys = ("positions", "t1_pass", "prefix_found", "window1_pass", "window2_pass", "bypass", "to_emit",
+                "slices_flagged", "slices")
         return dict(zip(keys, list(c)))
 
     def lookup(self, state, byte, g=0):
@@ -144,18 +141,15 @@ class Matcher:
     def last_info(self):
         info = (C.c_uint64 * 8)()
         check(lib.pfac_ctx_last_scan_info(self._h, info))
-        keys = ("launches", "tiles", "ctas", "smem_bytes", "h2d_bytes", "d2h_bytes", "chunks", "reserved")
+        keys = ("launches", "tiles", "ctas", "smem_bytes", "h2d_bytes", "d2h_bytes", "chunks", "flagged_tiles")
         return dict(zip(keys, list(info)))
 
     def derived_info(self):
         info = (C.c_uint64 * 16)()
         check(lib.pfac_ctx_derived_info(self._h, info))
-        keys = ("image_bytes", "t1_pairs", "t2_bits", "t2_set", "prefixes4", "has_short", "hot_slots", "hot_rows",
-                "hot_entries", "hot_probe", "smem_bytes", "table_bytes", "ring_stages", "t3_bits", "t3_set", "tm_keys")
-        d = dict(zip(keys, list(info)))
-        d["tm2_keys"] = d["tm_keys"] >> 32
-        d["tm_keys"] &= 0xFFFFFFFF
-        return d
+        keys = ("image_bytes", "t1_pairs", "t2_bits", "t2_set", "prefixes4", "has_short", "tm_keys", "tm2_keys",
+                "t3_bits", "t3_set", "smem_bytes", "table_bytes", "ring_stages", "tm2_bits")
+        return dict(zip(keys, list(info)))
 
     # -- device-resident input (raw pointers; torch tensors are accepted for convenience)
     def scan_device_raw(self, d_in, n_starts, n_valid, base_pos, d_out, cap, d_count, stream=0):

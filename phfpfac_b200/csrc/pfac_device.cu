@@ -31,7 +31,7 @@ struct Slot {
     Ctrl *d_ctrl = nullptr;
     Result *d_result = nullptr;
     Result *h_result = nullptr;   // pinned
-    unsigned int *d_tile_cnt = nullptr, *d_tile_mask = nullptr;
+    unsigned int *d_tile_cnt = nullptr, *d_tile_mask = nullptr, *d_flagged = nullptr;
     uint4 *d_slice_ent = nullptr;
     size_t tile_cap = 0;
     uint2 *d_scratch = nullptr;
@@ -55,8 +55,8 @@ struct pfac_ctx {
     int sm_count = 0;
     int n_streams = 1;
     size_t chunk_bytes = 0;
-    // tables (device): canonical r, {HT, val|flag}, idmap + the shared-memory image
-    int32_t *d_r = nullptr, *d_idmap = nullptr;
+    // tables (device): canonical s0Table, r, {HT, val}, idmap + the detector's shared-memory image
+    int32_t *d_r = nullptr, *d_idmap = nullptr, *d_s0 = nullptr;
     int2 *d_htval = nullptr;
     uint4 *d_image = nullptr;
     Derived dv;   // image layout and hash parameters (the image bytes are dropped after the upload)
@@ -108,6 +108,7 @@ void slot_free(Slot &s)
     if (s.h_result) cudaFreeHost(s.h_result);
     if (s.d_tile_cnt) cudaFree(s.d_tile_cnt);
     if (s.d_tile_mask) cudaFree(s.d_tile_mask);
+    if (s.d_flagged) cudaFree(s.d_flagged);
     if (s.d_slice_ent) cudaFree(s.d_slice_ent);
     if (s.d_scratch) cudaFree(s.d_scratch);
     s = Slot();
@@ -121,13 +122,15 @@ int slot_reserve(Slot &s, size_t n_tiles, size_t records, cudaStream_t stream)
         CU_TRY(cudaStreamSynchronize(stream));
         if (s.d_tile_cnt) cudaFree(s.d_tile_cnt);
         if (s.d_tile_mask) cudaFree(s.d_tile_mask);
+        if (s.d_flagged) cudaFree(s.d_flagged);
         if (s.d_slice_ent) cudaFree(s.d_slice_ent);
-        s.d_tile_cnt = s.d_tile_mask = nullptr;
+        s.d_tile_cnt = s.d_tile_mask = s.d_flagged = nullptr;
         s.d_slice_ent = nullptr;
         s.tile_cap = 0;
         const size_t n = std::max<size_t>(n_tiles, 1024);
         CU_TRY(cudaMalloc(&s.d_tile_cnt, n * sizeof(unsigned int)));
         CU_TRY(cudaMalloc(&s.d_tile_mask, n * sizeof(unsigned int)));
+        CU_TRY(cudaMalloc(&s.d_flagged, n * sizeof(unsigned int)));
         CU_TRY(cudaMalloc(&s.d_slice_ent, n * kSlicesPerTile * sizeof(uint4)));
         s.tile_cap = n;
     }
@@ -176,46 +179,58 @@ int launch_scan(pfac_ctx *ctx, Slot &slot, const void *d_in, uint64_t n_starts, 
     p.max_pat_len = (uint32_t)ctx->max_pat_len;
     p.use_ref_bound = ctx->max_pat_len > kRefHalo + 1;   // only then can the 4096+512 bound cut a walk
     p.base_pos = base_pos;
-    p.pos_bias = pos_bias;
-    p.r = ctx->d_r;
-    p.htval = ctx->d_htval;
-    p.idmap = ctx->d_idmap;
-    p.ht_size = ctx->ht_size;
-    p.width_bit = ctx->width_bit;
-    p.n_final = ctx->n_final;
     p.image = ctx->d_image;
     p.image_bytes = ctx->image_bytes;
-    p.off_t1 = ctx->dv.off_t1;
-    p.off_s0f = ctx->dv.off_s0f;
-    p.off_t2 = ctx->dv.off_t2;
     p.off_t1s = ctx->dv.off_t1s;
+    p.off_t2 = ctx->dv.off_t2;
     p.off_tm = ctx->dv.off_tm;
     p.off_tm2 = ctx->dv.off_tm2;
     p.off_t3 = ctx->dv.off_t3;
-    p.has_t3 = ctx->dv.has_t3;
-    p.t3_shift = ctx->dv.t3_shift;
-    p.off_hot = ctx->dv.off_hot;
     p.t2_shift = ctx->dv.t2_shift;
     p.has_short = ctx->dv.has_short;
-    p.hot_mask = ctx->dv.hot_mask;
-    p.hot_shift = ctx->dv.hot_shift;
-    p.hot_mul = ctx->dv.hot_mul;
-    p.hot_probe = ctx->dv.hot_probe;
-    p.state_mask = ctx->dv.state_mask;
-    p.hot_bit = ctx->dv.hot_bit;
-    p.single_bit = ctx->dv.single_bit;
+    p.has_t3 = ctx->dv.has_t3;
+    p.t3_shift = ctx->dv.t3_shift;
+    p.tm2_bits = ctx->dv.tm2_bits;
     p.n_stages = ctx->n_stages;
     e = slot_reserve(slot, p.n_tiles, (size_t)std::max<uint64_t>(cap, 4096), stream);
     if (e) return e;
-    p.scratch = slot.d_scratch;
-    p.scratch_cap = slot.scratch_cap;
     p.tile_cnt = slot.d_tile_cnt;
     p.tile_mask = slot.d_tile_mask;
-    p.slice_ent = slot.d_slice_ent;
+    p.flagged = slot.d_flagged;
     p.ctrl = slot.d_ctrl;
     p.debug = ctx->debug;
     const uint32_t grid = (uint32_t)std::min<uint64_t>(p.n_tiles, (uint64_t)ctx->sm_count);
     pfac_scan_kernel<<<grid, kThreads, ctx->smem_bytes, stream>>>(p);
+    CU_TRY(cudaGetLastError());
+
+    EmitParams ep;
+    memset(&ep, 0, sizeof ep);
+    ep.in_al = p.in_al;
+    ep.mis = p.mis;
+    ep.a_start_end = p.a_start_end;
+    ep.a_valid_end = p.a_valid_end;
+    ep.max_pat_len = p.max_pat_len;
+    ep.use_ref_bound = p.use_ref_bound;
+    ep.base_pos = base_pos;
+    ep.pos_bias = pos_bias;
+    ep.r = ctx->d_r;
+    ep.htval = ctx->d_htval;
+    ep.idmap = ctx->d_idmap;
+    ep.t1 = (const uint8_t *)ctx->d_image + ctx->dv.off_t1;
+    ep.s0 = ctx->d_s0;
+    ep.ht_size = ctx->ht_size;
+    ep.width_bit = ctx->width_bit;
+    ep.n_final = ctx->n_final;
+    ep.scratch = slot.d_scratch;
+    ep.scratch_cap = slot.scratch_cap;
+    ep.tile_cnt = slot.d_tile_cnt;
+    ep.tile_mask = slot.d_tile_mask;
+    ep.flagged = slot.d_flagged;
+    ep.slice_ent = slot.d_slice_ent;
+    ep.ctrl = slot.d_ctrl;
+    const uint32_t egrid = (uint32_t)std::min<uint64_t>((p.n_tiles + (kEmitThreads / 32) - 1) / (kEmitThreads / 32),
+                                                        (uint64_t)ctx->sm_count * 4);
+    pfac_emit_kernel<<<egrid, kEmitThreads, 0, stream>>>(ep);
     CU_TRY(cudaGetLastError());
 
     FinalizeParams f;
@@ -235,7 +250,7 @@ int launch_scan(pfac_ctx *ctx, Slot &slot, const void *d_in, uint64_t n_starts, 
     CU_TRY(cudaGetLastError());
     if (tiles_out) *tiles_out = p.n_tiles;
     if (ctas_out) *ctas_out = grid;
-    if (launches_out) *launches_out = 2;
+    if (launches_out) *launches_out = 3;
     return PFAC_OK;
 }
 
@@ -295,53 +310,61 @@ int pfac_ctx_create(int device, const pfac_tables *t, int part, int n_streams, s
     ctx->halo = (uint32_t)std::max(16, ((P.max_len > 0 ? P.max_len - 1 : 0) + 15) / 16 * 16);
     if (const char *dbg = getenv("PFAC_DEBUG")) ctx->debug = (uint32_t)atoi(dbg);
 
-    // shared-memory budget: the fixed parts first, then as much T2 / hot table as fits
+    // shared-memory budget: T1 and the per-warp queues are fixed; T3 / Tm2 / T2 shrink until at least
+    // four ring stages fit
     const size_t smem_max = (size_t)prop.sharedMemPerBlockOptin;
-    uint32_t t2_bytes = 16384, t3_bytes = 16384, hot_bytes = 16384;   // T2 only exists when the complete Tm does not
+    uint32_t t2_bytes = 32768, t3_bytes = 16384, tm2_bytes = 32768;
     if (const char *v = getenv("PFAC_T2_BYTES")) t2_bytes = (uint32_t)atoi(v);
     if (const char *v = getenv("PFAC_T3_BYTES")) t3_bytes = (uint32_t)atoi(v);
-    if (const char *v = getenv("PFAC_HOT_BYTES")) hot_bytes = (uint32_t)atoi(v);
+    if (const char *v = getenv("PFAC_TM2_BYTES")) tm2_bytes = (uint32_t)atoi(v);
     while (true) {
-        derive_tables(P, t2_bytes, t3_bytes, hot_bytes, ctx->dv);
+        derive_tables(P, t2_bytes, t3_bytes, tm2_bytes, ctx->dv);
         ctx->image_bytes = (uint32_t)ctx->dv.image.size();
         const size_t fixed = scan_smem_bytes(ctx->image_bytes, ctx->halo, 0);
         const size_t stride = scan_buf_stride(ctx->halo);
         const size_t fit = smem_max > fixed ? (smem_max - fixed) / stride : 0;
-        if (fit >= 4 || (fit >= 2 && hot_bytes == 0 && t2_bytes < 2048)) {
+        const bool minimal = t2_bytes < 2048 && t3_bytes < 2048 && tm2_bytes < 2048;
+        if (fit >= 4 || (fit >= 2 && minimal)) {
             ctx->n_stages = (uint32_t)std::min<size_t>(fit, kMaxStages);
             ctx->smem_bytes = scan_smem_bytes(ctx->image_bytes, ctx->halo, ctx->n_stages);
             break;
         }
-        if (hot_bytes >= 2048) hot_bytes /= 2;
-        else if (hot_bytes) hot_bytes = 0;
-        else if (t3_bytes >= 2048) t3_bytes /= 2;
-        else if (t3_bytes) t3_bytes = 0;
-        else if (t2_bytes >= 2048) t2_bytes /= 2;
-        else
+        if (minimal)
             return set_error(PFAC_ERR_CUDA, "scan kernel needs more than the %zu B of shared memory the device offers",
                              smem_max);
+        // halve the largest section that is actually in the image
+        if (ctx->dv.has_t3) {
+            if (t3_bytes > 8192) t3_bytes /= 2;          // T3 first: it only gets a little less selective
+            else if (tm2_bytes >= 2048) tm2_bytes /= 2;  // then level 2 (all or nothing per size)
+            else t3_bytes /= 2;
+        } else {
+            t3_bytes = tm2_bytes = 0;
+            t2_bytes /= 2;
+        }
     }
 
-    // canonical arrays -> device: r, {HT, val|hot flag} interleaved, idmap; + the shared-memory image
+    // canonical arrays -> device, unchanged: s0Table, r, {HT, val} interleaved, idmap; + the detector image
     const size_t n_r = std::max<size_t>(P.r.size(), 1), n_ht = std::max<size_t>((size_t)P.ht_size, 1);
     const size_t n_id = std::max<size_t>((size_t)P.n_final, 1);
     std::vector<int2> htval(n_ht, make_int2(-1, -1));
-    for (int32_t i = 0; i < P.ht_size; i++) htval[(size_t)i] = make_int2(P.HT[(size_t)i], ctx->dv.val_flagged[(size_t)i]);
+    for (int32_t i = 0; i < P.ht_size; i++) htval[(size_t)i] = make_int2(P.HT[(size_t)i], P.val[(size_t)i]);
+    std::vector<int32_t> s0(256, -1);
+    if (!P.s0.empty()) s0 = P.s0;
     CU_TRY(cudaMalloc(&ctx->d_r, n_r * sizeof(int32_t)));
     CU_TRY(cudaMalloc(&ctx->d_htval, n_ht * sizeof(int2)));
     CU_TRY(cudaMalloc(&ctx->d_idmap, n_id * sizeof(int32_t)));
+    CU_TRY(cudaMalloc(&ctx->d_s0, 256 * sizeof(int32_t)));
     CU_TRY(cudaMalloc(&ctx->d_image, ctx->image_bytes));
     CU_TRY(cudaMemset(ctx->d_r, 0xFF, n_r * sizeof(int32_t)));
     CU_TRY(cudaMemset(ctx->d_idmap, 0, n_id * sizeof(int32_t)));
     if (!P.r.empty()) CU_TRY(cudaMemcpy(ctx->d_r, P.r.data(), P.r.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
     CU_TRY(cudaMemcpy(ctx->d_htval, htval.data(), n_ht * sizeof(int2), cudaMemcpyHostToDevice));
     if (P.n_final) CU_TRY(cudaMemcpy(ctx->d_idmap, P.idmap.data(), (size_t)P.n_final * sizeof(int32_t), cudaMemcpyHostToDevice));
+    CU_TRY(cudaMemcpy(ctx->d_s0, s0.data(), 256 * sizeof(int32_t), cudaMemcpyHostToDevice));
     CU_TRY(cudaMemcpy(ctx->d_image, ctx->dv.image.data(), ctx->image_bytes, cudaMemcpyHostToDevice));
-    ctx->table_bytes = n_r * 4 + n_ht * 8 + n_id * 4 + ctx->image_bytes;
+    ctx->table_bytes = n_r * 4 + n_ht * 8 + n_id * 4 + 1024 + ctx->image_bytes;
     ctx->dv.image.clear();
     ctx->dv.image.shrink_to_fit();
-    ctx->dv.val_flagged.clear();
-    ctx->dv.val_flagged.shrink_to_fit();
 
     // the attribute is per function and device, not per context: always allow the device maximum
     CU_TRY(cudaFuncSetAttribute(pfac_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
@@ -367,6 +390,7 @@ void pfac_ctx_destroy(pfac_ctx *ctx)
     if (ctx->d_htval) cudaFree(ctx->d_htval);
     if (ctx->d_idmap) cudaFree(ctx->d_idmap);
     if (ctx->d_image) cudaFree(ctx->d_image);
+    if (ctx->d_s0) cudaFree(ctx->d_s0);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
 }
@@ -378,9 +402,9 @@ int pfac_ctx_derived_info(const pfac_ctx *ctx, uint64_t info[16])
     if (!ctx || !info) return set_error(PFAC_ERR_ARG, "bad arguments");
     const Derived &d = ctx->dv;
     const uint64_t v[16] = {ctx->image_bytes, d.t1_set, d.t2_shift >= 32 ? 0 : (1ull << (32 - d.t2_shift)), d.t2_set,
-                            d.n_depth4, d.has_short, d.hot_mask ? (uint64_t)d.hot_mask + 1 : 0, d.n_hot_rows,
-                            d.n_hot_entries, d.hot_probe, ctx->smem_bytes, ctx->table_bytes, ctx->n_stages,
-                            d.t3_shift >= 32 ? 0 : (1ull << (32 - d.t3_shift)), d.t3_set, d.tm_set | ((uint64_t)d.tm2_set << 32)};
+                            d.n_prefix4, d.has_short, d.tm_set, d.tm2_set,
+                            d.t3_shift >= 32 ? 0 : (1ull << (32 - d.t3_shift)), d.t3_set, ctx->smem_bytes,
+                            ctx->table_bytes, ctx->n_stages, d.tm2_bits, 0, 0};
     memcpy(info, v, sizeof v);
     return PFAC_OK;
 }
@@ -423,6 +447,7 @@ int pfac_scan_device_sync(pfac_ctx *ctx, const void *d_in, uint64_t n_starts, ui
         ctx->info[3] = ctx->smem_bytes;
         ctx->info[4] = ctx->info[5] = 0;
         ctx->info[6] = 1;
+        ctx->info[7] = ctx->own.h_result->n_flagged;
         if (ctx->own.h_result->error_flag)
             return set_error(PFAC_ERR_INTERNAL, "device watchdog tripped (code %u)", ctx->own.h_result->error_flag);
         *count = ctx->own.h_result->count;

@@ -1,19 +1,21 @@
 // PFAC scan kernels for sm_100a (B200).  Replace TraceTable_kernel + SUBSEG_MATCH
 // (reference master_kernel.cu:37-180).  Design notes: DESIGN.md section 3.
 //
-//   pfac_scan_kernel      persistent, one CTA per SM, warp specialised:
+//   pfac_scan_kernel      the detector: persistent, one CTA per SM, warp specialised.
 //     * producer warp: claims tile tickets and streams 16 KiB tiles (+ halo of max_pat_len-1
 //       bytes) into a shared-memory ring with cp.async.bulk (TMA bulk copy, SASS UBLKCP),
 //       full/empty mbarriers per stage, L2 evict-first hint on the streamed input;
 //     * consumer warps: claim 512-byte slices of the current tile.  Per slice
 //         stage 1  16 start positions per lane against T1 (64 KiB byte table over the first
-//                  two bytes, root fan-out folded in), survivors compacted in position order;
-//         stage 2  survivors against T2 (hashed 4-byte prefixes), compacted again;
-//         walk     the remaining starts walk the automaton: hot PHF rows from the shared-memory
-//                  hash, everything else through r[] / {HT,val} (read-only, L2-resident); lanes
-//                  refill from the warp queue as their walks end;
-//         emit     only slices that matched: one atomic reservation in the arrival-order
-//                  scratch, records written in (position, pattern length) order.
+//                  two bytes, root fan-out folded in), survivors compacted into the warp queue;
+//         stage 2  survivors against Tm/T3/Tm2 (two-point checks on the 4-byte prefix and on
+//                  the bytes that end the shortest pattern below it) or T2.
+//       A slice in which any start survives is FLAGGED; the detector decides nothing else.
+//       All its tables are shared-memory resident prefix filters derived from the first PHF rows.
+//   pfac_emit_kernel      one warp per tile with flagged slices: the plain PFAC walk of
+//                         SUBSEG_MATCH over every start of those slices, straight from the PHF
+//                         (r[] then {HT,val}, read-only, L2-resident), records written in
+//                         (position, pattern length) order into the arrival-order scratch.
 //   pfac_finalize_kernel  scans the per-tile counts and moves the records from arrival order to
 //                         position order (tile, slice, start, depth) -- the order main.cc:341-349
 //                         prints.  Output is deterministic run to run.
@@ -29,12 +31,14 @@ struct Ctrl {   // device-side control block; the finalize kernel resets it for 
     unsigned int ticket;
     unsigned int error_flag;
     unsigned long long alloc;   // records reserved in the arrival-order scratch
+    unsigned int n_flagged;     // tiles with at least one flagged slice
+    unsigned int pad;
 };
 
 struct Result {   // written by the finalize kernel, copied to the host
     unsigned long long count;
     unsigned int error_flag;
-    unsigned int pad;
+    unsigned int n_flagged;     // statistics
 };
 
 struct ScanParams {
@@ -47,27 +51,17 @@ struct ScanParams {
     uint32_t max_pat_len;
     int32_t use_ref_bound;    // reproduce the 4096+512 walk bound (master_kernel.cu:141-144)
     uint64_t base_pos;        // global position of the first start position
-    uint32_t pos_bias;        // added to every record position (sub-chunk offset inside a host call)
-    // canonical PHF in global memory (L2-resident)
-    const int32_t *r;         // r[]                                 (phf.c:197)
-    const int2 *htval;        // {HT[i], val[i] | hot flag}          (phf.c:211,216)
-    const int32_t *idmap;     // final state -> pattern id           (create_table_reorder.c:318)
-    int32_t ht_size, width_bit, n_final;
     // shared-memory image (pfac_derive.h)
     const uint4 *image;
-    uint32_t image_bytes, off_t1, off_s0f, off_t2, off_t1s, off_tm, off_tm2, off_t3, off_hot;
-    uint32_t has_t3, t3_shift;
-    uint32_t t2_shift, has_short, hot_mask, hot_shift, hot_mul, hot_probe;
-    uint32_t state_mask, hot_bit, single_bit;   // state-word layout (pfac_derive.h)
-    uint32_t n_stages;                          // depth of the input ring (as many as shared memory holds)
+    uint32_t image_bytes, off_t1s, off_t2, off_tm, off_tm2, off_t3;
+    uint32_t t2_shift, has_short, has_t3, t3_shift, tm2_bits;
+    uint32_t n_stages;                // depth of the input ring (as many as shared memory holds)
     // output
-    uint2 *scratch;                   // arrival-order records
-    unsigned long long scratch_cap;
-    unsigned int *tile_cnt;           // [n_tiles] matches per tile
-    unsigned int *tile_mask;          // [n_tiles] bit s set iff slice s of the tile matched
-    uint4 *slice_ent;                 // [n_tiles*32] {count, scratch offset lo, hi, -} of matching slices
+    unsigned int *tile_cnt;           // [n_tiles] 0 from the detector; the emit kernel fills it
+    unsigned int *tile_mask;          // [n_tiles] bit s set iff slice s of the tile is flagged
+    unsigned int *flagged;            // [n_tiles] ids of the tiles with a non-zero mask, arrival order
     Ctrl *ctrl;
-    uint32_t debug;           // PFAC_DEBUG bits (timing experiments only): 1 no walk, 4 no T1, 8 no T2/T3, 16 no T3
+    uint32_t debug;           // PFAC_DEBUG bits (timing experiments only): 4 no T1, 8 no stage 2
 };
 
 struct FinalizeParams {
@@ -90,11 +84,8 @@ constexpr int kTile = 16384;          // start positions per tile
 constexpr int kSlice = 512;           // start positions per warp step (32 lanes x 16 B)
 constexpr int kSlicesPerTile = kTile / kSlice;
 constexpr int kMaxStages = 8;
-constexpr int kQCap = 640;            // queue entries per warp (a batch stops growing at kBatchMin)
-constexpr int kBatchMin = 48;
-constexpr int kQueueBytes = kQCap * 2 + 128;   // u16 start positions + the batch's slice directory
+constexpr int kQueueBytes = kSlice * 2;   // per consumer warp: u16 start positions that passed stage 1
 constexpr int kCtrlBytes = 512;
-constexpr uint32_t kMatchedBit = 0x8000u;      // on a queue entry: this start reported at least one match
 constexpr unsigned kSpinLimit = 1u << 24;
 
 __host__ __device__ inline uint32_t scan_buf_stride(uint32_t halo) { return (kTile + halo + 32 + 127) & ~127u; }
@@ -187,41 +178,7 @@ __device__ __forceinline__ uint32_t filter16(const uint4 v, const uint32_t nx)
     return mask;
 }
 
-struct WalkCtx {
-    const int32_t *__restrict__ r;
-    const int2 *__restrict__ htval;
-    const uint2 *__restrict__ hot;   // shared
-    const uint32_t *__restrict__ s0f;   // shared
-    int32_t ht_size, width_bit, colmask, n_final;
-    uint32_t hot_mask, hot_shift, hot_mul, hot_probe;
-    uint32_t state_mask, hot_bit, single_bit;
-};
-
-// One transition (master_kernel.cu:52-64).  sw = state word (pfac_derive.h); returns the next
-// state word or 0xFFFFFFFF.  A hot row is complete in the shared-memory hash, so a miss there is
-// final; a single-edge row ends the walk on any other byte without touching L2.
-__device__ __forceinline__ uint32_t step_state(const WalkCtx &c, uint32_t sw, uint32_t byte)
-{
-    const uint32_t key = ((sw & c.state_mask) << 8) | byte;
-    if (sw & c.hot_bit) {
-        uint32_t slot = (key * c.hot_mul) >> c.hot_shift;
-        for (uint32_t pr = 0; pr < c.hot_probe; pr++) {
-            const uint2 e = c.hot[slot];
-            if (e.x == key) return e.y;
-            if (e.x == 0xFFFFFFFFu) break;
-            slot = (slot + 1) & c.hot_mask;
-        }
-        return 0xFFFFFFFFu;
-    }
-    if ((sw & c.single_bit) && (sw >> 24) != byte) return 0xFFFFFFFFu;
-    const int32_t row = (int32_t)key >> c.width_bit;                 // :53
-    const int32_t idx = __ldg(&c.r[row]) + ((int32_t)key & c.colmask);   // :54-55
-    if (idx < 0 || idx >= c.ht_size) return 0xFFFFFFFFu;            // :56-57
-    const int2 hv = __ldg(&c.htval[idx]);                            // :59-61
-    return hv.x == row ? (uint32_t)hv.y : 0xFFFFFFFFu;
-}
-
-// tile-relative walk bound of a start at tile-relative tpos
+// tile-relative bound of what a start at tile-relative tpos may read (master_kernel.cu:141-144 + input end)
 __device__ __forceinline__ uint32_t walk_limit(const ScanParams &p, uint32_t a0, uint32_t tpos)
 {
     uint32_t lim_a = p.a_valid_end;
@@ -237,53 +194,28 @@ __device__ __forceinline__ uint32_t walk_limit(const ScanParams &p, uint32_t a0,
     return lim_t < depth ? lim_t : depth;
 }
 
-// The walk of SUBSEG_MATCH (master_kernel.cu:39-73) for one start, start to end.  Returns the
-// number of final states visited; WRITE also stores one record per final state at scratch[o..],
-// in visiting order = pattern length ascending.
-template <bool WRITE>
-__device__ __forceinline__ uint32_t walk_full(const ScanParams &p, const WalkCtx &c, const uint8_t *__restrict__ buf,
-                                              uint32_t tpos, uint32_t lim_t, uint32_t rec_pos, unsigned long long o)
-{
-    uint32_t sw = c.s0f[buf[tpos]];                                  // :41
-    uint32_t q = tpos + 1, n = 0;
-    while (sw != 0xFFFFFFFFu) {
-        const uint32_t st = sw & c.state_mask;
-        if ((int32_t)st < c.n_final) {                               // :44-47, :67-70
-            if (WRITE && o + n < p.scratch_cap) p.scratch[o + n] = make_uint2(rec_pos, (uint32_t)__ldg(&p.idmap[st]));
-            n++;
-        }
-        if (q >= lim_t) break;                                       // :50
-        sw = step_state(c, sw, buf[q]);
-        q++;
-    }
-    return n;
-}
-
 __global__ void __launch_bounds__(kThreads, 1) pfac_scan_kernel(const ScanParams p)
 {
-    const uint32_t *s_s0f = reinterpret_cast<const uint32_t *>(smem + p.off_s0f);
-    const uint32_t *s_t2 = reinterpret_cast<const uint32_t *>(smem + p.off_t2);
     const uint32_t *s_t1s = reinterpret_cast<const uint32_t *>(smem + p.off_t1s);
+    const uint32_t *s_t2 = reinterpret_cast<const uint32_t *>(smem + p.off_t2);
     const uint16_t *s_tm = reinterpret_cast<const uint16_t *>(smem + p.off_tm);
     const uint16_t *s_tm2 = reinterpret_cast<const uint16_t *>(smem + p.off_tm2);
     const uint32_t *s_t3 = reinterpret_cast<const uint32_t *>(smem + p.off_t3);
-    const uint2 *s_hot = reinterpret_cast<const uint2 *>(smem + p.off_hot);
     uint8_t *ctl = smem + p.image_bytes;
     uint64_t *s_full = reinterpret_cast<uint64_t *>(ctl);               // [kMaxStages]
     uint64_t *s_empty = reinterpret_cast<uint64_t *>(ctl + 64);         // [kMaxStages]
     uint32_t *s_tile = reinterpret_cast<uint32_t *>(ctl + 128);         // [kMaxStages] tile id of the stage
     uint32_t *s_ticket = reinterpret_cast<uint32_t *>(ctl + 160);       // [kMaxStages] slice tickets
     uint32_t *s_done = reinterpret_cast<uint32_t *>(ctl + 192);         // [kMaxStages] warps finished
-    uint32_t *s_tcnt = reinterpret_cast<uint32_t *>(ctl + 224);         // [kMaxStages] matches in the tile
-    uint32_t *s_tmask = reinterpret_cast<uint32_t *>(ctl + 256);        // [kMaxStages] matching slices
+    uint32_t *s_tflag = reinterpret_cast<uint32_t *>(ctl + 224);        // [kMaxStages] flagged slices of the tile
     uint8_t *qbase = ctl + kCtrlBytes;
+    const uint32_t n_stages = p.n_stages;
     uint8_t *s_in = qbase + kConsumerWarps * kQueueBytes;
     const uint32_t stride = scan_buf_stride(p.halo);
-    const uint32_t n_stages = p.n_stages;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
-    {   // shared-memory image: T1, root row, T2, T1s, hot rows
+    {   // shared-memory image: T1, T1s, T2 or Tm/Tm2/T3
         uint4 *dst = reinterpret_cast<uint4 *>(smem);
         const uint32_t n16 = p.image_bytes >> 4;
         for (uint32_t i = tid; i < n16; i += kThreads) dst[i] = __ldg(&p.image[i]);
@@ -294,8 +226,7 @@ __global__ void __launch_bounds__(kThreads, 1) pfac_scan_kernel(const ScanParams
             mbar_init(&s_empty[s], kConsumerWarps);
             s_ticket[s] = 0;
             s_done[s] = 0;
-            s_tcnt[s] = 0;
-            s_tmask[s] = 0;
+            s_tflag[s] = 0;
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -336,26 +267,7 @@ __global__ void __launch_bounds__(kThreads, 1) pfac_scan_kernel(const ScanParams
     }
 
     // ---------------------------------------------------------------------- consumers
-    uint16_t *wq = reinterpret_cast<uint16_t *>(qbase + warp * kQueueBytes);   // start positions (+ kMatchedBit)
-    uint16_t *w_sid = wq + kQCap;       // [32] slice ids of the batch
-    uint16_t *w_send = w_sid + 32;      // [32] queue end of each slice of the batch
-    WalkCtx wk;
-    wk.r = p.r;
-    wk.htval = p.htval;
-    wk.hot = s_hot;
-    wk.s0f = s_s0f;
-    wk.ht_size = p.ht_size;
-    wk.width_bit = p.width_bit;
-    wk.colmask = (1 << p.width_bit) - 1;
-    wk.n_final = p.n_final;
-    wk.hot_mask = p.hot_mask;
-    wk.hot_shift = p.hot_shift;
-    wk.hot_mul = p.hot_mul;
-    wk.hot_probe = p.hot_probe;
-    wk.state_mask = p.state_mask;
-    wk.hot_bit = p.hot_bit;
-    wk.single_bit = p.single_bit;
-    const uint32_t lt_mask = (1u << lane) - 1u;
+    uint16_t *wq = reinterpret_cast<uint16_t *>(qbase + warp * kQueueBytes);   // stage-1 survivors of one slice
 
     uint32_t s = 0, round = 0;
     for (;; s = (s + 1 == n_stages) ? 0 : s + 1, round += (s == 0) ? 1u : 0u) {
@@ -369,229 +281,233 @@ __global__ void __launch_bounds__(kThreads, 1) pfac_scan_kernel(const ScanParams
         if (tile_starts > (uint32_t)kTile) tile_starts = kTile;
         const uint32_t n_slices = (tile_starts + kSlice - 1) / kSlice;
         const uint32_t valid_t = p.a_valid_end - a0;   // tile-relative end of readable input (may exceed the buffer)
+        uint32_t my_flags = 0;
 
         while (true) {
-            // ---- build a batch: filter slices until enough starts survive (or the tile is out of slices)
-            uint32_t nq = 0, nb = 0;
-            while (nq < (uint32_t)kBatchMin) {
-                uint32_t slice = 0;
-                if (lane == 0) slice = atomicAdd(&s_ticket[s], 1u);
-                slice = __shfl_sync(0xffffffffu, slice, 0);
-                if (slice >= n_slices) break;
-                const uint32_t q0 = nq;
-                // stage 1: T1 over 16 positions per lane, ordered compaction
-                const uint32_t off = slice * kSlice + lane * 16;
-                const uint4 v = *reinterpret_cast<const uint4 *>(buf + off);
-                const uint32_t nx = *reinterpret_cast<const uint32_t *>(buf + off + 16);
-                uint32_t mask = (p.debug & 4u) ? 0u : filter16(v, nx);
-                if (edge) {   // start positions are [mis, a_start_end) in aligned coordinates
-                    const uint32_t a = a0 + off;
-                    const uint32_t lo = p.mis > a ? p.mis - a : 0u;
-                    const uint32_t hi = p.a_start_end > a ? p.a_start_end - a : 0u;
-                    uint32_t keep = hi >= 16u ? 0xffffu : ((1u << hi) - 1u);
-                    keep &= lo >= 16u ? 0u : (0xffffu << lo);
-                    mask &= keep;
-                }
-                uint32_t incl = __popc(mask);
+            uint32_t slice = 0;
+            if (lane == 0) slice = atomicAdd(&s_ticket[s], 1u);
+            slice = __shfl_sync(0xffffffffu, slice, 0);
+            if (slice >= n_slices) break;
+            // stage 1: T1 over 16 positions per lane, compaction into the warp queue
+            const uint32_t off = slice * kSlice + lane * 16;
+            const uint4 v = *reinterpret_cast<const uint4 *>(buf + off);
+            const uint32_t nx = *reinterpret_cast<const uint32_t *>(buf + off + 16);
+            uint32_t mask = (p.debug & 4u) ? 0u : filter16(v, nx);
+            if (edge) {   // start positions are [mis, a_start_end) in aligned coordinates
+                const uint32_t a = a0 + off;
+                const uint32_t lo = p.mis > a ? p.mis - a : 0u;
+                const uint32_t hi = p.a_start_end > a ? p.a_start_end - a : 0u;
+                uint32_t keep = hi >= 16u ? 0xffffu : ((1u << hi) - 1u);
+                keep &= lo >= 16u ? 0u : (0xffffu << lo);
+                mask &= keep;
+            }
+            uint32_t incl = __popc(mask);
 #pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const uint32_t n = __shfl_up_sync(0xffffffffu, incl, o);
-                    if (lane >= o) incl += n;
-                }
-                uint32_t q = nq + incl - __popc(mask);
-                nq += __shfl_sync(0xffffffffu, incl, 31);
-                while (mask) {
-                    const uint32_t bit = __ffs(mask) - 1;
-                    wq[q++] = (uint16_t)(off + bit);
-                    mask &= mask - 1;
-                }
-                __syncwarp();
-                // stage 2: T2 over the 4-byte prefix, then T3 over the bytes [m-4, m) of the shortest
-                // pattern below that prefix; in-place ordered compaction
-                if (!(p.debug & 8u)) {
-                    uint32_t wr = q0;
-                    for (uint32_t e0 = q0; e0 < nq; e0 += 32) {
-                        const uint32_t e = e0 + lane;
-                        bool keep = false;
-                        uint32_t tpos = 0;
-                        if (e < nq) {
-                            tpos = wq[e];
-                            const uint32_t *wp = reinterpret_cast<const uint32_t *>(buf + (tpos & ~3u));
-                            const uint32_t w4 = __funnelshift_r(wp[0], wp[1], (tpos & 3u) * 8u);
-                            keep = tpos + 4u > valid_t;                      // fewer than 4 readable bytes
-                            if (p.has_short) {
-                                const uint32_t pair = w4 & 0xffffu;
-                                keep |= (s_t1s[pair >> 5] >> (pair & 31u)) & 1u;
-                            }
-                            bool pass = true;
-                            if (!p.has_t3) {
-                                const uint32_t h = (w4 * kHash4Mul) >> p.t2_shift;
-                                pass = (s_t2[h >> 5] >> (h & 31u)) & 1u;
-                            } else {
-                                // two-point checks: every pattern under a stored key is at least m bytes
-                                // long and has its bytes [m-4, m) in T3; unknown keys (m == 0) just walk
-                                const uint32_t lim = walk_limit(p, a0, tpos);
-                                const uint32_t m1 = tm1_lookup(s_tm, w4);   // complete: 0 = no such prefix
-                                {
-                                    pass = m1 != 0 && tpos + m1 <= lim;
-                                    if (pass) {
-                                        const uint32_t wo = tpos + m1 - 4u;
-                                        const uint32_t *we = reinterpret_cast<const uint32_t *>(buf + (wo & ~3u));
-                                        const uint32_t w1 = __funnelshift_r(we[0], we[1], (wo & 3u) * 8u);
-                                        const uint32_t h3 = hash_t3(w4, w1) >> p.t3_shift;
-                                        pass = (s_t3[h3 >> 5] >> (h3 & 31u)) & 1u;
-                                        if (pass) {
-                                            const uint32_t key2 = hash_key2(w4, w1);
-                                            const uint32_t m2 = tm_lookup(s_tm2, key2);
-                                            if (m2) {
-                                                pass = tpos + m2 <= lim;
-                                                if (pass) {
-                                                    const uint32_t wo2 = tpos + m2 - 4u;
-                                                    const uint32_t *wf = reinterpret_cast<const uint32_t *>(buf + (wo2 & ~3u));
-                                                    const uint32_t w2 = __funnelshift_r(wf[0], wf[1], (wo2 & 3u) * 8u);
-                                                    const uint32_t h4 = hash_t3(key2 ^ kT3Seed2, w2) >> p.t3_shift;
-                                                    pass = (s_t3[h4 >> 5] >> (h4 & 31u)) & 1u;
-                                                }
-                                            }
-                                        }
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t n = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += n;
+            }
+            uint32_t q = incl - __popc(mask);
+            const uint32_t nq = __shfl_sync(0xffffffffu, incl, 31);
+            while (mask) {
+                const uint32_t bit = __ffs(mask) - 1;
+                wq[q++] = (uint16_t)(off + bit);
+                mask &= mask - 1;
+            }
+            __syncwarp();
+            // stage 2: two-point checks (or T2); one surviving start flags the slice
+            bool any = false;
+            for (uint32_t e0 = 0; e0 < nq; e0 += 32) {
+                const uint32_t e = e0 + lane;
+                if (e >= nq) continue;
+                const uint32_t tpos = wq[e];
+                bool keep = true;
+                if (!(p.debug & 8u) && tpos + 4u <= valid_t) {   // with fewer than 4 readable bytes: let the emit kernel look
+                    const uint32_t *wp = reinterpret_cast<const uint32_t *>(buf + (tpos & ~3u));
+                    const uint32_t w4 = __funnelshift_r(wp[0], wp[1], (tpos & 3u) * 8u);
+                    bool shortp = false;
+                    if (p.has_short) {
+                        const uint32_t pair = w4 & 0xffffu;
+                        shortp = (s_t1s[pair >> 5] >> (pair & 31u)) & 1u;
+                    }
+                    if (!shortp) {
+                        if (!p.has_t3) {
+                            const uint32_t h = (w4 * kHash4Mul) >> p.t2_shift;
+                            keep = (s_t2[h >> 5] >> (h & 31u)) & 1u;
+                        } else {
+                            // every pattern under a key is at least m bytes long and has its bytes [m-4, m) in T3
+                            const uint32_t lim = walk_limit(p, a0, tpos);
+                            const uint32_t m1 = tm_lookup(s_tm, w4, kTmSlotBits);   // 0 = no such prefix
+                            keep = m1 != 0 && tpos + m1 <= lim;
+                            if (keep) {
+                                const uint32_t wo = tpos + m1 - 4u;
+                                const uint32_t *we = reinterpret_cast<const uint32_t *>(buf + (wo & ~3u));
+                                const uint32_t w1 = __funnelshift_r(we[0], we[1], (wo & 3u) * 8u);
+                                const uint32_t h3 = hash_t3(w4, w1) >> p.t3_shift;
+                                keep = (s_t3[h3 >> 5] >> (h3 & 31u)) & 1u;
+                                if (keep && p.tm2_bits) {
+                                    const uint32_t key2 = hash_key2(w4, w1);
+                                    const uint32_t m2 = tm_lookup(s_tm2, key2, p.tm2_bits);   // 0 = no such group
+                                    keep = m2 != 0 && tpos + m2 <= lim;
+                                    if (keep) {
+                                        const uint32_t wo2 = tpos + m2 - 4u;
+                                        const uint32_t *wf = reinterpret_cast<const uint32_t *>(buf + (wo2 & ~3u));
+                                        const uint32_t w2 = __funnelshift_r(wf[0], wf[1], (wo2 & 3u) * 8u);
+                                        const uint32_t h4 = hash_t3(key2 ^ kT3Seed2, w2) >> p.t3_shift;
+                                        keep = (s_t3[h4 >> 5] >> (h4 & 31u)) & 1u;
                                     }
                                 }
                             }
-                            keep |= pass;
                         }
-                        const uint32_t bal = __ballot_sync(0xffffffffu, keep);
-                        if (keep) wq[wr + __popc(bal & lt_mask)] = (uint16_t)tpos;
-                        wr += __popc(bal);
                     }
-                    nq = wr;
-                    __syncwarp();
                 }
-                if (lane == 0) {
-                    w_sid[nb] = (uint16_t)slice;
-                    w_send[nb] = (uint16_t)nq;
-                }
-                nb++;
-                if (nq + (uint32_t)kSlice > (uint32_t)kQCap) break;
+                any |= keep;
             }
-            if (nb == 0) break;   // the tile has no slices left
-            __syncwarp();
-
-            // ---- walk the batch: lanes refill from the queue as their walks end; starts that
-            //      matched get kMatchedBit on their queue entry
-            uint32_t any_match = 0;
-            if (!(p.debug & 1u) && nq) {
-                uint32_t head = 0, my_e = 0, q = 0, lim = 0, cnt = 0, sw = 0xFFFFFFFFu;
-                bool active = false;
-                while (true) {
-                    const uint32_t need = __ballot_sync(0xffffffffu, !active);
-                    if (need) {
-                        if (!active) {
-                            const uint32_t e = head + __popc(need & lt_mask);
-                            if (e < nq) {
-                                my_e = e;
-                                const uint32_t tpos = wq[e];
-                                sw = s_s0f[buf[tpos]];
-                                q = tpos + 1;
-                                lim = walk_limit(p, a0, tpos);
-                                cnt = 0;
-                                active = true;
-                            }
-                        }
-                        head += __popc(need);
-                    }
-                    if (!__any_sync(0xffffffffu, active)) break;
-                    if (active) {
-                        bool fin = (sw == 0xFFFFFFFFu);
-                        if (!fin) {
-                            cnt += ((int32_t)(sw & wk.state_mask) < wk.n_final) ? 1u : 0u;
-                            if (q >= lim) fin = true;
-                            else {
-                                sw = step_state(wk, sw, buf[q]);
-                                q++;
-                            }
-                        }
-                        if (fin) {
-                            if (cnt) {
-                                wq[my_e] |= (uint16_t)kMatchedBit;
-                                any_match = 1;
-                            }
-                            active = false;
-                        }
-                    }
-                }
-                any_match = __any_sync(0xffffffffu, any_match);
-            }
-            __syncwarp();
-
-            // ---- emit (rare): walk the matched starts again to count, reserve scratch space,
-            //      and a third time to write the records in (position, length) order
-            if (any_match) {
-                uint32_t total = 0;
-                for (uint32_t e = lane; e < nq; e += 32) {
-                    const uint32_t ent = wq[e];
-                    if (ent & kMatchedBit) {
-                        const uint32_t tpos = ent & (kMatchedBit - 1u);
-                        total += walk_full<false>(p, wk, buf, tpos, walk_limit(p, a0, tpos), 0u, 0ull);
-                    }
-                }
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
-                unsigned long long base = 0;
-                if (lane == 0) base = atomicAdd(&p.ctrl->alloc, (unsigned long long)total);
-                base = __shfl_sync(0xffffffffu, base, 0);
-                uint32_t run = 0, smask = 0, sl = 0, sl_run0 = 0;   // records so far; current slice; records before it
-                for (uint32_t e0 = 0; e0 < nq; e0 += 32) {
-                    const uint32_t e = e0 + lane;
-                    const uint32_t ent = e < nq ? wq[e] : 0u;
-                    const uint32_t tpos = ent & (kMatchedBit - 1u);
-                    const uint32_t lim = walk_limit(p, a0, tpos);
-                    const uint32_t c = (ent & kMatchedBit) ? walk_full<false>(p, wk, buf, tpos, lim, 0u, 0ull) : 0u;
-                    uint32_t incl = c;
-#pragma unroll
-                    for (int o = 1; o < 32; o <<= 1) {
-                        const uint32_t n = __shfl_up_sync(0xffffffffu, incl, o);
-                        if (lane >= o) incl += n;
-                    }
-                    if (c) walk_full<true>(p, wk, buf, tpos, lim, a0 + tpos - p.mis + p.pos_bias, base + run + incl - c);
-                    // close every slice of the batch that ends inside this chunk of 32 entries
-                    while (sl < nb && (uint32_t)w_send[sl] <= e0 + 32u) {
-                        const uint32_t li = (uint32_t)w_send[sl] - e0;   // entries of this chunk that belong to slices <= sl
-                        const uint32_t upto = run + (li ? __shfl_sync(0xffffffffu, incl, (int)li - 1) : 0u);
-                        if (upto != sl_run0) {
-                            const unsigned long long so = base + sl_run0;
-                            if (lane == 0)
-                                p.slice_ent[(size_t)tile * kSlicesPerTile + w_sid[sl]] =
-                                    make_uint4(upto - sl_run0, (uint32_t)so, (uint32_t)(so >> 32), 0u);
-                            smask |= 1u << w_sid[sl];
-                        }
-                        sl_run0 = upto;
-                        sl++;
-                    }
-                    run += __shfl_sync(0xffffffffu, incl, 31);
-                }
-                if (lane == 0) {
-                    atomicAdd(&s_tcnt[s], total);
-                    atomicOr(&s_tmask[s], smask);
-                }
-            }
+            if (__any_sync(0xffffffffu, any)) my_flags |= 1u << slice;
         }
 
-        // ---- this warp is done with the tile; the last one publishes the tile's totals
-        __syncwarp();
+        // ---- this warp is done with the tile; the last one publishes the tile's flags
         if (lane == 0) {
+            if (my_flags) atomicOr(&s_tflag[s], my_flags);
             __threadfence_block();
-            const uint32_t old = atomicAdd(&s_done[s], 1u);
-            if (old == (uint32_t)kConsumerWarps - 1u) {
+            if (atomicAdd(&s_done[s], 1u) == (uint32_t)kConsumerWarps - 1u) {
                 __threadfence_block();
-                p.tile_cnt[tile] = s_tcnt[s];
-                p.tile_mask[tile] = s_tmask[s];
-                s_tcnt[s] = 0;
-                s_tmask[s] = 0;
+                const uint32_t flags = s_tflag[s];
+                p.tile_cnt[tile] = 0;
+                p.tile_mask[tile] = flags;
+                if (flags) p.flagged[atomicAdd(&p.ctrl->n_flagged, 1u)] = tile;
+                s_tflag[s] = 0;
                 s_done[s] = 0;
                 s_ticket[s] = 0;
                 __threadfence_block();
             }
             mbar_arrive(&s_empty[s]);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Emit pass: one warp per tile that the detector flagged.  For every flagged 512-byte slice the
+// plain PFAC walk of SUBSEG_MATCH (master_kernel.cu:37-74) runs over every start position, straight
+// from the canonical PHF (state words are masked down to the state number; T1 -- read from the
+// global copy of the image -- only skips starts that cannot take a first step).  Two sweeps per
+// slice: count, reserve scratch space with one atomic, write the records in (position, length) order.
+struct EmitParams {
+    const uint8_t *in_al;
+    uint32_t mis, a_start_end, a_valid_end, max_pat_len;
+    int32_t use_ref_bound;
+    uint64_t base_pos;
+    uint32_t pos_bias;
+    const int32_t *r;
+    const int2 *htval;
+    const int32_t *idmap;
+    const uint8_t *t1;        // global copy of the image's T1 (offset 0)
+    const int32_t *s0;        // root row, s0Table (main.cc:200)
+    int32_t ht_size, width_bit, n_final;
+    uint2 *scratch;
+    unsigned long long scratch_cap;
+    unsigned int *tile_cnt, *tile_mask;
+    const unsigned int *flagged;
+    uint4 *slice_ent;
+    Ctrl *ctrl;
+};
+
+constexpr int kEmitThreads = 256;
+
+// master_kernel.cu:52-64 over the canonical arrays
+__device__ __forceinline__ int32_t phf_next(const EmitParams &p, int32_t state, uint32_t byte)
+{
+    const int32_t key = (state << 8) + (int32_t)byte;                // :52
+    const int32_t row = key >> p.width_bit;                          // :53
+    const int32_t idx = __ldg(&p.r[row]) + (key & ((1 << p.width_bit) - 1));   // :54-55
+    if (idx < 0 || idx >= p.ht_size) return -1;                      // :56-57
+    const int2 hv = __ldg(&p.htval[idx]);                            // :59-61
+    return hv.x == row ? hv.y : -1;
+}
+
+template <bool WRITE>
+__device__ __forceinline__ uint32_t emit_walk(const EmitParams &p, uint32_t a, uint32_t lim_a, unsigned long long o)
+{
+    int32_t state = __ldg(&p.s0[p.in_al[a]]);                        // :41
+    if (state < 0) return 0;                                         // :43
+    uint32_t n = 0, q = a + 1;
+    const uint32_t rec_pos = a - p.mis + p.pos_bias;
+    while (true) {
+        if (state < p.n_final) {                                     // :44-47, :67-70
+            if (WRITE && o + n < p.scratch_cap) p.scratch[o + n] = make_uint2(rec_pos, (uint32_t)__ldg(&p.idmap[state]));
+            n++;
+        }
+        if (q >= lim_a) break;                                       // :50
+        state = phf_next(p, state, p.in_al[q]);
+        if (state < 0) break;                                        // :63-64
+        q++;
+    }
+    return n;
+}
+
+__global__ void __launch_bounds__(kEmitThreads) pfac_emit_kernel(const EmitParams p)
+{
+    const int lane = threadIdx.x & 31;
+    const uint32_t warps_total = gridDim.x * (kEmitThreads / 32);
+    const uint32_t n_flagged = p.ctrl->n_flagged;
+    for (uint32_t i = blockIdx.x * (kEmitThreads / 32) + (threadIdx.x >> 5); i < n_flagged; i += warps_total) {
+        const uint32_t tile = p.flagged[i];
+        const uint32_t a0 = tile * (uint32_t)kTile;
+        uint32_t m = p.tile_mask[tile], out_mask = 0, tile_total = 0;
+        while (m) {
+            const uint32_t sl = __ffs(m) - 1;
+            m &= m - 1;
+            const uint32_t a_lane = a0 + sl * kSlice + lane * 16;   // aligned coordinates of this lane's 16 starts
+            // which of the 16 starts can match at all: inside [mis, a_start_end) and passing T1
+            uint32_t cand = 0;
+            for (uint32_t j = 0; j < 16; j++) {
+                const uint32_t a = a_lane + j;
+                if (a < p.mis || a >= p.a_start_end) continue;
+                const uint32_t c0 = p.in_al[a], c1 = a + 1 < p.a_valid_end ? p.in_al[a + 1] : 0u;
+                const uint32_t r0 = ((c0 << 2) | (c0 >> 6)) & 0xffu, r1 = ((c1 << 2) | (c1 >> 6)) & 0xffu;
+                if (__ldg(&p.t1[r0 | (r1 << 8)])) cand |= 1u << j;
+            }
+            auto limit = [&](uint32_t a) {
+                uint32_t lim_a = p.a_valid_end;
+                if (p.use_ref_bound) {   // reference tiles: 4096 bytes of global positions + 512-byte halo
+                    const unsigned long long g = p.base_pos + (unsigned long long)(a - p.mis);
+                    const unsigned long long lim2 = ((g & ~4095ull) + 4608ull) - p.base_pos + p.mis;
+                    if (lim2 < lim_a) lim_a = (uint32_t)lim2;
+                }
+                const unsigned long long depth = (unsigned long long)a + p.max_pat_len;
+                return depth < lim_a ? (uint32_t)depth : lim_a;
+            };
+            uint32_t cnt = 0, hit = 0;
+            for (uint32_t c = cand; c; c &= c - 1) {
+                const uint32_t j = __ffs(c) - 1;
+                const uint32_t n = emit_walk<false>(p, a_lane + j, limit(a_lane + j), 0ull);
+                if (n) hit |= 1u << j;
+                cnt += n;
+            }
+            uint32_t incl = cnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t n = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += n;
+            }
+            const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+            if (!total) continue;
+            unsigned long long base = 0;
+            if (lane == 0) base = atomicAdd(&p.ctrl->alloc, (unsigned long long)total);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            unsigned long long o = base + incl - cnt;
+            for (uint32_t c = hit; c; c &= c - 1) {
+                const uint32_t j = __ffs(c) - 1;
+                o += emit_walk<true>(p, a_lane + j, limit(a_lane + j), o);
+            }
+            if (lane == 0)
+                p.slice_ent[(size_t)tile * kSlicesPerTile + sl] = make_uint4(total, (uint32_t)base, (uint32_t)(base >> 32), 0u);
+            out_mask |= 1u << sl;
+            tile_total += total;
+        }
+        if (lane == 0) {
+            p.tile_cnt[tile] = tile_total;
+            p.tile_mask[tile] = out_mask;
         }
     }
 }
@@ -664,10 +580,12 @@ __global__ void __launch_bounds__(kFinThreads) pfac_finalize_kernel(const Finali
     if (tid == 0 && lo < hi && hi == f.n_tiles) {   // the CTA whose range ends the input owns the total
         f.result->count = s_run;
         f.result->error_flag = f.ctrl->error_flag;
+        f.result->n_flagged = f.ctrl->n_flagged;
         if (f.count_out) *f.count_out = s_run;
         f.ctrl->ticket = 0;
         f.ctrl->error_flag = 0;
         f.ctrl->alloc = 0;
+        f.ctrl->n_flagged = 0;
     }
 }
 

@@ -465,17 +465,17 @@ const int32_t *pfac_tables_HT(const pfac_tables *t, int part) { const Partition 
 const int32_t *pfac_tables_val(const pfac_tables *t, int part) { const Partition *P = part_of(t, part); return P ? P->val.data() : nullptr; }
 const int32_t *pfac_tables_idmap(const pfac_tables *t, int part) { const Partition *P = part_of(t, part); return P ? P->idmap.data() : nullptr; }
 
-int pfac_tables_derive_check(const pfac_tables *t, int part, uint32_t t2_bytes, uint32_t t3_bytes, uint32_t hot_bytes,
+int pfac_tables_derive_check(const pfac_tables *t, int part, uint32_t t2_bytes, uint32_t t3_bytes, uint32_t tm2_bytes,
                              uint64_t stats[10])
 {
     const Partition *P = part_of(t, part);
     if (!P) return set_error(PFAC_ERR_ARG, "bad partition index");
     try {
         Derived d;
-        derive_tables(*P, t2_bytes, t3_bytes, hot_bytes, d);
+        derive_tables(*P, t2_bytes, t3_bytes, tm2_bytes, d);
         if (stats) {
-            const uint64_t v[10] = {d.image.size(), d.t1_set, d.t2_set, d.n_depth4, d.has_short, d.n_hot_rows,
-                                    d.n_hot_entries, d.hot_probe, d.tm_set | ((uint64_t)d.tm2_set << 32), d.t3_set};
+            const uint64_t v[10] = {d.image.size(), d.t1_set, d.t2_set, d.n_prefix4, d.has_short, d.has_t3,
+                                    d.tm_set, d.tm2_set, d.t3_set, d.tm2_bits};
             memcpy(stats, v, sizeof v);
         }
         const int bad = derive_selfcheck(*P, d);
@@ -486,14 +486,14 @@ int pfac_tables_derive_check(const pfac_tables *t, int part, uint32_t t2_bytes, 
     }
 }
 
-int pfac_tables_filter_profile(const pfac_tables *t, int part, uint32_t t2_bytes, uint32_t t3_bytes, uint32_t hot_bytes,
+int pfac_tables_filter_profile(const pfac_tables *t, int part, uint32_t t2_bytes, uint32_t t3_bytes, uint32_t tm2_bytes,
                                const void *text, uint64_t n, uint64_t counts[12])
 {
     const Partition *P = part_of(t, part);
     if (!P || (!text && n) || !counts) return set_error(PFAC_ERR_ARG, "bad arguments");
     try {
         Derived d;
-        derive_tables(*P, t2_bytes, t3_bytes, hot_bytes, d);
+        derive_tables(*P, t2_bytes, t3_bytes, tm2_bytes, d);
         derive_profile(*P, d, (const uint8_t *)text, (size_t)n, counts);
         return PFAC_OK;
     } catch (const std::bad_alloc &) {

@@ -160,11 +160,12 @@ def test_derived_device_tables_selfcheck(fixtures, case):
             }.get(case) or fixtures[case]
     for width in (256, 64, 4096):
         t = pf.Tables.from_bytes(blob, 1, width)
-        for t2b, t3b, hotb in ((8192, 16384, 16384), (1024, 1024, 2048), (0, 0, 0), (65536, 0, 1024), (4096, 65536, 0)):
-            st = t.derive_check(0, t2b, t3b, hotb)
+        for t2b, t3b, tm2b in ((32768, 32768, 32768), (1024, 1024, 2048), (0, 0, 0), (65536, 0, 1024), (4096, 65536, 0),
+                               (0, 16384, 128)):
+            st = t.derive_check(0, t2b, t3b, tm2b)
             assert st["t1_pairs"] > 0
-            if hotb == 0:
-                assert st["hot_rows"] == 0
+            if t3b == 0:
+                assert st["has_t3"] == 0 and st["tm_keys"] == 0
     p = pf.Tables.from_bytes(blob, 1, 256).part(0)
     t2 = pf.Tables.from_arrays(p.s0, p.r, p.HT, p.val, 256, p.state_num, p.n_final, p.idmap, p.max_len)
     assert t2.derive_check() == pf.Tables.from_bytes(blob, 1, 256).derive_check()

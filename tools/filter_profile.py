@@ -8,15 +8,16 @@ from bench import WORKLOADS
 ap = argparse.ArgumentParser()
 ap.add_argument("--workload", default="config3")
 ap.add_argument("--mib", type=int, default=8)
-ap.add_argument("--t2", type=int, default=8192)
-ap.add_argument("--t3", type=int, default=16384)
-ap.add_argument("--hot", type=int, default=8192)
+ap.add_argument("--t2", type=int, default=32768)
+ap.add_argument("--t3", type=int, default=32768)
+ap.add_argument("--tm2", type=int, default=32768)
 a = ap.parse_args()
 pk, cnt, pseed, lo, hi, tk, tseed, nbytes, desc = WORKLOADS[a.workload]
 pats = pf.synth_patterns(pk, cnt, pseed, lo, hi)
 t = pf.Tables.from_bytes(pats)
 text = pf.synth_text(tk, tseed, a.mib << 20, patterns=pats)
-c = t.filter_profile(text, 0, a.t2, a.t3, a.hot)
+print(t.derive_check(0, a.t2, a.t3, a.tm2))
+c = t.filter_profile(text, 0, a.t2, a.t3, a.tm2)
 n = c["positions"]
 for k, v in c.items():
     print(f"{k:15s} {v:12d}  {v / n:.5f} per byte")

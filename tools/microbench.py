@@ -35,4 +35,8 @@ for n in sizes:
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / a.iters
     print(f"{a.workload} debug={os.environ.get('PFAC_DEBUG','0')} n={n>>20}MiB {ms:.3f} ms {n/ms/1e6:.1f} GB/s matches={int(cntd.item())} info={m.last_info()}", flush=True)
+import ctypes as C
+cnt = C.c_uint64(0)
+pf.lib.pfac_scan_device_sync(m._h, d.data_ptr(), sizes[0], sizes[0], 0, out.data_ptr(), cap, C.byref(cnt), None)
+print("sync scan:", cnt.value, m.last_info(), flush=True)
 m.close(); tables.close()
