@@ -147,6 +147,13 @@ void pfac_host_free(void *ptr);
  * flagged for the emit kernel (pfac_scan_device_sync only) */
 int pfac_ctx_last_scan_info(const pfac_ctx *ctx, uint64_t info[8]);
 
+/* Optional CUDA-event timing of the detector kernel (pfac_scan_kernel) alone, for roofline
+ * reports: after pfac_ctx_set_timing(ctx, 1) every scan records an event pair around that kernel
+ * on the scan's stream (ring of 256 launches); pfac_ctx_kernel_time synchronises the device, sums
+ * the recorded launches since the last call and resets the ring. */
+int pfac_ctx_set_timing(pfac_ctx *ctx, int enable);
+int pfac_ctx_kernel_time(pfac_ctx *ctx, double *ms_total, int *n_launches);
+
 /* Derived (shared-memory) table statistics of this context, for DESIGN.md / bench.py:
  * info[0] = image bytes, [1] = T1 pairs set, [2] = T2 bits, [3] = T2 bits set, [4] = 4-byte prefixes,
  * [5] = short patterns (<= 3 bytes) present, [6] = Tm keys, [7] = Tm2 keys, [8] = T3 bits,

@@ -144,6 +144,15 @@ class Matcher:
         keys = ("launches", "tiles", "ctas", "smem_bytes", "h2d_bytes", "d2h_bytes", "chunks", "flagged_tiles")
         return dict(zip(keys, list(info)))
 
+    def set_timing(self, enable=True):
+        check(lib.pfac_ctx_set_timing(self._h, 1 if enable else 0))
+
+    def kernel_time(self):
+        """(total ms, launches) of the detector kernel since the last call (needs set_timing)."""
+        ms, n = C.c_double(0), C.c_int(0)
+        check(lib.pfac_ctx_kernel_time(self._h, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
     def derived_info(self):
         info = (C.c_uint64 * 16)()
         check(lib.pfac_ctx_derived_info(self._h, info))

@@ -19,7 +19,7 @@ ABI_SYMBOLS = [
     "pfac_tables_idmap", "pfac_tables_lookup", "pfac_tables_derive_check", "pfac_tables_filter_profile",
     "pfac_device_count", "pfac_ctx_create", "pfac_ctx_destroy", "pfac_ctx_device",
     "pfac_scan_device", "pfac_scan_device_sync", "pfac_scan_host", "pfac_host_alloc", "pfac_host_free",
-    "pfac_ctx_last_scan_info", "pfac_ctx_derived_info",
+    "pfac_ctx_last_scan_info", "pfac_ctx_derived_info", "pfac_ctx_set_timing", "pfac_ctx_kernel_time",
     "pfac_job_create", "pfac_job_destroy", "pfac_job_run", "pfac_job_n_segments", "pfac_job_segment",
     "pfac_job_last_timing", "pfac_job_plan",
     "pfac_write_begin", "pfac_write_records", "pfac_write_end", "pfac_format_records",
@@ -79,6 +79,8 @@ def _load():
     lib.pfac_host_free.argtypes = [_vp]
     lib.pfac_host_free.restype = None
     lib.pfac_ctx_last_scan_info.argtypes = [_vp, C.POINTER(C.c_uint64)]
+    lib.pfac_ctx_set_timing.argtypes = [_vp, C.c_int]
+    lib.pfac_ctx_kernel_time.argtypes = [_vp, C.POINTER(C.c_double), C.POINTER(C.c_int)]
     lib.pfac_ctx_derived_info.argtypes = [_vp, C.POINTER(C.c_uint64)]
     lib.pfac_job_create.argtypes = [_vp, C.POINTER(C.c_int), C.c_int, C.c_int, C.c_size_t, C.POINTER(_vp)]
     lib.pfac_job_destroy.argtypes = [_vp]

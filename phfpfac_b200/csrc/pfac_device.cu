@@ -71,6 +71,10 @@ struct pfac_ctx {
     Slot own;
     std::vector<Stage> stages;
     uint64_t info[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    // optional CUDA-event timing of the detector kernel alone (bench.py's roofline leg)
+    bool timing = false;
+    std::vector<cudaEvent_t> ev;   // pairs (before, after), used as a ring
+    size_t ev_next = 0, ev_count = 0;
     uint32_t debug = 0;   // PFAC_DEBUG env (timing experiments only)
     std::mutex mu;
 };
@@ -200,8 +204,17 @@ int launch_scan(pfac_ctx *ctx, Slot &slot, const void *d_in, uint64_t n_starts, 
     p.ctrl = slot.d_ctrl;
     p.debug = ctx->debug;
     const uint32_t grid = (uint32_t)std::min<uint64_t>(p.n_tiles, (uint64_t)ctx->sm_count);
+    cudaEvent_t ev_after = nullptr;
+    if (ctx->timing && !ctx->ev.empty()) {
+        const size_t slot_i = ctx->ev_next;
+        ctx->ev_next = (ctx->ev_next + 2) % ctx->ev.size();
+        ctx->ev_count = std::min(ctx->ev_count + 1, ctx->ev.size() / 2);
+        CU_TRY(cudaEventRecord(ctx->ev[slot_i], stream));
+        ev_after = ctx->ev[slot_i + 1];
+    }
     pfac_scan_kernel<<<grid, kThreads, ctx->smem_bytes, stream>>>(p);
     CU_TRY(cudaGetLastError());
+    if (ev_after) CU_TRY(cudaEventRecord(ev_after, stream));
 
     EmitParams ep;
     memset(&ep, 0, sizeof ep);
@@ -391,11 +404,47 @@ void pfac_ctx_destroy(pfac_ctx *ctx)
     if (ctx->d_idmap) cudaFree(ctx->d_idmap);
     if (ctx->d_image) cudaFree(ctx->d_image);
     if (ctx->d_s0) cudaFree(ctx->d_s0);
+    for (auto e : ctx->ev)
+        if (e) cudaEventDestroy(e);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
 }
 
 int pfac_ctx_device(const pfac_ctx *ctx) { return ctx ? ctx->device : -1; }
+
+int pfac_ctx_set_timing(pfac_ctx *ctx, int enable)
+{
+    if (!ctx) return set_error(PFAC_ERR_ARG, "bad arguments");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    DeviceGuard g(ctx->device);
+    if (enable && ctx->ev.empty()) {
+        ctx->ev.resize(512, nullptr);
+        for (auto &e : ctx->ev) CU_TRY(cudaEventCreate(&e));
+    }
+    ctx->timing = enable != 0;
+    ctx->ev_next = ctx->ev_count = 0;
+    return PFAC_OK;
+}
+
+int pfac_ctx_kernel_time(pfac_ctx *ctx, double *ms_total, int *n_launches)
+{
+    if (!ctx || !ms_total || !n_launches) return set_error(PFAC_ERR_ARG, "bad arguments");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    DeviceGuard g(ctx->device);
+    CU_TRY(cudaDeviceSynchronize());
+    double total = 0;
+    const size_t pairs = ctx->ev.size() / 2;
+    for (size_t k = 0; k < ctx->ev_count; k++) {
+        const size_t i = ((ctx->ev_next / 2 + pairs - 1 - k) % pairs) * 2;
+        float ms = 0;
+        CU_TRY(cudaEventElapsedTime(&ms, ctx->ev[i], ctx->ev[i + 1]));
+        total += ms;
+    }
+    *ms_total = total;
+    *n_launches = (int)ctx->ev_count;
+    ctx->ev_next = ctx->ev_count = 0;
+    return PFAC_OK;
+}
 
 int pfac_ctx_derived_info(const pfac_ctx *ctx, uint64_t info[16])
 {
