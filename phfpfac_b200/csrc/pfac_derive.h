@@ -55,18 +55,25 @@ PFAC_HD inline uint32_t hash_key2(uint32_t prefix, uint32_t window)
 }
 PFAC_HD inline uint32_t tm_slot1(uint32_t key, uint32_t bits) { return (key * 0xC2B2AE35u) >> (32 - bits); }
 PFAC_HD inline uint32_t tm_slot2(uint32_t key, uint32_t bits) { return (key * 0x27D4EB2Fu + 0x7F4A7C15u) >> (32 - bits); }
-PFAC_HD inline uint32_t tm_tag(uint32_t key) { return (key * 0xFD7046C5u) >> 24; }
-// complete cuckoo table of 2^bits buckets x 2 slots (u16: tag << 8 | m): m of `key`, 0 = not a key
+// tags are 1..255 so that an empty slot (0) never matches
+PFAC_HD inline uint32_t tm_tag(uint32_t key)
+{
+    const uint32_t t = (key * 0xFD7046C5u) >> 24;
+    return t ? t : 1u;
+}
+// complete cuckoo table of 2^bits buckets x 2 slots (u16: tag << 8 | m): m of `key`, 0 = not a key.
+// Probe order: bucket 1 low, bucket 1 high, bucket 2 low, bucket 2 high.
 PFAC_HD inline uint32_t tm_lookup(const uint16_t *tab, uint32_t key, uint32_t bits)
 {
     const uint32_t tag = tm_tag(key);
     const uint32_t *t32 = reinterpret_cast<const uint32_t *>(tab);
     const uint32_t a = t32[tm_slot1(key, bits)], b = t32[tm_slot2(key, bits)];
-    if ((a & 0xffffu) && ((a >> 8) & 0xffu) == tag) return a & 255u;
-    if ((a >> 16) && (a >> 24) == tag) return (a >> 16) & 255u;
-    if ((b & 0xffffu) && ((b >> 8) & 0xffu) == tag) return b & 255u;
-    if ((b >> 16) && (b >> 24) == tag) return (b >> 16) & 255u;
-    return 0;
+    uint32_t m = 0;
+    if ((b >> 24) == tag) m = (b >> 16) & 255u;
+    if (((b >> 8) & 255u) == tag) m = b & 255u;
+    if ((a >> 24) == tag) m = (a >> 16) & 255u;
+    if (((a >> 8) & 255u) == tag) m = a & 255u;
+    return m;
 }
 // rotl2 of a byte (T1 index)
 PFAC_HD inline uint32_t rot2(uint32_t c) { return ((c << 2) | (c >> 6)) & 0xFFu; }

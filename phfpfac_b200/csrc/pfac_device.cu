@@ -32,6 +32,7 @@ struct Slot {
     Result *d_result = nullptr;
     Result *h_result = nullptr;   // pinned
     unsigned int *d_tile_cnt = nullptr, *d_tile_mask = nullptr, *d_flagged = nullptr;
+    uint16_t *d_cand = nullptr;
     uint4 *d_slice_ent = nullptr;
     size_t tile_cap = 0;
     uint2 *d_scratch = nullptr;
@@ -113,6 +114,7 @@ void slot_free(Slot &s)
     if (s.d_tile_cnt) cudaFree(s.d_tile_cnt);
     if (s.d_tile_mask) cudaFree(s.d_tile_mask);
     if (s.d_flagged) cudaFree(s.d_flagged);
+    if (s.d_cand) cudaFree(s.d_cand);
     if (s.d_slice_ent) cudaFree(s.d_slice_ent);
     if (s.d_scratch) cudaFree(s.d_scratch);
     s = Slot();
@@ -127,14 +129,17 @@ int slot_reserve(Slot &s, size_t n_tiles, size_t records, cudaStream_t stream)
         if (s.d_tile_cnt) cudaFree(s.d_tile_cnt);
         if (s.d_tile_mask) cudaFree(s.d_tile_mask);
         if (s.d_flagged) cudaFree(s.d_flagged);
+        if (s.d_cand) cudaFree(s.d_cand);
         if (s.d_slice_ent) cudaFree(s.d_slice_ent);
         s.d_tile_cnt = s.d_tile_mask = s.d_flagged = nullptr;
+        s.d_cand = nullptr;
         s.d_slice_ent = nullptr;
         s.tile_cap = 0;
         const size_t n = std::max<size_t>(n_tiles, 1024);
         CU_TRY(cudaMalloc(&s.d_tile_cnt, n * sizeof(unsigned int)));
         CU_TRY(cudaMalloc(&s.d_tile_mask, n * sizeof(unsigned int)));
         CU_TRY(cudaMalloc(&s.d_flagged, n * sizeof(unsigned int)));
+        CU_TRY(cudaMalloc(&s.d_cand, n * kCandPerTile * sizeof(uint16_t)));
         CU_TRY(cudaMalloc(&s.d_slice_ent, n * kSlicesPerTile * sizeof(uint4)));
         s.tile_cap = n;
     }
@@ -201,6 +206,7 @@ int launch_scan(pfac_ctx *ctx, Slot &slot, const void *d_in, uint64_t n_starts, 
     p.tile_cnt = slot.d_tile_cnt;
     p.tile_mask = slot.d_tile_mask;
     p.flagged = slot.d_flagged;
+    p.cand = slot.d_cand;
     p.ctrl = slot.d_ctrl;
     p.debug = ctx->debug;
     const uint32_t grid = (uint32_t)std::min<uint64_t>(p.n_tiles, (uint64_t)ctx->sm_count);
@@ -239,6 +245,7 @@ int launch_scan(pfac_ctx *ctx, Slot &slot, const void *d_in, uint64_t n_starts, 
     ep.tile_cnt = slot.d_tile_cnt;
     ep.tile_mask = slot.d_tile_mask;
     ep.flagged = slot.d_flagged;
+    ep.cand = slot.d_cand;
     ep.slice_ent = slot.d_slice_ent;
     ep.ctrl = slot.d_ctrl;
     const uint32_t egrid = (uint32_t)std::min<uint64_t>((p.n_tiles + (kEmitThreads / 32) - 1) / (kEmitThreads / 32),
@@ -337,7 +344,7 @@ int pfac_ctx_create(int device, const pfac_tables *t, int part, int n_streams, s
         const size_t stride = scan_buf_stride(ctx->halo);
         const size_t fit = smem_max > fixed ? (smem_max - fixed) / stride : 0;
         const bool minimal = t2_bytes < 2048 && t3_bytes < 2048 && tm2_bytes < 2048;
-        if (fit >= 4 || (fit >= 2 && minimal)) {
+        if (fit >= 3 || (fit >= 2 && minimal)) {
             ctx->n_stages = (uint32_t)std::min<size_t>(fit, kMaxStages);
             ctx->smem_bytes = scan_smem_bytes(ctx->image_bytes, ctx->halo, ctx->n_stages);
             break;

@@ -57,8 +57,10 @@ struct ScanParams {
     uint32_t t2_shift, has_short, has_t3, t3_shift, tm2_bits;
     uint32_t n_stages;                // depth of the input ring (as many as shared memory holds)
     // output
-    unsigned int *tile_cnt;           // [n_tiles] 0 from the detector; the emit kernel fills it
+    unsigned int *tile_cnt;           // [n_tiles] detector: candidates of the tile (kCandOverflow: too many);
+                                      //           the emit kernel overwrites it with the tile's match count
     unsigned int *tile_mask;          // [n_tiles] bit s set iff slice s of the tile is flagged
+    uint16_t *cand;                   // [n_tiles*kCandPerTile] tile-relative start positions that survived every filter
     unsigned int *flagged;            // [n_tiles] ids of the tiles with a non-zero mask, arrival order
     Ctrl *ctrl;
     uint32_t debug;           // PFAC_DEBUG bits (timing experiments only): 4 no T1, 8 no stage 2
@@ -78,14 +80,17 @@ struct FinalizeParams {
     unsigned long long *count_out;    // caller's device counter (may be null)
 };
 
-constexpr int kConsumerWarps = 24;
+constexpr int kConsumerWarps = 31;
 constexpr int kThreads = (kConsumerWarps + 1) * 32;   // + the producer warp
 constexpr int kTile = 16384;          // start positions per tile
 constexpr int kSlice = 512;           // start positions per warp step (32 lanes x 16 B)
 constexpr int kSlicesPerTile = kTile / kSlice;
 constexpr int kMaxStages = 8;
-constexpr int kQueueBytes = kSlice * 2;   // per consumer warp: u16 start positions that passed stage 1
-constexpr int kCtrlBytes = 512;
+constexpr int kQ2Cap = 64;                // per consumer warp: starts that passed the prefix check of stage 2
+constexpr int kQueueBytes = kSlice * 2 + kQ2Cap * 4;   // + u16 start positions that passed stage 1
+constexpr int kCtrlBytes = 1024;
+constexpr int kCandPerTile = 32;          // candidate starts the detector hands over per tile (more: whole slices)
+constexpr unsigned kCandOverflow = 0xFFFFFFFFu;
 constexpr unsigned kSpinLimit = 1u << 24;
 
 __host__ __device__ inline uint32_t scan_buf_stride(uint32_t halo) { return (kTile + halo + 32 + 127) & ~127u; }
@@ -194,6 +199,14 @@ __device__ __forceinline__ uint32_t walk_limit(const ScanParams &p, uint32_t a0,
     return lim_t < depth ? lim_t : depth;
 }
 
+// A start that survived every filter: remember it for the emit kernel (per tile; past
+// kCandPerTile the counter keeps growing and the tile is handed over slice by slice instead)
+__device__ __forceinline__ void add_candidate(uint32_t *n, uint16_t *list, uint32_t tpos)
+{
+    const uint32_t i = atomicAdd(n, 1u);
+    if (i < (uint32_t)kCandPerTile) list[i] = (uint16_t)tpos;
+}
+
 __global__ void __launch_bounds__(kThreads, 1) pfac_scan_kernel(const ScanParams p)
 {
     const uint32_t *s_t1s = reinterpret_cast<const uint32_t *>(smem + p.off_t1s);
@@ -208,6 +221,8 @@ __global__ void __launch_bounds__(kThreads, 1) pfac_scan_kernel(const ScanParams
     uint32_t *s_ticket = reinterpret_cast<uint32_t *>(ctl + 160);       // [kMaxStages] slice tickets
     uint32_t *s_done = reinterpret_cast<uint32_t *>(ctl + 192);         // [kMaxStages] warps finished
     uint32_t *s_tflag = reinterpret_cast<uint32_t *>(ctl + 224);        // [kMaxStages] flagged slices of the tile
+    uint32_t *s_ncand = reinterpret_cast<uint32_t *>(ctl + 256);        // [kMaxStages] candidates (or kCandOverflow)
+    uint16_t *s_cand = reinterpret_cast<uint16_t *>(ctl + 512);         // [kMaxStages][kCandPerTile]
     uint8_t *qbase = ctl + kCtrlBytes;
     const uint32_t n_stages = p.n_stages;
     uint8_t *s_in = qbase + kConsumerWarps * kQueueBytes;
@@ -227,6 +242,7 @@ __global__ void __launch_bounds__(kThreads, 1) pfac_scan_kernel(const ScanParams
             s_ticket[s] = 0;
             s_done[s] = 0;
             s_tflag[s] = 0;
+            s_ncand[s] = 0;
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -268,6 +284,8 @@ __global__ void __launch_bounds__(kThreads, 1) pfac_scan_kernel(const ScanParams
 
     // ---------------------------------------------------------------------- consumers
     uint16_t *wq = reinterpret_cast<uint16_t *>(qbase + warp * kQueueBytes);   // stage-1 survivors of one slice
+    uint32_t *wq2 = reinterpret_cast<uint32_t *>(wq + kSlice);                  // stage-2a survivors: tpos | m1 << 16
+    const uint32_t lt_mask = (1u << lane) - 1u;
 
     uint32_t s = 0, round = 0;
     for (;; s = (s + 1 == n_stages) ? 0 : s + 1, round += (s == 0) ? 1u : 0u) {
@@ -281,6 +299,8 @@ __global__ void __launch_bounds__(kThreads, 1) pfac_scan_kernel(const ScanParams
         if (tile_starts > (uint32_t)kTile) tile_starts = kTile;
         const uint32_t n_slices = (tile_starts + kSlice - 1) / kSlice;
         const uint32_t valid_t = p.a_valid_end - a0;   // tile-relative end of readable input (may exceed the buffer)
+        // an interior tile: no start of it can reach the end of the input or a reference walk bound
+        const bool interior = !p.use_ref_bound && valid_t >= (uint32_t)kTile + p.max_pat_len;
         uint32_t my_flags = 0;
 
         while (true) {
@@ -315,53 +335,89 @@ __global__ void __launch_bounds__(kThreads, 1) pfac_scan_kernel(const ScanParams
                 mask &= mask - 1;
             }
             __syncwarp();
-            // stage 2: two-point checks (or T2); one surviving start flags the slice
+            // stage 2a: the 4-byte prefix (complete Tm, or T2).  What survives is queued with its m1;
+            // starts that cannot be judged here (short patterns, end of the input) flag the slice.
             bool any = false;
+            uint32_t n2 = 0;
             for (uint32_t e0 = 0; e0 < nq; e0 += 32) {
                 const uint32_t e = e0 + lane;
-                if (e >= nq) continue;
-                const uint32_t tpos = wq[e];
-                bool keep = true;
-                if (!(p.debug & 8u) && tpos + 4u <= valid_t) {   // with fewer than 4 readable bytes: let the emit kernel look
-                    const uint32_t *wp = reinterpret_cast<const uint32_t *>(buf + (tpos & ~3u));
-                    const uint32_t w4 = __funnelshift_r(wp[0], wp[1], (tpos & 3u) * 8u);
-                    bool shortp = false;
-                    if (p.has_short) {
-                        const uint32_t pair = w4 & 0xffffu;
-                        shortp = (s_t1s[pair >> 5] >> (pair & 31u)) & 1u;
-                    }
-                    if (!shortp) {
-                        if (!p.has_t3) {
+                uint32_t tpos = 0, m1 = 0;
+                bool keep = false;
+                if (e < nq) {
+                    tpos = wq[e];
+                    if ((p.debug & 8u) || tpos + 4u > valid_t) {
+                        any = true;
+                        add_candidate(s_ncand + s, s_cand + s * kCandPerTile, tpos);
+                    } else {
+                        const uint32_t *wp = reinterpret_cast<const uint32_t *>(buf + (tpos & ~3u));
+                        const uint32_t w4 = __funnelshift_r(wp[0], wp[1], (tpos & 3u) * 8u);
+                        bool shortp = false;
+                        if (p.has_short) {
+                            const uint32_t pair = w4 & 0xffffu;
+                            shortp = (s_t1s[pair >> 5] >> (pair & 31u)) & 1u;
+                        }
+                        if (shortp) {
+                            any = true;
+                            add_candidate(s_ncand + s, s_cand + s * kCandPerTile, tpos);
+                        } else if (!p.has_t3) {
                             const uint32_t h = (w4 * kHash4Mul) >> p.t2_shift;
-                            keep = (s_t2[h >> 5] >> (h & 31u)) & 1u;
-                        } else {
-                            // every pattern under a key is at least m bytes long and has its bytes [m-4, m) in T3
-                            const uint32_t lim = walk_limit(p, a0, tpos);
-                            const uint32_t m1 = tm_lookup(s_tm, w4, kTmSlotBits);   // 0 = no such prefix
-                            keep = m1 != 0 && tpos + m1 <= lim;
-                            if (keep) {
-                                const uint32_t wo = tpos + m1 - 4u;
-                                const uint32_t *we = reinterpret_cast<const uint32_t *>(buf + (wo & ~3u));
-                                const uint32_t w1 = __funnelshift_r(we[0], we[1], (wo & 3u) * 8u);
-                                const uint32_t h3 = hash_t3(w4, w1) >> p.t3_shift;
-                                keep = (s_t3[h3 >> 5] >> (h3 & 31u)) & 1u;
-                                if (keep && p.tm2_bits) {
-                                    const uint32_t key2 = hash_key2(w4, w1);
-                                    const uint32_t m2 = tm_lookup(s_tm2, key2, p.tm2_bits);   // 0 = no such group
-                                    keep = m2 != 0 && tpos + m2 <= lim;
-                                    if (keep) {
-                                        const uint32_t wo2 = tpos + m2 - 4u;
-                                        const uint32_t *wf = reinterpret_cast<const uint32_t *>(buf + (wo2 & ~3u));
-                                        const uint32_t w2 = __funnelshift_r(wf[0], wf[1], (wo2 & 3u) * 8u);
-                                        const uint32_t h4 = hash_t3(key2 ^ kT3Seed2, w2) >> p.t3_shift;
-                                        keep = (s_t3[h4 >> 5] >> (h4 & 31u)) & 1u;
-                                    }
-                                }
+                            if ((s_t2[h >> 5] >> (h & 31u)) & 1u) {
+                                any = true;
+                                add_candidate(s_ncand + s, s_cand + s * kCandPerTile, tpos);
                             }
+                        } else {
+                            m1 = tm_lookup(s_tm, w4, kTmSlotBits);   // 0 = no pattern has this prefix
+                            keep = m1 != 0;
                         }
                     }
                 }
-                any |= keep;
+                const uint32_t bal = __ballot_sync(0xffffffffu, keep);
+                if (keep) {
+                    const uint32_t idx = n2 + __popc(bal & lt_mask);
+                    if (idx < (uint32_t)kQ2Cap) wq2[idx] = tpos | (m1 << 16);
+                    else {   // more prefix hits than the queue holds: the emit kernel looks at the whole slice
+                        any = true;
+                        atomicOr(s_ncand + s, 0x80000000u);   // no candidate list for this tile
+                    }
+                }
+                n2 += __popc(bal);
+            }
+            if (n2 > (uint32_t)kQ2Cap) n2 = kQ2Cap;
+            __syncwarp();
+            // stage 2b: two-point checks -- every pattern under a key is at least m bytes long and has
+            // its bytes [m-4, m) in T3
+            for (uint32_t e0 = 0; e0 < n2; e0 += 32) {
+                const uint32_t e = e0 + lane;
+                if (e >= n2) continue;
+                const uint32_t ent = wq2[e];
+                const uint32_t tpos = ent & 0xffffu, m1 = ent >> 16;
+                const uint32_t lim = interior ? 0xffffffffu : walk_limit(p, a0, tpos);
+                bool keep = tpos + m1 <= lim;
+                if (keep) {
+                    const uint32_t *wp = reinterpret_cast<const uint32_t *>(buf + (tpos & ~3u));
+                    const uint32_t w4 = __funnelshift_r(wp[0], wp[1], (tpos & 3u) * 8u);
+                    const uint32_t wo = tpos + m1 - 4u;
+                    const uint32_t *we = reinterpret_cast<const uint32_t *>(buf + (wo & ~3u));
+                    const uint32_t w1 = __funnelshift_r(we[0], we[1], (wo & 3u) * 8u);
+                    const uint32_t h3 = hash_t3(w4, w1) >> p.t3_shift;
+                    keep = (s_t3[h3 >> 5] >> (h3 & 31u)) & 1u;
+                    if (keep && p.tm2_bits) {
+                        const uint32_t key2 = hash_key2(w4, w1);
+                        const uint32_t m2 = tm_lookup(s_tm2, key2, p.tm2_bits);   // 0 = no such group
+                        keep = m2 != 0 && tpos + m2 <= lim;
+                        if (keep) {
+                            const uint32_t wo2 = tpos + m2 - 4u;
+                            const uint32_t *wf = reinterpret_cast<const uint32_t *>(buf + (wo2 & ~3u));
+                            const uint32_t w2 = __funnelshift_r(wf[0], wf[1], (wo2 & 3u) * 8u);
+                            const uint32_t h4 = hash_t3(key2 ^ kT3Seed2, w2) >> p.t3_shift;
+                            keep = (s_t3[h4 >> 5] >> (h4 & 31u)) & 1u;
+                        }
+                    }
+                }
+                if (keep) {
+                    any = true;
+                    add_candidate(s_ncand + s, s_cand + s * kCandPerTile, tpos);
+                }
             }
             if (__any_sync(0xffffffffu, any)) my_flags |= 1u << slice;
         }
@@ -373,10 +429,17 @@ __global__ void __launch_bounds__(kThreads, 1) pfac_scan_kernel(const ScanParams
             if (atomicAdd(&s_done[s], 1u) == (uint32_t)kConsumerWarps - 1u) {
                 __threadfence_block();
                 const uint32_t flags = s_tflag[s];
-                p.tile_cnt[tile] = 0;
+                uint32_t nc = s_ncand[s];
+                if (nc > (uint32_t)kCandPerTile) nc = kCandOverflow;   // too many (or the overflow bit is set)
+                p.tile_cnt[tile] = flags ? nc : 0u;
                 p.tile_mask[tile] = flags;
-                if (flags) p.flagged[atomicAdd(&p.ctrl->n_flagged, 1u)] = tile;
+                if (flags) {
+                    p.flagged[atomicAdd(&p.ctrl->n_flagged, 1u)] = tile;
+                    if (nc != kCandOverflow)
+                        for (uint32_t i = 0; i < nc; i++) p.cand[(size_t)tile * kCandPerTile + i] = s_cand[s * kCandPerTile + i];
+                }
                 s_tflag[s] = 0;
+                s_ncand[s] = 0;
                 s_done[s] = 0;
                 s_ticket[s] = 0;
                 __threadfence_block();
@@ -408,6 +471,7 @@ struct EmitParams {
     unsigned long long scratch_cap;
     unsigned int *tile_cnt, *tile_mask;
     const unsigned int *flagged;
+    const uint16_t *cand;
     uint4 *slice_ent;
     Ctrl *ctrl;
 };
@@ -454,6 +518,72 @@ __global__ void __launch_bounds__(kEmitThreads) pfac_emit_kernel(const EmitParam
         const uint32_t tile = p.flagged[i];
         const uint32_t a0 = tile * (uint32_t)kTile;
         uint32_t m = p.tile_mask[tile], out_mask = 0, tile_total = 0;
+        auto limit = [&](uint32_t a) {
+            uint32_t lim_a = p.a_valid_end;
+            if (p.use_ref_bound) {   // reference tiles: 4096 bytes of global positions + 512-byte halo
+                const unsigned long long g = p.base_pos + (unsigned long long)(a - p.mis);
+                const unsigned long long lim2 = ((g & ~4095ull) + 4608ull) - p.base_pos + p.mis;
+                if (lim2 < lim_a) lim_a = (uint32_t)lim2;
+            }
+            const unsigned long long depth = (unsigned long long)a + p.max_pat_len;
+            return depth < lim_a ? (uint32_t)depth : lim_a;
+        };
+        const uint32_t nc = p.tile_cnt[tile];
+        if (nc != kCandOverflow) {
+            // ---- candidate mode: the detector named every start that can match (at most 32): one lane
+            //      per candidate, sorted by position
+            uint32_t key = (uint32_t)lane < nc ? (uint32_t)p.cand[(size_t)tile * kCandPerTile + lane] : 0xFFFFu;
+#pragma unroll
+            for (int k = 2; k <= 32; k <<= 1)
+#pragma unroll
+                for (int j = k >> 1; j > 0; j >>= 1) {   // bitonic sort across the warp
+                    const uint32_t other = __shfl_xor_sync(0xffffffffu, key, j);
+                    const bool up = ((lane & k) == 0) == ((lane & j) == 0);
+                    key = up ? min(key, other) : max(key, other);
+                }
+            const bool live = key != 0xFFFFu;
+            const uint32_t a = a0 + key;
+            const uint32_t cnt = live ? emit_walk<false>(p, a, limit(a), 0ull) : 0u;
+            uint32_t incl = cnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t n = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += n;
+            }
+            const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+            if (total) {
+                unsigned long long base = 0;
+                if (lane == 0) base = atomicAdd(&p.ctrl->alloc, (unsigned long long)total);
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (cnt) emit_walk<true>(p, a, limit(a), base + incl - cnt);
+                // per-slice directory: records of a slice are contiguous (sorted by position)
+                const uint32_t my_slice = live ? key / kSlice : 0xFFFFFFFFu;
+                while (m) {
+                    const uint32_t sl = __ffs(m) - 1;
+                    m &= m - 1;
+                    const uint32_t mine = my_slice == sl ? cnt : 0u;
+                    uint32_t ssum = mine;
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) ssum += __shfl_xor_sync(0xffffffffu, ssum, o);
+                    if (!ssum) continue;
+                    // offset of the slice = records of all candidates in earlier slices
+                    uint32_t before = (live && my_slice < sl) ? cnt : 0u;
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) before += __shfl_xor_sync(0xffffffffu, before, o);
+                    const unsigned long long so = base + before;
+                    if (lane == 0)
+                        p.slice_ent[(size_t)tile * kSlicesPerTile + sl] = make_uint4(ssum, (uint32_t)so, (uint32_t)(so >> 32), 0u);
+                    out_mask |= 1u << sl;
+                }
+                tile_total = total;
+            }
+            if (lane == 0) {
+                p.tile_cnt[tile] = tile_total;
+                p.tile_mask[tile] = out_mask;
+            }
+            continue;
+        }
+        // ---- slice mode: too many candidates; every start of the flagged slices is examined
         while (m) {
             const uint32_t sl = __ffs(m) - 1;
             m &= m - 1;
@@ -467,16 +597,6 @@ __global__ void __launch_bounds__(kEmitThreads) pfac_emit_kernel(const EmitParam
                 const uint32_t r0 = ((c0 << 2) | (c0 >> 6)) & 0xffu, r1 = ((c1 << 2) | (c1 >> 6)) & 0xffu;
                 if (__ldg(&p.t1[r0 | (r1 << 8)])) cand |= 1u << j;
             }
-            auto limit = [&](uint32_t a) {
-                uint32_t lim_a = p.a_valid_end;
-                if (p.use_ref_bound) {   // reference tiles: 4096 bytes of global positions + 512-byte halo
-                    const unsigned long long g = p.base_pos + (unsigned long long)(a - p.mis);
-                    const unsigned long long lim2 = ((g & ~4095ull) + 4608ull) - p.base_pos + p.mis;
-                    if (lim2 < lim_a) lim_a = (uint32_t)lim2;
-                }
-                const unsigned long long depth = (unsigned long long)a + p.max_pat_len;
-                return depth < lim_a ? (uint32_t)depth : lim_a;
-            };
             uint32_t cnt = 0, hit = 0;
             for (uint32_t c = cand; c; c &= c - 1) {
                 const uint32_t j = __ffs(c) - 1;
