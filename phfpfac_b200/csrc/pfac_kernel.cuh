@@ -82,9 +82,9 @@ struct FinalizeParams {
 
 constexpr int kConsumerWarps = 31;
 constexpr int kThreads = (kConsumerWarps + 1) * 32;   // + the producer warp
-constexpr int kTile = 16384;          // start positions per tile
 constexpr int kSlice = 512;           // start positions per warp step (32 lanes x 16 B)
-constexpr int kSlicesPerTile = kTile / kSlice;
+constexpr int kSlicesPerTile = kConsumerWarps;   // every consumer warp owns one slice of every tile
+constexpr int kTile = kSlicesPerTile * kSlice;   // 15,872 start positions per tile
 constexpr int kMaxStages = 8;
 constexpr int kQ2Cap = 64;                // per consumer warp: starts that passed the prefix check of stage 2
 constexpr int kQueueBytes = kSlice * 2 + kQ2Cap * 4;   // + u16 start positions that passed stage 1
@@ -218,8 +218,6 @@ __global__ void __launch_bounds__(kThreads, 1) pfac_scan_kernel(const ScanParams
     uint64_t *s_full = reinterpret_cast<uint64_t *>(ctl);               // [kMaxStages]
     uint64_t *s_empty = reinterpret_cast<uint64_t *>(ctl + 64);         // [kMaxStages]
     uint32_t *s_tile = reinterpret_cast<uint32_t *>(ctl + 128);         // [kMaxStages] tile id of the stage
-    uint32_t *s_ticket = reinterpret_cast<uint32_t *>(ctl + 160);       // [kMaxStages] slice tickets
-    uint32_t *s_done = reinterpret_cast<uint32_t *>(ctl + 192);         // [kMaxStages] warps finished
     uint32_t *s_tflag = reinterpret_cast<uint32_t *>(ctl + 224);        // [kMaxStages] flagged slices of the tile
     uint32_t *s_ncand = reinterpret_cast<uint32_t *>(ctl + 256);        // [kMaxStages] candidates (or kCandOverflow)
     uint16_t *s_cand = reinterpret_cast<uint16_t *>(ctl + 512);         // [kMaxStages][kCandPerTile]
@@ -239,8 +237,6 @@ __global__ void __launch_bounds__(kThreads, 1) pfac_scan_kernel(const ScanParams
         for (uint32_t s = 0; s < n_stages; s++) {
             mbar_init(&s_full[s], 1);
             mbar_init(&s_empty[s], kConsumerWarps);
-            s_ticket[s] = 0;
-            s_done[s] = 0;
             s_tflag[s] = 0;
             s_ncand[s] = 0;
         }
@@ -250,15 +246,37 @@ __global__ void __launch_bounds__(kThreads, 1) pfac_scan_kernel(const ScanParams
 
     if (warp == kConsumerWarps) {
         // ------------------------------------------------------------------ producer
+        // Streams tiles into the ring and, once every consumer warp has released a stage, publishes
+        // that tile's result (flag mask, candidate list) before the stage is refilled.
         if (lane == 0) {
             const uint64_t policy = policy_evict_first();
+            uint32_t held[kMaxStages];   // tile held by each stage (0xFFFFFFFF: none)
+            for (int i = 0; i < kMaxStages; i++) held[i] = 0xFFFFFFFFu;
+            auto publish = [&](uint32_t st, uint32_t tile) {
+                const uint32_t flags = s_tflag[st];
+                uint32_t nc = s_ncand[st];
+                if (nc > (uint32_t)kCandPerTile) nc = kCandOverflow;   // too many (or the overflow bit is set)
+                p.tile_cnt[tile] = flags ? nc : 0u;
+                p.tile_mask[tile] = flags;
+                if (flags) {
+                    p.flagged[atomicAdd(&p.ctrl->n_flagged, 1u)] = tile;
+                    if (nc != kCandOverflow)
+                        for (uint32_t i = 0; i < nc; i++) p.cand[(size_t)tile * kCandPerTile + i] = s_cand[st * kCandPerTile + i];
+                    s_tflag[st] = 0;
+                    s_ncand[st] = 0;
+                }
+            };
             uint32_t s = 0, round = 0;
             uint32_t t = atomicAdd(&p.ctrl->ticket, 1u);
+            bool ok = true;
             while (true) {
                 // the next ticket is claimed before this stage is waited for: its latency hides there
                 const uint32_t t_next = t < p.n_tiles ? atomicAdd(&p.ctrl->ticket, 1u) : t;
-                if (round)
-                    if (!mbar_wait(&s_empty[s], (round - 1) & 1u, &p.ctrl->error_flag, 3u)) break;
+                if (held[s] != 0xFFFFFFFFu) {
+                    if (!mbar_wait(&s_empty[s], (round - 1) & 1u, &p.ctrl->error_flag, 3u)) { ok = false; break; }
+                    publish(s, held[s]);
+                    held[s] = 0xFFFFFFFFu;
+                }
                 s_tile[s] = t;
                 if (t >= p.n_tiles) {   // sentinel: consumers leave when they see it
                     mbar_arrive(&s_full[s]);
@@ -275,17 +293,28 @@ __global__ void __launch_bounds__(kThreads, 1) pfac_scan_kernel(const ScanParams
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 mbar_expect_tx(&s_full[s], nb16);
                 if (nb16) bulk_g2s(buf, p.in_al + a0, nb16, &s_full[s], policy);
+                held[s] = t;
                 t = t_next;
                 if (++s == n_stages) { s = 0; round++; }
+            }
+            // drain: the tiles still in the ring were filled in this round (stages < s) or the previous one
+            for (uint32_t k = 1; ok && k < n_stages; k++) {
+                const uint32_t st = (s + n_stages - k) % n_stages;
+                if (held[st] == 0xFFFFFFFFu) continue;
+                const uint32_t fill_round = st < s ? round : round - 1;
+                if (!mbar_wait(&s_empty[st], fill_round & 1u, &p.ctrl->error_flag, 4u)) break;
+                publish(st, held[st]);
             }
         }
         return;
     }
 
     // ---------------------------------------------------------------------- consumers
-    uint16_t *wq = reinterpret_cast<uint16_t *>(qbase + warp * kQueueBytes);   // stage-1 survivors of one slice
+    uint16_t *wq = reinterpret_cast<uint16_t *>(qbase + warp * kQueueBytes);   // stage-1 survivors of the slice
     uint32_t *wq2 = reinterpret_cast<uint32_t *>(wq + kSlice);                  // stage-2a survivors: tpos | m1 << 16
     const uint32_t lt_mask = (1u << lane) - 1u;
+    const uint32_t slice = (uint32_t)warp;   // this warp's slice of every tile
+    const uint32_t off = slice * kSlice + lane * 16;
 
     uint32_t s = 0, round = 0;
     for (;; s = (s + 1 == n_stages) ? 0 : s + 1, round += (s == 0) ? 1u : 0u) {
@@ -294,26 +323,18 @@ __global__ void __launch_bounds__(kThreads, 1) pfac_scan_kernel(const ScanParams
         if (tile >= p.n_tiles) break;
         const uint8_t *buf = s_in + s * stride;
         const uint32_t a0 = tile * (uint32_t)kTile;
-        const bool edge = (a0 < p.mis) || (a0 + (uint32_t)kTile > p.a_start_end);
-        uint32_t tile_starts = p.a_start_end - a0;
-        if (tile_starts > (uint32_t)kTile) tile_starts = kTile;
-        const uint32_t n_slices = (tile_starts + kSlice - 1) / kSlice;
         const uint32_t valid_t = p.a_valid_end - a0;   // tile-relative end of readable input (may exceed the buffer)
-        // an interior tile: no start of it can reach the end of the input or a reference walk bound
-        const bool interior = !p.use_ref_bound && valid_t >= (uint32_t)kTile + p.max_pat_len;
-        uint32_t my_flags = 0;
-
-        while (true) {
-            uint32_t slice = 0;
-            if (lane == 0) slice = atomicAdd(&s_ticket[s], 1u);
-            slice = __shfl_sync(0xffffffffu, slice, 0);
-            if (slice >= n_slices) break;
+        // an interior tile: every start of it is a start position and none can reach the end of the
+        // input or a reference walk bound
+        const bool interior = !p.use_ref_bound && a0 >= p.mis && valid_t >= (uint32_t)kTile + p.max_pat_len &&
+                              a0 + (uint32_t)kTile <= p.a_start_end;
+        bool any = false;
+        if (a0 + slice * kSlice < p.a_start_end) {   // the slice holds start positions
             // stage 1: T1 over 16 positions per lane, compaction into the warp queue
-            const uint32_t off = slice * kSlice + lane * 16;
             const uint4 v = *reinterpret_cast<const uint4 *>(buf + off);
             const uint32_t nx = *reinterpret_cast<const uint32_t *>(buf + off + 16);
             uint32_t mask = (p.debug & 4u) ? 0u : filter16(v, nx);
-            if (edge) {   // start positions are [mis, a_start_end) in aligned coordinates
+            if (!interior) {   // start positions are [mis, a_start_end) in aligned coordinates
                 const uint32_t a = a0 + off;
                 const uint32_t lo = p.mis > a ? p.mis - a : 0u;
                 const uint32_t hi = p.a_start_end > a ? p.a_start_end - a : 0u;
@@ -336,8 +357,7 @@ __global__ void __launch_bounds__(kThreads, 1) pfac_scan_kernel(const ScanParams
             }
             __syncwarp();
             // stage 2a: the 4-byte prefix (complete Tm, or T2).  What survives is queued with its m1;
-            // starts that cannot be judged here (short patterns, end of the input) flag the slice.
-            bool any = false;
+            // starts that cannot be judged here (short patterns, end of the input) are candidates.
             uint32_t n2 = 0;
             for (uint32_t e0 = 0; e0 < nq; e0 += 32) {
                 const uint32_t e = e0 + lane;
@@ -419,32 +439,12 @@ __global__ void __launch_bounds__(kThreads, 1) pfac_scan_kernel(const ScanParams
                     add_candidate(s_ncand + s, s_cand + s * kCandPerTile, tpos);
                 }
             }
-            if (__any_sync(0xffffffffu, any)) my_flags |= 1u << slice;
         }
-
-        // ---- this warp is done with the tile; the last one publishes the tile's flags
+        // ---- done with the tile: flag the slice if any start survived, release the stage
+        any = __any_sync(0xffffffffu, any);
         if (lane == 0) {
-            if (my_flags) atomicOr(&s_tflag[s], my_flags);
-            __threadfence_block();
-            if (atomicAdd(&s_done[s], 1u) == (uint32_t)kConsumerWarps - 1u) {
-                __threadfence_block();
-                const uint32_t flags = s_tflag[s];
-                uint32_t nc = s_ncand[s];
-                if (nc > (uint32_t)kCandPerTile) nc = kCandOverflow;   // too many (or the overflow bit is set)
-                p.tile_cnt[tile] = flags ? nc : 0u;
-                p.tile_mask[tile] = flags;
-                if (flags) {
-                    p.flagged[atomicAdd(&p.ctrl->n_flagged, 1u)] = tile;
-                    if (nc != kCandOverflow)
-                        for (uint32_t i = 0; i < nc; i++) p.cand[(size_t)tile * kCandPerTile + i] = s_cand[s * kCandPerTile + i];
-                }
-                s_tflag[s] = 0;
-                s_ncand[s] = 0;
-                s_done[s] = 0;
-                s_ticket[s] = 0;
-                __threadfence_block();
-            }
-            mbar_arrive(&s_empty[s]);
+            if (any) atomicOr(&s_tflag[s], 1u << slice);
+            mbar_arrive(&s_empty[s]);   // release: orders the shared-memory updates above before the producer's reads
         }
     }
 }
