@@ -151,7 +151,6 @@ void derive_tables(const Partition &P, uint32_t t2_bytes, uint32_t t3_bytes, uin
 
     // ---- T1 / T1s over the first two bytes, the list of 4-byte prefixes, T2
     std::vector<uint8_t> t1(65536, 0);
-    std::vector<uint32_t> t1s(2048, 0);
     uint32_t t2_bits = pow2_bits_for_bytes(t2_bytes);
     std::vector<uint32_t> t2(t2_bits / 32, 0);
     const uint32_t t2_shift = t2_bits ? 32u - log2u(t2_bits) : 32u;
@@ -162,37 +161,32 @@ void derive_tables(const Partition &P, uint32_t t2_bytes, uint32_t t3_bytes, uin
         if (s1 < 0) continue;
         if (g.is_final(s1)) {   // a 1-byte pattern: every pair starting with b0 reports a match
             any_short = true;
-            for (int b1 = 0; b1 < kCharSet; b1++) {
-                t1[rot2((uint32_t)b0) | (rot2((uint32_t)b1) << 8)] = 1;
-                const uint32_t pair = (uint32_t)b0 | ((uint32_t)b1 << 8);
-                t1s[pair >> 5] |= 1u << (pair & 31);
-            }
+            for (int b1 = 0; b1 < kCharSet; b1++) t1[t1_index((uint32_t)b0, (uint32_t)b1)] |= kT1P01 | kT1Short;
         }
         for (uint32_t e1 = g.begin(s1); e1 < g.end(s1); e1++) {
             const int32_t b1 = g.edges[e1].byte, s2 = g.edges[e1].next;
             const uint32_t pair = (uint32_t)b0 | ((uint32_t)b1 << 8);
-            t1[rot2((uint32_t)b0) | (rot2((uint32_t)b1) << 8)] = 1;
+            t1[t1_index((uint32_t)b0, (uint32_t)b1)] |= kT1P01;
             bool shortp = g.is_final(s2);
             for (uint32_t e2 = g.begin(s2); e2 < g.end(s2); e2++) {
                 const int32_t b2 = g.edges[e2].byte, s3 = g.edges[e2].next;
                 if (g.is_final(s3)) shortp = true;
-                if (too_many) continue;
+                t1[t1_index((uint32_t)b1, (uint32_t)b2)] |= kT1P12;
                 for (uint32_t e3 = g.begin(s3); e3 < g.end(s3); e3++) {
+                    t1[t1_index((uint32_t)b2, (uint32_t)g.edges[e3].byte)] |= kT1P23;
+                    if (too_many) continue;
                     const uint32_t w = pair | ((uint32_t)b2 << 16) | ((uint32_t)g.edges[e3].byte << 24);
                     if (t2_bits) {
                         const uint32_t h = (w * kHash4Mul) >> t2_shift;
                         t2[h >> 5] |= 1u << (h & 31);
                     }
                     prefix4.push_back({w, g.edges[e3].next});
-                    if (prefix4.size() > kPathLimit) {
-                        too_many = true;
-                        break;
-                    }
+                    if (prefix4.size() > kPathLimit) too_many = true;
                 }
             }
             if (shortp) {
                 any_short = true;
-                t1s[pair >> 5] |= 1u << (pair & 31);
+                t1[t1_index((uint32_t)b0, (uint32_t)b1)] |= kT1Short;
             }
         }
     }
@@ -342,8 +336,6 @@ void derive_tables(const Partition &P, uint32_t t2_bytes, uint32_t t3_bytes, uin
     uint32_t off = 0;
     out.off_t1 = off;
     off = align128(off + 65536);
-    out.off_t1s = off;
-    if (any_short) off = align128(off + 8192);
     out.off_t2 = off;
     off = align128(off + t2_bits / 8);
     out.off_tm = off;
@@ -354,7 +346,6 @@ void derive_tables(const Partition &P, uint32_t t2_bytes, uint32_t t3_bytes, uin
     off = align128(off + t3_bits / 8);
     out.image.assign(off, 0);
     memcpy(out.image.data() + out.off_t1, t1.data(), 65536);
-    if (any_short) memcpy(out.image.data() + out.off_t1s, t1s.data(), 8192);
     if (t2_bits) memcpy(out.image.data() + out.off_t2, t2.data(), t2_bits / 8);
     if (t3_bits) {
         memcpy(out.image.data() + out.off_tm, tm.data(), kTm1Slots * 2);
@@ -364,12 +355,24 @@ void derive_tables(const Partition &P, uint32_t t2_bytes, uint32_t t3_bytes, uin
         for (uint16_t e : tm) out.tm_set += e ? 1u : 0u;
         for (uint16_t e : tm2) out.tm2_set += e ? 1u : 0u;
     }
-    for (uint8_t b : t1) out.t1_set += b;
+    for (uint8_t b : t1) out.t1_set += b & kT1P01;
     if (t2_bits)
         for (uint32_t w : t2) out.t2_set += (uint32_t)__builtin_popcount(w);
 }
 
 namespace {
+
+// The detector's stage 1 on the bytes t[0, len) (bytes past len read as 0, like stale shared memory
+// may read as anything): P01 of the first pair, and either the short plane or P12 and P23 further on.
+bool stage1_pass(const Derived &d, const uint8_t *t, size_t len)
+{
+    const uint8_t *t1 = d.image.data() + d.off_t1;
+    auto at = [&](size_t i) { return i < len ? (uint32_t)t[i] : 0u; };
+    const uint32_t v0 = t1[t1_index(at(0), at(1))];
+    if (!(v0 & kT1P01)) return false;
+    if (v0 & kT1Short) return true;
+    return (t1[t1_index(at(1), at(2))] & kT1P12) && (t1[t1_index(at(2), at(3))] & kT1P23);
+}
 
 // The detector's stage 2 on the bytes t[0, len): may a pattern start here?  (stage 1 = T1 passed)
 // `stage` (optional) receives how far the start got: 1 bypass, 2 T2/Tm pass, 3 level-1 window pass,
@@ -377,7 +380,7 @@ namespace {
 bool stage2_pass(const Derived &d, const uint8_t *t, size_t len, int *stage)
 {
     const uint8_t *img = d.image.data();
-    const uint32_t *t1s = reinterpret_cast<const uint32_t *>(img + d.off_t1s);
+    const uint8_t *t1 = img + d.off_t1;
     const uint32_t *t2 = reinterpret_cast<const uint32_t *>(img + d.off_t2);
     const uint16_t *tm = reinterpret_cast<const uint16_t *>(img + d.off_tm);
     const uint16_t *tm2 = reinterpret_cast<const uint16_t *>(img + d.off_tm2);
@@ -385,7 +388,7 @@ bool stage2_pass(const Derived &d, const uint8_t *t, size_t len, int *stage)
     if (stage) *stage = 1;
     if (len < 4) return true;   // fewer than 4 readable bytes: the emit kernel decides
     const uint32_t w4 = le32(t);
-    if (d.has_short && bit(t1s, w4 & 0xffffu)) return true;
+    if (d.has_short && (t1[t1_index(w4 & 255u, (w4 >> 8) & 255u)] & kT1Short)) return true;
     if (!d.has_t3) {
         if (d.t2_shift < 32 && !bit(t2, (w4 * kHash4Mul) >> d.t2_shift)) return false;
         if (stage) *stage = 2;
@@ -410,15 +413,13 @@ bool stage2_pass(const Derived &d, const uint8_t *t, size_t len, int *stage)
 
 void derive_profile(const Partition &P, const Derived &d, const uint8_t *text, size_t n, uint64_t out[12])
 {
-    const uint8_t *t1 = d.image.data() + d.off_t1;
     for (int i = 0; i < 12; i++) out[i] = 0;
     const size_t maxlen = (size_t)std::max(P.max_len, 1);
     uint64_t slices = 0;
     size_t last_slice = (size_t)-1;
     for (size_t i = 0; i < n; i++) {
         out[0]++;
-        const uint32_t c0 = text[i], c1 = i + 1 < n ? text[i + 1] : 0;
-        if (!t1[rot2(c0) | (rot2(c1) << 8)]) continue;
+        if (!stage1_pass(d, text + i, n - i)) continue;
         out[1]++;   // stage 1 survivors
         int stage = 0;
         const bool pass = stage2_pass(d, text + i, std::min(n - i, maxlen), &stage);
@@ -442,22 +443,21 @@ int derive_selfcheck(const Partition &P, const Derived &d)
     if (d.image.empty()) return 100;
     const uint8_t *img = d.image.data();
     const uint8_t *t1 = img + d.off_t1;
-    const uint32_t *t1s = reinterpret_cast<const uint32_t *>(img + d.off_t1s);
     auto is_final = [&](int32_t s) { return s >= 0 && s < P.n_final; };
     // T1 is exact over the first two bytes; T1s covers every pair that can end a pattern of <= 3 bytes
     for (int b0 = 0; b0 < kCharSet; b0++) {
         const int32_t s1 = P.s0.empty() ? -1 : P.s0[(size_t)b0];
         for (int b1 = 0; b1 < kCharSet; b1++) {
             const int32_t s2 = s1 < 0 ? -1 : P.lookup(s1, b1);
-            const uint32_t pair = (uint32_t)b0 | ((uint32_t)b1 << 8);
-            const bool pass = t1[rot2((uint32_t)b0) | (rot2((uint32_t)b1) << 8)] != 0;
+            const uint32_t v = t1[t1_index((uint32_t)b0, (uint32_t)b1)];
+            const bool pass = (v & kT1P01) != 0;
             const bool want = s1 >= 0 && (is_final(s1) || s2 >= 0);
             if (want != pass) return want ? 3 : 4;
             if (!want) continue;
             bool shortp = is_final(s1) || is_final(s2);
             if (s2 >= 0 && !shortp)
                 for (int b2 = 0; b2 < kCharSet && !shortp; b2++) shortp = is_final(P.lookup(s2, b2));
-            if (shortp && !(d.has_short && bit(t1s, pair))) return 7;
+            if (shortp && !(d.has_short && (v & kT1Short))) return 7;
         }
     }
     // stage 2 must pass every pattern: run it over each pattern's own bytes (strings of the
@@ -489,6 +489,7 @@ int derive_selfcheck(const Partition &P, const Derived &d)
         for (int32_t x = f; x >= 0; x = par[(size_t)x]) str.push_back(pbyte[(size_t)x]);
         std::reverse(str.begin(), str.end());
         int stage = 0;
+        if (!stage1_pass(d, str.data(), str.size())) return 8;
         if (!stage2_pass(d, str.data(), str.size(), &stage)) return 10 + stage;
     }
     return 0;

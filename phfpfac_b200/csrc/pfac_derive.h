@@ -6,12 +6,16 @@
 // derived here is the shared-memory image of the DETECTOR kernel: prefix filters computed from the
 // first rows of the PHF.  Every one of them is a superset test -- it may pass a start position
 // that cannot match, it never rejects one that can:
-//   T1    65,536 x u8 : byte 1 iff a walk that starts with bytes (c0,c1) matches a 1-byte pattern
-//                       or has a second edge  (root fan-out, s0Table of main.cc:200, folded in).
+//   T1    65,536 x u8 : four bit-planes per 2-byte window (x,y), one LDS.U8 per start position:
+//                         P01   a walk starting with (x,y) matches a 1-byte pattern or has a second
+//                               edge (root fan-out, s0Table of main.cc:200, folded in) -- exact
+//                         P12   (x,y) are bytes 1-2 of some path of the automaton
+//                         P23   (x,y) are bytes 2-3 of some path
+//                         Short (x,y) as bytes 0-1 can complete a pattern of <= 3 bytes
+//                       a start at i passes stage 1 iff P01(i) and (Short(i) or P12(i+1) and
+//                       P23(i+2)) -- the windows of the next two positions are looked up anyway.
 //                       Indexed with both bytes rotated left by 2 so that the low, high-entropy
 //                       bits of ASCII text select the shared-memory bank.
-//   T1s   65,536 bits : pair (c0,c1) can complete a pattern of length <= 3 (such starts skip the
-//                       4-byte checks below)
 //   Tm    8192 x u16  : COMPLETE cuckoo table (2 buckets x 2 tagged slots) of every 4-byte prefix
 //                       -> m1 = (at most) the shortest pattern length below it.  A miss rejects.
 //   Tm2   2^k x 2 u16 : same structure, (prefix, level-1 window) group -> m2
@@ -75,15 +79,17 @@ PFAC_HD inline uint32_t tm_lookup(const uint16_t *tab, uint32_t key, uint32_t bi
     if (((a >> 8) & 255u) == tag) m = a & 255u;
     return m;
 }
-// rotl2 of a byte (T1 index)
+// rotl2 of a byte; T1 index of the window (c0, c1); T1 bit-planes
 PFAC_HD inline uint32_t rot2(uint32_t c) { return ((c << 2) | (c >> 6)) & 0xFFu; }
+PFAC_HD inline uint32_t t1_index(uint32_t c0, uint32_t c1) { return rot2(c0) | (rot2(c1) << 8); }
+constexpr uint8_t kT1P01 = 1, kT1P12 = 2, kT1P23 = 4, kT1Short = 8;
 
 struct Derived {
     // shared-memory image, copied verbatim by the detector kernel (sections 128-byte aligned)
     std::vector<uint8_t> image;
-    uint32_t off_t1 = 0, off_t2 = 0, off_t1s = 0, off_tm = 0, off_tm2 = 0, off_t3 = 0;
+    uint32_t off_t1 = 0, off_t2 = 0, off_tm = 0, off_tm2 = 0, off_t3 = 0;
     uint32_t t2_shift = 32;      // index = (w * kHash4Mul) >> t2_shift   (32: no T2)
-    uint32_t has_short = 0;      // patterns of length <= 3 exist (T1s present)
+    uint32_t has_short = 0;      // patterns of length <= 3 exist (T1's Short plane is not empty)
     uint32_t has_t3 = 0;         // Tm + T3 present (then no T2)
     uint32_t t3_shift = 32;
     uint32_t tm2_bits = 0;       // log2 buckets of Tm2 (0: no level 2)

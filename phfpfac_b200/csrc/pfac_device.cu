@@ -190,7 +190,6 @@ int launch_scan(pfac_ctx *ctx, Slot &slot, const void *d_in, uint64_t n_starts, 
     p.base_pos = base_pos;
     p.image = ctx->d_image;
     p.image_bytes = ctx->image_bytes;
-    p.off_t1s = ctx->dv.off_t1s;
     p.off_t2 = ctx->dv.off_t2;
     p.off_tm = ctx->dv.off_tm;
     p.off_tm2 = ctx->dv.off_tm2;

@@ -53,7 +53,7 @@ struct ScanParams {
     uint64_t base_pos;        // global position of the first start position
     // shared-memory image (pfac_derive.h)
     const uint4 *image;
-    uint32_t image_bytes, off_t1s, off_t2, off_tm, off_tm2, off_t3;
+    uint32_t image_bytes, off_t2, off_tm, off_tm2, off_t3;
     uint32_t t2_shift, has_short, has_t3, t3_shift, tm2_bits;
     uint32_t n_stages;                // depth of the input ring (as many as shared memory holds)
     // output
@@ -163,24 +163,36 @@ __device__ __forceinline__ uint32_t rot2x4(uint32_t w)
 // are LDS.U8 [index + constant] with no address arithmetic.
 extern __shared__ __align__(128) uint8_t smem[];
 
-// 16 start positions per lane: bit i of the result is set iff T1 passes the 2-byte window at byte i
-__device__ __forceinline__ uint32_t filter16(const uint4 v, const uint32_t nx)
+// 16 start positions per lane.  T1 holds four bit-planes per 2-byte window (pfac_derive.h); the
+// result has one nibble per position, bit 0 of nibble j set iff start j passes stage 1:
+//     P01(j) and (Short(j) or (P12(j+1) and P23(j+2)))
+// lo = positions 0..7, hi = positions 8..15.  18 windows are looked up (16 + the two after them).
+__device__ __forceinline__ void filter16(const uint4 v, const uint32_t nx, uint32_t &lo, uint32_t &hi)
 {
     const uint8_t *t1 = smem;
     const uint32_t w[5] = {rot2x4(v.x), rot2x4(v.y), rot2x4(v.z), rot2x4(v.w), rot2x4(nx)};
-    uint32_t mask = 0;
+    uint32_t acc[2] = {0u, 0u};
 #pragma unroll
     for (int k = 0; k < 4; k++) {
         const uint32_t i0 = w[k] & 0xffffu;
         const uint32_t i1 = __byte_perm(w[k], 0u, 0x4421);
         const uint32_t i2 = w[k] >> 16;
         const uint32_t i3 = __funnelshift_r(w[k], w[k + 1], 24) & 0xffffu;
-        mask += (uint32_t)t1[i0] << (4 * k);
-        mask += (uint32_t)t1[i1] << (4 * k + 1);
-        mask += (uint32_t)t1[i2] << (4 * k + 2);
-        mask += (uint32_t)t1[i3] << (4 * k + 3);
+        uint32_t &a = acc[k >> 1];
+        const int sh = (k & 1) * 16;
+        a += (uint32_t)t1[i0] << sh;
+        a += (uint32_t)t1[i1] << (sh + 4);
+        a += (uint32_t)t1[i2] << (sh + 8);
+        a += (uint32_t)t1[i3] << (sh + 12);
     }
-    return mask;
+    // windows 16 and 17 (their P12 / P23 planes belong to starts 14..15)
+    const uint32_t ex = (uint32_t)t1[w[4] & 0xffffu] | ((uint32_t)t1[__byte_perm(w[4], 0u, 0x4421)] << 4);
+    // plane bits: 1 = P01, 2 = P12, 4 = P23, 8 = Short.  Align P12 of j+1 (shift 4+1), P23 of j+2
+    // (shift 8+2) and Short of j (shift 3) with bit 0 of nibble j.
+    const uint32_t y_lo = __funnelshift_r(acc[0], acc[1], 5), y_hi = __funnelshift_r(acc[1], ex, 5);
+    const uint32_t z_lo = __funnelshift_r(acc[0], acc[1], 10), z_hi = __funnelshift_r(acc[1], ex, 10);
+    lo = acc[0] & ((y_lo & z_lo) | (acc[0] >> 3)) & 0x11111111u;
+    hi = acc[1] & ((y_hi & z_hi) | (acc[1] >> 3)) & 0x11111111u;
 }
 
 // tile-relative bound of what a start at tile-relative tpos may read (master_kernel.cu:141-144 + input end)
@@ -209,7 +221,6 @@ __device__ __forceinline__ void add_candidate(uint32_t *n, uint16_t *list, uint3
 
 __global__ void __launch_bounds__(kThreads, 1) pfac_scan_kernel(const ScanParams p)
 {
-    const uint32_t *s_t1s = reinterpret_cast<const uint32_t *>(smem + p.off_t1s);
     const uint32_t *s_t2 = reinterpret_cast<const uint32_t *>(smem + p.off_t2);
     const uint16_t *s_tm = reinterpret_cast<const uint16_t *>(smem + p.off_tm);
     const uint16_t *s_tm2 = reinterpret_cast<const uint16_t *>(smem + p.off_tm2);
@@ -333,27 +344,42 @@ __global__ void __launch_bounds__(kThreads, 1) pfac_scan_kernel(const ScanParams
             // stage 1: T1 over 16 positions per lane, compaction into the warp queue
             const uint4 v = *reinterpret_cast<const uint4 *>(buf + off);
             const uint32_t nx = *reinterpret_cast<const uint32_t *>(buf + off + 16);
-            uint32_t mask = (p.debug & 4u) ? 0u : filter16(v, nx);
+            uint32_t lo = 0, hi = 0;   // one nibble per start, bit 0 = passes stage 1
+            if (!(p.debug & 4u)) filter16(v, nx, lo, hi);
             if (!interior) {   // start positions are [mis, a_start_end) in aligned coordinates
                 const uint32_t a = a0 + off;
-                const uint32_t lo = p.mis > a ? p.mis - a : 0u;
-                const uint32_t hi = p.a_start_end > a ? p.a_start_end - a : 0u;
-                uint32_t keep = hi >= 16u ? 0xffffu : ((1u << hi) - 1u);
-                keep &= lo >= 16u ? 0u : (0xffffu << lo);
-                mask &= keep;
+                const uint32_t first = p.mis > a ? p.mis - a : 0u;
+                const uint32_t last = p.a_start_end > a ? p.a_start_end - a : 0u;
+                uint32_t keep = last >= 16u ? 0xffffu : ((1u << last) - 1u);
+                keep &= first >= 16u ? 0u : (0xffffu << first);
+                // spread the 16-bit keep mask to nibbles
+                uint32_t klo = 0, khi = 0;
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    klo |= ((keep >> j) & 1u) << (4 * j);
+                    khi |= ((keep >> (8 + j)) & 1u) << (4 * j);
+                }
+                lo &= klo;
+                hi &= khi;
             }
-            uint32_t incl = __popc(mask);
+            const uint32_t mine = __popc(lo) + __popc(hi);
+            uint32_t incl = mine;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
                 const uint32_t n = __shfl_up_sync(0xffffffffu, incl, o);
                 if (lane >= o) incl += n;
             }
-            uint32_t q = incl - __popc(mask);
+            uint32_t q = incl - mine;
             const uint32_t nq = __shfl_sync(0xffffffffu, incl, 31);
-            while (mask) {
-                const uint32_t bit = __ffs(mask) - 1;
-                wq[q++] = (uint16_t)(off + bit);
-                mask &= mask - 1;
+            while (lo) {
+                const uint32_t bit = __ffs(lo) - 1;
+                wq[q++] = (uint16_t)(off + (bit >> 2));
+                lo &= lo - 1;
+            }
+            while (hi) {
+                const uint32_t bit = __ffs(hi) - 1;
+                wq[q++] = (uint16_t)(off + 8 + (bit >> 2));
+                hi &= hi - 1;
             }
             __syncwarp();
             // stage 2a: the 4-byte prefix (complete Tm, or T2).  What survives is queued with its m1;
@@ -372,10 +398,7 @@ __global__ void __launch_bounds__(kThreads, 1) pfac_scan_kernel(const ScanParams
                         const uint32_t *wp = reinterpret_cast<const uint32_t *>(buf + (tpos & ~3u));
                         const uint32_t w4 = __funnelshift_r(wp[0], wp[1], (tpos & 3u) * 8u);
                         bool shortp = false;
-                        if (p.has_short) {
-                            const uint32_t pair = w4 & 0xffffu;
-                            shortp = (s_t1s[pair >> 5] >> (pair & 31u)) & 1u;
-                        }
+                        if (p.has_short) shortp = (smem[rot2x4(w4) & 0xffffu] & kT1Short) != 0;
                         if (shortp) {
                             any = true;
                             add_candidate(s_ncand + s, s_cand + s * kCandPerTile, tpos);
@@ -595,7 +618,7 @@ __global__ void __launch_bounds__(kEmitThreads) pfac_emit_kernel(const EmitParam
                 if (a < p.mis || a >= p.a_start_end) continue;
                 const uint32_t c0 = p.in_al[a], c1 = a + 1 < p.a_valid_end ? p.in_al[a + 1] : 0u;
                 const uint32_t r0 = ((c0 << 2) | (c0 >> 6)) & 0xffu, r1 = ((c1 << 2) | (c1 >> 6)) & 0xffu;
-                if (__ldg(&p.t1[r0 | (r1 << 8)])) cand |= 1u << j;
+                if (__ldg(&p.t1[r0 | (r1 << 8)]) & kT1P01) cand |= 1u << j;
             }
             uint32_t cnt = 0, hit = 0;
             for (uint32_t c = cand; c; c &= c - 1) {
