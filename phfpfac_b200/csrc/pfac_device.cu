@@ -332,7 +332,7 @@ int pfac_ctx_create(int device, const pfac_tables *t, int part, int n_streams, s
     // shared-memory budget: T1 and the per-warp queues are fixed; T3 / Tm2 / T2 shrink until at least
     // four ring stages fit
     const size_t smem_max = (size_t)prop.sharedMemPerBlockOptin;
-    uint32_t t2_bytes = 32768, t3_bytes = 16384, tm2_bytes = 32768;
+    uint32_t t2_bytes = 32768, t3_bytes = 32768, tm2_bytes = 32768;
     if (const char *v = getenv("PFAC_T2_BYTES")) t2_bytes = (uint32_t)atoi(v);
     if (const char *v = getenv("PFAC_T3_BYTES")) t3_bytes = (uint32_t)atoi(v);
     if (const char *v = getenv("PFAC_TM2_BYTES")) tm2_bytes = (uint32_t)atoi(v);

@@ -86,8 +86,9 @@ constexpr int kSlice = 512;           // start positions per warp step (32 lanes
 constexpr int kSlicesPerTile = kConsumerWarps;   // every consumer warp owns one slice of every tile
 constexpr int kTile = kSlicesPerTile * kSlice;   // 15,872 start positions per tile
 constexpr int kMaxStages = 8;
-constexpr int kQ2Cap = 64;                // per consumer warp: starts that passed the prefix check of stage 2
-constexpr int kQueueBytes = kSlice * 2 + kQ2Cap * 4;   // + u16 start positions that passed stage 1
+constexpr int kQ1Cap = 128;               // per consumer warp: starts of one slice that passed stage 1 (u16)
+constexpr int kQ2Cap = 64;                // ... and the prefix check of stage 2 (u32: tpos | m1 << 16)
+constexpr int kQueueBytes = kQ1Cap * 2 + kQ2Cap * 4;   // a slice with more survivors is handed over whole
 constexpr int kCtrlBytes = 1024;
 constexpr int kCandPerTile = 32;          // candidate starts the detector hands over per tile (more: whole slices)
 constexpr unsigned kCandOverflow = 0xFFFFFFFFu;
@@ -322,7 +323,7 @@ __global__ void __launch_bounds__(kThreads, 1) pfac_scan_kernel(const ScanParams
 
     // ---------------------------------------------------------------------- consumers
     uint16_t *wq = reinterpret_cast<uint16_t *>(qbase + warp * kQueueBytes);   // stage-1 survivors of the slice
-    uint32_t *wq2 = reinterpret_cast<uint32_t *>(wq + kSlice);                  // stage-2a survivors: tpos | m1 << 16
+    uint32_t *wq2 = reinterpret_cast<uint32_t *>(wq + kQ1Cap);                  // stage-2a survivors: tpos | m1 << 16
     const uint32_t lt_mask = (1u << lane) - 1u;
     const uint32_t slice = (uint32_t)warp;   // this warp's slice of every tile
     const uint32_t off = slice * kSlice + lane * 16;
@@ -370,7 +371,13 @@ __global__ void __launch_bounds__(kThreads, 1) pfac_scan_kernel(const ScanParams
                 if (lane >= o) incl += n;
             }
             uint32_t q = incl - mine;
-            const uint32_t nq = __shfl_sync(0xffffffffu, incl, 31);
+            uint32_t nq = __shfl_sync(0xffffffffu, incl, 31);
+            if (nq > (uint32_t)kQ1Cap) {   // dense slice: the emit kernel looks at all of it
+                any = true;
+                if (lane == 0) atomicOr(s_ncand + s, 0x80000000u);
+                nq = 0;
+                lo = hi = 0;
+            }
             while (lo) {
                 const uint32_t bit = __ffs(lo) - 1;
                 wq[q++] = (uint16_t)(off + (bit >> 2));
