@@ -204,7 +204,6 @@ int launch_scan(pfac_ctx *ctx, Slot &slot, const void *d_in, uint64_t n_starts, 
     if (e) return e;
     p.tile_cnt = slot.d_tile_cnt;
     p.tile_mask = slot.d_tile_mask;
-    p.flagged = slot.d_flagged;
     p.cand = slot.d_cand;
     p.ctrl = slot.d_ctrl;
     p.debug = ctx->debug;
@@ -243,7 +242,7 @@ int launch_scan(pfac_ctx *ctx, Slot &slot, const void *d_in, uint64_t n_starts, 
     ep.scratch_cap = slot.scratch_cap;
     ep.tile_cnt = slot.d_tile_cnt;
     ep.tile_mask = slot.d_tile_mask;
-    ep.flagged = slot.d_flagged;
+    ep.n_tiles = p.n_tiles;
     ep.cand = slot.d_cand;
     ep.slice_ent = slot.d_slice_ent;
     ep.ctrl = slot.d_ctrl;
@@ -502,7 +501,6 @@ int pfac_scan_device_sync(pfac_ctx *ctx, const void *d_in, uint64_t n_starts, ui
         ctx->info[3] = ctx->smem_bytes;
         ctx->info[4] = ctx->info[5] = 0;
         ctx->info[6] = 1;
-        ctx->info[7] = ctx->own.h_result->n_flagged;
         if (ctx->own.h_result->error_flag)
             return set_error(PFAC_ERR_INTERNAL, "device watchdog tripped (code %u)", ctx->own.h_result->error_flag);
         *count = ctx->own.h_result->count;

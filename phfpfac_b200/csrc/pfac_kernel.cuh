@@ -31,14 +31,13 @@ struct Ctrl {   // device-side control block; the finalize kernel resets it for 
     unsigned int ticket;
     unsigned int error_flag;
     unsigned long long alloc;   // records reserved in the arrival-order scratch
-    unsigned int n_flagged;     // tiles with at least one flagged slice
-    unsigned int pad;
+    unsigned int pad[2];
 };
 
 struct Result {   // written by the finalize kernel, copied to the host
     unsigned long long count;
     unsigned int error_flag;
-    unsigned int n_flagged;     // statistics
+    unsigned int pad;
 };
 
 struct ScanParams {
@@ -128,6 +127,8 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity)
     return ok != 0;
 }
 // returns false if the watchdog tripped (never expected)
+// SLEEP_NS > 0: back off between polls (the producer warp, which would otherwise burn issue slots)
+template <unsigned SLEEP_NS = 0>
 __device__ __forceinline__ bool mbar_wait(uint64_t *bar, uint32_t parity, unsigned int *error_flag, unsigned code)
 {
     unsigned spins = 0;
@@ -136,6 +137,7 @@ __device__ __forceinline__ bool mbar_wait(uint64_t *bar, uint32_t parity, unsign
             atomicExch(error_flag, code);
             return false;
         }
+        if (SLEEP_NS) __nanosleep(SLEEP_NS);
     }
     return true;
 }
@@ -271,7 +273,6 @@ __global__ void __launch_bounds__(kThreads, 1) pfac_scan_kernel(const ScanParams
                 p.tile_cnt[tile] = flags ? nc : 0u;
                 p.tile_mask[tile] = flags;
                 if (flags) {
-                    p.flagged[atomicAdd(&p.ctrl->n_flagged, 1u)] = tile;
                     if (nc != kCandOverflow)
                         for (uint32_t i = 0; i < nc; i++) p.cand[(size_t)tile * kCandPerTile + i] = s_cand[st * kCandPerTile + i];
                     s_tflag[st] = 0;
@@ -280,12 +281,13 @@ __global__ void __launch_bounds__(kThreads, 1) pfac_scan_kernel(const ScanParams
             };
             uint32_t s = 0, round = 0;
             uint32_t t = atomicAdd(&p.ctrl->ticket, 1u);
+            uint32_t t_next = t < p.n_tiles ? atomicAdd(&p.ctrl->ticket, 1u) : t;
             bool ok = true;
             while (true) {
-                // the next ticket is claimed before this stage is waited for: its latency hides there
-                const uint32_t t_next = t < p.n_tiles ? atomicAdd(&p.ctrl->ticket, 1u) : t;
+                // tickets are claimed two tiles ahead: the atomic's latency hides behind a whole tile
+                const uint32_t t_next2 = t_next < p.n_tiles ? atomicAdd(&p.ctrl->ticket, 1u) : t_next;
                 if (held[s] != 0xFFFFFFFFu) {
-                    if (!mbar_wait(&s_empty[s], (round - 1) & 1u, &p.ctrl->error_flag, 3u)) { ok = false; break; }
+                    if (!mbar_wait<200>(&s_empty[s], (round - 1) & 1u, &p.ctrl->error_flag, 3u)) { ok = false; break; }
                     publish(s, held[s]);
                     held[s] = 0xFFFFFFFFu;
                 }
@@ -307,6 +309,7 @@ __global__ void __launch_bounds__(kThreads, 1) pfac_scan_kernel(const ScanParams
                 if (nb16) bulk_g2s(buf, p.in_al + a0, nb16, &s_full[s], policy);
                 held[s] = t;
                 t = t_next;
+                t_next = t_next2;
                 if (++s == n_stages) { s = 0; round++; }
             }
             // drain: the tiles still in the ring were filled in this round (stages < s) or the previous one
@@ -314,7 +317,7 @@ __global__ void __launch_bounds__(kThreads, 1) pfac_scan_kernel(const ScanParams
                 const uint32_t st = (s + n_stages - k) % n_stages;
                 if (held[st] == 0xFFFFFFFFu) continue;
                 const uint32_t fill_round = st < s ? round : round - 1;
-                if (!mbar_wait(&s_empty[st], fill_round & 1u, &p.ctrl->error_flag, 4u)) break;
+                if (!mbar_wait<200>(&s_empty[st], fill_round & 1u, &p.ctrl->error_flag, 4u)) break;
                 publish(st, held[st]);
             }
         }
@@ -363,30 +366,26 @@ __global__ void __launch_bounds__(kThreads, 1) pfac_scan_kernel(const ScanParams
                 lo &= klo;
                 hi &= khi;
             }
-            const uint32_t mine = __popc(lo) + __popc(hi);
-            uint32_t incl = mine;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const uint32_t n = __shfl_up_sync(0xffffffffu, incl, o);
-                if (lane >= o) incl += n;
+            // compaction into the warp queue: every round, each lane that still has survivors hands over
+            // its lowest one (rank by ballot).  Few lanes have any, so this beats a prefix scan; the
+            // order of the queue does not matter (the emit kernel sorts the few candidates).
+            uint32_t nq = 0;
+            while (true) {
+                const uint32_t bal = __ballot_sync(0xffffffffu, (lo | hi) != 0u);
+                if (!bal) break;
+                if (lo | hi) {
+                    uint32_t pos;
+                    if (lo) { pos = (__ffs(lo) - 1) >> 2; lo &= lo - 1; }
+                    else { pos = 8 + ((__ffs(hi) - 1) >> 2); hi &= hi - 1; }
+                    const uint32_t idx = nq + __popc(bal & lt_mask);
+                    if (idx < (uint32_t)kQ1Cap) wq[idx] = (uint16_t)(off + pos);
+                }
+                nq += __popc(bal);
             }
-            uint32_t q = incl - mine;
-            uint32_t nq = __shfl_sync(0xffffffffu, incl, 31);
             if (nq > (uint32_t)kQ1Cap) {   // dense slice: the emit kernel looks at all of it
                 any = true;
                 if (lane == 0) atomicOr(s_ncand + s, 0x80000000u);
                 nq = 0;
-                lo = hi = 0;
-            }
-            while (lo) {
-                const uint32_t bit = __ffs(lo) - 1;
-                wq[q++] = (uint16_t)(off + (bit >> 2));
-                lo &= lo - 1;
-            }
-            while (hi) {
-                const uint32_t bit = __ffs(hi) - 1;
-                wq[q++] = (uint16_t)(off + 8 + (bit >> 2));
-                hi &= hi - 1;
             }
             __syncwarp();
             // stage 2a: the 4-byte prefix (complete Tm, or T2).  What survives is queued with its m1;
@@ -500,7 +499,7 @@ struct EmitParams {
     uint2 *scratch;
     unsigned long long scratch_cap;
     unsigned int *tile_cnt, *tile_mask;
-    const unsigned int *flagged;
+    uint32_t n_tiles;
     const uint16_t *cand;
     uint4 *slice_ent;
     Ctrl *ctrl;
@@ -543,11 +542,11 @@ __global__ void __launch_bounds__(kEmitThreads) pfac_emit_kernel(const EmitParam
 {
     const int lane = threadIdx.x & 31;
     const uint32_t warps_total = gridDim.x * (kEmitThreads / 32);
-    const uint32_t n_flagged = p.ctrl->n_flagged;
-    for (uint32_t i = blockIdx.x * (kEmitThreads / 32) + (threadIdx.x >> 5); i < n_flagged; i += warps_total) {
-        const uint32_t tile = p.flagged[i];
+    // tiles are dealt round-robin to the warps of the grid; only flagged tiles cost anything
+    for (uint32_t tile = blockIdx.x * (kEmitThreads / 32) + (threadIdx.x >> 5); tile < p.n_tiles; tile += warps_total) {
+      uint32_t m = p.tile_mask[tile], out_mask = 0, tile_total = 0;
+      if (m) {
         const uint32_t a0 = tile * (uint32_t)kTile;
-        uint32_t m = p.tile_mask[tile], out_mask = 0, tile_total = 0;
         auto limit = [&](uint32_t a) {
             uint32_t lim_a = p.a_valid_end;
             if (p.use_ref_bound) {   // reference tiles: 4096 bytes of global positions + 512-byte halo
@@ -659,6 +658,7 @@ __global__ void __launch_bounds__(kEmitThreads) pfac_emit_kernel(const EmitParam
             p.tile_cnt[tile] = tile_total;
             p.tile_mask[tile] = out_mask;
         }
+      }
     }
 }
 
@@ -730,12 +730,11 @@ __global__ void __launch_bounds__(kFinThreads) pfac_finalize_kernel(const Finali
     if (tid == 0 && lo < hi && hi == f.n_tiles) {   // the CTA whose range ends the input owns the total
         f.result->count = s_run;
         f.result->error_flag = f.ctrl->error_flag;
-        f.result->n_flagged = f.ctrl->n_flagged;
         if (f.count_out) *f.count_out = s_run;
         f.ctrl->ticket = 0;
         f.ctrl->error_flag = 0;
         f.ctrl->alloc = 0;
-        f.ctrl->n_flagged = 0;
+
     }
 }
 
