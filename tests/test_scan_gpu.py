@@ -164,6 +164,29 @@ def test_dense_matches_and_capacity_overflow():
     m.close()
 
 
+@pytest.mark.parametrize("n_plants", [1, 31, 32, 33, 40, 200, 3000])
+def test_candidate_list_boundaries(n_plants):
+    """The detector hands a tile's surviving starts to the emit kernel as a list of at most 32
+    candidates; beyond that (or when a slice has too many stage-1 survivors) whole slices are handed
+    over.  Plant 1..3000 matches inside one 15,872-byte tile and across its borders."""
+    torch = torch_cuda()
+    pats = pf.synth_patterns(1, 3000, 3, 4, 64)
+    lines = pats.split(b"\n")[:-1]
+    n = 100000
+    rng = np.random.default_rng(n_plants)
+    text = rng.integers(0, 256, n).astype(np.uint8)
+    text[text == 10] = 11
+    base = 15872 * 2 - 300          # straddles the border of tiles 1 and 2
+    at = base
+    for i in range(n_plants):
+        p = lines[int(rng.integers(0, len(lines)))]
+        if at + len(p) + 2 >= n:
+            break
+        text[at:at + len(p)] = np.frombuffer(p, dtype=np.uint8)
+        at += len(p) + int(rng.integers(0, 3))
+    check_both_paths(pats, text, n_streams=2, chunk_bytes=65536, oracle_parts=4)
+
+
 def test_long_patterns_reference_tile_bound():
     """Patterns longer than 513 bytes: the reference cuts a walk at its 4096-byte tile + 512-byte
     halo (master_kernel.cu:141-144); positions are global (base_pos)."""
