@@ -6,7 +6,7 @@ HOSTCXX := g++
 ARCH := -gencode arch=compute_100a,code=sm_100a
 B := phfpfac_b200/_build
 SRC := phfpfac_b200/csrc
-NVFLAGS := $(ARCH) -lineinfo -O3 -std=c++17 -ccbin $(HOSTCXX) -Iinclude -I$(SRC) \
+NVFLAGS := $(EXTRA) $(ARCH) -lineinfo -O3 -std=c++17 -ccbin $(HOSTCXX) -Iinclude -I$(SRC) \
            -Xcompiler -fPIC,-Wall,-Wextra,-pthread -Xptxas -v
 HOST_SRCS := $(SRC)/pfac_tables.cc $(SRC)/pfac_writer.cc $(SRC)/pfac_job.cc $(SRC)/pfac_synth.cc $(SRC)/pfac_derive.cc
 CUDA_SRCS := $(SRC)/pfac_device.cu

@@ -80,7 +80,11 @@ PFAC_HD inline uint32_t tm_lookup(const uint16_t *tab, uint32_t key, uint32_t bi
     return m;
 }
 // rotl2 of a byte; T1 index of the window (c0, c1); T1 bit-planes
+#ifndef PFAC_NO_ROT2
 PFAC_HD inline uint32_t rot2(uint32_t c) { return ((c << 2) | (c >> 6)) & 0xFFu; }
+#else
+PFAC_HD inline uint32_t rot2(uint32_t c) { return c; }
+#endif
 PFAC_HD inline uint32_t t1_index(uint32_t c0, uint32_t c1) { return rot2(c0) | (rot2(c1) << 8); }
 constexpr uint8_t kT1P01 = 1, kT1P12 = 2, kT1P23 = 4, kT1Short = 8;
 

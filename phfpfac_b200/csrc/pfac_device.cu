@@ -31,7 +31,8 @@ struct Slot {
     Ctrl *d_ctrl = nullptr;
     Result *d_result = nullptr;
     Result *h_result = nullptr;   // pinned
-    unsigned int *d_tile_cnt = nullptr, *d_tile_mask = nullptr, *d_flagged = nullptr;
+    unsigned long long *d_partial = nullptr;   // [kMaxParts] matches per tile range (emit -> finalize)
+    unsigned int *d_tile_cnt = nullptr, *d_tile_mask = nullptr, *d_tile_nc = nullptr;
     uint16_t *d_cand = nullptr;
     uint4 *d_slice_ent = nullptr;
     size_t tile_cap = 0;
@@ -102,6 +103,7 @@ int slot_init(Slot &s)
     CU_TRY(cudaMalloc(&s.d_ctrl, sizeof(Ctrl)));
     CU_TRY(cudaMemset(s.d_ctrl, 0, sizeof(Ctrl)));
     CU_TRY(cudaMalloc(&s.d_result, sizeof(Result)));
+    CU_TRY(cudaMalloc(&s.d_partial, kMaxParts * sizeof(unsigned long long)));
     CU_TRY(cudaHostAlloc(&s.h_result, sizeof(Result), cudaHostAllocPortable));
     return PFAC_OK;
 }
@@ -110,10 +112,11 @@ void slot_free(Slot &s)
 {
     if (s.d_ctrl) cudaFree(s.d_ctrl);
     if (s.d_result) cudaFree(s.d_result);
+    if (s.d_partial) cudaFree(s.d_partial);
     if (s.h_result) cudaFreeHost(s.h_result);
     if (s.d_tile_cnt) cudaFree(s.d_tile_cnt);
     if (s.d_tile_mask) cudaFree(s.d_tile_mask);
-    if (s.d_flagged) cudaFree(s.d_flagged);
+    if (s.d_tile_nc) cudaFree(s.d_tile_nc);
     if (s.d_cand) cudaFree(s.d_cand);
     if (s.d_slice_ent) cudaFree(s.d_slice_ent);
     if (s.d_scratch) cudaFree(s.d_scratch);
@@ -128,17 +131,17 @@ int slot_reserve(Slot &s, size_t n_tiles, size_t records, cudaStream_t stream)
         CU_TRY(cudaStreamSynchronize(stream));
         if (s.d_tile_cnt) cudaFree(s.d_tile_cnt);
         if (s.d_tile_mask) cudaFree(s.d_tile_mask);
-        if (s.d_flagged) cudaFree(s.d_flagged);
+        if (s.d_tile_nc) cudaFree(s.d_tile_nc);
         if (s.d_cand) cudaFree(s.d_cand);
         if (s.d_slice_ent) cudaFree(s.d_slice_ent);
-        s.d_tile_cnt = s.d_tile_mask = s.d_flagged = nullptr;
+        s.d_tile_cnt = s.d_tile_mask = s.d_tile_nc = nullptr;
         s.d_cand = nullptr;
         s.d_slice_ent = nullptr;
         s.tile_cap = 0;
         const size_t n = std::max<size_t>(n_tiles, 1024);
         CU_TRY(cudaMalloc(&s.d_tile_cnt, n * sizeof(unsigned int)));
         CU_TRY(cudaMalloc(&s.d_tile_mask, n * sizeof(unsigned int)));
-        CU_TRY(cudaMalloc(&s.d_flagged, n * sizeof(unsigned int)));
+        CU_TRY(cudaMalloc(&s.d_tile_nc, n * sizeof(unsigned int)));
         CU_TRY(cudaMalloc(&s.d_cand, n * kCandPerTile * sizeof(uint16_t)));
         CU_TRY(cudaMalloc(&s.d_slice_ent, n * kSlicesPerTile * sizeof(uint4)));
         s.tile_cap = n;
@@ -204,7 +207,9 @@ int launch_scan(pfac_ctx *ctx, Slot &slot, const void *d_in, uint64_t n_starts, 
     if (e) return e;
     p.tile_cnt = slot.d_tile_cnt;
     p.tile_mask = slot.d_tile_mask;
+    p.tile_nc = slot.d_tile_nc;
     p.cand = slot.d_cand;
+    p.partial = slot.d_partial;
     p.ctrl = slot.d_ctrl;
     p.debug = ctx->debug;
     const uint32_t grid = (uint32_t)std::min<uint64_t>(p.n_tiles, (uint64_t)ctx->sm_count);
@@ -242,12 +247,19 @@ int launch_scan(pfac_ctx *ctx, Slot &slot, const void *d_in, uint64_t n_starts, 
     ep.scratch_cap = slot.scratch_cap;
     ep.tile_cnt = slot.d_tile_cnt;
     ep.tile_mask = slot.d_tile_mask;
+    ep.tile_nc = slot.d_tile_nc;
     ep.n_tiles = p.n_tiles;
+    const uint32_t fgrid = (uint32_t)std::min<uint64_t>((p.n_tiles + kFinThreads - 1) / kFinThreads,
+                                                        (uint64_t)std::min(ctx->sm_count, (int)kMaxParts));
+    const uint32_t tiles_per_part = (p.n_tiles + fgrid - 1) / fgrid;
+    ep.tiles_per_part = tiles_per_part;
+    ep.partial = slot.d_partial;
     ep.cand = slot.d_cand;
     ep.slice_ent = slot.d_slice_ent;
     ep.ctrl = slot.d_ctrl;
+    // pass B deals one tile per warp: size the grid for it
     const uint32_t egrid = (uint32_t)std::min<uint64_t>((p.n_tiles + (kEmitThreads / 32) - 1) / (kEmitThreads / 32),
-                                                        (uint64_t)ctx->sm_count * 4);
+                                                        (uint64_t)ctx->sm_count * 8);
     pfac_emit_kernel<<<egrid, kEmitThreads, 0, stream>>>(ep);
     CU_TRY(cudaGetLastError());
 
@@ -260,10 +272,11 @@ int launch_scan(pfac_ctx *ctx, Slot &slot, const void *d_in, uint64_t n_starts, 
     f.out = (uint2 *)d_out;
     f.cap = cap;
     f.n_tiles = p.n_tiles;
+    f.tiles_per_part = tiles_per_part;
+    f.partial = slot.d_partial;
     f.ctrl = slot.d_ctrl;
     f.result = slot.d_result;
     f.count_out = (unsigned long long *)d_count;
-    const uint32_t fgrid = (uint32_t)std::min<uint64_t>((p.n_tiles + kFinThreads - 1) / kFinThreads, (uint64_t)ctx->sm_count);
     pfac_finalize_kernel<<<fgrid, kFinThreads, 0, stream>>>(f);
     CU_TRY(cudaGetLastError());
     if (tiles_out) *tiles_out = p.n_tiles;

@@ -2,18 +2,22 @@
 // (reference master_kernel.cu:37-180).  Design notes: DESIGN.md section 3.
 //
 //   pfac_scan_kernel      the detector: persistent, one CTA per SM, warp specialised.
-//     * producer warp: claims tile tickets and streams 16 KiB tiles (+ halo of max_pat_len-1
-//       bytes) into a shared-memory ring with cp.async.bulk (TMA bulk copy, SASS UBLKCP),
-//       full/empty mbarriers per stage, L2 evict-first hint on the streamed input;
-//     * consumer warps: claim 512-byte slices of the current tile.  Per slice
-//         stage 1  16 start positions per lane against T1 (64 KiB byte table over the first
-//                  two bytes, root fan-out folded in), survivors compacted into the warp queue;
+//     * producer warp: claims tile tickets and streams tiles of 31 x 512 bytes (+ halo of
+//       max_pat_len-1 bytes) into a shared-memory ring with cp.async.bulk (TMA bulk copy, SASS
+//       UBLKCP), full/empty mbarriers per stage, L2 evict-first hint on the streamed input; it
+//       also publishes every finished tile's result (flag mask, candidate list);
+//     * 31 consumer warps, each owning one 512-byte slice of every tile.  Per slice
+//         stage 1  16 start positions per lane against T1 (64 KiB byte table over 2-byte windows,
+//                  four bit-planes: root fan-out + depth-1 rows, bytes 1-2, bytes 2-3, short
+//                  patterns), survivors compacted into the warp queue by ballot rank;
 //         stage 2  survivors against Tm/T3/Tm2 (two-point checks on the 4-byte prefix and on
 //                  the bytes that end the shortest pattern below it) or T2.
-//       A slice in which any start survives is FLAGGED; the detector decides nothing else.
-//       All its tables are shared-memory resident prefix filters derived from the first PHF rows.
+//       A start that survives becomes a CANDIDATE of its tile and flags its slice; the detector
+//       decides nothing else.  All its tables are shared-memory resident prefix filters derived
+//       from the first PHF rows.
 //   pfac_emit_kernel      one warp per tile with flagged slices: the plain PFAC walk of
-//                         SUBSEG_MATCH over every start of those slices, straight from the PHF
+//                         SUBSEG_MATCH over the tile's candidates (or, when there are too many,
+//                         over every start of the flagged slices), straight from the PHF
 //                         (r[] then {HT,val}, read-only, L2-resident), records written in
 //                         (position, pattern length) order into the arrival-order scratch.
 //   pfac_finalize_kernel  scans the per-tile counts and moves the records from arrival order to
@@ -56,11 +60,12 @@ struct ScanParams {
     uint32_t t2_shift, has_short, has_t3, t3_shift, tm2_bits;
     uint32_t n_stages;                // depth of the input ring (as many as shared memory holds)
     // output
-    unsigned int *tile_cnt;           // [n_tiles] detector: candidates of the tile (kCandOverflow: too many);
-                                      //           the emit kernel overwrites it with the tile's match count
+    unsigned int *tile_cnt;           // [n_tiles] 0 from the detector; the emit kernel writes the tile's match count
+    unsigned int *tile_nc;            // [n_tiles] candidates of the tile (kCandOverflow: too many, whole slices instead)
     unsigned int *tile_mask;          // [n_tiles] bit s set iff slice s of the tile is flagged
     uint16_t *cand;                   // [n_tiles*kCandPerTile] tile-relative start positions that survived every filter
     unsigned int *flagged;            // [n_tiles] ids of the tiles with a non-zero mask, arrival order
+    unsigned long long *partial;      // [kMaxParts] zeroed here; the emit kernel sums matches per tile range into it
     Ctrl *ctrl;
     uint32_t debug;           // PFAC_DEBUG bits (timing experiments only): 4 no T1, 8 no stage 2
 };
@@ -73,7 +78,8 @@ struct FinalizeParams {
     unsigned long long scratch_cap;
     uint2 *out;
     unsigned long long cap;
-    uint32_t n_tiles;
+    uint32_t n_tiles, tiles_per_part;
+    const unsigned long long *partial;
     Ctrl *ctrl;
     Result *result;
     unsigned long long *count_out;    // caller's device counter (may be null)
@@ -89,6 +95,7 @@ constexpr int kQ1Cap = 128;               // per consumer warp: starts of one sl
 constexpr int kQ2Cap = 64;                // ... and the prefix check of stage 2 (u32: tpos | m1 << 16)
 constexpr int kQueueBytes = kQ1Cap * 2 + kQ2Cap * 4;   // a slice with more survivors is handed over whole
 constexpr int kCtrlBytes = 1024;
+constexpr int kMaxParts = 1024;           // tile ranges of the ordering pass (one per finalize CTA)
 constexpr int kCandPerTile = 32;          // candidate starts the detector hands over per tile (more: whole slices)
 constexpr unsigned kCandOverflow = 0xFFFFFFFFu;
 constexpr unsigned kSpinLimit = 1u << 24;
@@ -159,7 +166,11 @@ __device__ __forceinline__ uint64_t policy_evict_first()
 // rotl2 of each of the 4 bytes (pfac_derive.h rot2): bank-spreads the T1 index for ASCII text
 __device__ __forceinline__ uint32_t rot2x4(uint32_t w)
 {
+#ifndef PFAC_NO_ROT2
     return ((w << 2) & 0xFCFCFCFCu) | ((w >> 6) & 0x03030303u);
+#else
+    return w;
+#endif
 }
 
 // The kernel's dynamic shared memory.  T1 sits at offset 0 (pfac_derive.cc) so that its lookups
@@ -242,7 +253,9 @@ __global__ void __launch_bounds__(kThreads, 1) pfac_scan_kernel(const ScanParams
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
-    {   // shared-memory image: T1, T1s, T2 or Tm/Tm2/T3
+    if (blockIdx.x == 0)
+        for (int i = tid; i < kMaxParts; i += kThreads) p.partial[i] = 0ull;
+    {   // shared-memory image: T1, T2 or Tm/Tm2/T3
         uint4 *dst = reinterpret_cast<uint4 *>(smem);
         const uint32_t n16 = p.image_bytes >> 4;
         for (uint32_t i = tid; i < n16; i += kThreads) dst[i] = __ldg(&p.image[i]);
@@ -270,7 +283,8 @@ __global__ void __launch_bounds__(kThreads, 1) pfac_scan_kernel(const ScanParams
                 const uint32_t flags = s_tflag[st];
                 uint32_t nc = s_ncand[st];
                 if (nc > (uint32_t)kCandPerTile) nc = kCandOverflow;   // too many (or the overflow bit is set)
-                p.tile_cnt[tile] = flags ? nc : 0u;
+                p.tile_cnt[tile] = 0u;
+                p.tile_nc[tile] = flags ? nc : 0u;
                 p.tile_mask[tile] = flags;
                 if (flags) {
                     if (nc != kCandOverflow)
@@ -499,7 +513,9 @@ struct EmitParams {
     uint2 *scratch;
     unsigned long long scratch_cap;
     unsigned int *tile_cnt, *tile_mask;
-    uint32_t n_tiles;
+    const unsigned int *tile_nc;
+    uint32_t n_tiles, tiles_per_part;
+    unsigned long long *partial;
     const uint16_t *cand;
     uint4 *slice_ent;
     Ctrl *ctrl;
@@ -542,22 +558,41 @@ __global__ void __launch_bounds__(kEmitThreads) pfac_emit_kernel(const EmitParam
 {
     const int lane = threadIdx.x & 31;
     const uint32_t warps_total = gridDim.x * (kEmitThreads / 32);
-    // tiles are dealt round-robin to the warps of the grid; only flagged tiles cost anything
-    for (uint32_t tile = blockIdx.x * (kEmitThreads / 32) + (threadIdx.x >> 5); tile < p.n_tiles; tile += warps_total) {
-      uint32_t m = p.tile_mask[tile], out_mask = 0, tile_total = 0;
-      if (m) {
+    auto limit = [&](uint32_t a) {
+        uint32_t lim_a = p.a_valid_end;
+        if (p.use_ref_bound) {   // reference tiles: 4096 bytes of global positions + 512-byte halo
+            const unsigned long long g = p.base_pos + (unsigned long long)(a - p.mis);
+            const unsigned long long lim2 = ((g & ~4095ull) + 4608ull) - p.base_pos + p.mis;
+            if (lim2 < lim_a) lim_a = (uint32_t)lim2;
+        }
+        const unsigned long long depth = (unsigned long long)a + p.max_pat_len;
+        return depth < lim_a ? (uint32_t)depth : lim_a;
+    };
+    const uint32_t warp_g = blockIdx.x * (kEmitThreads / 32) + (threadIdx.x >> 5);
+    // ---- pass A: tiles with exactly one candidate (the common case), one lane per tile
+    for (uint32_t t0 = warp_g * 32u; t0 < p.n_tiles; t0 += warps_total * 32u) {
+        const uint32_t my_tile = t0 + lane;
+        if (my_tile >= p.n_tiles || p.tile_nc[my_tile] != 1u) continue;
+        const uint32_t key = p.cand[(size_t)my_tile * kCandPerTile];
+        const uint32_t a = my_tile * (uint32_t)kTile + key, lim = limit(a);
+        const uint32_t cnt = emit_walk<false>(p, a, lim, 0ull);
+        if (cnt) {
+            const unsigned long long base = atomicAdd(&p.ctrl->alloc, (unsigned long long)cnt);
+            emit_walk<true>(p, a, lim, base);
+            p.slice_ent[(size_t)my_tile * kSlicesPerTile + key / kSlice] = make_uint4(cnt, (uint32_t)base, (uint32_t)(base >> 32), 0u);
+            atomicAdd(&p.partial[my_tile / p.tiles_per_part], (unsigned long long)cnt);
+        }
+        p.tile_cnt[my_tile] = cnt;
+        p.tile_mask[my_tile] = cnt ? 1u << (key / kSlice) : 0u;
+    }
+    // ---- pass B: the other flagged tiles (several candidates, or whole slices), one warp per tile,
+    //      dealt round-robin.  tile_nc is never written here, so the two passes cannot confuse each other.
+    for (uint32_t tile = warp_g; tile < p.n_tiles; tile += warps_total) {
+      const uint32_t nc = p.tile_nc[tile];
+      if (nc == 0u || nc == 1u) continue;
+      {
+        uint32_t m = p.tile_mask[tile], out_mask = 0, tile_total = 0;
         const uint32_t a0 = tile * (uint32_t)kTile;
-        auto limit = [&](uint32_t a) {
-            uint32_t lim_a = p.a_valid_end;
-            if (p.use_ref_bound) {   // reference tiles: 4096 bytes of global positions + 512-byte halo
-                const unsigned long long g = p.base_pos + (unsigned long long)(a - p.mis);
-                const unsigned long long lim2 = ((g & ~4095ull) + 4608ull) - p.base_pos + p.mis;
-                if (lim2 < lim_a) lim_a = (uint32_t)lim2;
-            }
-            const unsigned long long depth = (unsigned long long)a + p.max_pat_len;
-            return depth < lim_a ? (uint32_t)depth : lim_a;
-        };
-        const uint32_t nc = p.tile_cnt[tile];
         if (nc != kCandOverflow) {
             // ---- candidate mode: the detector named every start that can match (at most 32): one lane
             //      per candidate, sorted by position
@@ -609,6 +644,7 @@ __global__ void __launch_bounds__(kEmitThreads) pfac_emit_kernel(const EmitParam
             if (lane == 0) {
                 p.tile_cnt[tile] = tile_total;
                 p.tile_mask[tile] = out_mask;
+                if (tile_total) atomicAdd(&p.partial[tile / p.tiles_per_part], (unsigned long long)tile_total);
             }
             continue;
         }
@@ -623,8 +659,7 @@ __global__ void __launch_bounds__(kEmitThreads) pfac_emit_kernel(const EmitParam
                 const uint32_t a = a_lane + j;
                 if (a < p.mis || a >= p.a_start_end) continue;
                 const uint32_t c0 = p.in_al[a], c1 = a + 1 < p.a_valid_end ? p.in_al[a + 1] : 0u;
-                const uint32_t r0 = ((c0 << 2) | (c0 >> 6)) & 0xffu, r1 = ((c1 << 2) | (c1 >> 6)) & 0xffu;
-                if (__ldg(&p.t1[r0 | (r1 << 8)]) & kT1P01) cand |= 1u << j;
+                if (__ldg(&p.t1[t1_index(c0, c1)]) & kT1P01) cand |= 1u << j;
             }
             uint32_t cnt = 0, hit = 0;
             for (uint32_t c = cand; c; c &= c - 1) {
@@ -657,6 +692,7 @@ __global__ void __launch_bounds__(kEmitThreads) pfac_emit_kernel(const EmitParam
         if (lane == 0) {
             p.tile_cnt[tile] = tile_total;
             p.tile_mask[tile] = out_mask;
+            if (tile_total) atomicAdd(&p.partial[tile / p.tiles_per_part], (unsigned long long)tile_total);
         }
       }
     }
@@ -664,8 +700,8 @@ __global__ void __launch_bounds__(kEmitThreads) pfac_emit_kernel(const EmitParam
 
 // ---------------------------------------------------------------------------------------------
 // Position-ordering pass: exclusive scan of the per-tile counts, then every matching slice's
-// records move from the arrival-order scratch to their final place.  Grid-stride by tile range;
-// each CTA sums the counts before its range itself (n_tiles * 4 bytes, L2-resident).
+// records move from the arrival-order scratch to their final place.  One CTA per tile range; the
+// matches of the ranges before it come from the partial sums the emit kernel accumulated.
 constexpr int kFinThreads = 256;
 
 __global__ void __launch_bounds__(kFinThreads) pfac_finalize_kernel(const FinalizeParams f)
@@ -675,11 +711,11 @@ __global__ void __launch_bounds__(kFinThreads) pfac_finalize_kernel(const Finali
     __shared__ unsigned int s_cnt[kFinThreads];
     __shared__ unsigned long long s_run;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t per = (f.n_tiles + gridDim.x - 1) / gridDim.x;
+    const uint32_t per = f.tiles_per_part;   // CTA b owns tiles [b*per, (b+1)*per); partial[b] = matches in them
     const uint32_t lo = min(f.n_tiles, blockIdx.x * per), hi = min(f.n_tiles, lo + per);
 
     unsigned long long sum = 0;
-    for (uint32_t i = tid; i < lo; i += kFinThreads) sum += f.tile_cnt[i];
+    for (uint32_t i = tid; i < blockIdx.x; i += kFinThreads) sum += f.partial[i];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
     if (lane == 0) s_red[warp] = sum;
