@@ -75,6 +75,32 @@ def make_shard(pf, pats, mpl, tk, tseed, n, rank, world, out=None):
     return buf, n
 
 
+def bind_to_gpu_numa_node(index):
+    """Best effort: run this rank (and first-touch its pinned buffers) on the NUMA node its GPU hangs
+    off, so that eight ranks do not pull their H2D traffic across the socket interconnect."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(index)).busId
+        bus = (bus.decode() if isinstance(bus, bytes) else bus).lower()
+        if len(bus.split(":")[0]) == 8:       # 00000000:1B:00.0 -> 0000:1b:00.0
+            bus = bus[4:]
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return node
+    except Exception:
+        pass
+    return None
+
+
 class ClockSampler(threading.Thread):
     """Samples SM clock and throttle reasons through NVML while the timed regions run."""
 
@@ -202,6 +228,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a GPU: the PFAC scan has no CPU path")
     torch.cuda.set_device(local_rank)
+    numa_node = bind_to_gpu_numa_node(local_rank) if world > 1 else None
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -322,7 +349,7 @@ def main():
                        "matches_per_gpu_step": n_matches, "total_matches": total_matches,
                        "tables": m.derived_info(),
                        "l2": "input per step (>= 256 MiB) exceeds the 126 MB L2; no flush needed",
-                       "parallelism": f"input sharded x{world}, no collective"},
+                       "parallelism": f"input sharded x{world}, no collective", "numa_node_rank0": numa_node},
             "clocks": sampler.summary(),
             "e2e": {"value": world * n * e2e_steps / e2e_s / 1e9, "unit": "GB/s", "steps": e2e_steps,
                     "h2d_bytes_per_step": int(info["h2d_bytes"]), "d2h_bytes_per_step": int(info["d2h_bytes"]),

@@ -92,8 +92,7 @@ constexpr int kSlicesPerTile = kConsumerWarps;   // every consumer warp owns one
 constexpr int kTile = kSlicesPerTile * kSlice;   // 15,872 start positions per tile
 constexpr int kMaxStages = 8;
 constexpr int kQ1Cap = 128;               // per consumer warp: starts of one slice that passed stage 1 (u16)
-constexpr int kQ2Cap = 64;                // ... and the prefix check of stage 2 (u32: tpos | m1 << 16)
-constexpr int kQueueBytes = kQ1Cap * 2 + kQ2Cap * 4;   // a slice with more survivors is handed over whole
+constexpr int kQueueBytes = kQ1Cap * 2;   // a slice with more survivors is handed over whole
 constexpr int kCtrlBytes = 1024;
 constexpr int kMaxParts = 1024;           // tile ranges of the ordering pass (one per finalize CTA)
 constexpr int kCandPerTile = 32;          // candidate starts the detector hands over per tile (more: whole slices)
@@ -340,7 +339,6 @@ __global__ void __launch_bounds__(kThreads, 1) pfac_scan_kernel(const ScanParams
 
     // ---------------------------------------------------------------------- consumers
     uint16_t *wq = reinterpret_cast<uint16_t *>(qbase + warp * kQueueBytes);   // stage-1 survivors of the slice
-    uint32_t *wq2 = reinterpret_cast<uint32_t *>(wq + kQ1Cap);                  // stage-2a survivors: tpos | m1 << 16
     const uint32_t lt_mask = (1u << lane) - 1u;
     const uint32_t slice = (uint32_t)warp;   // this warp's slice of every tile
     const uint32_t off = slice * kSlice + lane * 16;
@@ -402,78 +400,46 @@ __global__ void __launch_bounds__(kThreads, 1) pfac_scan_kernel(const ScanParams
                 nq = 0;
             }
             __syncwarp();
-            // stage 2a: the 4-byte prefix (complete Tm, or T2).  What survives is queued with its m1;
-            // starts that cannot be judged here (short patterns, end of the input) are candidates.
-            uint32_t n2 = 0;
+            // stage 2: the 4-byte prefix (complete Tm, or T2), then the two-point checks -- every pattern
+            // under a key is at least m bytes long and has its bytes [m-4, m) in T3.  Starts that cannot
+            // be judged here (short patterns, end of the input) are candidates straight away.
             for (uint32_t e0 = 0; e0 < nq; e0 += 32) {
                 const uint32_t e = e0 + lane;
-                uint32_t tpos = 0, m1 = 0;
-                bool keep = false;
-                if (e < nq) {
-                    tpos = wq[e];
-                    if ((p.debug & 8u) || tpos + 4u > valid_t) {
-                        any = true;
-                        add_candidate(s_ncand + s, s_cand + s * kCandPerTile, tpos);
-                    } else {
-                        const uint32_t *wp = reinterpret_cast<const uint32_t *>(buf + (tpos & ~3u));
-                        const uint32_t w4 = __funnelshift_r(wp[0], wp[1], (tpos & 3u) * 8u);
-                        bool shortp = false;
-                        if (p.has_short) shortp = (smem[rot2x4(w4) & 0xffffu] & kT1Short) != 0;
-                        if (shortp) {
-                            any = true;
-                            add_candidate(s_ncand + s, s_cand + s * kCandPerTile, tpos);
-                        } else if (!p.has_t3) {
-                            const uint32_t h = (w4 * kHash4Mul) >> p.t2_shift;
-                            if ((s_t2[h >> 5] >> (h & 31u)) & 1u) {
-                                any = true;
-                                add_candidate(s_ncand + s, s_cand + s * kCandPerTile, tpos);
-                            }
-                        } else {
-                            m1 = tm_lookup(s_tm, w4, kTmSlotBits);   // 0 = no pattern has this prefix
-                            keep = m1 != 0;
-                        }
-                    }
-                }
-                const uint32_t bal = __ballot_sync(0xffffffffu, keep);
-                if (keep) {
-                    const uint32_t idx = n2 + __popc(bal & lt_mask);
-                    if (idx < (uint32_t)kQ2Cap) wq2[idx] = tpos | (m1 << 16);
-                    else {   // more prefix hits than the queue holds: the emit kernel looks at the whole slice
-                        any = true;
-                        atomicOr(s_ncand + s, 0x80000000u);   // no candidate list for this tile
-                    }
-                }
-                n2 += __popc(bal);
-            }
-            if (n2 > (uint32_t)kQ2Cap) n2 = kQ2Cap;
-            __syncwarp();
-            // stage 2b: two-point checks -- every pattern under a key is at least m bytes long and has
-            // its bytes [m-4, m) in T3
-            for (uint32_t e0 = 0; e0 < n2; e0 += 32) {
-                const uint32_t e = e0 + lane;
-                if (e >= n2) continue;
-                const uint32_t ent = wq2[e];
-                const uint32_t tpos = ent & 0xffffu, m1 = ent >> 16;
-                const uint32_t lim = interior ? 0xffffffffu : walk_limit(p, a0, tpos);
-                bool keep = tpos + m1 <= lim;
-                if (keep) {
+                if (e >= nq) continue;
+                const uint32_t tpos = wq[e];
+                bool keep = true;
+                if (!(p.debug & 8u) && tpos + 4u <= valid_t) {
                     const uint32_t *wp = reinterpret_cast<const uint32_t *>(buf + (tpos & ~3u));
                     const uint32_t w4 = __funnelshift_r(wp[0], wp[1], (tpos & 3u) * 8u);
-                    const uint32_t wo = tpos + m1 - 4u;
-                    const uint32_t *we = reinterpret_cast<const uint32_t *>(buf + (wo & ~3u));
-                    const uint32_t w1 = __funnelshift_r(we[0], we[1], (wo & 3u) * 8u);
-                    const uint32_t h3 = hash_t3(w4, w1) >> p.t3_shift;
-                    keep = (s_t3[h3 >> 5] >> (h3 & 31u)) & 1u;
-                    if (keep && p.tm2_bits) {
-                        const uint32_t key2 = hash_key2(w4, w1);
-                        const uint32_t m2 = tm_lookup(s_tm2, key2, p.tm2_bits);   // 0 = no such group
-                        keep = m2 != 0 && tpos + m2 <= lim;
-                        if (keep) {
-                            const uint32_t wo2 = tpos + m2 - 4u;
-                            const uint32_t *wf = reinterpret_cast<const uint32_t *>(buf + (wo2 & ~3u));
-                            const uint32_t w2 = __funnelshift_r(wf[0], wf[1], (wo2 & 3u) * 8u);
-                            const uint32_t h4 = hash_t3(key2 ^ kT3Seed2, w2) >> p.t3_shift;
-                            keep = (s_t3[h4 >> 5] >> (h4 & 31u)) & 1u;
+                    bool shortp = false;
+                    if (p.has_short) shortp = (smem[rot2x4(w4) & 0xffffu] & kT1Short) != 0;
+                    if (!shortp) {
+                        if (!p.has_t3) {
+                            const uint32_t h = (w4 * kHash4Mul) >> p.t2_shift;
+                            keep = (s_t2[h >> 5] >> (h & 31u)) & 1u;
+                        } else {
+                            const uint32_t m1 = tm_lookup(s_tm, w4, kTmSlotBits);   // 0 = no pattern has this prefix
+                            const uint32_t lim = interior ? 0xffffffffu : walk_limit(p, a0, tpos);
+                            keep = m1 != 0 && tpos + m1 <= lim;
+                            if (keep) {
+                                const uint32_t wo = tpos + m1 - 4u;
+                                const uint32_t *we = reinterpret_cast<const uint32_t *>(buf + (wo & ~3u));
+                                const uint32_t w1 = __funnelshift_r(we[0], we[1], (wo & 3u) * 8u);
+                                const uint32_t h3 = hash_t3(w4, w1) >> p.t3_shift;
+                                keep = (s_t3[h3 >> 5] >> (h3 & 31u)) & 1u;
+                                if (keep && p.tm2_bits) {
+                                    const uint32_t key2 = hash_key2(w4, w1);
+                                    const uint32_t m2 = tm_lookup(s_tm2, key2, p.tm2_bits);   // 0 = no such group
+                                    keep = m2 != 0 && tpos + m2 <= lim;
+                                    if (keep) {
+                                        const uint32_t wo2 = tpos + m2 - 4u;
+                                        const uint32_t *wf = reinterpret_cast<const uint32_t *>(buf + (wo2 & ~3u));
+                                        const uint32_t w2 = __funnelshift_r(wf[0], wf[1], (wo2 & 3u) * 8u);
+                                        const uint32_t h4 = hash_t3(key2 ^ kT3Seed2, w2) >> p.t3_shift;
+                                        keep = (s_t3[h4 >> 5] >> (h4 & 31u)) & 1u;
+                                    }
+                                }
+                            }
                         }
                     }
                 }
