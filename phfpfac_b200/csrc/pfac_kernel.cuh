@@ -419,7 +419,7 @@ __global__ void __launch_bounds__(kThreads, 1) pfac_scan_kernel(const ScanParams
                             keep = (s_t2[h >> 5] >> (h & 31u)) & 1u;
                         } else {
                             const uint32_t m1 = tm_lookup(s_tm, w4, kTmSlotBits);   // 0 = no pattern has this prefix
-                            const uint32_t lim = interior ? 0xffffffffu : walk_limit(p, a0, tpos);
+                            const uint32_t lim = interior ? tpos + p.max_pat_len : walk_limit(p, a0, tpos);   // never past the staged halo
                             keep = m1 != 0 && tpos + m1 <= lim;
                             if (keep) {
                                 const uint32_t wo = tpos + m1 - 4u;

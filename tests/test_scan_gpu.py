@@ -187,6 +187,25 @@ def test_candidate_list_boundaries(n_plants):
     check_both_paths(pats, text, n_streams=2, chunk_bytes=65536, oracle_parts=4)
 
 
+def test_tables_from_reference_arrays_and_determinism(fixtures):
+    """Tables handed over as canonical arrays (the thread_data fields of main.cc:19-32, here the
+    oracle's) give the same records as tables built by the library, run after run."""
+    torch = torch_cuda()
+    o = Oracle(fixtures["dictionary"], n_parts=1, width=256)
+    p = o.part(0)
+    t = pf.Tables.from_arrays(p.s0, p.r, p.HT, p.val, 256, p.state_num, p.n_final, p.idmap, o.max_pat_len)
+    data = np.frombuffer(fixtures["1M"][:-1], dtype=np.uint8)
+    pos, ids = o.scan(data)
+    m = pf.Matcher(t, device=0, n_streams=3, chunk_bytes=1 << 18)
+    d = torch.from_numpy(data.copy()).cuda()
+    first = m.scan_device(d)
+    assert np.array_equal(first["pos"], pos) and np.array_equal(first["id"], ids)
+    for _ in range(3):
+        assert np.array_equal(m.scan_device(d), first)
+        assert np.array_equal(m.scan_host(data), first)
+    m.close()
+
+
 def test_long_patterns_reference_tile_bound():
     """Patterns longer than 513 bytes: the reference cuts a walk at its 4096-byte tile + 512-byte
     halo (master_kernel.cu:141-144); positions are global (base_pos)."""
