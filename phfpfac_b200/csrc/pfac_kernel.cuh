@@ -122,19 +122,36 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar)
 {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+#ifndef PFAC_WAIT_HINT_NS
+#define PFAC_WAIT_HINT_NS 0      // suspend-time hint of mbarrier.try_wait (0: none)
+#endif
+#ifndef PFAC_CONS_SLEEP_NS
+#define PFAC_CONS_SLEEP_NS 32    // consumer back-off between polls of a full barrier
+#endif
+#ifndef PFAC_PROD_SLEEP_NS
+#define PFAC_PROD_SLEEP_NS 64    // producer back-off between polls of an empty barrier
+#endif
 __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity)
 {
     uint32_t ok;
+#if PFAC_WAIT_HINT_NS > 0
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"   // %3: suspend-time hint (ns)
         "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity), "r"(4000u) : "memory");
+        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity), "r"((unsigned)PFAC_WAIT_HINT_NS) : "memory");
+#else
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+#endif
     return ok != 0;
 }
-// returns false if the watchdog tripped (never expected)
-// SLEEP_NS > 0: back off between polls (the producer warp, which would otherwise burn issue slots)
-template <unsigned SLEEP_NS = 0>
+// returns false if the watchdog tripped (never expected).  SLEEP_NS > 0: back off between polls so
+// that a waiting warp does not burn the issue slots of the warps that work.
+template <unsigned SLEEP_NS>
 __device__ __forceinline__ bool mbar_wait(uint64_t *bar, uint32_t parity, unsigned int *error_flag, unsigned code)
 {
     unsigned spins = 0;
@@ -300,7 +317,7 @@ __global__ void __launch_bounds__(kThreads, 1) pfac_scan_kernel(const ScanParams
                 // tickets are claimed two tiles ahead: the atomic's latency hides behind a whole tile
                 const uint32_t t_next2 = t_next < p.n_tiles ? atomicAdd(&p.ctrl->ticket, 1u) : t_next;
                 if (held[s] != 0xFFFFFFFFu) {
-                    if (!mbar_wait<200>(&s_empty[s], (round - 1) & 1u, &p.ctrl->error_flag, 3u)) { ok = false; break; }
+                    if (!mbar_wait<PFAC_PROD_SLEEP_NS>(&s_empty[s], (round - 1) & 1u, &p.ctrl->error_flag, 3u)) { ok = false; break; }
                     publish(s, held[s]);
                     held[s] = 0xFFFFFFFFu;
                 }
@@ -330,7 +347,7 @@ __global__ void __launch_bounds__(kThreads, 1) pfac_scan_kernel(const ScanParams
                 const uint32_t st = (s + n_stages - k) % n_stages;
                 if (held[st] == 0xFFFFFFFFu) continue;
                 const uint32_t fill_round = st < s ? round : round - 1;
-                if (!mbar_wait<200>(&s_empty[st], fill_round & 1u, &p.ctrl->error_flag, 4u)) break;
+                if (!mbar_wait<PFAC_PROD_SLEEP_NS>(&s_empty[st], fill_round & 1u, &p.ctrl->error_flag, 4u)) break;
                 publish(st, held[st]);
             }
         }
@@ -345,7 +362,7 @@ __global__ void __launch_bounds__(kThreads, 1) pfac_scan_kernel(const ScanParams
 
     uint32_t s = 0, round = 0;
     for (;; s = (s + 1 == n_stages) ? 0 : s + 1, round += (s == 0) ? 1u : 0u) {
-        if (!mbar_wait(&s_full[s], round & 1u, &p.ctrl->error_flag, 2u)) break;
+        if (!mbar_wait<PFAC_CONS_SLEEP_NS>(&s_full[s], round & 1u, &p.ctrl->error_flag, 2u)) break;
         const uint32_t tile = s_tile[s];
         if (tile >= p.n_tiles) break;
         const uint8_t *buf = s_in + s * stride;
