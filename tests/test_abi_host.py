@@ -94,6 +94,12 @@ def test_writer_matches_reference_format(tmp_path, golden):
     pf.write_result(f, [(base, big)])
     assert f.read_bytes() == want
     assert pf.format_records(np.zeros(0, dtype=pf.MATCH_DTYPE)) == b""
+    # the multi-threaded path (>= 2^20 records) writes the same bytes as the sequential formatter
+    many = np.zeros((1 << 20) + 12345, dtype=pf.MATCH_DTYPE)
+    many["pos"] = np.arange(len(many), dtype=np.uint32) * 3
+    many["id"] = (np.arange(len(many)) % 9973) + 1
+    pf.write_result(f, [(7, many[:1000]), (7, many[1000:])])
+    assert f.read_bytes() == pf.format_records(many, base_pos=7)
 
 
 def test_synth_is_deterministic_and_shaped():
