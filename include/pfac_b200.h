@@ -158,7 +158,8 @@ int pfac_ctx_kernel_time(pfac_ctx *ctx, double *ms_total, int *n_launches);
  * info[0] = image bytes, [1] = T1 pairs set, [2] = T2 bits, [3] = T2 bits set, [4] = 4-byte prefixes,
  * [5] = short patterns (<= 3 bytes) present, [6] = Tm keys, [7] = Tm2 keys, [8] = T3 bits,
  * [9] = T3 bits set, [10] = dynamic smem bytes, [11] = table bytes in HBM, [12] = input ring stages,
- * [13] = log2 Tm2 buckets, [14..15] = reserved */
+ * [13] = log2 Tm2 buckets, [14] = mode (0 two-point checks from shared memory, 1 T2 only,
+ * 2 two-point tables in global memory), [15] = log2 Tm buckets */
 int pfac_ctx_derived_info(const pfac_ctx *ctx, uint64_t info[16]);
 
 /* ------------------------------------------------------------------------------ multi-GPU job

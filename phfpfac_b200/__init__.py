@@ -157,7 +157,7 @@ class Matcher:
         info = (C.c_uint64 * 16)()
         check(lib.pfac_ctx_derived_info(self._h, info))
         keys = ("image_bytes", "t1_pairs", "t2_bits", "t2_set", "prefixes4", "has_short", "tm_keys", "tm2_keys",
-                "t3_bits", "t3_set", "smem_bytes", "table_bytes", "ring_stages", "tm2_bits")
+                "t3_bits", "t3_set", "smem_bytes", "table_bytes", "ring_stages", "tm2_bits", "mode", "tm_bits")
         return dict(zip(keys, list(info)))
 
     # -- device-resident input (raw pointers; torch tensors are accepted for convenience)

@@ -194,12 +194,27 @@ void derive_tables(const Partition &P, uint32_t t2_bytes, uint32_t t3_bytes, uin
     out.has_short = any_short ? 1u : 0u;
     out.n_prefix4 = (uint32_t)std::min<size_t>(prefix4.size(), 0xFFFFFFFFu);
 
-    // ---- Tm / Tm2 / T3: two-point checks (pfac_derive.h)
+    // ---- Tm / Tm2 / T3: two-point checks (pfac_derive.h).  First with the shared-memory sizes; if the
+    // 4-byte prefixes do not fit Tm there and the set has no short patterns, once more with tables
+    // sized for the key counts, to live in global memory (L2-resident).
     uint32_t t3_bits = too_many ? 0 : pow2_bits_for_bytes(t3_bytes);
     std::vector<uint16_t> tm, tm2;
-    std::vector<uint32_t> t3(t3_bits / 32, 0);
-    uint32_t tm2_bits = 0;
-    if (t3_bits) {
+    std::vector<uint32_t> t3;
+    uint32_t tm2_bits = 0, tm_bits = kTmSlotBits;
+    bool global_mode = false;
+    for (int attempt = 0; attempt < 2 && t3_bits; attempt++) {
+        if (attempt == 1) {
+            if (any_short || prefix4.size() > (1u << 22)) { t3_bits = 0; break; }
+            global_mode = true;
+            tm_bits = 10;
+            while ((size_t)(2u << tm_bits) * 7 / 10 < prefix4.size()) tm_bits++;
+            t3_bits = 1u << 20;
+            while (t3_bits < 64ull * prefix4.size() && t3_bits < (1u << 28)) t3_bits *= 2;
+        }
+        t3.assign(t3_bits / 32, 0);
+        tm.clear();
+        tm2.clear();
+        tm2_bits = 0;
         out.t3_shift = 32u - log2u(t3_bits);
         // shortest distance from every state to a final state (reverse breadth-first search)
         const uint32_t kInf = 0xFFFFFFFFu;
@@ -248,7 +263,7 @@ void derive_tables(const Partition &P, uint32_t t2_bytes, uint32_t t3_bytes, uin
             }
             i = j;
         }
-        bool ok = place_all(k1, kTmSlotBits, tm);
+        bool ok = place_all(k1, tm_bits, tm);
 
         // every string of exactly `len` bytes that continues (state, str); str holds the bytes so far
         uint64_t visited = 0;
@@ -287,7 +302,7 @@ void derive_tables(const Partition &P, uint32_t t2_bytes, uint32_t t3_bytes, uin
             }
         }
         // level 2 keys: groups by key2; m2 = the shortest pattern length over the members
-        if (ok && tm2_bytes >= 64) {
+        if (ok && (tm2_bytes >= 64 || global_mode)) {
             std::sort(members.begin(), members.end(), [](const Member &x, const Member &y) { return x.key2 < y.key2; });
             std::vector<Key> k2;
             std::vector<std::pair<size_t, size_t>> k2_range;
@@ -303,7 +318,10 @@ void derive_tables(const Partition &P, uint32_t t2_bytes, uint32_t t3_bytes, uin
                 i = j;
             }
             uint32_t bits = 4;
-            while ((4ull << (bits + 1)) <= tm2_bytes) bits++;   // 2^bits buckets x 2 slots x 2 bytes <= tm2_bytes
+            if (!global_mode)
+                while ((4ull << (bits + 1)) <= tm2_bytes) bits++;   // 2^bits buckets x 2 slots x 2 bytes <= tm2_bytes
+            else
+                while ((size_t)(2u << bits) * 7 / 10 < k2.size()) bits++;
             if (place_all(k2, bits, tm2)) {
                 tm2_bits = bits;
                 for (size_t i = 0; i < k2.size() && ok; i++)
@@ -320,37 +338,72 @@ void derive_tables(const Partition &P, uint32_t t2_bytes, uint32_t t3_bytes, uin
                 tm2.clear();
             }
         }
-        if (!ok) {   // too many prefixes for Tm, or not a tree: no two-point checks, T2 alone filters
-            t3_bits = 0;
-            tm2_bits = 0;
-            out.t3_shift = 32;
-        } else {
+        if (ok) {
             out.has_t3 = 1;
+            out.tm_bits = tm_bits;
             out.tm2_bits = tm2_bits;
-            t2_bits = 0;   // the complete Tm stands in for T2
+            out.mode = global_mode ? 2u : 0u;
+            if (!global_mode) t2_bits = 0;   // the complete shared-memory Tm stands in for T2
+            break;
         }
+        // too many prefixes for this Tm, or not a tree
+        const bool paths_overflow = visited > kPathLimit;
+        out.t3_shift = 32;
+        if (attempt == 1 || paths_overflow) { t3_bits = 0; tm2_bits = 0; }
+    }
+    if (!out.has_t3) {   // no two-point checks: T2 alone filters
+        t3_bits = 0;
+        tm2_bits = 0;
+        out.t3_shift = 32;
+        out.mode = 1;
+        global_mode = false;
+        tm.clear();
+        tm2.clear();
     }
     if (t2_bits) out.t2_shift = t2_shift;
 
-    // ---- image
+    // ---- images.  Shared memory: T1 + (Tm, Tm2, T3 | T2) -- or, in global mode, T2 alone; global
+    // memory (mode 2): T1 (for the emit kernel), Tm, Tm2, T3.
+    const uint32_t tm_bytes = out.has_t3 ? (uint32_t)tm.size() * 2 : 0, tm2_bytes_used = (uint32_t)tm2.size() * 2;
     uint32_t off = 0;
-    out.off_t1 = off;
-    off = align128(off + 65536);
-    out.off_t2 = off;
-    off = align128(off + t2_bits / 8);
-    out.off_tm = off;
-    if (t3_bits) off = align128(off + kTm1Slots * 2);
-    out.off_tm2 = off;
-    if (tm2_bits) off = align128(off + (uint32_t)tm2.size() * 2);
-    out.off_t3 = off;
-    off = align128(off + t3_bits / 8);
-    out.image.assign(off, 0);
-    memcpy(out.image.data() + out.off_t1, t1.data(), 65536);
-    if (t2_bits) memcpy(out.image.data() + out.off_t2, t2.data(), t2_bits / 8);
-    if (t3_bits) {
-        memcpy(out.image.data() + out.off_tm, tm.data(), kTm1Slots * 2);
-        if (tm2_bits) memcpy(out.image.data() + out.off_tm2, tm2.data(), tm2.size() * 2);
-        memcpy(out.image.data() + out.off_t3, t3.data(), t3_bits / 8);
+    if (!global_mode) {
+        out.off_t1 = off;
+        off = align128(off + 65536);
+        out.off_t2 = off;
+        off = align128(off + t2_bits / 8);
+        out.off_tm = off;
+        off = align128(off + tm_bytes);
+        out.off_tm2 = off;
+        off = align128(off + tm2_bytes_used);
+        out.off_t3 = off;
+        off = align128(off + t3_bits / 8);
+        out.image.assign(off, 0);
+        memcpy(out.image.data() + out.off_t1, t1.data(), 65536);
+        if (t2_bits) memcpy(out.image.data() + out.off_t2, t2.data(), t2_bits / 8);
+        if (out.has_t3) {
+            memcpy(out.image.data() + out.off_tm, tm.data(), tm_bytes);
+            if (tm2_bits) memcpy(out.image.data() + out.off_tm2, tm2.data(), tm2_bytes_used);
+            memcpy(out.image.data() + out.off_t3, t3.data(), t3_bits / 8);
+        }
+    } else {
+        out.off_t2 = 0;
+        out.image.assign(align128(t2_bits / 8), 0);
+        if (t2_bits) memcpy(out.image.data(), t2.data(), t2_bits / 8);
+        out.off_t1 = 0;   // offsets below are into gimage
+        off = 65536;
+        out.off_tm = off;
+        off = align128(off + tm_bytes);
+        out.off_tm2 = off;
+        off = align128(off + tm2_bytes_used);
+        out.off_t3 = off;
+        off = align128(off + t3_bits / 8);
+        out.gimage.assign(off, 0);
+        memcpy(out.gimage.data(), t1.data(), 65536);
+        memcpy(out.gimage.data() + out.off_tm, tm.data(), tm_bytes);
+        if (tm2_bits) memcpy(out.gimage.data() + out.off_tm2, tm2.data(), tm2_bytes_used);
+        memcpy(out.gimage.data() + out.off_t3, t3.data(), t3_bits / 8);
+    }
+    if (out.has_t3) {
         for (uint32_t w : t3) out.t3_set += (uint32_t)__builtin_popcount(w);
         for (uint16_t e : tm) out.tm_set += e ? 1u : 0u;
         for (uint16_t e : tm2) out.tm2_set += e ? 1u : 0u;
@@ -366,6 +419,11 @@ namespace {
 // may read as anything): P01 of the first pair, and either the short plane or P12 and P23 further on.
 bool stage1_pass(const Derived &d, const uint8_t *t, size_t len)
 {
+    if (d.mode == 2) {   // global mode: stage 1 is T2 over the 4-byte prefix (no pattern is shorter than 4)
+        if (len < 4) return false;
+        const uint32_t *t2 = reinterpret_cast<const uint32_t *>(d.image.data() + d.off_t2);
+        return d.t2_shift >= 32 || bit(t2, (le32(t) * kHash4Mul) >> d.t2_shift);
+    }
     const uint8_t *t1 = d.image.data() + d.off_t1;
     auto at = [&](size_t i) { return i < len ? (uint32_t)t[i] : 0u; };
     const uint32_t v0 = t1[t1_index(at(0), at(1))];
@@ -379,9 +437,9 @@ bool stage1_pass(const Derived &d, const uint8_t *t, size_t len)
 // 4 level-2 pass.
 bool stage2_pass(const Derived &d, const uint8_t *t, size_t len, int *stage)
 {
-    const uint8_t *img = d.image.data();
+    const uint8_t *img = d.mode == 2 ? d.gimage.data() : d.image.data();   // where T1/Tm/Tm2/T3 live
     const uint8_t *t1 = img + d.off_t1;
-    const uint32_t *t2 = reinterpret_cast<const uint32_t *>(img + d.off_t2);
+    const uint32_t *t2 = reinterpret_cast<const uint32_t *>(d.image.data() + d.off_t2);
     const uint16_t *tm = reinterpret_cast<const uint16_t *>(img + d.off_tm);
     const uint16_t *tm2 = reinterpret_cast<const uint16_t *>(img + d.off_tm2);
     const uint32_t *t3 = reinterpret_cast<const uint32_t *>(img + d.off_t3);
@@ -394,7 +452,7 @@ bool stage2_pass(const Derived &d, const uint8_t *t, size_t len, int *stage)
         if (stage) *stage = 2;
         return true;
     }
-    const uint32_t m1 = tm_lookup(tm, w4, kTmSlotBits);
+    const uint32_t m1 = tm_lookup(tm, w4, d.tm_bits);
     if (!m1 || m1 > len) return false;
     if (stage) *stage = 2;
     const uint32_t w1 = le32(t + m1 - 4);
@@ -441,8 +499,7 @@ void derive_profile(const Partition &P, const Derived &d, const uint8_t *text, s
 int derive_selfcheck(const Partition &P, const Derived &d)
 {
     if (d.image.empty()) return 100;
-    const uint8_t *img = d.image.data();
-    const uint8_t *t1 = img + d.off_t1;
+    const uint8_t *t1 = (d.mode == 2 ? d.gimage.data() : d.image.data()) + d.off_t1;
     auto is_final = [&](int32_t s) { return s >= 0 && s < P.n_final; };
     // T1 is exact over the first two bytes; T1s covers every pair that can end a pattern of <= 3 bytes
     for (int b0 = 0; b0 < kCharSet; b0++) {

@@ -24,7 +24,9 @@
 //                       that key (Wu-Manber style two-point checks; they settle the starts that
 //                       share a long prefix with many patterns without walking it)
 //   T2    2^k2 bits   : multiplicative hash of every 4-byte prefix -- only for pattern sets whose
-//                       prefixes do not fit Tm (then there is no Tm/Tm2/T3)
+//                       prefixes do not fit the shared-memory Tm.  Such sets (e.g. 100,000 patterns)
+//                       get Tm/Tm2/T3 sized for their key counts in GLOBAL memory (a few MB, L2
+//                       resident) and T2, filling shared memory, becomes stage 1.
 #pragma once
 #include <cstdint>
 #include <vector>
@@ -96,7 +98,12 @@ struct Derived {
     uint32_t has_short = 0;      // patterns of length <= 3 exist (T1's Short plane is not empty)
     uint32_t has_t3 = 0;         // Tm + T3 present (then no T2)
     uint32_t t3_shift = 32;
-    uint32_t tm2_bits = 0;       // log2 buckets of Tm2 (0: no level 2)
+    uint32_t tm_bits = 0, tm2_bits = 0;   // log2 buckets of Tm / Tm2 (0: absent)
+    // mode 0: two-point checks from shared memory; 1: T2 alone; 2: stage 1 = T2 (the whole shared
+    // image), Tm/Tm2/T3 sized for the key counts in `gimage` (global memory, L2-resident) -- offsets
+    // off_t1/off_tm/off_tm2/off_t3 then refer to gimage, which starts with a copy of T1
+    uint32_t mode = 1;
+    std::vector<uint8_t> gimage;
     // statistics (pfac_ctx_derived_info)
     uint32_t t1_set = 0, t2_set = 0, t3_set = 0, tm_set = 0, tm2_set = 0, n_prefix4 = 0;
 };

@@ -61,6 +61,7 @@ struct pfac_ctx {
     int32_t *d_r = nullptr, *d_idmap = nullptr, *d_s0 = nullptr;
     int2 *d_htval = nullptr;
     uint4 *d_image = nullptr;
+    uint8_t *d_gimage = nullptr;   // mode 2: T1 | Tm | Tm2 | T3 in global memory
     Derived dv;   // image layout and hash parameters (the image bytes are dropped after the upload)
     uint32_t image_bytes = 0;
     int32_t ht_size = 0, width_bit = 0, n_final = 0, max_pat_len = 0;
@@ -201,7 +202,9 @@ int launch_scan(pfac_ctx *ctx, Slot &slot, const void *d_in, uint64_t n_starts, 
     p.has_short = ctx->dv.has_short;
     p.has_t3 = ctx->dv.has_t3;
     p.t3_shift = ctx->dv.t3_shift;
+    p.tm_bits = ctx->dv.tm_bits;
     p.tm2_bits = ctx->dv.tm2_bits;
+    p.gimage = ctx->d_gimage;
     p.n_stages = ctx->n_stages;
     e = slot_reserve(slot, p.n_tiles, (size_t)std::max<uint64_t>(cap, 4096), stream);
     if (e) return e;
@@ -221,7 +224,8 @@ int launch_scan(pfac_ctx *ctx, Slot &slot, const void *d_in, uint64_t n_starts, 
         CU_TRY(cudaEventRecord(ctx->ev[slot_i], stream));
         ev_after = ctx->ev[slot_i + 1];
     }
-    pfac_scan_kernel<<<grid, kThreads, ctx->smem_bytes, stream>>>(p);
+    if (ctx->dv.mode == 2) pfac_scan_kernel<2><<<grid, kThreads, ctx->smem_bytes, stream>>>(p);
+    else pfac_scan_kernel<0><<<grid, kThreads, ctx->smem_bytes, stream>>>(p);
     CU_TRY(cudaGetLastError());
     if (ev_after) CU_TRY(cudaEventRecord(ev_after, stream));
 
@@ -238,7 +242,7 @@ int launch_scan(pfac_ctx *ctx, Slot &slot, const void *d_in, uint64_t n_starts, 
     ep.r = ctx->d_r;
     ep.htval = ctx->d_htval;
     ep.idmap = ctx->d_idmap;
-    ep.t1 = (const uint8_t *)ctx->d_image + ctx->dv.off_t1;
+    ep.t1 = (ctx->dv.mode == 2 ? (const uint8_t *)ctx->d_gimage : (const uint8_t *)ctx->d_image) + ctx->dv.off_t1;
     ep.s0 = ctx->d_s0;
     ep.ht_size = ctx->ht_size;
     ep.width_bit = ctx->width_bit;
@@ -348,13 +352,20 @@ int pfac_ctx_create(int device, const pfac_tables *t, int part, int n_streams, s
     if (const char *v = getenv("PFAC_T2_BYTES")) t2_bytes = (uint32_t)atoi(v);
     if (const char *v = getenv("PFAC_T3_BYTES")) t3_bytes = (uint32_t)atoi(v);
     if (const char *v = getenv("PFAC_TM2_BYTES")) tm2_bytes = (uint32_t)atoi(v);
+    bool widened = false;
     while (true) {
         derive_tables(P, t2_bytes, t3_bytes, tm2_bytes, ctx->dv);
+        if (ctx->dv.mode == 2 && !widened && !getenv("PFAC_T2_BYTES")) {
+            // global mode: T2 is stage 1 and the only shared-memory table -- give it all the room
+            widened = true;
+            t2_bytes = 131072;
+            continue;
+        }
         ctx->image_bytes = (uint32_t)ctx->dv.image.size();
         const size_t fixed = scan_smem_bytes(ctx->image_bytes, ctx->halo, 0);
         const size_t stride = scan_buf_stride(ctx->halo);
         const size_t fit = smem_max > fixed ? (smem_max - fixed) / stride : 0;
-        const bool minimal = t2_bytes < 2048 && t3_bytes < 2048 && tm2_bytes < 2048;
+        const bool minimal = t2_bytes < 2048 && (ctx->dv.mode == 2 || (t3_bytes < 2048 && tm2_bytes < 2048));
         if (fit >= 3 || (fit >= 2 && minimal)) {
             ctx->n_stages = (uint32_t)std::min<size_t>(fit, kMaxStages);
             ctx->smem_bytes = scan_smem_bytes(ctx->image_bytes, ctx->halo, ctx->n_stages);
@@ -364,7 +375,9 @@ int pfac_ctx_create(int device, const pfac_tables *t, int part, int n_streams, s
             return set_error(PFAC_ERR_CUDA, "scan kernel needs more than the %zu B of shared memory the device offers",
                              smem_max);
         // halve the largest section that is actually in the image
-        if (ctx->dv.has_t3) {
+        if (ctx->dv.mode == 2) {
+            t2_bytes /= 2;
+        } else if (ctx->dv.has_t3) {
             if (t3_bytes > 8192) t3_bytes /= 2;          // T3 first: it only gets a little less selective
             else if (tm2_bytes >= 2048) tm2_bytes /= 2;  // then level 2 (all or nothing per size)
             else t3_bytes /= 2;
@@ -393,14 +406,24 @@ int pfac_ctx_create(int device, const pfac_tables *t, int part, int n_streams, s
     if (P.n_final) CU_TRY(cudaMemcpy(ctx->d_idmap, P.idmap.data(), (size_t)P.n_final * sizeof(int32_t), cudaMemcpyHostToDevice));
     CU_TRY(cudaMemcpy(ctx->d_s0, s0.data(), 256 * sizeof(int32_t), cudaMemcpyHostToDevice));
     CU_TRY(cudaMemcpy(ctx->d_image, ctx->dv.image.data(), ctx->image_bytes, cudaMemcpyHostToDevice));
-    ctx->table_bytes = n_r * 4 + n_ht * 8 + n_id * 4 + 1024 + ctx->image_bytes;
+    if (!ctx->dv.gimage.empty()) {
+        CU_TRY(cudaMalloc(&ctx->d_gimage, ctx->dv.gimage.size()));
+        CU_TRY(cudaMemcpy(ctx->d_gimage, ctx->dv.gimage.data(), ctx->dv.gimage.size(), cudaMemcpyHostToDevice));
+    }
+    ctx->table_bytes = n_r * 4 + n_ht * 8 + n_id * 4 + 1024 + ctx->image_bytes + ctx->dv.gimage.size();
     ctx->dv.image.clear();
     ctx->dv.image.shrink_to_fit();
+    ctx->dv.gimage.clear();
+    ctx->dv.gimage.shrink_to_fit();
 
     // the attribute is per function and device, not per context: always allow the device maximum
-    CU_TRY(cudaFuncSetAttribute(pfac_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
+    CU_TRY(cudaFuncSetAttribute(pfac_scan_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
+    CU_TRY(cudaFuncSetAttribute(pfac_scan_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
     int bps = 0;
-    CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, pfac_scan_kernel, kThreads, ctx->smem_bytes));
+    if (ctx->dv.mode == 2)
+        CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, pfac_scan_kernel<2>, kThreads, ctx->smem_bytes));
+    else
+        CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, pfac_scan_kernel<0>, kThreads, ctx->smem_bytes));
     if (bps < 1) return set_error(PFAC_ERR_CUDA, "scan kernel does not fit on an SM (smem %zu B)", ctx->smem_bytes);
 
     CU_TRY(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
@@ -422,6 +445,7 @@ void pfac_ctx_destroy(pfac_ctx *ctx)
     if (ctx->d_idmap) cudaFree(ctx->d_idmap);
     if (ctx->d_image) cudaFree(ctx->d_image);
     if (ctx->d_s0) cudaFree(ctx->d_s0);
+    if (ctx->d_gimage) cudaFree(ctx->d_gimage);
     for (auto e : ctx->ev)
         if (e) cudaEventDestroy(e);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
@@ -471,7 +495,7 @@ int pfac_ctx_derived_info(const pfac_ctx *ctx, uint64_t info[16])
     const uint64_t v[16] = {ctx->image_bytes, d.t1_set, d.t2_shift >= 32 ? 0 : (1ull << (32 - d.t2_shift)), d.t2_set,
                             d.n_prefix4, d.has_short, d.tm_set, d.tm2_set,
                             d.t3_shift >= 32 ? 0 : (1ull << (32 - d.t3_shift)), d.t3_set, ctx->smem_bytes,
-                            ctx->table_bytes, ctx->n_stages, d.tm2_bits, 0, 0};
+                            ctx->table_bytes, ctx->n_stages, d.tm2_bits, d.mode, d.tm_bits};
     memcpy(info, v, sizeof v);
     return PFAC_OK;
 }

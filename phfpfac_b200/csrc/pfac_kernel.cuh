@@ -57,7 +57,8 @@ struct ScanParams {
     // shared-memory image (pfac_derive.h)
     const uint4 *image;
     uint32_t image_bytes, off_t2, off_tm, off_tm2, off_t3;
-    uint32_t t2_shift, has_short, has_t3, t3_shift, tm2_bits;
+    uint32_t t2_shift, has_short, has_t3, t3_shift, tm_bits, tm2_bits;
+    const uint8_t *gimage;            // mode 2: T1 | Tm | Tm2 | T3 in global memory (offsets above refer to it)
     uint32_t n_stages;                // depth of the input ring (as many as shared memory holds)
     // output
     unsigned int *tile_cnt;           // [n_tiles] 0 from the detector; the emit kernel writes the tile's match count
@@ -225,6 +226,27 @@ __device__ __forceinline__ void filter16(const uint4 v, const uint32_t nx, uint3
     hi = acc[1] & ((y_hi & z_hi) | (acc[1] >> 3)) & 0x11111111u;
 }
 
+// Stage 1 of the global mode (pattern sets whose prefixes do not fit the shared-memory Tm): the
+// hashed 4-byte prefix of each of the 16 starts against T2, which fills shared memory.  Same result
+// format as filter16.
+__device__ __forceinline__ void filter16_t2(const uint4 v, const uint32_t nx, const uint32_t *__restrict__ t2,
+                                            uint32_t shift, uint32_t &lo, uint32_t &hi)
+{
+    const uint32_t w[5] = {v.x, v.y, v.z, v.w, nx};
+    uint32_t acc[2] = {0u, 0u};
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const uint32_t w4 = j == 0 ? w[k] : __funnelshift_r(w[k], w[k + 1], 8 * j);
+            const uint32_t h = (w4 * kHash4Mul) >> shift;
+            acc[k >> 1] |= ((t2[h >> 5] >> (h & 31u)) & 1u) << (((k & 1) * 4 + j) * 4);
+        }
+    }
+    lo = acc[0];
+    hi = acc[1];
+}
+
 // tile-relative bound of what a start at tile-relative tpos may read (master_kernel.cu:141-144 + input end)
 __device__ __forceinline__ uint32_t walk_limit(const ScanParams &p, uint32_t a0, uint32_t tpos)
 {
@@ -249,12 +271,16 @@ __device__ __forceinline__ void add_candidate(uint32_t *n, uint16_t *list, uint3
     if (i < (uint32_t)kCandPerTile) list[i] = (uint16_t)tpos;
 }
 
+// MODE 0: all filter tables in shared memory (stage 1 = T1).  MODE 2: stage 1 = T2 (the whole
+// shared image), Tm / Tm2 / T3 in global memory.
+template <int MODE>
 __global__ void __launch_bounds__(kThreads, 1) pfac_scan_kernel(const ScanParams p)
 {
     const uint32_t *s_t2 = reinterpret_cast<const uint32_t *>(smem + p.off_t2);
-    const uint16_t *s_tm = reinterpret_cast<const uint16_t *>(smem + p.off_tm);
-    const uint16_t *s_tm2 = reinterpret_cast<const uint16_t *>(smem + p.off_tm2);
-    const uint32_t *s_t3 = reinterpret_cast<const uint32_t *>(smem + p.off_t3);
+    const uint8_t *tab = MODE == 2 ? p.gimage : smem;   // where Tm / Tm2 / T3 live
+    const uint16_t *s_tm = reinterpret_cast<const uint16_t *>(tab + p.off_tm);
+    const uint16_t *s_tm2 = reinterpret_cast<const uint16_t *>(tab + p.off_tm2);
+    const uint32_t *s_t3 = reinterpret_cast<const uint32_t *>(tab + p.off_t3);
     uint8_t *ctl = smem + p.image_bytes;
     uint64_t *s_full = reinterpret_cast<uint64_t *>(ctl);               // [kMaxStages]
     uint64_t *s_empty = reinterpret_cast<uint64_t *>(ctl + 64);         // [kMaxStages]
@@ -378,7 +404,10 @@ __global__ void __launch_bounds__(kThreads, 1) pfac_scan_kernel(const ScanParams
             const uint4 v = *reinterpret_cast<const uint4 *>(buf + off);
             const uint32_t nx = *reinterpret_cast<const uint32_t *>(buf + off + 16);
             uint32_t lo = 0, hi = 0;   // one nibble per start, bit 0 = passes stage 1
-            if (!(p.debug & 4u)) filter16(v, nx, lo, hi);
+            if (!(p.debug & 4u)) {
+                if (MODE == 2) filter16_t2(v, nx, s_t2, p.t2_shift, lo, hi);
+                else filter16(v, nx, lo, hi);
+            }
             if (!interior) {   // start positions are [mis, a_start_end) in aligned coordinates
                 const uint32_t a = a0 + off;
                 const uint32_t first = p.mis > a ? p.mis - a : 0u;
@@ -429,13 +458,13 @@ __global__ void __launch_bounds__(kThreads, 1) pfac_scan_kernel(const ScanParams
                     const uint32_t *wp = reinterpret_cast<const uint32_t *>(buf + (tpos & ~3u));
                     const uint32_t w4 = __funnelshift_r(wp[0], wp[1], (tpos & 3u) * 8u);
                     bool shortp = false;
-                    if (p.has_short) shortp = (smem[rot2x4(w4) & 0xffffu] & kT1Short) != 0;
+                    if (MODE != 2 && p.has_short) shortp = (smem[rot2x4(w4) & 0xffffu] & kT1Short) != 0;
                     if (!shortp) {
                         if (!p.has_t3) {
                             const uint32_t h = (w4 * kHash4Mul) >> p.t2_shift;
                             keep = (s_t2[h >> 5] >> (h & 31u)) & 1u;
                         } else {
-                            const uint32_t m1 = tm_lookup(s_tm, w4, kTmSlotBits);   // 0 = no pattern has this prefix
+                            const uint32_t m1 = tm_lookup(s_tm, w4, p.tm_bits);   // 0 = no pattern has this prefix
                             const uint32_t lim = interior ? tpos + p.max_pat_len : walk_limit(p, a0, tpos);   // never past the staged halo
                             keep = m1 != 0 && tpos + m1 <= lim;
                             if (keep) {
