@@ -342,6 +342,37 @@ def test_job_all_gpus_and_segments():
         job.close()
 
 
+def test_job_multi_segment_64bit_positions():
+    """A shard larger than one 1 GiB segment: records carry 32-bit positions relative to a 64-bit
+    segment base (the reference's int positions stop at 2 GiB, main.cc:79).  Properties: globally
+    sorted, every record re-verified against its pattern, a match planted across the segment
+    border is found, and the rendered lines carry positions > 2^30."""
+    torch = torch_cuda()
+    pats = pf.synth_patterns(0, 1000, 1, 8, 32)
+    lines = pats.split(b"\n")[:-1]
+    n = (1 << 30) + (3 << 20) + 17
+    text = pf.synth_text(0, 2, n, patterns=pats)
+    border = 1 << 30
+    p0 = lines[5]
+    text[border - 3:border - 3 + len(p0)] = np.frombuffer(p0, dtype=np.uint8)      # straddles the segment border
+    text[n - len(lines[9]):n] = np.frombuffer(lines[9], dtype=np.uint8)            # ends exactly at input_size
+    t = pf.Tables.from_bytes(pats, 1, 256)
+    job = pf.Job(t, devices=[0], streams_per_gpu=4)
+    total, segs = job.run(text)
+    assert len(segs) == 2 and segs[1][0] == border
+    gp = np.concatenate([s[1][:, 0].astype(np.int64) + s[0] for s in segs])
+    gi = np.concatenate([s[1][:, 1].astype(np.int64) for s in segs])
+    assert total == len(gp) >= n // 65536
+    assert (np.diff(gp * 4096 + gi) > 0).all()
+    assert (border - 3) in gp and (n - len(lines[9])) in gp
+    for k in range(0, len(gp), max(1, len(gp) // 3000)):
+        pat = lines[int(gi[k]) - 1]
+        assert text[int(gp[k]):int(gp[k]) + len(pat)].tobytes() == pat
+    tail = pf.format_records(np.array([(int(gp[-1] - segs[1][0]), int(gi[-1]))], dtype=pf.MATCH_DTYPE), base_pos=segs[1][0])
+    assert tail == b"At position %4d, match pattern %d\n" % (int(gp[-1]), int(gi[-1]))
+    job.close()
+
+
 def test_cli_byte_identical_result_file(fixtures, golden, tmp_path):
     """gphf <pattern file> <streams> <width> <input file> -> GPU_match_result.txt (main.cc:94,335)."""
     pat = tmp_path / "experimentpattern"
