@@ -67,6 +67,15 @@ int pfac_abi_version(void);
  * partition count).  `width` is the PHF key-table width, argv[3]. */
 int pfac_tables_build_file(const char *pattern_file, int n_parts, int width, pfac_tables **out);
 int pfac_tables_build_mem(const void *pattern_bytes, size_t len, int n_parts, int width, pfac_tables **out);
+/* The same with front-end flags.  PFAC_PATTERNS_ESCAPES reads the pattern file through the
+ * reference's escape-processing reader, read_pattern_ext / fgetc_ext (create_table_reorder.c:131-185,
+ * ctdef.h:37-99: \ooo, \xhh, \a \b \t \n \v \f \r \' \" \\) -- code the reference ships but its
+ * main() never calls, hence behind a flag. */
+#define PFAC_PATTERNS_ESCAPES 1u
+int pfac_tables_build_file_ext(const char *pattern_file, int n_parts, int width, unsigned flags,
+                               pfac_tables **out);
+int pfac_tables_build_mem_ext(const void *pattern_bytes, size_t len, int n_parts, int width,
+                              unsigned flags, pfac_tables **out);
 /* Wrap caller-built canonical arrays (the thread_data fields of main.cc:19-32) as a
  * one-partition table set; arrays are copied.  n_r = state_num*256/width + 1
  * (master_kernel.cu:221). */

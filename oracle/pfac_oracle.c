@@ -152,6 +152,102 @@ static int read_patterns_mem(const unsigned char *buf, size_t len, opattern **ou
     return ORACLE_OK;
 }
 
+/* ctdef.h:37-99 (fgetc_ext) over a memory buffer: merges a backslash and what follows into one
+ * byte.  Returns the byte, REF_EOL for a raw newline (pattern separator), -1 at end of input.
+ * fscanf("%3o") / fscanf("%2x") are restated as "up to 3 octal / 2 hex digits"; %2x skips leading
+ * white space like scanf does.  (Not restated: scanf's optional sign and 0x prefix inside %x.) */
+#define REF_EOL 0x10A   /* ctdef.h:13 */
+static int fgetc_ext_mem(const unsigned char *buf, size_t len, size_t *pi)
+{
+    size_t i = *pi;
+    int ch0 = i < len ? buf[i] : -1;
+    i++;
+    if (ch0 == '\\') {                                   /* :46 */
+        int ch1 = i < len ? buf[i] : -1;
+        i++;
+        if (ch1 < 0) { *pi = i; return ch0; }             /* :50-52 feof */
+        if (ch1 >= '0' && ch1 <= '9') {                   /* :55-59 isdigit, then %3o */
+            int value = 0, nd = 0;
+            i--;
+            while (nd < 3 && i < len && buf[i] >= '0' && buf[i] <= '7') { value = value * 8 + (buf[i] - '0'); i++; nd++; }
+            *pi = i;
+            return (int)((char)value);
+        }
+        *pi = i;
+        switch (ch1) {                                    /* :61-91 */
+        case 'a': return '\a';
+        case 'b': return '\b';
+        case 't': return '\t';
+        case 'n': return '\n';
+        case 'v': return '\v';
+        case 'f': return '\f';
+        case 'r': return '\r';
+        case '\'': case '\"': case '\\': return ch1;
+        case 'x': {                                       /* :80-86 %2x */
+            int value = 0, nd = 0;
+            while (i < len && (buf[i] == ' ' || (buf[i] >= 9 && buf[i] <= 13))) i++;
+            while (nd < 2 && i < len) {
+                int c = buf[i], d;
+                if (c >= '0' && c <= '9') d = c - '0';
+                else if (c >= 'a' && c <= 'f') d = c - 'a' + 10;
+                else if (c >= 'A' && c <= 'F') d = c - 'A' + 10;
+                else break;
+                value = value * 16 + d; i++; nd++;
+            }
+            *pi = i;
+            return (int)((char)value);
+        }
+        default:                                          /* :87-90 not an escape */
+            *pi = i - 1;
+            return ch0;
+        }
+    }
+    *pi = i;
+    if (ch0 == '\n') return REF_EOL;                      /* :94-96 */
+    return ch0;
+}
+
+/* create_table_reorder.c:131-185 (read_pattern_ext): like read_pattern but through fgetc_ext. */
+static int read_patterns_ext_mem(const unsigned char *buf, size_t len, opattern **out, int *n_out)
+{
+    size_t cap = 1024, n = 0, i = 0;
+    opattern *all = (opattern *)malloc(cap * sizeof(opattern));
+    char str[REF_MAX_PATTERN_BUF];
+    int rc = ORACLE_OK;
+    if (!all) return ORACLE_ERR_NOMEM;
+    if (len == 0) { free(all); return ORACLE_ERR_PATTERN_TOO_LONG; }
+    while (1) {
+        int str_len = 0;
+        while (1) {
+            int ch = fgetc_ext_mem(buf, len, &i);          /* :152 */
+            if (str_len >= REF_MAX_PATTERN_BUF - 1) { rc = ORACLE_ERR_PATTERN_TOO_LONG; goto fail; }   /* :155-158 */
+            str[str_len++] = (char)ch;
+            if (ch == REF_EOL) { str_len -= 1; break; }    /* :160-164 */
+        }
+        if (str_len == 0) { rc = ORACLE_ERR_EMPTY_PATTERN; goto fail; }
+        if (n == cap) {
+            cap *= 2;
+            opattern *t = (opattern *)realloc(all, cap * sizeof(opattern));
+            if (!t) { rc = ORACLE_ERR_NOMEM; goto fail; }
+            all = t;
+        }
+        all[n].pattern_id = (int)n + 1;                    /* :168 */
+        all[n].pattern_len = str_len;
+        all[n].pat = (char *)malloc((size_t)str_len);
+        memcpy(all[n].pat, str, (size_t)str_len);
+        n++;
+        if (i >= len) break;                                /* :174-180 */
+    }
+    qsort(all, n, sizeof(opattern), comp_pat);              /* :183 */
+    *out = all;
+    *n_out = (int)n;
+    return ORACLE_OK;
+fail:
+    for (size_t k = 0; k < n; k++) free(all[k].pat);
+    free(all);
+    return rc;
+}
+
 /* ------------------------------------------------------------------ PFAC trie */
 
 static int part_grow(opart *p, int need)
@@ -325,14 +421,25 @@ void oracle_free(oracle_t *o)
  * + main.cc:120-126 (one FFDM per partition).  The reference always makes
  * n_parts = 4*streamnum partitions (GPU_S = 4, :207,217); n_parts is a parameter here
  * so tests can also build the single automaton the product scans with. */
+static oracle_t *oracle_build_any(const unsigned char *buf, size_t len, int n_parts, int width, int escapes, int *err);
 oracle_t *oracle_build_mem(const unsigned char *buf, size_t len, int n_parts, int width, int *err)
+{
+    return oracle_build_any(buf, len, n_parts, width, 0, err);
+}
+/* the same flow with read_pattern_ext as the front-end (unused by the reference's main, kept behind a flag) */
+oracle_t *oracle_build_mem_ext(const unsigned char *buf, size_t len, int n_parts, int width, int *err)
+{
+    return oracle_build_any(buf, len, n_parts, width, 1, err);
+}
+static oracle_t *oracle_build_any(const unsigned char *buf, size_t len, int n_parts, int width, int escapes, int *err)
 {
     int e = ORACLE_OK;
     oracle_t *o = (oracle_t *)calloc(1, sizeof(oracle_t));
     if (!o) { if (err) *err = ORACLE_ERR_NOMEM; return NULL; }
     if (n_parts < 1 || width < 1) { e = ORACLE_ERR_ARG; goto fail; }
     o->width = width;
-    e = read_patterns_mem(buf, len, &o->patterns, &o->n_patterns);
+    e = escapes ? read_patterns_ext_mem(buf, len, &o->patterns, &o->n_patterns)
+                : read_patterns_mem(buf, len, &o->patterns, &o->n_patterns);
     if (e) goto fail;
     o->n_parts = n_parts;
     o->parts = (opart *)calloc((size_t)n_parts, sizeof(opart));

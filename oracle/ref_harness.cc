@@ -33,6 +33,8 @@ int create_PFAC_table_reorder(char *patternfilename, int *state_num, int *final_
                               int ***PFACs, int **patternIdMaps);
 /* create_table_reorder.c:53, :277 */
 ref_pattern_s *read_pattern(char *patternfilename, int *pattern_num, ref_pattern_s all_pattern[]);
+/* create_table_reorder.c:131 */
+void read_pattern_ext(char *patternfilename, int *pattern_num, ref_pattern_s all_pattern[]);
 int **patternsToPFAC(ref_pattern_s patterns[], int pattern_num, int **PFAC, int *max_pat_length,
                      int *state_num, int patternIdMap[]);
 extern int INITIAL_PFAC_SIZE;   /* create_table_reorder.c:10 */
@@ -117,6 +119,27 @@ ref_tables *ref_build_single(const char *pattern_file, int width, int pfac_rows)
     int n = 0;
     ref_pattern_s *all = (ref_pattern_s *)malloc((size_t)INITIAL_SIZE * sizeof(ref_pattern_s));
     all = read_pattern((char *)pattern_file, &n, all);
+    t->PFACs[0] = (int **)malloc((size_t)INITIAL_PFAC_SIZE * sizeof(int *));
+    t->idmaps[0] = (int *)malloc((size_t)(n > 0 ? n : 1) * sizeof(int));
+    t->PFACs[0] = patternsToPFAC(&all[1], n, t->PFACs[0], &t->max_len_arr[0], &t->state_num[0],
+                                 t->idmaps[0]);
+    t->final_num[0] = n;
+    t->max_pat_len = t->max_len_arr[0];
+    t->HTSize[0] = FFDM(t->PFACs[0], t->state_num[0], width, t->r[0], t->HT[0], t->val[0]);
+    return t;
+}
+
+/* The same with the reference's escape-processing reader (read_pattern_ext + fgetc_ext). */
+ref_tables *ref_build_single_ext(const char *pattern_file, int width, int pfac_rows)
+{
+    quiet q;
+    ref_tables *t = alloc_tables(1, width);
+    INITIAL_PFAC_SIZE = pfac_rows;
+    t->pfac_rows = pfac_rows;
+    INITIAL_SIZE = 100000;
+    int n = 0;
+    ref_pattern_s *all = (ref_pattern_s *)malloc((size_t)INITIAL_SIZE * sizeof(ref_pattern_s));
+    read_pattern_ext((char *)pattern_file, &n, all);
     t->PFACs[0] = (int **)malloc((size_t)INITIAL_PFAC_SIZE * sizeof(int *));
     t->idmaps[0] = (int *)malloc((size_t)(n > 0 ? n : 1) * sizeof(int));
     t->PFACs[0] = patternsToPFAC(&all[1], n, t->PFACs[0], &t->max_len_arr[0], &t->state_num[0],

@@ -60,16 +60,17 @@ class Tables:
         self.width = lib.pfac_tables_width(handle)
 
     @classmethod
-    def from_file(cls, path, n_parts=1, width=256):
+    def from_file(cls, path, n_parts=1, width=256, escapes=False):
         h = C.c_void_p()
-        check(lib.pfac_tables_build_file(str(path).encode(), n_parts, width, C.byref(h)))
+        check(lib.pfac_tables_build_file_ext(str(path).encode(), n_parts, width, 1 if escapes else 0, C.byref(h)))
         return cls(h)
 
     @classmethod
-    def from_bytes(cls, data, n_parts=1, width=256):
+    def from_bytes(cls, data, n_parts=1, width=256, escapes=False):
+        """escapes=True: read_pattern_ext / fgetc_ext front-end (create_table_reorder.c:131, ctdef.h:37)."""
         data = bytes(data)
         h = C.c_void_p()
-        check(lib.pfac_tables_build_mem(data, len(data), n_parts, width, C.byref(h)))
+        check(lib.pfac_tables_build_mem_ext(data, len(data), n_parts, width, 1 if escapes else 0, C.byref(h)))
         return cls(h)
 
     @classmethod

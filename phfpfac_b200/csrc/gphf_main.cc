@@ -41,7 +41,9 @@ int main(int argc, char **argv)
 
     double t0 = now();
     pfac_tables *tables = nullptr;
-    if (pfac_tables_build_file(argv[1], 1, width, &tables)) return fail("create PFAC/PHF tables");
+    // GPHF_ESCAPES=1: read the patterns through the reference's (unused) escape reader, read_pattern_ext
+    const unsigned pflags = getenv("GPHF_ESCAPES") && atoi(getenv("GPHF_ESCAPES")) ? PFAC_PATTERNS_ESCAPES : 0u;
+    if (pfac_tables_build_file_ext(argv[1], 1, width, pflags, &tables)) return fail("create PFAC/PHF tables");
     double t1 = now();
     int32_t info[9];
     pfac_tables_part_info(tables, 0, info);

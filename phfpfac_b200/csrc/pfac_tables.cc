@@ -99,6 +99,87 @@ int read_patterns(const unsigned char *buf, size_t len, std::vector<Pattern> &ou
     return PFAC_OK;
 }
 
+// ctdef.h:37-99 (fgetc_ext): a backslash and what follows merge into one byte.  Returns the byte
+// (0..255), kEol for a raw newline, -1 at the end of the buffer.  "%3o" / "%2x" = up to 3 octal /
+// 2 hex digits (scanf's white-space skip before %x is kept, its sign / 0x prefix handling is not).
+constexpr int kEol = 0x10A;   // ctdef.h:13
+int next_escaped(const unsigned char *buf, size_t len, size_t &i)
+{
+    const int ch0 = i < len ? buf[i] : -1;
+    i++;
+    if (ch0 == '\\') {
+        const int ch1 = i < len ? buf[i] : -1;
+        i++;
+        if (ch1 < 0) return ch0;                                  // :50-52
+        if (ch1 >= '0' && ch1 <= '9') {                           // :55-59
+            int value = 0, nd = 0;
+            i--;
+            while (nd < 3 && i < len && buf[i] >= '0' && buf[i] <= '7') { value = value * 8 + (buf[i] - '0'); i++; nd++; }
+            return value & 255;
+        }
+        switch (ch1) {                                            // :61-91
+        case 'a': return '\a';
+        case 'b': return '\b';
+        case 't': return '\t';
+        case 'n': return '\n';
+        case 'v': return '\v';
+        case 'f': return '\f';
+        case 'r': return '\r';
+        case '\'': case '\"': case '\\': return ch1;
+        case 'x': {
+            int value = 0, nd = 0;
+            while (i < len && (buf[i] == ' ' || (buf[i] >= 9 && buf[i] <= 13))) i++;
+            while (nd < 2 && i < len) {
+                const int c = buf[i];
+                int d;
+                if (c >= '0' && c <= '9') d = c - '0';
+                else if (c >= 'a' && c <= 'f') d = c - 'a' + 10;
+                else if (c >= 'A' && c <= 'F') d = c - 'A' + 10;
+                else break;
+                value = value * 16 + d;
+                i++;
+                nd++;
+            }
+            return value & 255;
+        }
+        default:                                                  // :87-90: not an escape
+            i--;
+            return ch0;
+        }
+    }
+    if (ch0 == '\n') return kEol;                                 // :94-96
+    return ch0;
+}
+
+// create_table_reorder.c:131-185 (read_pattern_ext): read_pattern through fgetc_ext.  The decoded
+// bytes live in `arena` (never reallocated: a decoded pattern is not longer than its source).
+int read_patterns_ext(const unsigned char *buf, size_t len, std::vector<unsigned char> &arena, std::vector<Pattern> &out)
+{
+    if (len == 0) return set_error(PFAC_ERR_PATTERN_TOO_LONG, "pattern file is empty");
+    arena.clear();
+    arena.reserve(len + 1);
+    size_t i = 0;
+    while (true) {
+        const size_t start = arena.size();
+        while (true) {
+            if (i >= len)   // the reference spins on EOF until the 1024 limit trips (:155-158)
+                return set_error(PFAC_ERR_PATTERN_TOO_LONG, "pattern %zu: file does not end with a newline", out.size() + 1);
+            const int ch = next_escaped(buf, len, i);
+            if (ch == kEol) break;
+            if (arena.size() - start >= (size_t)kMaxPatternBytes)
+                return set_error(PFAC_ERR_PATTERN_TOO_LONG, "Pattern %zu length over 1024.", out.size() + 1);
+            arena.push_back((unsigned char)(ch & 255));
+        }
+        const size_t plen = arena.size() - start;
+        if (plen == 0) return set_error(PFAC_ERR_EMPTY_PATTERN, "pattern %zu is empty", out.size() + 1);
+        out.push_back(Pattern{arena.data() + start, (int)plen, (int)out.size() + 1});
+        if (i >= len) break;
+    }
+    std::stable_sort(out.begin(), out.end(),
+                     [](const Pattern &a, const Pattern &b) { return comp_pat(a, b) < 0; });
+    return PFAC_OK;
+}
+
 // create_table_reorder.c:277-378 (patternsToPFAC) for an already sorted slice.
 // State numbering: finals 0..n-1 = index in the slice (:366), n unused, initial n+1 (:288),
 // interior states from n+2 in creation order (:292,331-333).
@@ -341,13 +422,14 @@ int ffdm(Partition &P, int width)
     return PFAC_OK;
 }
 
-int build(const unsigned char *buf, size_t len, int n_parts, int width, pfac_tables **out)
+int build(const unsigned char *buf, size_t len, int n_parts, int width, unsigned flags, pfac_tables **out)
 {
     if (!out || n_parts < 1) return set_error(PFAC_ERR_ARG, "bad arguments");
     if (width_bits(width) < 0)
         return set_error(PFAC_ERR_WIDTH, "width must be a power of two in [1,4096], got %d", width);
     std::vector<Pattern> pats;
-    int e = read_patterns(buf, len, pats);
+    std::vector<unsigned char> arena;
+    int e = (flags & PFAC_PATTERNS_ESCAPES) ? read_patterns_ext(buf, len, arena, pats) : read_patterns(buf, len, pats);
     if (e) return e;
     std::unique_ptr<pfac_tables> t(new pfac_tables);
     t->n_patterns = (int)pats.size();
@@ -382,15 +464,26 @@ int pfac_abi_version(void) { return PFAC_B200_ABI_VERSION; }
 
 int pfac_tables_build_mem(const void *pattern_bytes, size_t len, int n_parts, int width, pfac_tables **out)
 {
+    return pfac_tables_build_mem_ext(pattern_bytes, len, n_parts, width, 0u, out);
+}
+
+int pfac_tables_build_mem_ext(const void *pattern_bytes, size_t len, int n_parts, int width, unsigned flags,
+                              pfac_tables **out)
+{
     if (!pattern_bytes && len) return set_error(PFAC_ERR_ARG, "null pattern buffer");
     try {
-        return build((const unsigned char *)pattern_bytes, len, n_parts, width, out);
+        return build((const unsigned char *)pattern_bytes, len, n_parts, width, flags, out);
     } catch (const std::bad_alloc &) {
         return set_error(PFAC_ERR_NOMEM, "out of memory building tables");
     }
 }
 
 int pfac_tables_build_file(const char *pattern_file, int n_parts, int width, pfac_tables **out)
+{
+    return pfac_tables_build_file_ext(pattern_file, n_parts, width, 0u, out);
+}
+
+int pfac_tables_build_file_ext(const char *pattern_file, int n_parts, int width, unsigned flags, pfac_tables **out)
 {
     FILE *f = pattern_file ? fopen(pattern_file, "rb") : nullptr;
     if (!f) return set_error(PFAC_ERR_IO, "Open input file failed: %s", pattern_file ? pattern_file : "(null)");
@@ -399,7 +492,7 @@ int pfac_tables_build_file(const char *pattern_file, int n_parts, int width, pfa
     size_t got;
     while ((got = fread(tmp, 1, sizeof tmp, f)) > 0) buf.insert(buf.end(), tmp, tmp + got);
     fclose(f);
-    return pfac_tables_build_mem(buf.data(), buf.size(), n_parts, width, out);
+    return pfac_tables_build_mem_ext(buf.data(), buf.size(), n_parts, width, flags, out);
 }
 
 int pfac_tables_from_arrays(const int32_t *s0, const int32_t *r, int32_t n_r, const int32_t *HT,

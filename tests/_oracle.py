@@ -34,6 +34,8 @@ def _load_oracle():
     lib = C.CDLL(ORACLE_SO)
     lib.oracle_build_mem.restype = C.c_void_p
     lib.oracle_build_mem.argtypes = [C.c_char_p, C.c_size_t, C.c_int, C.c_int, C.POINTER(C.c_int)]
+    lib.oracle_build_mem_ext.restype = C.c_void_p
+    lib.oracle_build_mem_ext.argtypes = [C.c_char_p, C.c_size_t, C.c_int, C.c_int, C.POINTER(C.c_int)]
     lib.oracle_build_file.restype = C.c_void_p
     lib.oracle_build_file.argtypes = [C.c_char_p, C.c_int, C.c_int, C.POINTER(C.c_int)]
     lib.oracle_free.argtypes = [C.c_void_p]
@@ -102,11 +104,12 @@ class PartTables:
 
 
 class Oracle:
-    def __init__(self, pattern_bytes, n_parts=4, width=256):
+    def __init__(self, pattern_bytes, n_parts=4, width=256, escapes=False):
         lib = oracle_lib()
         err = C.c_int(0)
         self._lib = lib
-        self._h = lib.oracle_build_mem(pattern_bytes, len(pattern_bytes), n_parts, width, C.byref(err))
+        build = lib.oracle_build_mem_ext if escapes else lib.oracle_build_mem
+        self._h = build(pattern_bytes, len(pattern_bytes), n_parts, width, C.byref(err))
         if not self._h:
             raise ValueError(f"oracle build failed: {err.value}")
         self.err = err.value
@@ -195,6 +198,8 @@ def ref_lib():
         lib.ref_build.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int]
         lib.ref_build_single.restype = C.c_void_p
         lib.ref_build_single.argtypes = [C.c_char_p, C.c_int, C.c_int]
+        lib.ref_build_single_ext.restype = C.c_void_p
+        lib.ref_build_single_ext.argtypes = [C.c_char_p, C.c_int, C.c_int]
         lib.ref_free.argtypes = [C.c_void_p]
         lib.ref_n_parts.argtypes = [C.c_void_p]
         lib.ref_max_pat_len.argtypes = [C.c_void_p]
@@ -211,13 +216,15 @@ def ref_lib():
 class RefBuild:
     """Tables built by the reference's own create_PFAC_table_reorder / patternsToPFAC / FFDM."""
 
-    def __init__(self, pattern_file, streamnum=1, width=256, single=False, pfac_rows=None):
+    def __init__(self, pattern_file, streamnum=1, width=256, single=False, pfac_rows=None, escapes=False):
         lib = ref_lib()
         if pfac_rows is None:
             pfac_rows = os.path.getsize(pattern_file) + 16
         self._lib = lib
         self.width = width
-        if single:
+        if escapes:
+            self._h = lib.ref_build_single_ext(pattern_file.encode(), width, pfac_rows)
+        elif single:
             self._h = lib.ref_build_single(pattern_file.encode(), width, pfac_rows)
         else:
             self._h = lib.ref_build(pattern_file.encode(), streamnum, width, pfac_rows)

@@ -169,3 +169,45 @@ def test_derived_device_tables_selfcheck(fixtures, case):
     p = pf.Tables.from_bytes(blob, 1, 256).part(0)
     t2 = pf.Tables.from_arrays(p.s0, p.r, p.HT, p.val, 256, p.state_num, p.n_final, p.idmap, p.max_len)
     assert t2.derive_check() == pf.Tables.from_bytes(blob, 1, 256).derive_check()
+
+
+ESCAPED = (b"GET \\x2f\\x2Findex\n"          # \xhh
+           b"tab\\there\n"                   # \t
+           b"nul\\0byte\\101\\7z\n"          # \o, \ooo (\101 = 'A'), \7
+           b"quote\\\"\\'\\\\end\n"          # \" \' \\
+           b"line\\nfeed\\r\n"               # \n inside a pattern, \r
+           b"not\\qescape\\\n"               # \q is not an escape: the backslash stays; trailing backslash + EOL
+           b"\\a\\b\\v\\f\n"
+           b"hi\\xffgh\\x7\n")               # \xff, one-digit \x7
+
+
+def test_escape_front_end_matches_oracle_and_reference(tmp_path):
+    """PFAC_PATTERNS_ESCAPES = read_pattern_ext / fgetc_ext (create_table_reorder.c:131-185,
+    ctdef.h:37-99).  Product == oracle restatement == the reference's own reader (where built)."""
+    o = Oracle(ESCAPED, n_parts=1, width=256, escapes=True)
+    t = pf.Tables.from_bytes(ESCAPED, n_parts=1, width=256, escapes=True)
+    assert t.n_patterns == o.n_patterns == 8
+    assert same(t.part(0), o.part(0))
+    # decoded bytes, checked by walking the automaton: "GET //index", "tab\there", "line\nfeed\r", ...
+    p = t.part(0)
+    for want in (b"GET //index", b"tab\there", b"nul\x00byteA\x07z", b"quote\"'\\end", b"line\nfeed\r",
+                 b"not\\qescape\\", b"\a\b\v\f", b"hi\xffgh\x07"):
+        s = int(p.s0[want[0]])
+        for b in want[1:]:
+            s = t.lookup(s, b)
+            assert s >= 0, want
+        assert s < p.n_final, want
+    # without the flag the bytes are taken literally (read_pattern, the reference's live path)
+    plain = pf.Tables.from_bytes(ESCAPED, n_parts=1, width=256)
+    assert plain.max_pat_len > t.max_pat_len
+    f = tmp_path / "esc"
+    f.write_bytes(ESCAPED)
+    assert same(pf.Tables.from_file(str(f), 1, 256, escapes=True).part(0), t.part(0))
+    if ref_available() and os.path.isdir("/root/reference"):
+        rb = RefBuild(str(f), width=256, escapes=True)
+        assert same(t.part(0), rb.part(0)) and same(o.part(0), rb.part(0))
+    for blob in (b"abc\\", b"\\x41", b"\n"):     # no trailing newline / empty pattern
+        with pytest.raises(pf.PfacError):
+            pf.Tables.from_bytes(blob, 1, 256, escapes=True)
+        with pytest.raises(ValueError):
+            Oracle(blob, 1, 256, escapes=True)
