@@ -149,6 +149,11 @@ int pfac_scan_host(pfac_ctx *ctx, const void *h_in, uint64_t n_starts, uint64_t 
 /* Pinned host memory (cudaHostAlloc portable, as main.cc:147,161). */
 int pfac_host_alloc(void **ptr, size_t bytes);
 void pfac_host_free(void *ptr);
+/* Pin memory the caller already has (e.g. an mmap of the input file, read_only = 1) so that H2D
+ * copies run at link speed without a staging copy; the reference freads the whole file into a
+ * cudaHostAlloc buffer instead (main.cc:147-155).  Failure is not fatal: scan from pageable memory. */
+int pfac_host_register(const void *ptr, size_t bytes, int read_only);
+void pfac_host_unregister(const void *ptr);
 
 /* Counters of the last scan on this context (for bench.py's gpu_launches / roofline):
  * info[0] = kernel launches, info[1] = tiles, info[2] = CTAs, info[3] = dynamic smem bytes,

@@ -241,6 +241,23 @@ class Job:
         self.close()
 
 
+class pinned:
+    """Context manager: pin a numpy array in place (pfac_host_register) for link-speed H2D copies."""
+
+    def __init__(self, arr, read_only=False):
+        self.arr, self.read_only, self.ok = arr, read_only, False
+
+    def __enter__(self):
+        check(lib.pfac_host_register(self.arr.ctypes.data, self.arr.nbytes, int(self.read_only)))
+        self.ok = True
+        return self.arr
+
+    def __exit__(self, *exc):
+        if self.ok:
+            lib.pfac_host_unregister(self.arr.ctypes.data)
+        return False
+
+
 def plan_shard(n, n_shards, max_pat_len, i):
     """pfac_job_plan: (start, n_starts, n_valid) of shard i -- contiguous chunk + halo of max_pat_len-1."""
     a, b, c = C.c_uint64(0), C.c_uint64(0), C.c_uint64(0)

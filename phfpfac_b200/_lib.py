@@ -18,7 +18,7 @@ ABI_SYMBOLS = [
     "pfac_tables_part_info", "pfac_tables_s0", "pfac_tables_r", "pfac_tables_HT", "pfac_tables_val",
     "pfac_tables_idmap", "pfac_tables_lookup", "pfac_tables_derive_check", "pfac_tables_filter_profile",
     "pfac_device_count", "pfac_ctx_create", "pfac_ctx_destroy", "pfac_ctx_device",
-    "pfac_scan_device", "pfac_scan_device_sync", "pfac_scan_host", "pfac_host_alloc", "pfac_host_free",
+    "pfac_scan_device", "pfac_scan_device_sync", "pfac_scan_host", "pfac_host_alloc", "pfac_host_free", "pfac_host_register", "pfac_host_unregister",
     "pfac_ctx_last_scan_info", "pfac_ctx_derived_info", "pfac_ctx_set_timing", "pfac_ctx_kernel_time",
     "pfac_job_create", "pfac_job_destroy", "pfac_job_run", "pfac_job_n_segments", "pfac_job_segment",
     "pfac_job_last_timing", "pfac_job_plan",
@@ -80,6 +80,9 @@ def _load():
     lib.pfac_host_alloc.argtypes = [C.POINTER(_vp), C.c_size_t]
     lib.pfac_host_free.argtypes = [_vp]
     lib.pfac_host_free.restype = None
+    lib.pfac_host_register.argtypes = [_vp, C.c_size_t, C.c_int]
+    lib.pfac_host_unregister.argtypes = [_vp]
+    lib.pfac_host_unregister.restype = None
     lib.pfac_ctx_last_scan_info.argtypes = [_vp, C.POINTER(C.c_uint64)]
     lib.pfac_ctx_set_timing.argtypes = [_vp, C.c_int]
     lib.pfac_ctx_kernel_time.argtypes = [_vp, C.POINTER(C.c_double), C.POINTER(C.c_int)]

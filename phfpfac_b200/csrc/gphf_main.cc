@@ -12,6 +12,11 @@
 #include <cstring>
 #include <vector>
 
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
 #include "pfac_b200.h"
 
 static double now()
@@ -50,14 +55,20 @@ int main(int argc, char **argv)
     printf("state num : %d\nfinal state num : %d\nmax pattern length : %d\nhash table size : %d\n", info[0],
            info[1], info[2], info[3]);
 
-    FILE *fpin = fopen(argv[4], "rb");   // main.cc:131
-    if (!fpin) {
+    // Input: the reference freads the file into a cudaHostAlloc buffer (main.cc:131-155).  Here the
+    // file is mapped and the mapping pinned in place (no second copy of a multi-GB input); if either
+    // step is refused, fall back to the reference's way.  GPHF_READER=fread forces the fallback.
+    int fd = open(argv[4], O_RDONLY);
+    if (fd < 0) {
         perror("Open input file failed.");
         return 1;
     }
-    fseek(fpin, 0, SEEK_END);
-    long long fsize = ftell(fpin);
-    rewind(fpin);
+    struct stat sb;
+    if (fstat(fd, &sb) != 0) {
+        perror("Open input file failed.");
+        return 1;
+    }
+    const long long fsize = (long long)sb.st_size;
     const uint64_t input_size = fsize > 0 ? (uint64_t)fsize - 1 : 0;   // main.cc:138 (drops the last byte)
     printf("input size is %llu char\n", (unsigned long long)input_size);
 
@@ -65,13 +76,31 @@ int main(int argc, char **argv)
     if (pfac_device_count(&n_gpu) || n_gpu < 1) return fail("no CUDA device");   // main.cc:50
     if (getenv("GPHF_GPUS")) n_gpu = std::max(1, std::min(n_gpu, atoi(getenv("GPHF_GPUS"))));
 
-    void *input = nullptr;
-    if (pfac_host_alloc(&input, (size_t)input_size + 1)) return fail("cudaHostAlloc input");   // main.cc:147
-    if (input_size && fread(input, 1, (size_t)input_size, fpin) != (size_t)input_size) {         // main.cc:154
-        fprintf(stderr, "short read on %s\n", argv[4]);
-        return 1;
+    void *input = nullptr, *mapped = nullptr;
+    bool registered = false;
+    const bool want_mmap = !(getenv("GPHF_READER") && !strcmp(getenv("GPHF_READER"), "fread"));
+    if (want_mmap && fsize > 0) {
+        mapped = mmap(nullptr, (size_t)fsize, PROT_READ, MAP_PRIVATE | MAP_POPULATE, fd, 0);
+        if (mapped == MAP_FAILED) mapped = nullptr;
     }
-    fclose(fpin);
+    if (mapped) {
+        registered = pfac_host_register(mapped, (size_t)fsize, 1) == 0;
+        input = mapped;
+        printf("input reader: mmap%s\n", registered ? " + pinned in place" : " (pageable)");
+    } else {
+        if (pfac_host_alloc(&input, (size_t)input_size + 1)) return fail("cudaHostAlloc input");   // main.cc:147
+        size_t got = 0;
+        while (got < (size_t)input_size) {                                                          // main.cc:154
+            ssize_t r = read(fd, (char *)input + got, (size_t)input_size - got);
+            if (r <= 0) {
+                fprintf(stderr, "short read on %s\n", argv[4]);
+                return 1;
+            }
+            got += (size_t)r;
+        }
+        printf("input reader: fread into pinned memory\n");
+    }
+    close(fd);
 
     pfac_job *job = nullptr;
     if (pfac_job_create(tables, nullptr, n_gpu, streamnum, 0, &job)) return fail("create GPU contexts");
@@ -100,7 +129,12 @@ int main(int argc, char **argv)
     printf("matching process finshed\n");
     printf("/////////////////////////////////////////////\n");
     pfac_job_destroy(job);
-    pfac_host_free(input);
+    if (mapped) {
+        if (registered) pfac_host_unregister(mapped);
+        munmap(mapped, (size_t)fsize);
+    } else {
+        pfac_host_free(input);
+    }
     pfac_tables_destroy(tables);
     return 0;
 }

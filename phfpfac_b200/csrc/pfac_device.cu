@@ -559,6 +559,24 @@ void pfac_host_free(void *ptr)
     if (ptr) cudaFreeHost(ptr);
 }
 
+int pfac_host_register(const void *ptr, size_t bytes, int read_only)
+{
+    if (!ptr || !bytes) return set_error(PFAC_ERR_ARG, "bad arguments to pfac_host_register");
+    unsigned flags = cudaHostRegisterPortable;
+    if (read_only) flags |= cudaHostRegisterReadOnly;
+    cudaError_t e = cudaHostRegister(const_cast<void *>(ptr), bytes, flags);
+    if (e != cudaSuccess) {
+        cudaGetLastError();   // not sticky: the caller may go on with pageable memory
+        return set_error(PFAC_ERR_CUDA, "cudaHostRegister(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
+    }
+    return PFAC_OK;
+}
+
+void pfac_host_unregister(const void *ptr)
+{
+    if (ptr) cudaHostUnregister(const_cast<void *>(ptr));
+}
+
 int pfac_ctx_last_scan_info(const pfac_ctx *ctx, uint64_t info[8])
 {
     if (!ctx || !info) return set_error(PFAC_ERR_ARG, "bad arguments");

@@ -373,6 +373,21 @@ def test_job_multi_segment_64bit_positions():
     job.close()
 
 
+def test_host_register_in_place(fixtures):
+    """pfac_host_register: scanning from caller memory pinned in place gives the same records."""
+    t = pf.Tables.from_bytes(fixtures["dictionary"], 1, 256)
+    m = pf.Matcher(t)
+    text = np.frombuffer(fixtures["1M"], dtype=np.uint8).copy()
+    want = m.scan_host(text)
+    with pf.pinned(text) as a:
+        got = m.scan_host(a)
+    assert np.array_equal(got, want)
+    with pytest.raises(pf.PfacError) as e:
+        pf.check(pf.lib.pfac_host_register(None, 0, 0))
+    assert e.value.code == -4
+    m.close()
+
+
 def test_cli_byte_identical_result_file(fixtures, golden, tmp_path):
     """gphf <pattern file> <streams> <width> <input file> -> GPU_match_result.txt (main.cc:94,335)."""
     pat = tmp_path / "experimentpattern"
@@ -387,9 +402,11 @@ def test_cli_byte_identical_result_file(fixtures, golden, tmp_path):
     # dictionary, other stream counts / widths: still the same bytes; and equal to the oracle CLI
     dic = tmp_path / "dict"
     dic.write_bytes(fixtures["dictionary"])
-    for streams, width in ((4, 64), (2, 4096)):
-        r = subprocess.run([GPHF, str(dic), str(streams), str(width), str(inp)], cwd=tmp_path, capture_output=True, text=True)
+    for (streams, width), reader in zip(((4, 64), (2, 4096)), ("mmap", "fread")):
+        r = subprocess.run([GPHF, str(dic), str(streams), str(width), str(inp)], cwd=tmp_path, capture_output=True,
+                           text=True, env=dict(os.environ, GPHF_READER=reader))
         assert r.returncode == 0, r.stderr
+        assert f"input reader: {reader}" in r.stdout
         out = (tmp_path / "GPU_match_result.txt").read_bytes()
         assert hashlib.md5(out).hexdigest() == golden["results"]["dictionary_x_1M"]["md5"]
     # usage / error behaviour (main.cc:93-96, :131-135)
