@@ -206,6 +206,7 @@ int launch_scan(pfac_ctx *ctx, Slot &slot, const void *d_in, uint64_t n_starts, 
     p.tm2_bits = ctx->dv.tm2_bits;
     p.gimage = ctx->d_gimage;
     p.n_stages = ctx->n_stages;
+    p.stage_magic = (uint32_t)((1ull << 32) / ctx->n_stages) + 1u;
     e = slot_reserve(slot, p.n_tiles, (size_t)std::max<uint64_t>(cap, 4096), stream);
     if (e) return e;
     p.tile_cnt = slot.d_tile_cnt;

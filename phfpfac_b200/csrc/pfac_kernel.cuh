@@ -59,7 +59,7 @@ struct ScanParams {
     uint32_t image_bytes, off_t2, off_tm, off_tm2, off_t3;
     uint32_t t2_shift, has_short, has_t3, t3_shift, tm_bits, tm2_bits;
     const uint8_t *gimage;            // mode 2: T1 | Tm | Tm2 | T3 in global memory (offsets above refer to it)
-    uint32_t n_stages;                // depth of the input ring (as many as shared memory holds)
+    uint32_t n_stages, stage_magic;   // depth of the input ring (as many as shared memory holds); floor(2^32 / n_stages) + 1
     // output
     unsigned int *tile_cnt;           // [n_tiles] 0 from the detector; the emit kernel writes the tile's match count
     unsigned int *tile_nc;            // [n_tiles] candidates of the tile (kCandOverflow: too many, whole slices instead)
@@ -285,6 +285,7 @@ __global__ void __launch_bounds__(kThreads, 1) pfac_scan_kernel(const ScanParams
     uint64_t *s_full = reinterpret_cast<uint64_t *>(ctl);               // [kMaxStages]
     uint64_t *s_empty = reinterpret_cast<uint64_t *>(ctl + 64);         // [kMaxStages]
     uint32_t *s_tile = reinterpret_cast<uint32_t *>(ctl + 128);         // [kMaxStages] tile id of the stage
+    uint32_t *s_grab = reinterpret_cast<uint32_t *>(ctl + 192);         // next (tile, slice) slot of this CTA
     uint32_t *s_tflag = reinterpret_cast<uint32_t *>(ctl + 224);        // [kMaxStages] flagged slices of the tile
     uint32_t *s_ncand = reinterpret_cast<uint32_t *>(ctl + 256);        // [kMaxStages] candidates (or kCandOverflow)
     uint16_t *s_cand = reinterpret_cast<uint16_t *>(ctl + 512);         // [kMaxStages][kCandPerTile]
@@ -309,6 +310,7 @@ __global__ void __launch_bounds__(kThreads, 1) pfac_scan_kernel(const ScanParams
             s_tflag[s] = 0;
             s_ncand[s] = 0;
         }
+        *s_grab = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -381,13 +383,23 @@ __global__ void __launch_bounds__(kThreads, 1) pfac_scan_kernel(const ScanParams
     }
 
     // ---------------------------------------------------------------------- consumers
+    // Slices are not bound to warps: the CTA's tiles form one sequence of (tile, slice) slots and a
+    // warp that is done takes the next one, so a warp the scheduler favours (or one whose slices have
+    // few survivors) simply does more slices instead of spinning on the ring behind the slowest warp.
+    // Slot g belongs to the CTA's k-th tile, k = g / 31: stage k % n_stages, phase k / n_stages.
+    // Every warp leaves on its first slot of the sentinel tile, so no slot past it is ever waited on.
     uint16_t *wq = reinterpret_cast<uint16_t *>(qbase + warp * kQueueBytes);   // stage-1 survivors of the slice
     const uint32_t lt_mask = (1u << lane) - 1u;
-    const uint32_t slice = (uint32_t)warp;   // this warp's slice of every tile
-    const uint32_t off = slice * kSlice + lane * 16;
 
-    uint32_t s = 0, round = 0;
-    for (;; s = (s + 1 == n_stages) ? 0 : s + 1, round += (s == 0) ? 1u : 0u) {
+    for (;;) {
+        uint32_t g = 0;
+        if (lane == 0) g = atomicAdd(s_grab, 1u);
+        g = __shfl_sync(0xffffffffu, g, 0);
+        const uint32_t k = g / (uint32_t)kSlicesPerTile;
+        const uint32_t slice = g - k * (uint32_t)kSlicesPerTile;
+        const uint32_t round = __umulhi(k, p.stage_magic);   // k / n_stages, exact for k < 2^32 / n_stages
+        const uint32_t s = k - round * n_stages;
+        const uint32_t off = slice * kSlice + lane * 16;
         if (!mbar_wait<PFAC_CONS_SLEEP_NS>(&s_full[s], round & 1u, &p.ctrl->error_flag, 2u)) break;
         const uint32_t tile = s_tile[s];
         if (tile >= p.n_tiles) break;

@@ -384,7 +384,7 @@ def test_host_register_in_place(fixtures):
     assert np.array_equal(got, want)
     with pytest.raises(pf.PfacError) as e:
         pf.check(pf.lib.pfac_host_register(None, 0, 0))
-    assert e.value.code == -4
+    assert e.value.code == -5
     m.close()
 
 
