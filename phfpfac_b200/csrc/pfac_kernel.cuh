@@ -88,17 +88,24 @@ struct FinalizeParams {
 
 constexpr int kConsumerWarps = 31;
 constexpr int kThreads = (kConsumerWarps + 1) * 32;   // + the producer warp
-constexpr int kSlice = 512;           // start positions per warp step (32 lanes x 16 B)
-constexpr int kSlicesPerTile = kConsumerWarps;   // every consumer warp owns one slice of every tile
-constexpr int kTile = kSlicesPerTile * kSlice;   // 15,872 start positions per tile
+constexpr int kSlice = 512;           // start positions per stage-1 step of a warp (32 lanes x 16 B)
+constexpr int kSlicesPerTile = 32;    // one bit each in tile_mask
+constexpr int kTile = kSlicesPerTile * kSlice;   // 16,384 start positions per tile
+#ifndef PFAC_SLOT_SLICES
+#define PFAC_SLOT_SLICES 2
+#endif
+constexpr int kSlotSlices = PFAC_SLOT_SLICES;    // slices a warp takes at a time: stage 2 then runs over the survivors of all of them
+constexpr int kSlotsPerTile = kSlicesPerTile / kSlotSlices;
+constexpr int kSentinelTiles = (kConsumerWarps + kSlotsPerTile - 1) / kSlotsPerTile;   // end-of-work tiles per CTA
+static_assert(kSlicesPerTile % kSlotSlices == 0, "slots tile the tile");
 constexpr int kMaxStages = 8;
-constexpr int kQ1Cap = 128;               // per consumer warp: starts of one slice that passed stage 1 (u16)
-constexpr int kQueueBytes = kQ1Cap * 2;   // a slice with more survivors is handed over whole
+constexpr int kQ1Cap = 64 * kSlotSlices;  // per consumer warp: starts of one slot that passed stage 1 (u16)
+constexpr int kQueueBytes = kQ1Cap * 2;   // a slot with more survivors is handed over whole
 constexpr int kCtrlBytes = 1024;
 constexpr int kMaxParts = 1024;           // tile ranges of the ordering pass (one per finalize CTA)
 constexpr int kCandPerTile = 32;          // candidate starts the detector hands over per tile (more: whole slices)
 constexpr unsigned kCandOverflow = 0xFFFFFFFFu;
-constexpr unsigned kSpinLimit = 1u << 24;
+constexpr unsigned kSpinLimit = 1u << 21;
 
 __host__ __device__ inline uint32_t scan_buf_stride(uint32_t halo) { return (kTile + halo + 32 + 127) & ~127u; }
 __host__ inline size_t scan_smem_bytes(uint32_t image_bytes, uint32_t halo, uint32_t n_stages)
@@ -306,7 +313,7 @@ __global__ void __launch_bounds__(kThreads, 1) pfac_scan_kernel(const ScanParams
     if (tid == 0) {
         for (uint32_t s = 0; s < n_stages; s++) {
             mbar_init(&s_full[s], 1);
-            mbar_init(&s_empty[s], kConsumerWarps);
+            mbar_init(&s_empty[s], kSlotsPerTile);   // one arrival per slot
             s_tflag[s] = 0;
             s_ncand[s] = 0;
         }
@@ -341,6 +348,7 @@ __global__ void __launch_bounds__(kThreads, 1) pfac_scan_kernel(const ScanParams
             uint32_t t = atomicAdd(&p.ctrl->ticket, 1u);
             uint32_t t_next = t < p.n_tiles ? atomicAdd(&p.ctrl->ticket, 1u) : t;
             bool ok = true;
+            uint32_t n_sent = 0;
             while (true) {
                 // tickets are claimed two tiles ahead: the atomic's latency hides behind a whole tile
                 const uint32_t t_next2 = t_next < p.n_tiles ? atomicAdd(&p.ctrl->ticket, 1u) : t_next;
@@ -350,9 +358,13 @@ __global__ void __launch_bounds__(kThreads, 1) pfac_scan_kernel(const ScanParams
                     held[s] = 0xFFFFFFFFu;
                 }
                 s_tile[s] = t;
-                if (t >= p.n_tiles) {   // sentinel: consumers leave when they see it
+                if (t >= p.n_tiles) {
+                    // sentinel: consumers leave when they see it.  Every warp takes exactly one slot at
+                    // or past the first sentinel tile, so kSentinelTiles tiles hold all of those slots.
                     mbar_arrive(&s_full[s]);
-                    break;
+                    if (++n_sent == (uint32_t)kSentinelTiles) break;
+                    if (++s == n_stages) { s = 0; round++; }
+                    continue;
                 }
                 uint8_t *buf = s_in + s * stride;
                 const uint32_t a0 = t * (uint32_t)kTile;
@@ -383,23 +395,23 @@ __global__ void __launch_bounds__(kThreads, 1) pfac_scan_kernel(const ScanParams
     }
 
     // ---------------------------------------------------------------------- consumers
-    // Slices are not bound to warps: the CTA's tiles form one sequence of (tile, slice) slots and a
-    // warp that is done takes the next one, so a warp the scheduler favours (or one whose slices have
-    // few survivors) simply does more slices instead of spinning on the ring behind the slowest warp.
-    // Slot g belongs to the CTA's k-th tile, k = g / 31: stage k % n_stages, phase k / n_stages.
-    // Every warp leaves on its first slot of the sentinel tile, so no slot past it is ever waited on.
-    uint16_t *wq = reinterpret_cast<uint16_t *>(qbase + warp * kQueueBytes);   // stage-1 survivors of the slice
+    // Slots (kSlotSlices consecutive slices) are not bound to warps: the CTA's tiles form one sequence
+    // of slots and a warp that is done takes the next one, so a warp the scheduler favours (or one
+    // whose slots have few survivors) simply does more of them instead of spinning on the ring behind
+    // the slowest warp.  Slot g belongs to the CTA's k-th tile, k = g / kSlotsPerTile: stage
+    // k % n_stages, phase k / n_stages.  Every warp leaves on its first slot of the sentinel tile, so
+    // no slot past it is ever waited on.
+    uint16_t *wq = reinterpret_cast<uint16_t *>(qbase + warp * kQueueBytes);   // stage-1 survivors of the slot
     const uint32_t lt_mask = (1u << lane) - 1u;
 
     for (;;) {
         uint32_t g = 0;
         if (lane == 0) g = atomicAdd(s_grab, 1u);
         g = __shfl_sync(0xffffffffu, g, 0);
-        const uint32_t k = g / (uint32_t)kSlicesPerTile;
-        const uint32_t slice = g - k * (uint32_t)kSlicesPerTile;
+        const uint32_t k = g / (uint32_t)kSlotsPerTile;
+        const uint32_t slice0 = (g - k * (uint32_t)kSlotsPerTile) * (uint32_t)kSlotSlices;   // first slice of the slot
         const uint32_t round = __umulhi(k, p.stage_magic);   // k / n_stages, exact for k < 2^32 / n_stages
         const uint32_t s = k - round * n_stages;
-        const uint32_t off = slice * kSlice + lane * 16;
         if (!mbar_wait<PFAC_CONS_SLEEP_NS>(&s_full[s], round & 1u, &p.ctrl->error_flag, 2u)) break;
         const uint32_t tile = s_tile[s];
         if (tile >= p.n_tiles) break;
@@ -410,15 +422,23 @@ __global__ void __launch_bounds__(kThreads, 1) pfac_scan_kernel(const ScanParams
         // input or a reference walk bound
         const bool interior = !p.use_ref_bound && a0 >= p.mis && valid_t >= (uint32_t)kTile + p.max_pat_len &&
                               a0 + (uint32_t)kTile <= p.a_start_end;
-        bool any = false;
-        if (a0 + slice * kSlice < p.a_start_end) {   // the slice holds start positions
-            // stage 1: T1 over 16 positions per lane, compaction into the warp queue
+        uint32_t anym = 0;   // bit h: slice slice0 + h has a start that survived
+        uint32_t nq = 0;
+        // stage 1: T1 over 16 positions per lane and slice, compaction into the warp queue
+#pragma unroll
+        for (int h = 0; h < kSlotSlices; h++) {
+            const uint32_t off = (slice0 + h) * kSlice + lane * 16;
+            if (a0 + (slice0 + h) * kSlice >= p.a_start_end) break;   // no start positions from here on
             const uint4 v = *reinterpret_cast<const uint4 *>(buf + off);
             const uint32_t nx = *reinterpret_cast<const uint32_t *>(buf + off + 16);
             uint32_t lo = 0, hi = 0;   // one nibble per start, bit 0 = passes stage 1
             if (!(p.debug & 4u)) {
                 if (MODE == 2) filter16_t2(v, nx, s_t2, p.t2_shift, lo, hi);
                 else filter16(v, nx, lo, hi);
+            }
+            if (p.debug & 16u) {   // diagnostics: stage 1 alone (its result is consumed, nothing survives)
+                if ((lo ^ hi) == 0x9e3779b9u) anym |= 1u << h;
+                lo = hi = 0;
             }
             if (!interior) {   // start positions are [mis, a_start_end) in aligned coordinates
                 const uint32_t a = a0 + off;
@@ -439,7 +459,6 @@ __global__ void __launch_bounds__(kThreads, 1) pfac_scan_kernel(const ScanParams
             // compaction into the warp queue: every round, each lane that still has survivors hands over
             // its lowest one (rank by ballot).  Few lanes have any, so this beats a prefix scan; the
             // order of the queue does not matter (the emit kernel sorts the few candidates).
-            uint32_t nq = 0;
             while (true) {
                 const uint32_t bal = __ballot_sync(0xffffffffu, (lo | hi) != 0u);
                 if (!bal) break;
@@ -452,65 +471,65 @@ __global__ void __launch_bounds__(kThreads, 1) pfac_scan_kernel(const ScanParams
                 }
                 nq += __popc(bal);
             }
-            if (nq > (uint32_t)kQ1Cap) {   // dense slice: the emit kernel looks at all of it
-                any = true;
-                if (lane == 0) atomicOr(s_ncand + s, 0x80000000u);
-                nq = 0;
-            }
-            __syncwarp();
-            // stage 2: the 4-byte prefix (complete Tm, or T2), then the two-point checks -- every pattern
-            // under a key is at least m bytes long and has its bytes [m-4, m) in T3.  Starts that cannot
-            // be judged here (short patterns, end of the input) are candidates straight away.
-            for (uint32_t e0 = 0; e0 < nq; e0 += 32) {
-                const uint32_t e = e0 + lane;
-                if (e >= nq) continue;
-                const uint32_t tpos = wq[e];
-                bool keep = true;
-                if (!(p.debug & 8u) && tpos + 4u <= valid_t) {
-                    const uint32_t *wp = reinterpret_cast<const uint32_t *>(buf + (tpos & ~3u));
-                    const uint32_t w4 = __funnelshift_r(wp[0], wp[1], (tpos & 3u) * 8u);
-                    bool shortp = false;
-                    if (MODE != 2 && p.has_short) shortp = (smem[rot2x4(w4) & 0xffffu] & kT1Short) != 0;
-                    if (!shortp) {
-                        if (!p.has_t3) {
-                            const uint32_t h = (w4 * kHash4Mul) >> p.t2_shift;
-                            keep = (s_t2[h >> 5] >> (h & 31u)) & 1u;
-                        } else {
-                            const uint32_t m1 = tm_lookup(s_tm, w4, p.tm_bits);   // 0 = no pattern has this prefix
-                            const uint32_t lim = interior ? tpos + p.max_pat_len : walk_limit(p, a0, tpos);   // never past the staged halo
-                            keep = m1 != 0 && tpos + m1 <= lim;
-                            if (keep) {
-                                const uint32_t wo = tpos + m1 - 4u;
-                                const uint32_t *we = reinterpret_cast<const uint32_t *>(buf + (wo & ~3u));
-                                const uint32_t w1 = __funnelshift_r(we[0], we[1], (wo & 3u) * 8u);
-                                const uint32_t h3 = hash_t3(w4, w1) >> p.t3_shift;
-                                keep = (s_t3[h3 >> 5] >> (h3 & 31u)) & 1u;
-                                if (keep && p.tm2_bits) {
-                                    const uint32_t key2 = hash_key2(w4, w1);
-                                    const uint32_t m2 = tm_lookup(s_tm2, key2, p.tm2_bits);   // 0 = no such group
-                                    keep = m2 != 0 && tpos + m2 <= lim;
-                                    if (keep) {
-                                        const uint32_t wo2 = tpos + m2 - 4u;
-                                        const uint32_t *wf = reinterpret_cast<const uint32_t *>(buf + (wo2 & ~3u));
-                                        const uint32_t w2 = __funnelshift_r(wf[0], wf[1], (wo2 & 3u) * 8u);
-                                        const uint32_t h4 = hash_t3(key2 ^ kT3Seed2, w2) >> p.t3_shift;
-                                        keep = (s_t3[h4 >> 5] >> (h4 & 31u)) & 1u;
-                                    }
+        }
+        if (nq > (uint32_t)kQ1Cap) {   // dense slot: the emit kernel looks at all of it
+            anym = (1u << kSlotSlices) - 1u;
+            if (lane == 0) atomicOr(s_ncand + s, 0x80000000u);
+            nq = 0;
+        }
+        __syncwarp();
+        // stage 2: the 4-byte prefix (complete Tm, or T2), then the two-point checks -- every pattern
+        // under a key is at least m bytes long and has its bytes [m-4, m) in T3.  Starts that cannot
+        // be judged here (short patterns, end of the input) are candidates straight away.
+        for (uint32_t e0 = 0; e0 < nq; e0 += 32) {
+            const uint32_t e = e0 + lane;
+            if (e >= nq) continue;
+            const uint32_t tpos = wq[e];
+            bool keep = true;
+            if (!(p.debug & 8u) && tpos + 4u <= valid_t) {
+                const uint32_t *wp = reinterpret_cast<const uint32_t *>(buf + (tpos & ~3u));
+                const uint32_t w4 = __funnelshift_r(wp[0], wp[1], (tpos & 3u) * 8u);
+                bool shortp = false;
+                if (MODE != 2 && p.has_short) shortp = (smem[rot2x4(w4) & 0xffffu] & kT1Short) != 0;
+                if (!shortp) {
+                    if (!p.has_t3) {
+                        const uint32_t h = (w4 * kHash4Mul) >> p.t2_shift;
+                        keep = (s_t2[h >> 5] >> (h & 31u)) & 1u;
+                    } else {
+                        const uint32_t m1 = tm_lookup(s_tm, w4, p.tm_bits);   // 0 = no pattern has this prefix
+                        const uint32_t lim = interior ? tpos + p.max_pat_len : walk_limit(p, a0, tpos);   // never past the staged halo
+                        keep = m1 != 0 && tpos + m1 <= lim;
+                        if (keep) {
+                            const uint32_t wo = tpos + m1 - 4u;
+                            const uint32_t *we = reinterpret_cast<const uint32_t *>(buf + (wo & ~3u));
+                            const uint32_t w1 = __funnelshift_r(we[0], we[1], (wo & 3u) * 8u);
+                            const uint32_t h3 = hash_t3(w4, w1) >> p.t3_shift;
+                            keep = (s_t3[h3 >> 5] >> (h3 & 31u)) & 1u;
+                            if (keep && p.tm2_bits) {
+                                const uint32_t key2 = hash_key2(w4, w1);
+                                const uint32_t m2 = tm_lookup(s_tm2, key2, p.tm2_bits);   // 0 = no such group
+                                keep = m2 != 0 && tpos + m2 <= lim;
+                                if (keep) {
+                                    const uint32_t wo2 = tpos + m2 - 4u;
+                                    const uint32_t *wf = reinterpret_cast<const uint32_t *>(buf + (wo2 & ~3u));
+                                    const uint32_t w2 = __funnelshift_r(wf[0], wf[1], (wo2 & 3u) * 8u);
+                                    const uint32_t h4 = hash_t3(key2 ^ kT3Seed2, w2) >> p.t3_shift;
+                                    keep = (s_t3[h4 >> 5] >> (h4 & 31u)) & 1u;
                                 }
                             }
                         }
                     }
                 }
-                if (keep) {
-                    any = true;
-                    add_candidate(s_ncand + s, s_cand + s * kCandPerTile, tpos);
-                }
+            }
+            if (keep) {
+                anym |= 1u << (tpos / (uint32_t)kSlice - slice0);
+                add_candidate(s_ncand + s, s_cand + s * kCandPerTile, tpos);
             }
         }
-        // ---- done with the tile: flag the slice if any start survived, release the stage
-        any = __any_sync(0xffffffffu, any);
+        // ---- done with the slot: flag the slices in which a start survived, release the stage
+        anym = __reduce_or_sync(0xffffffffu, anym);
         if (lane == 0) {
-            if (any) atomicOr(&s_tflag[s], 1u << slice);
+            if (anym) atomicOr(&s_tflag[s], anym << slice0);
             mbar_arrive(&s_empty[s]);   // release: orders the shared-memory updates above before the producer's reads
         }
     }

@@ -168,7 +168,7 @@ def test_dense_matches_and_capacity_overflow():
 def test_candidate_list_boundaries(n_plants):
     """The detector hands a tile's surviving starts to the emit kernel as a list of at most 32
     candidates; beyond that (or when a slice has too many stage-1 survivors) whole slices are handed
-    over.  Plant 1..3000 matches inside one 15,872-byte tile and across its borders."""
+    over.  Plant 1..3000 matches inside one 16,384-byte tile and across its borders."""
     torch = torch_cuda()
     pats = pf.synth_patterns(1, 3000, 3, 4, 64)
     lines = pats.split(b"\n")[:-1]
@@ -176,7 +176,7 @@ def test_candidate_list_boundaries(n_plants):
     rng = np.random.default_rng(n_plants)
     text = rng.integers(0, 256, n).astype(np.uint8)
     text[text == 10] = 11
-    base = 15872 * 2 - 300          # straddles the border of tiles 1 and 2
+    base = 16384 * 2 - 300          # straddles the border of tiles 1 and 2
     at = base
     for i in range(n_plants):
         p = lines[int(rng.integers(0, len(lines)))]
