@@ -89,14 +89,16 @@ struct FinalizeParams {
 constexpr int kConsumerWarps = 31;
 constexpr int kThreads = (kConsumerWarps + 1) * 32;   // + the producer warp
 constexpr int kSlice = 512;           // start positions per stage-1 step of a warp (32 lanes x 16 B)
-constexpr int kSlicesPerTile = 32;    // one bit each in tile_mask
+#ifndef PFAC_TILE_SLICES
+#define PFAC_TILE_SLICES 32
+#endif
+constexpr int kSlicesPerTile = PFAC_TILE_SLICES;    // one bit each in tile_mask (<= 32)
 constexpr int kTile = kSlicesPerTile * kSlice;   // 16,384 start positions per tile
 #ifndef PFAC_SLOT_SLICES
 #define PFAC_SLOT_SLICES 2
 #endif
 constexpr int kSlotSlices = PFAC_SLOT_SLICES;    // slices a warp takes at a time: stage 2 then runs over the survivors of all of them
 constexpr int kSlotsPerTile = kSlicesPerTile / kSlotSlices;
-constexpr int kSentinelTiles = (kConsumerWarps + kSlotsPerTile - 1) / kSlotsPerTile;   // end-of-work tiles per CTA
 static_assert(kSlicesPerTile % kSlotSlices == 0, "slots tile the tile");
 constexpr int kMaxStages = 8;
 constexpr int kQ1Cap = 64 * kSlotSlices;  // per consumer warp: starts of one slot that passed stage 1 (u16)
@@ -293,6 +295,7 @@ __global__ void __launch_bounds__(kThreads, 1) pfac_scan_kernel(const ScanParams
     uint64_t *s_empty = reinterpret_cast<uint64_t *>(ctl + 64);         // [kMaxStages]
     uint32_t *s_tile = reinterpret_cast<uint32_t *>(ctl + 128);         // [kMaxStages] tile id of the stage
     uint32_t *s_grab = reinterpret_cast<uint32_t *>(ctl + 192);         // next (tile, slice) slot of this CTA
+    uint32_t *s_kend = reinterpret_cast<uint32_t *>(ctl + 196);         // sequence number of the CTA's sentinel tile
     uint32_t *s_tflag = reinterpret_cast<uint32_t *>(ctl + 224);        // [kMaxStages] flagged slices of the tile
     uint32_t *s_ncand = reinterpret_cast<uint32_t *>(ctl + 256);        // [kMaxStages] candidates (or kCandOverflow)
     uint16_t *s_cand = reinterpret_cast<uint16_t *>(ctl + 512);         // [kMaxStages][kCandPerTile]
@@ -318,6 +321,7 @@ __global__ void __launch_bounds__(kThreads, 1) pfac_scan_kernel(const ScanParams
             s_ncand[s] = 0;
         }
         *s_grab = 0;
+        *s_kend = 0xFFFFFFFFu;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -348,7 +352,6 @@ __global__ void __launch_bounds__(kThreads, 1) pfac_scan_kernel(const ScanParams
             uint32_t t = atomicAdd(&p.ctrl->ticket, 1u);
             uint32_t t_next = t < p.n_tiles ? atomicAdd(&p.ctrl->ticket, 1u) : t;
             bool ok = true;
-            uint32_t n_sent = 0;
             while (true) {
                 // tickets are claimed two tiles ahead: the atomic's latency hides behind a whole tile
                 const uint32_t t_next2 = t_next < p.n_tiles ? atomicAdd(&p.ctrl->ticket, 1u) : t_next;
@@ -359,12 +362,11 @@ __global__ void __launch_bounds__(kThreads, 1) pfac_scan_kernel(const ScanParams
                 }
                 s_tile[s] = t;
                 if (t >= p.n_tiles) {
-                    // sentinel: consumers leave when they see it.  Every warp takes exactly one slot at
-                    // or past the first sentinel tile, so kSentinelTiles tiles hold all of those slots.
-                    mbar_arrive(&s_full[s]);
-                    if (++n_sent == (uint32_t)kSentinelTiles) break;
-                    if (++s == n_stages) { s = 0; round++; }
-                    continue;
+                    // sentinel: consumers leave when they see it; s_kend releases the warps whose slot
+                    // lies past the sentinel tile (its stage is never filled)
+                    *reinterpret_cast<volatile uint32_t *>(s_kend) = round * n_stages + s;
+                    mbar_arrive(&s_full[s]);   // release: orders the store above
+                    break;
                 }
                 uint8_t *buf = s_in + s * stride;
                 const uint32_t a0 = t * (uint32_t)kTile;
@@ -382,6 +384,7 @@ __global__ void __launch_bounds__(kThreads, 1) pfac_scan_kernel(const ScanParams
                 t_next = t_next2;
                 if (++s == n_stages) { s = 0; round++; }
             }
+            if (!ok) *reinterpret_cast<volatile uint32_t *>(s_kend) = 0u;   // watchdog tripped: let the consumers go
             // drain: the tiles still in the ring were filled in this round (stages < s) or the previous one
             for (uint32_t k = 1; ok && k < n_stages; k++) {
                 const uint32_t st = (s + n_stages - k) % n_stages;
@@ -399,8 +402,8 @@ __global__ void __launch_bounds__(kThreads, 1) pfac_scan_kernel(const ScanParams
     // of slots and a warp that is done takes the next one, so a warp the scheduler favours (or one
     // whose slots have few survivors) simply does more of them instead of spinning on the ring behind
     // the slowest warp.  Slot g belongs to the CTA's k-th tile, k = g / kSlotsPerTile: stage
-    // k % n_stages, phase k / n_stages.  Every warp leaves on its first slot of the sentinel tile, so
-    // no slot past it is ever waited on.
+    // k % n_stages, phase k / n_stages.  A warp leaves on a slot of the sentinel tile or, told by
+    // s_kend, on one past it.
     uint16_t *wq = reinterpret_cast<uint16_t *>(qbase + warp * kQueueBytes);   // stage-1 survivors of the slot
     const uint32_t lt_mask = (1u << lane) - 1u;
 
@@ -412,7 +415,17 @@ __global__ void __launch_bounds__(kThreads, 1) pfac_scan_kernel(const ScanParams
         const uint32_t slice0 = (g - k * (uint32_t)kSlotsPerTile) * (uint32_t)kSlotSlices;   // first slice of the slot
         const uint32_t round = __umulhi(k, p.stage_magic);   // k / n_stages, exact for k < 2^32 / n_stages
         const uint32_t s = k - round * n_stages;
-        if (!mbar_wait<PFAC_CONS_SLEEP_NS>(&s_full[s], round & 1u, &p.ctrl->error_flag, 2u)) break;
+        bool leave = false;
+        for (unsigned spins = 0; !mbar_try_wait(&s_full[s], round & 1u);) {
+            if (*reinterpret_cast<volatile uint32_t *>(s_kend) < k) { leave = true; break; }   // a slot past the end of the work
+            if (++spins > kSpinLimit) {
+                atomicExch(&p.ctrl->error_flag, 2u);
+                leave = true;
+                break;
+            }
+            if (PFAC_CONS_SLEEP_NS) __nanosleep(PFAC_CONS_SLEEP_NS);
+        }
+        if (leave) break;
         const uint32_t tile = s_tile[s];
         if (tile >= p.n_tiles) break;
         const uint8_t *buf = s_in + s * stride;
