@@ -363,13 +363,13 @@ int pfac_ctx_create(int device, const pfac_tables *t, int part, int n_streams, s
             continue;
         }
         ctx->image_bytes = (uint32_t)ctx->dv.image.size();
-        const size_t fixed = scan_smem_bytes(ctx->image_bytes, ctx->halo, 0);
+        const size_t fixed = scan_smem_bytes(ctx->image_bytes, ctx->halo, 0, ctx->dv.mode);
         const size_t stride = scan_buf_stride(ctx->halo);
         const size_t fit = smem_max > fixed ? (smem_max - fixed) / stride : 0;
         const bool minimal = t2_bytes < 2048 && (ctx->dv.mode == 2 || (t3_bytes < 2048 && tm2_bytes < 2048));
         if (fit >= 3 || (fit >= 2 && minimal)) {
             ctx->n_stages = (uint32_t)std::min<size_t>(fit, kMaxStages);
-            ctx->smem_bytes = scan_smem_bytes(ctx->image_bytes, ctx->halo, ctx->n_stages);
+            ctx->smem_bytes = scan_smem_bytes(ctx->image_bytes, ctx->halo, ctx->n_stages, ctx->dv.mode);
             break;
         }
         if (minimal)

@@ -94,15 +94,20 @@ constexpr int kSlice = 512;           // start positions per stage-1 step of a w
 #endif
 constexpr int kSlicesPerTile = PFAC_TILE_SLICES;    // one bit each in tile_mask (<= 32)
 constexpr int kTile = kSlicesPerTile * kSlice;   // 16,384 start positions per tile
+// Slices a warp takes at a time (a slot): stage 2 then runs over the survivors of all of them.
+// Shared-memory mode: 2 (more would leave too few slots in flight for the ring to prefetch).  Global
+// mode: 4 -- stage 2 waits on L2 there, and a fuller queue means more loads in flight per wait.
 #ifndef PFAC_SLOT_SLICES
 #define PFAC_SLOT_SLICES 2
 #endif
-constexpr int kSlotSlices = PFAC_SLOT_SLICES;    // slices a warp takes at a time: stage 2 then runs over the survivors of all of them
-constexpr int kSlotsPerTile = kSlicesPerTile / kSlotSlices;
-static_assert(kSlicesPerTile % kSlotSlices == 0, "slots tile the tile");
+#ifndef PFAC_SLOT_SLICES_GLOBAL
+#define PFAC_SLOT_SLICES_GLOBAL 4
+#endif
+__host__ __device__ constexpr int slot_slices(int mode) { return mode == 2 ? PFAC_SLOT_SLICES_GLOBAL : PFAC_SLOT_SLICES; }
+__host__ __device__ constexpr int q1_cap(int mode) { return 64 * slot_slices(mode); }   // per consumer warp: starts of one slot that passed stage 1 (u16)
+__host__ __device__ constexpr int queue_bytes(int mode) { return q1_cap(mode) * 2; }     // a slot with more survivors is handed over whole
+static_assert(kSlicesPerTile % PFAC_SLOT_SLICES == 0 && kSlicesPerTile % PFAC_SLOT_SLICES_GLOBAL == 0, "slots tile the tile");
 constexpr int kMaxStages = 8;
-constexpr int kQ1Cap = 64 * kSlotSlices;  // per consumer warp: starts of one slot that passed stage 1 (u16)
-constexpr int kQueueBytes = kQ1Cap * 2;   // a slot with more survivors is handed over whole
 constexpr int kCtrlBytes = 1024;
 constexpr int kMaxParts = 1024;           // tile ranges of the ordering pass (one per finalize CTA)
 constexpr int kCandPerTile = 32;          // candidate starts the detector hands over per tile (more: whole slices)
@@ -110,9 +115,9 @@ constexpr unsigned kCandOverflow = 0xFFFFFFFFu;
 constexpr unsigned kSpinLimit = 1u << 21;
 
 __host__ __device__ inline uint32_t scan_buf_stride(uint32_t halo) { return (kTile + halo + 32 + 127) & ~127u; }
-__host__ inline size_t scan_smem_bytes(uint32_t image_bytes, uint32_t halo, uint32_t n_stages)
+__host__ inline size_t scan_smem_bytes(uint32_t image_bytes, uint32_t halo, uint32_t n_stages, int mode)
 {
-    return (size_t)image_bytes + kCtrlBytes + (size_t)kConsumerWarps * kQueueBytes +
+    return (size_t)image_bytes + kCtrlBytes + (size_t)kConsumerWarps * queue_bytes(mode) +
            (size_t)n_stages * scan_buf_stride(halo);
 }
 
@@ -301,6 +306,8 @@ __global__ void __launch_bounds__(kThreads, 1) pfac_scan_kernel(const ScanParams
     uint16_t *s_cand = reinterpret_cast<uint16_t *>(ctl + 512);         // [kMaxStages][kCandPerTile]
     uint8_t *qbase = ctl + kCtrlBytes;
     const uint32_t n_stages = p.n_stages;
+    constexpr int kSlotSlices = slot_slices(MODE), kSlotsPerTile = kSlicesPerTile / kSlotSlices;
+    constexpr int kQ1Cap = q1_cap(MODE), kQueueBytes = queue_bytes(MODE);
     uint8_t *s_in = qbase + kConsumerWarps * kQueueBytes;
     const uint32_t stride = scan_buf_stride(p.halo);
 
@@ -443,7 +450,10 @@ __global__ void __launch_bounds__(kThreads, 1) pfac_scan_kernel(const ScanParams
             const uint32_t off = (slice0 + h) * kSlice + lane * 16;
             if (a0 + (slice0 + h) * kSlice >= p.a_start_end) break;   // no start positions from here on
             const uint4 v = *reinterpret_cast<const uint4 *>(buf + off);
-            const uint32_t nx = *reinterpret_cast<const uint32_t *>(buf + off + 16);
+            // the 4 bytes after the lane's 16 are the next lane's first word (a strided shared-memory
+            // read of them would be a 4-way bank conflict); lane 31 reads its own
+            uint32_t nx = __shfl_down_sync(0xffffffffu, v.x, 1);
+            if (lane == 31) nx = *reinterpret_cast<const uint32_t *>(buf + off + 16);
             uint32_t lo = 0, hi = 0;   // one nibble per start, bit 0 = passes stage 1
             if (!(p.debug & 4u)) {
                 if (MODE == 2) filter16_t2(v, nx, s_t2, p.t2_shift, lo, hi);
