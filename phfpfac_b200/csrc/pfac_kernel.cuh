@@ -212,11 +212,12 @@ extern __shared__ __align__(128) uint8_t smem[];
 // result has one nibble per position, bit 0 of nibble j set iff start j passes stage 1:
 //     P01(j) and (Short(j) or (P12(j+1) and P23(j+2)))
 // lo = positions 0..7, hi = positions 8..15.  18 windows are looked up (16 + the two after them).
-__device__ __forceinline__ void filter16(const uint4 v, const uint32_t nx, uint32_t &lo, uint32_t &hi)
+__device__ __forceinline__ void filter16(const uint4 v, const uint32_t nx, const int lane, uint32_t &lo, uint32_t &hi)
 {
     const uint8_t *t1 = smem;
     const uint32_t w[5] = {rot2x4(v.x), rot2x4(v.y), rot2x4(v.z), rot2x4(v.w), rot2x4(nx)};
     uint32_t acc[2] = {0u, 0u};
+    uint32_t first2 = 0;   // T1 of the lane's windows 0 and 1
 #pragma unroll
     for (int k = 0; k < 4; k++) {
         const uint32_t i0 = w[k] & 0xffffu;
@@ -225,13 +226,17 @@ __device__ __forceinline__ void filter16(const uint4 v, const uint32_t nx, uint3
         const uint32_t i3 = __funnelshift_r(w[k], w[k + 1], 24) & 0xffffu;
         uint32_t &a = acc[k >> 1];
         const int sh = (k & 1) * 16;
-        a += (uint32_t)t1[i0] << sh;
-        a += (uint32_t)t1[i1] << (sh + 4);
+        const uint32_t e0 = t1[i0], e1 = t1[i1];
+        if (k == 0) first2 = e0 | (e1 << 4);
+        a += e0 << sh;
+        a += e1 << (sh + 4);
         a += (uint32_t)t1[i2] << (sh + 8);
         a += (uint32_t)t1[i3] << (sh + 12);
     }
-    // windows 16 and 17 (their P12 / P23 planes belong to starts 14..15)
-    const uint32_t ex = (uint32_t)t1[w[4] & 0xffffu] | ((uint32_t)t1[__byte_perm(w[4], 0u, 0x4421)] << 4);
+    // windows 16 and 17 (their P12 / P23 planes belong to starts 14..15) are the next lane's windows
+    // 0 and 1: one shuffle instead of two more bank-conflicted look-ups; lane 31 has no neighbour
+    uint32_t ex = __shfl_down_sync(0xffffffffu, first2, 1);
+    if (lane == 31) ex = (uint32_t)t1[w[4] & 0xffffu] | ((uint32_t)t1[__byte_perm(w[4], 0u, 0x4421)] << 4);
     // plane bits: 1 = P01, 2 = P12, 4 = P23, 8 = Short.  Align P12 of j+1 (shift 4+1), P23 of j+2
     // (shift 8+2) and Short of j (shift 3) with bit 0 of nibble j.
     const uint32_t y_lo = __funnelshift_r(acc[0], acc[1], 5), y_hi = __funnelshift_r(acc[1], ex, 5);
@@ -457,7 +462,7 @@ __global__ void __launch_bounds__(kThreads, 1) pfac_scan_kernel(const ScanParams
             uint32_t lo = 0, hi = 0;   // one nibble per start, bit 0 = passes stage 1
             if (!(p.debug & 4u)) {
                 if (MODE == 2) filter16_t2(v, nx, s_t2, p.t2_shift, lo, hi);
-                else filter16(v, nx, lo, hi);
+                else filter16(v, nx, lane, lo, hi);
             }
             if (p.debug & 16u) {   // diagnostics: stage 1 alone (its result is consumed, nothing survives)
                 if ((lo ^ hi) == 0x9e3779b9u) anym |= 1u << h;
