@@ -625,6 +625,42 @@ __device__ __forceinline__ uint32_t emit_walk(const EmitParams &p, uint32_t a, u
     return n;
 }
 
+// The same walk, once: counts the matches of start a and keeps the first kWalkKeep final states in
+// registers, so that the records can be written after the scratch space is reserved without walking
+// the (latency-bound) chain a second time.  Starts with more matches than that are walked again.
+constexpr int kWalkKeep = 4;
+__device__ __forceinline__ uint32_t walk_collect(const EmitParams &p, uint32_t a, uint32_t lim_a, int32_t (&st)[kWalkKeep])
+{
+    int32_t state = __ldg(&p.s0[p.in_al[a]]);                        // :41
+    if (state < 0) return 0;                                         // :43
+    uint32_t n = 0, q = a + 1;
+    while (true) {
+        if (state < p.n_final) {                                     // :44-47, :67-70
+#pragma unroll
+            for (int i = 0; i < kWalkKeep; i++)
+                if (n == (uint32_t)i) st[i] = state;
+            n++;
+        }
+        if (q >= lim_a) break;                                       // :50
+        state = phf_next(p, state, p.in_al[q]);
+        if (state < 0) break;                                        // :63-64
+        q++;
+    }
+    return n;
+}
+__device__ __forceinline__ void write_collected(const EmitParams &p, uint32_t a, uint32_t lim_a, uint32_t n,
+                                                const int32_t (&st)[kWalkKeep], unsigned long long o)
+{
+    if (n > (uint32_t)kWalkKeep) {
+        emit_walk<true>(p, a, lim_a, o);
+        return;
+    }
+    const uint32_t rec_pos = a - p.mis + p.pos_bias;
+#pragma unroll
+    for (int i = 0; i < kWalkKeep; i++)
+        if ((uint32_t)i < n && o + i < p.scratch_cap) p.scratch[o + i] = make_uint2(rec_pos, (uint32_t)__ldg(&p.idmap[st[i]]));
+}
+
 __global__ void __launch_bounds__(kEmitThreads) pfac_emit_kernel(const EmitParams p)
 {
     const int lane = threadIdx.x & 31;
@@ -646,10 +682,11 @@ __global__ void __launch_bounds__(kEmitThreads) pfac_emit_kernel(const EmitParam
         if (my_tile >= p.n_tiles || p.tile_nc[my_tile] != 1u) continue;
         const uint32_t key = p.cand[(size_t)my_tile * kCandPerTile];
         const uint32_t a = my_tile * (uint32_t)kTile + key, lim = limit(a);
-        const uint32_t cnt = emit_walk<false>(p, a, lim, 0ull);
+        int32_t st[kWalkKeep];
+        const uint32_t cnt = walk_collect(p, a, lim, st);
         if (cnt) {
             const unsigned long long base = atomicAdd(&p.ctrl->alloc, (unsigned long long)cnt);
-            emit_walk<true>(p, a, lim, base);
+            write_collected(p, a, lim, cnt, st, base);
             p.slice_ent[(size_t)my_tile * kSlicesPerTile + key / kSlice] = make_uint4(cnt, (uint32_t)base, (uint32_t)(base >> 32), 0u);
             atomicAdd(&p.partial[my_tile / p.tiles_per_part], (unsigned long long)cnt);
         }
@@ -678,7 +715,8 @@ __global__ void __launch_bounds__(kEmitThreads) pfac_emit_kernel(const EmitParam
                 }
             const bool live = key != 0xFFFFu;
             const uint32_t a = a0 + key;
-            const uint32_t cnt = live ? emit_walk<false>(p, a, limit(a), 0ull) : 0u;
+            int32_t st[kWalkKeep];
+            const uint32_t cnt = live ? walk_collect(p, a, limit(a), st) : 0u;
             uint32_t incl = cnt;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
@@ -690,7 +728,7 @@ __global__ void __launch_bounds__(kEmitThreads) pfac_emit_kernel(const EmitParam
                 unsigned long long base = 0;
                 if (lane == 0) base = atomicAdd(&p.ctrl->alloc, (unsigned long long)total);
                 base = __shfl_sync(0xffffffffu, base, 0);
-                if (cnt) emit_walk<true>(p, a, limit(a), base + incl - cnt);
+                if (cnt) write_collected(p, a, limit(a), cnt, st, base + incl - cnt);
                 // per-slice directory: records of a slice are contiguous (sorted by position)
                 const uint32_t my_slice = live ? key / kSlice : 0xFFFFFFFFu;
                 while (m) {

@@ -187,6 +187,24 @@ def test_candidate_list_boundaries(n_plants):
     check_both_paths(pats, text, n_streams=2, chunk_bytes=65536, oracle_parts=4)
 
 
+@pytest.mark.parametrize("min_len", [1, 4])
+@pytest.mark.parametrize("spacing", [0, 37, 700])
+def test_nested_patterns_many_matches_per_start(spacing, min_len):
+    """One start position reporting 1..12 nested patterns (a, ab, abc, ...): the emit kernel keeps
+    the first few final states of a walk in registers and walks again only past that; both ways,
+    in single-candidate tiles (sparse), sorted candidate lists and whole-slice mode (dense)."""
+    word = b"qwertyuiopas"
+    pats = b"".join(word[:k] + b"\n" for k in range(min_len, len(word) + 1)) + b"zzzzzz\nwerty\n"
+    rng = np.random.default_rng(spacing)
+    chunks = []
+    for i in range(3000 if spacing else 20000):
+        chunks.append(word[:int(rng.integers(min_len, len(word) + 1))])
+        chunks.append(b"." * spacing)
+    text = np.frombuffer(b"".join(chunks), dtype=np.uint8)
+    pos, ids, _ = check_both_paths(pats, text, n_streams=2, chunk_bytes=1 << 20, oracle_parts=1)
+    assert len(pos) > 3 * len(chunks) // 2
+
+
 def test_tables_from_reference_arrays_and_determinism(fixtures):
     """Tables handed over as canonical arrays (the thread_data fields of main.cc:19-32, here the
     oracle's) give the same records as tables built by the library, run after run."""
