@@ -255,7 +255,7 @@ int launch_scan(pfac_ctx *ctx, Slot &slot, const void *d_in, uint64_t n_starts, 
     ep.tile_nc = slot.d_tile_nc;
     ep.n_tiles = p.n_tiles;
     const uint32_t fgrid = (uint32_t)std::min<uint64_t>((p.n_tiles + kFinThreads - 1) / kFinThreads,
-                                                        (uint64_t)std::min(ctx->sm_count, (int)kMaxParts));
+                                                        (uint64_t)std::min(4 * ctx->sm_count, (int)kMaxParts));
     const uint32_t tiles_per_part = (p.n_tiles + fgrid - 1) / fgrid;
     ep.tiles_per_part = tiles_per_part;
     ep.partial = slot.d_partial;

@@ -812,6 +812,7 @@ __global__ void __launch_bounds__(kEmitThreads) pfac_emit_kernel(const EmitParam
 // records move from the arrival-order scratch to their final place.  One CTA per tile range; the
 // matches of the ranges before it come from the partial sums the emit kernel accumulated.
 constexpr int kFinThreads = 256;
+constexpr int kFinSmall = 8;   // records a single thread moves by itself
 
 __global__ void __launch_bounds__(kFinThreads) pfac_finalize_kernel(const FinalizeParams f)
 {
@@ -850,9 +851,26 @@ __global__ void __launch_bounds__(kFinThreads) pfac_finalize_kernel(const Finali
         unsigned long long wbase = 0;
         for (int w = 0; w < warp; w++) wbase += s_red[w];
         s_base[tid] = s_run + wbase + incl - c;
-        s_cnt[tid] = c;
+        // a tile with a few records (the common case: one match) is moved by the thread that owns it,
+        // all tiles of the chunk in parallel -- the dependent loads tile_mask -> slice_ent -> scratch
+        // are latency, not bandwidth; tiles with many records are left to whole warps below
+        const bool small = c != 0u && c <= (unsigned)kFinSmall;
+        if (small) {
+            unsigned long long dst = s_base[tid];
+            unsigned int m = f.tile_mask[i];
+            while (m) {
+                const int sl = __ffs(m) - 1;
+                m &= m - 1;
+                const uint4 ent = f.slice_ent[(size_t)i * kSlicesPerTile + sl];
+                const unsigned long long src = (unsigned long long)ent.y | ((unsigned long long)ent.z << 32);
+                for (uint32_t k = 0; k < ent.x; k++)
+                    if (src + k < f.scratch_cap && dst + k < f.cap) f.out[dst + k] = f.scratch[src + k];
+                dst += ent.x;
+            }
+        }
+        s_cnt[tid] = small ? 0u : c;
         __syncthreads();
-        // one warp per matching tile
+        // one warp per remaining matching tile
         for (int j = warp; j < kFinThreads; j += kFinThreads / 32) {
             if (!s_cnt[j]) continue;
             const uint32_t tile = c0 + j;
@@ -869,7 +887,7 @@ __global__ void __launch_bounds__(kFinThreads) pfac_finalize_kernel(const Finali
             }
         }
         __syncthreads();
-        if (tid == kFinThreads - 1) s_run = s_base[tid] + s_cnt[tid];
+        if (tid == kFinThreads - 1) s_run = s_base[tid] + c;
         __syncthreads();
     }
     if (tid == 0 && lo < hi && hi == f.n_tiles) {   // the CTA whose range ends the input owns the total
