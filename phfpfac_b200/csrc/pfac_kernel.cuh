@@ -2,14 +2,16 @@
 // (reference master_kernel.cu:37-180).  Design notes: DESIGN.md section 3.
 //
 //   pfac_scan_kernel      the detector: persistent, one CTA per SM, warp specialised.
-//     * producer warp: claims tile tickets and streams tiles of 31 x 512 bytes (+ halo of
+//     * producer warp: claims tile tickets and streams tiles of 32 x 512 bytes (+ halo of
 //       max_pat_len-1 bytes) into a shared-memory ring with cp.async.bulk (TMA bulk copy, SASS
 //       UBLKCP), full/empty mbarriers per stage, L2 evict-first hint on the streamed input; it
 //       also publishes every finished tile's result (flag mask, candidate list);
-//     * 31 consumer warps, each owning one 512-byte slice of every tile.  Per slice
+//     * 31 consumer warps taking slots (2 or 4 consecutive 512-byte slices) of the CTA's tiles
+//       from a shared counter.  Per slice
 //         stage 1  16 start positions per lane against T1 (64 KiB byte table over 2-byte windows,
 //                  four bit-planes: root fan-out + depth-1 rows, bytes 1-2, bytes 2-3, short
 //                  patterns), survivors compacted into the warp queue by ballot rank;
+//       and per slot
 //         stage 2  survivors against Tm/T3/Tm2 (two-point checks on the 4-byte prefix and on
 //                  the bytes that end the shortest pattern below it) or T2.
 //       A start that survives becomes a CANDIDATE of its tile and flags its slice; the detector
