@@ -36,6 +36,7 @@
 namespace pfac {
 
 constexpr uint32_t kHash4Mul = 0x9E3779B1u;
+constexpr uint32_t kHash4Mul2 = 0x85EBCA77u;   // T2 is a two-hash Bloom filter: both bits must be set
 constexpr uint32_t kTmSlotBits = 12;
 constexpr uint32_t kTm1Slots = 2u << kTmSlotBits;   // level 1: 4096 buckets x 2 slots (u16: tag << 8 | m, 0 = empty)
 constexpr uint32_t kT3Seed2 = 0x5bd1e995u;
