@@ -45,8 +45,7 @@ def pytest_collection_modifyitems(config, items):
             item.add_marker(skip)
 
 
-@pytest.fixture(scope="session")
-def fixtures():
+def load_fixtures():
     fx = json.load(open(os.path.join(GOLDEN, "fixtures.json")))
     out = {
         "experimentpattern": bytes.fromhex(fx["experimentpattern_hex"]),
@@ -65,6 +64,11 @@ def fixtures():
         out[name] = d[off:off + n]
         off += n
     return out
+
+
+@pytest.fixture(scope="session")
+def fixtures():
+    return load_fixtures()
 
 
 @pytest.fixture(scope="session")
