@@ -131,7 +131,9 @@ int pfac_ctx_device(const pfac_ctx *ctx);
  * d_out: device array of `cap` pfac_match; d_count: device uint64 receiving the number of
  * matches found.  If it exceeds cap nothing is written past d_out[cap) and the contents
  * of d_out are unspecified: size the buffer from the count and scan again.
- * Asynchronous on `stream`. */
+ * Asynchronous on `stream`.  Scans of one context share one working set: a call on another
+ * stream than the previous one is ordered after it on the device (use one context per stream
+ * for scans that should overlap). */
 int pfac_scan_device(pfac_ctx *ctx, const void *d_in, uint64_t n_starts, uint64_t n_valid,
                      uint64_t base_pos, void *d_out, uint64_t cap, void *d_count, void *stream);
 /* Same, synchronous; *count receives the device count.  PFAC_ERR_OUTPUT_FULL if *count > cap. */

@@ -71,7 +71,10 @@ struct pfac_ctx {
     size_t table_bytes = 0;
     // pfac_scan_device: own stream and slot
     cudaStream_t own_stream = nullptr;
-    Slot own;
+    Slot own;                          // working set of pfac_scan_device[_sync]
+    cudaEvent_t own_done = nullptr;    // end of the last device scan; a call on another stream waits for it
+    cudaStream_t own_last = nullptr;
+    bool own_used = false;
     std::vector<Stage> stages;
     uint64_t info[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     // optional CUDA-event timing of the detector kernel alone (bench.py's roofline leg)
@@ -428,6 +431,7 @@ int pfac_ctx_create(int device, const pfac_tables *t, int part, int n_streams, s
     if (bps < 1) return set_error(PFAC_ERR_CUDA, "scan kernel does not fit on an SM (smem %zu B)", ctx->smem_bytes);
 
     CU_TRY(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
+    CU_TRY(cudaEventCreateWithFlags(&ctx->own_done, cudaEventDisableTiming));
     int e = slot_init(ctx->own);
     if (e) return e;
     *out = ctx.release();
@@ -450,6 +454,7 @@ void pfac_ctx_destroy(pfac_ctx *ctx)
     for (auto e : ctx->ev)
         if (e) cudaEventDestroy(e);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    if (ctx->own_done) cudaEventDestroy(ctx->own_done);
     delete ctx;
 }
 
@@ -501,6 +506,21 @@ int pfac_ctx_derived_info(const pfac_ctx *ctx, uint64_t info[16])
     return PFAC_OK;
 }
 
+// Device scans of one context share one working set (control block, tile directory, scratch): a scan
+// enqueued on another stream than the one before it is ordered after it.
+static int own_enter(pfac_ctx *ctx, cudaStream_t st)
+{
+    if (ctx->own_used && ctx->own_last != st) CU_TRY(cudaStreamWaitEvent(st, ctx->own_done, 0));
+    return PFAC_OK;
+}
+static int own_leave(pfac_ctx *ctx, cudaStream_t st)
+{
+    CU_TRY(cudaEventRecord(ctx->own_done, st));
+    ctx->own_last = st;
+    ctx->own_used = true;
+    return PFAC_OK;
+}
+
 int pfac_scan_device(pfac_ctx *ctx, const void *d_in, uint64_t n_starts, uint64_t n_valid, uint64_t base_pos,
                      void *d_out, uint64_t cap, void *d_count, void *stream)
 {
@@ -509,7 +529,11 @@ int pfac_scan_device(pfac_ctx *ctx, const void *d_in, uint64_t n_starts, uint64_
     DeviceGuard g(ctx->device);
     cudaStream_t st = stream ? (cudaStream_t)stream : ctx->own_stream;
     uint64_t tiles = 0, ctas = 0, launches = 0;
-    int e = launch_scan(ctx, ctx->own, d_in, n_starts, n_valid, base_pos, 0u, d_out, cap, d_count, st, &tiles, &ctas, &launches);
+    int e = own_enter(ctx, st);
+    if (e) return e;
+    e = launch_scan(ctx, ctx->own, d_in, n_starts, n_valid, base_pos, 0u, d_out, cap, d_count, st, &tiles, &ctas, &launches);
+    if (e) return e;
+    e = own_leave(ctx, st);
     if (e) return e;
     ctx->info[0] = launches;
     ctx->info[1] = tiles;
@@ -529,9 +553,13 @@ int pfac_scan_device_sync(pfac_ctx *ctx, const void *d_in, uint64_t n_starts, ui
         std::lock_guard<std::mutex> lk(ctx->mu);
         DeviceGuard g(ctx->device);
         uint64_t tiles = 0, ctas = 0, launches = 0;
-        int e = launch_scan(ctx, ctx->own, d_in, n_starts, n_valid, base_pos, 0u, d_out, cap, nullptr, st, &tiles, &ctas, &launches);
+        int e = own_enter(ctx, st);
+        if (e) return e;
+        e = launch_scan(ctx, ctx->own, d_in, n_starts, n_valid, base_pos, 0u, d_out, cap, nullptr, st, &tiles, &ctas, &launches);
         if (e) return e;
         CU_TRY(cudaMemcpyAsync(ctx->own.h_result, ctx->own.d_result, sizeof(Result), cudaMemcpyDeviceToHost, st));
+        e = own_leave(ctx, st);
+        if (e) return e;
         CU_TRY(cudaStreamSynchronize(st));
         ctx->info[0] = launches;
         ctx->info[1] = tiles;

@@ -391,6 +391,34 @@ def test_job_multi_segment_64bit_positions():
     job.close()
 
 
+def test_device_scans_on_two_streams_share_one_context(fixtures):
+    """pfac_scan_device calls of one context enqueued on different streams are ordered on the device
+    (they share the control block and the tile directory): interleave two inputs on two streams."""
+    torch = torch_cuda()
+    t = pf.Tables.from_bytes(fixtures["dictionary"], 1, 256)
+    m = pf.Matcher(t)
+    rng = np.random.default_rng(5)
+    base = np.frombuffer(fixtures["1M"], dtype=np.uint8)
+    texts = [base[:700000].copy(), np.roll(base, 12345)[:400000].copy()]
+    want = [m.scan_host(x) for x in texts]
+    d_in = [torch.from_numpy(x).cuda() for x in texts]
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    outs = [torch.empty((len(w) + 16, 2), dtype=torch.int32, device="cuda") for w in want]
+    cnts = [torch.zeros(1, dtype=torch.int64, device="cuda") for _ in want]
+    torch.cuda.synchronize()
+    for rep in range(6):
+        i = rep & 1
+        m.scan_device_raw(d_in[i].data_ptr(), len(texts[i]), len(texts[i]), 0, outs[i].data_ptr(), outs[i].shape[0],
+                          cnts[i].data_ptr(), streams[i].cuda_stream)
+    torch.cuda.synchronize()
+    for i in range(2):
+        n = int(cnts[i].item())
+        assert n == len(want[i])
+        got = outs[i][:n].cpu().numpy()
+        assert np.array_equal(got[:, 0].astype(np.uint32), want[i]["pos"]) and np.array_equal(got[:, 1].astype(np.uint32), want[i]["id"])
+    m.close()
+
+
 def test_host_register_in_place(fixtures):
     """pfac_host_register: scanning from caller memory pinned in place gives the same records."""
     t = pf.Tables.from_bytes(fixtures["dictionary"], 1, 256)
