@@ -208,6 +208,8 @@ int launch_scan(pfac_ctx *ctx, Slot &slot, const void *d_in, uint64_t n_starts, 
     p.tm_bits = ctx->dv.tm_bits;
     p.tm2_bits = ctx->dv.tm2_bits;
     p.gimage = ctx->d_gimage;
+    if (ctx->n_stages < (uint32_t)min_stages((int)ctx->dv.mode))
+        return set_error(PFAC_ERR_INTERNAL, "input ring of %u stages is too shallow for the slot scheme", ctx->n_stages);
     p.n_stages = ctx->n_stages;
     p.stage_magic = (uint32_t)((1ull << 32) / ctx->n_stages) + 1u;
     e = slot_reserve(slot, p.n_tiles, (size_t)std::max<uint64_t>(cap, 4096), stream);
@@ -370,7 +372,8 @@ int pfac_ctx_create(int device, const pfac_tables *t, int part, int n_streams, s
         const size_t stride = scan_buf_stride(ctx->halo);
         const size_t fit = smem_max > fixed ? (smem_max - fixed) / stride : 0;
         const bool minimal = t2_bytes < 2048 && (ctx->dv.mode == 2 || (t3_bytes < 2048 && tm2_bytes < 2048));
-        if (fit >= 3 || (fit >= 2 && minimal)) {
+        const size_t need = (size_t)min_stages((int)ctx->dv.mode);   // 2 (shared-memory mode) or 4 (global mode)
+        if (fit >= std::max<size_t>(3, need) || (fit >= need && minimal)) {
             ctx->n_stages = (uint32_t)std::min<size_t>(fit, kMaxStages);
             ctx->smem_bytes = scan_smem_bytes(ctx->image_bytes, ctx->halo, ctx->n_stages, ctx->dv.mode);
             break;

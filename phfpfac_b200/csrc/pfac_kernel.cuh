@@ -108,6 +108,14 @@ constexpr int kTile = kSlicesPerTile * kSlice;   // 16,384 start positions per t
 __host__ __device__ constexpr int slot_slices(int mode) { return mode == 2 ? PFAC_SLOT_SLICES_GLOBAL : PFAC_SLOT_SLICES; }
 __host__ __device__ constexpr int q1_cap(int mode) { return 64 * slot_slices(mode); }   // per consumer warp: starts of one slot that passed stage 1 (u16)
 __host__ __device__ constexpr int queue_bytes(int mode) { return q1_cap(mode) * 2; }     // a slot with more survivors is handed over whole
+// Ring depth the slot scheme needs.  Each warp holds one slot; when the ring is exhausted (or the
+// work has ended) the warps block on slots of the next ceil(31 / slots per tile) tiles.  A blocked
+// slot's tile must be the NEXT fill of its stage, not the one after -- an mbarrier phase parity
+// cannot tell those apart -- so the ring has to be at least that many stages deep.
+__host__ __device__ constexpr int min_stages(int mode)
+{
+    return (kConsumerWarps + kSlicesPerTile / slot_slices(mode) - 1) / (kSlicesPerTile / slot_slices(mode));
+}
 static_assert(kSlicesPerTile % PFAC_SLOT_SLICES == 0 && kSlicesPerTile % PFAC_SLOT_SLICES_GLOBAL == 0, "slots tile the tile");
 constexpr int kMaxStages = 8;
 constexpr int kCtrlBytes = 1024;
