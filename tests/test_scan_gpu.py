@@ -391,6 +391,30 @@ def test_job_multi_segment_64bit_positions():
     job.close()
 
 
+def test_shallow_ring(monkeypatch):
+    """A larger level-2 table leaves the input ring 3 stages instead of 4: the slot scheme (warps
+    taking slots from a counter, sentinel + s_kend at the end) must not depend on the depth."""
+    torch = torch_cuda()
+    monkeypatch.setenv("PFAC_TM2_BYTES", "65536")
+    pats = pf.synth_patterns(1, 3000, 3, 4, 64)
+    t = pf.Tables.from_bytes(pats, 1, 256)
+    m = pf.Matcher(t)
+    assert m.derived_info()["ring_stages"] == 3
+    text = pf.synth_text(1, 9, 3 << 20, patterns=pats)
+    got = m.scan_host(text)
+    m.close()
+    monkeypatch.delenv("PFAC_TM2_BYTES")
+    m2 = pf.Matcher(t)
+    assert m2.derived_info()["ring_stages"] >= 4
+    want = m2.scan_host(text)
+    m2.close()
+    assert len(want) > 0 and np.array_equal(got, want)
+    o = Oracle(pats, 1, 256)
+    pos, ids = o.scan(np.frombuffer(text, dtype=np.uint8)[:1 << 20])
+    k = int((want["pos"] < (1 << 20) - 64).sum())
+    assert np.array_equal(want["pos"][:k].astype(np.int64), pos[:k]) and np.array_equal(want["id"][:k].astype(np.int32), ids[:k])
+
+
 def test_device_scans_on_two_streams_share_one_context(fixtures):
     """pfac_scan_device calls of one context enqueued on different streams are ordered on the device
     (they share the control block and the tile directory): interleave two inputs on two streams."""
