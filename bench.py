@@ -324,6 +324,16 @@ def main():
         total_matches = n_matches
     sampler.stop()
     launches_e2e = info["launches"] * e2e_steps
+    # the ceiling of the e2e leg: a bare H2D copy of the same pinned buffer (rank 0, after the timed regions)
+    link_gbs = None
+    if rank == 0:
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for _ in range(2):
+            ev0.record()
+            d_text.copy_(h_text, non_blocking=True)
+            ev1.record()
+            torch.cuda.synchronize()
+        link_gbs = h_text.numel() / ev0.elapsed_time(ev1) / 1e6
 
     if rank == 0:
         peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -354,7 +364,10 @@ def main():
             "clocks": sampler.summary(),
             "e2e": {"value": world * n * e2e_steps / e2e_s / 1e9, "unit": "GB/s", "steps": e2e_steps,
                     "h2d_bytes_per_step": int(info["h2d_bytes"]), "d2h_bytes_per_step": int(info["d2h_bytes"]),
-                    "launches_per_step": int(info["launches"])},
+                    "launches_per_step": int(info["launches"]),
+                    "h2d_copy_alone_gbs": link_gbs,
+                    "note": "h2d_copy_alone_gbs = a bare cudaMemcpyAsync of one rank's pinned input, measured in this "
+                            "run: the PCIe ceiling of this leg per GPU"},
             "gpu_launches": int(world * (launches + launches_e2e)),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
