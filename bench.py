@@ -109,6 +109,7 @@ class ClockSampler(threading.Thread):
         self.samples, self.reasons, self.max_mhz = [], set(), None
         self._stop = threading.Event()
         self.active = threading.Event()
+        self.period = float(os.environ.get("PFAC_BENCH_SAMPLE_MS", "1")) * 1e-3
         try:
             import pynvml
             pynvml.nvmlInit()
@@ -139,7 +140,7 @@ class ClockSampler(threading.Thread):
                             self.reasons.add(name)
                 except Exception:
                     pass
-            time.sleep(0.001)
+            time.sleep(self.period)
 
     def stop(self):
         self._stop.set()
