@@ -156,7 +156,7 @@ def cpu_baseline(tables, text, nthreads=None, budget_s=12.0):
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     from _oracle import oracle_lib, scan_tables_cpu
     lib = oracle_lib()
-    cores = nthreads or lib.oracle_max_threads()
+    cores = nthreads or max(lib.oracle_max_threads(), len(os.sched_getaffinity(0)))
     part = tables.part(0)
     cal = min(len(text), 4 << 20)
     t0 = time.perf_counter()
@@ -182,7 +182,8 @@ def run_reference(args):
     pf, pats, tables, n, tk, tseed, desc = make_workload(args, 0)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     from _oracle import oracle_lib, scan_tables_cpu
-    cores = oracle_lib().oracle_max_threads()
+    # torchrun sets OMP_NUM_THREADS=1 for its workers: take the cores this process may run on instead
+    cores = max(oracle_lib().oracle_max_threads(), len(os.sched_getaffinity(0)))
     part = tables.part(0)
     # bounded sample per step so K+W steps end within a few minutes
     cal_n = 4 << 20
