@@ -211,3 +211,38 @@ def test_escape_front_end_matches_oracle_and_reference(tmp_path):
             pf.Tables.from_bytes(blob, 1, 256, escapes=True)
         with pytest.raises(ValueError):
             Oracle(blob, 1, 256, escapes=True)
+
+
+def test_escape_front_end_fuzz(tmp_path):
+    """Random escape soup: the product's reader, the oracle's restatement and (where built) the
+    reference's own read_pattern_ext agree on the tables -- or all refuse the file."""
+    rng = np.random.default_rng(2024)
+    atoms = [b"a", b"b", b"Z", b"0", b" ", b"\\n", b"\\t", b"\\r", b"\\0", b"\\7", b"\\12", b"\\101", b"\\377", b"\\x41",
+             b"\\x4", b"\\xff", b"\\xZ", b"\\q", b"\\\\", b"\\\"", b"\\'", b"\\a", b"\\b", b"\\f", b"\\v", b"\\8", b"\\x", b"\\"]
+    have_ref = ref_available() and os.path.isdir("/root/reference")
+    agreed = refused = 0
+    for trial in range(150):
+        lines = []
+        for _ in range(int(rng.integers(1, 12))):
+            k = int(rng.integers(1, 7))
+            lines.append(b"".join(atoms[int(i)] for i in rng.integers(0, len(atoms), k)))
+        blob = b"\n".join(lines) + b"\n"
+        try:
+            o = Oracle(blob, 1, 256, escapes=True)
+        except ValueError:
+            o = None
+        try:
+            t = pf.Tables.from_bytes(blob, 1, 256, escapes=True)
+        except pf.PfacError:
+            t = None
+        assert (o is None) == (t is None), (trial, blob)
+        if o is None:
+            refused += 1
+            continue
+        assert t.n_patterns == o.n_patterns and same(t.part(0), o.part(0)), (trial, blob)
+        if have_ref:
+            f = tmp_path / f"e{trial}"
+            f.write_bytes(blob)
+            assert same(t.part(0), RefBuild(str(f), width=256, escapes=True).part(0)), (trial, blob)
+        agreed += 1
+    assert agreed > 50
