@@ -9,8 +9,10 @@
 //   * SortRows' O(R^2) exchange sort (phf.c:126-139), whose tie order decides the packing, is
 //     reproduced exactly by moving elements along the chain of strict running maxima with a
 //     max-segment-tree (O(R log R));
-//   * the first-fit search (phf.c:188-195) walks free slots through a hierarchical bitmap
-//     instead of every offset.
+//   * the first-fit search (phf.c:188-195) tests 64 candidate slots per step against the row's
+//     columns with word-wide occupancy masks, and skips full regions through a hierarchical bitmap,
+//     instead of trying every offset (100,000 patterns: 2 s at width 256, 84 s at width 4096
+//     where one offset at a time took 20 minutes).
 // tests/test_tables_*.py pin this against the reference's own code (oracle/_ref) and the
 // plain-C restatement (oracle/pfac_oracle.c).
 #include <algorithm>
@@ -310,6 +312,30 @@ struct SlotMap {
             if (l1[w1] == ~0ULL) l2[w1 >> 6] |= 1ULL << (w1 & 63);
         }
     }
+    // 64 occupancy bits starting at an arbitrary slot
+    uint64_t bits_at(size_t pos) const
+    {
+        const size_t w = pos >> 6, b = pos & 63;
+        uint64_t v = l0[w] >> b;
+        if (b) v |= l0[w + 1] << (64 - b);
+        return v;
+    }
+    // phf.c:188-195 for a whole row at once: the first free slot s >= start such that s + d[i] is
+    // free for every i (d = the row's other columns relative to its first).  Same answer as trying
+    // the free slots one by one, 64 candidates per step.
+    size_t first_fit(size_t start, const uint32_t *d, int nd)
+    {
+        size_t s = next_free(start);
+        const size_t reach = nd ? (size_t)d[nd - 1] + 192 : 192;
+        while (true) {
+            const size_t w = s >> 6;
+            ensure((w << 6) + reach);
+            uint64_t cand = ~l0[w] & (~0ULL << (s & 63));
+            for (int i = 0; i < nd && cand; i++) cand &= ~bits_at((w << 6) + d[i]);
+            if (cand) return (w << 6) + (size_t)__builtin_ctzll(cand);
+            s = next_free((w + 1) << 6);
+        }
+    }
     size_t next_free(size_t s)
     {
         ensure(s);
@@ -375,6 +401,7 @@ int ffdm(Partition &P, int width)
 
     // first fit, fullest rows first (phf.c:184-229)
     SlotMap slots;
+    std::vector<uint32_t> delta;
     std::vector<int32_t> HT, val;
     int32_t MaxOffset = 0;
     for (int ndx = 0; ndx < MaxRow; ndx++) {
@@ -383,16 +410,10 @@ int ffdm(Partition &P, int width)
         if (c <= 0) break;                                                // phf.c:184
         const size_t kb = row_begin[(size_t)row];
         const int32_t col0 = P.keys[kb] % width;
-        size_t s = slots.next_free(0);
-        int64_t offset;
-        while (true) {                                                    // phf.c:188-195
-            offset = (int64_t)s - col0;
-            int i = 1;
-            for (; i < c; i++)
-                if (slots.used((size_t)(offset + P.keys[kb + (size_t)i] % width))) break;
-            if (i == c) break;
-            s = slots.next_free(s + 1);
-        }
+        delta.resize((size_t)c - 1);
+        for (int i = 1; i < c; i++) delta[(size_t)i - 1] = (uint32_t)(P.keys[kb + (size_t)i] % width - col0);
+        const size_t s = slots.first_fit(0, delta.data(), c - 1);         // phf.c:188-195
+        const int64_t offset = (int64_t)s - col0;
         if (offset > INT32_MAX - width)
             return set_error(PFAC_ERR_LIMIT, "hash table offset exceeds 32 bits");
         P.r[(size_t)row] = (int32_t)offset;                               // phf.c:197
