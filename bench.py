@@ -347,6 +347,18 @@ def main():
         tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
         if os.path.exists(tpath):
             traffic = json.load(open(tpath)).get(args.workload if not args.bytes else "", None)
+        ncu = None   # selected metrics of the committed ncu capture of the dominant kernel (not measured in this run)
+        npath = os.path.join(ROOT, "profiles", "r1_ncu_full_detector_1GiB.json")
+        if os.path.exists(npath) and args.workload == "config3" and not args.bytes:
+            capture = json.load(open(npath))[0]
+            pick = {"smem_pipe_pct_of_peak": "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed",
+                    "issue_active_pct": "smsp__issue_active.avg.pct_of_peak_sustained_active",
+                    "alu_pipe_pct": "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active",
+                    "dram_pct_of_peak": "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+                    "warp_instructions": "smsp__inst_executed.sum",
+                    "threads_per_instruction": "smsp__thread_inst_executed_per_inst_executed.ratio"}
+            ncu = {k: float(capture[v].split()[0]) for k, v in pick.items() if v in capture}
+            ncu["source"] = "profiles/r1_ncu_full_detector_1GiB.json (ncu --set full, same workload)"
         ms_step = ms_max / args.steps
         alg_bytes = n + 8 * n_matches           # per launch: input bytes + 8 B per match record
         # dominant kernel = pfac_scan_kernel (the detector); its own CUDA-event time per launch
@@ -373,7 +385,7 @@ def main():
             "gpu_launches": int(world * (launches + launches_e2e)),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                         "kernel": "pfac_scan_kernel", "algorithmic_bytes_per_launch": alg_bytes,
+                         "kernel": "pfac_scan_kernel", "ncu": ncu, "algorithmic_bytes_per_launch": alg_bytes,
                          "kernel_ms_per_launch": kernel_ms, "kernel_launches_timed": kernel_launches,
                          "kernel_share_of_step": kernel_ms / (ms / args.steps),
                          "note": "a step = pfac_scan_kernel + pfac_emit_kernel + pfac_finalize_kernel; `value` "
