@@ -152,3 +152,27 @@ def test_sharded_oracle_scan_equals_whole_scan(fixtures):
             ps.append(p[keep] + start)
             is_.append(d[keep])
         assert np.array_equal(np.concatenate(ps), pos) and np.array_equal(np.concatenate(is_), ids)
+
+
+def _build_c_example(tmp_path):
+    import subprocess
+    exe = tmp_path / "host_c_abi"
+    build = os.path.join(ROOT, "phfpfac_b200", "_build")
+    r = subprocess.run(["gcc", "-std=c11", "-Wall", "-Wextra", "-Werror", "-I" + os.path.join(ROOT, "include"),
+                        os.path.join(ROOT, "examples", "host_c_abi.c"), "-L" + build, "-lpfac_b200",
+                        "-Wl,-rpath," + build, "-o", str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    return exe
+
+
+def test_header_is_plain_c_and_example_links(tmp_path, fixtures):
+    """include/pfac_b200.h compiles as C11 with no CUDA or C++ in sight, and the INTEGRATION.md host
+    program links against the library; its table half runs without a GPU."""
+    import subprocess
+    exe = _build_c_example(tmp_path)
+    pat = tmp_path / "pat"
+    pat.write_bytes(fixtures["experimentpattern"])
+    r = subprocess.run([str(exe), str(pat), "256"], capture_output=True, text=True)
+    assert r.returncode == 0 and "4 patterns, max length 4" in r.stdout, (r.stdout, r.stderr)
+    assert subprocess.run([str(exe), str(tmp_path / "nope"), "256"], capture_output=True).returncode == 1
+    assert subprocess.run([str(exe)], capture_output=True).returncode == 255

@@ -484,3 +484,19 @@ def test_cli_byte_identical_result_file(fixtures, golden, tmp_path):
     assert subprocess.run([GPHF, str(pat), "1", "256", str(tmp_path / "nope")], cwd=tmp_path, capture_output=True).returncode == 1
     assert subprocess.run([GPHF, str(tmp_path / "nope"), "1", "256", str(inp)], cwd=tmp_path, capture_output=True).returncode == 1
     assert subprocess.run([GPHF, str(pat), "1", "100", str(inp)], cwd=tmp_path, capture_output=True).returncode == 1
+
+
+def test_c_host_example_end_to_end(fixtures, golden, tmp_path):
+    """examples/host_c_abi.c (plain C against include/pfac_b200.h): tables, multi-GPU job, writer --
+    byte-identical GPU_match_result.txt."""
+    from test_abi_host import _build_c_example
+    torch_cuda()
+    exe = _build_c_example(tmp_path)
+    pat = tmp_path / "dict"
+    pat.write_bytes(fixtures["dictionary"])
+    inp = tmp_path / "1M"
+    inp.write_bytes(fixtures["1M"])
+    r = subprocess.run([str(exe), str(pat), "256", str(inp)], cwd=tmp_path, capture_output=True, text=True)
+    assert r.returncode == 0, (r.stdout, r.stderr)
+    out = (tmp_path / "GPU_match_result.txt").read_bytes()
+    assert hashlib.md5(out).hexdigest() == golden["results"]["dictionary_x_1M"]["md5"]
