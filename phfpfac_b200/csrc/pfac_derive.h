@@ -23,7 +23,7 @@
 //                       whose text at offset m-4 is not in T3 cannot complete any pattern under
 //                       that key (Wu-Manber style two-point checks; they settle the starts that
 //                       share a long prefix with many patterns without walking it)
-//   T2    2^k2 bits   : multiplicative hash of every 4-byte prefix -- only for pattern sets whose
+//   T2    2^k2 bits   : two multiplicative hashes (Bloom pair) of every 4-byte prefix -- only for pattern sets whose
 //                       prefixes do not fit the shared-memory Tm.  Such sets (e.g. 100,000 patterns)
 //                       get Tm/Tm2/T3 sized for their key counts in GLOBAL memory (a few MB, L2
 //                       resident) and T2, filling shared memory, becomes stage 1.
@@ -95,7 +95,7 @@ struct Derived {
     // shared-memory image, copied verbatim by the detector kernel (sections 128-byte aligned)
     std::vector<uint8_t> image;
     uint32_t off_t1 = 0, off_t2 = 0, off_tm = 0, off_tm2 = 0, off_t3 = 0;
-    uint32_t t2_shift = 32;      // index = (w * kHash4Mul) >> t2_shift   (32: no T2)
+    uint32_t t2_shift = 32;      // indices = (w * kHash4Mul) >> t2_shift and (w * kHash4Mul2) >> t2_shift   (32: no T2)
     uint32_t has_short = 0;      // patterns of length <= 3 exist (T1's Short plane is not empty)
     uint32_t has_t3 = 0;         // Tm + T3 present (then no T2)
     uint32_t t3_shift = 32;
