@@ -1,0 +1,69 @@
+#!/usr/bin/env python
+"""The reference's own GPU path (GPU_Malloc_Memory / GPU_TraceTable / GPU_Free_memory of
+master_kernel.cu, built for sm_100a by `make -C oracle refgpu`) on this box: a baseline number for
+the same pattern set, and its dense result as one more parity check of the product's records.
+Test infrastructure (lives under tests/): the product never loads oracle/_ref.  The reference's dense result is
+4 * max_pat_len bytes per input byte and indexed in 32 bits, so the input is limited to
+2^32 / (4 * max_pat_len) bytes (config 3, max_pat_len 64: 16 MiB)."""
+import argparse, ctypes as C, json, os, sys, time
+import numpy as np
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import phfpfac_b200 as pf
+from bench import WORKLOADS
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--workload", default="config3")
+ap.add_argument("--mib", type=int, default=0, help="input MiB (default: the largest the reference can index)")
+a = ap.parse_args()
+so = os.path.join(ROOT, "oracle", "_ref", "libphfpfac_refgpu.so")
+if not os.path.exists(so):
+    print(json.dumps({"impl": "reference-gpu", "unavailable": "oracle/_ref/libphfpfac_refgpu.so not built (make -C oracle refgpu)"}))
+    sys.exit(0)
+ref = C.CDLL(so)
+ref.refgpu_scan.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p,
+                            C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_double)]
+
+pk, cnt, pseed, lo, hi, tk, tseed, nbytes, desc = WORKLOADS[a.workload]
+pats = pf.synth_patterns(pk, cnt, pseed, lo, hi)
+tables = pf.Tables.from_bytes(pats, 1, 256)
+p = tables.part(0)
+mpl = tables.max_pat_len
+n_max = ((1 << 32) // (4 * mpl)) - 4096
+n = min(a.mib << 20, n_max) if a.mib else n_max
+text = pf.synth_text(tk, tseed, n, patterns=pats)
+
+def pinned(nbytes):
+    ptr = C.c_void_p()
+    pf.check(pf.lib.pfac_host_alloc(C.byref(ptr), nbytes))
+    return ptr
+
+h_in = pinned(n + 4096)
+C.memmove(h_in, text.ctypes.data, n)
+h_res = pinned(n * mpl * 4)
+s0 = np.ascontiguousarray(p.s0, dtype=np.int32); r = np.ascontiguousarray(p.r, dtype=np.int32)
+HT = np.ascontiguousarray(p.HT, dtype=np.int32); val = np.ascontiguousarray(p.val, dtype=np.int32)
+best = None
+for rep in range(2):
+    ms = (C.c_double * 3)()
+    rc = ref.refgpu_scan(h_in, n, p.state_num, p.n_final, p.ht_size, 256, s0.ctypes.data, mpl, r.ctypes.data, HT.ctypes.data,
+                         val.ctypes.data, h_res, ms)
+    assert rc == 0
+    if best is None or sum(ms) < sum(best):
+        best = list(ms)
+res = np.ctypeslib.as_array(C.cast(h_res, C.POINTER(C.c_uint32)), shape=(n, mpl))
+t0 = time.perf_counter()
+rows, cols = np.nonzero(res != 0xFFFFFFFF)       # the host-side sift of main.cc:304-350
+states = res[rows, cols]
+ids = np.asarray(p.idmap)[states]
+sift_s = time.perf_counter() - t0
+m = pf.Matcher(tables)
+ours = m.scan_host(text)
+same = len(ours) == len(rows) and np.array_equal(ours["pos"].astype(np.int64), rows) and np.array_equal(ours["id"].astype(np.int64), ids.astype(np.int64))
+total_ms = sum(best)
+print(json.dumps({
+    "impl": "reference-gpu", "workload": desc, "bytes": int(n), "max_pat_len": int(mpl), "matches": int(len(rows)),
+    "records_equal_to_product": bool(same),
+    "ms": {"malloc_memset": best[0], "trace_h2d_kernel_d2h": best[1], "free": best[2], "numpy_sift_of_dense_result": sift_s * 1e3},
+    "gbs_end_to_end": n / total_ms / 1e6,
+    "note": "GPU_TraceTable prints its own H2D / kernel / D2H split above; dense result = %d bytes per input byte" % (4 * mpl)}))

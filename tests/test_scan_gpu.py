@@ -3,6 +3,7 @@ Runs on the GPU box only; nothing here reads /root/reference."""
 import hashlib
 import os
 import subprocess
+import sys
 
 import numpy as np
 import pytest
@@ -500,3 +501,18 @@ def test_c_host_example_end_to_end(fixtures, golden, tmp_path):
     assert r.returncode == 0, (r.stdout, r.stderr)
     out = (tmp_path / "GPU_match_result.txt").read_bytes()
     assert hashlib.md5(out).hexdigest() == golden["results"]["dictionary_x_1M"]["md5"]
+
+
+def test_records_equal_the_reference_gpu_kernel():
+    """The reference's own TraceTable_kernel (master_kernel.cu built for sm_100a by `make -C oracle
+    refgpu`, texture fetches replaced by __ldg) run on this GPU: its dense result, sifted the way
+    main.cc:304-350 does, equals the product's records for the config-3 pattern set."""
+    import json
+    torch_cuda()
+    tool = os.path.join(os.path.dirname(os.path.abspath(__file__)), "refgpu_bench.py")
+    r = subprocess.run([sys.executable, tool, "--mib", "3"], capture_output=True, text=True, timeout=170)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    if "unavailable" in line:
+        pytest.skip(line["unavailable"])
+    assert line["records_equal_to_product"] is True and line["matches"] > 0, line
