@@ -215,8 +215,38 @@ def run_reference(args):
         "e2e": {"value": v, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    line["reference_gpu"] = reference_gpu_leg(args)
     print(json.dumps(line))
     return 0
+
+
+def reference_gpu_leg(args):
+    """Context for the reference arm: the reference's own GPU path (master_kernel.cu built for
+    sm_100a, oracle/_ref) on the largest input its 32-bit dense result can index, in a subprocess.
+    Reported beside the CPU number, never instead of it; None where it cannot run."""
+    import re
+    import subprocess
+    tool = os.path.join(ROOT, "tests", "refgpu_bench.py")
+    so = os.path.join(ROOT, "oracle", "_ref", "libphfpfac_refgpu.so")
+    try:
+        import torch
+        if not (os.path.exists(tool) and os.path.exists(so) and torch.cuda.is_available()):
+            return None
+        r = subprocess.run([sys.executable, tool, "--workload", args.workload, "--no-compare"], capture_output=True,
+                           text=True, timeout=150)
+        if r.returncode != 0:
+            return None
+        out = json.loads(r.stdout.strip().splitlines()[-1])
+        k = re.findall(r"2\. MASTER: The elapsed time is ([0-9.]+) ms", r.stdout)
+        kernel_ms = min(float(x) for x in k) if k else None
+        return {"bytes": out["bytes"], "kernel_ms": kernel_ms,
+                "kernel_gbs": out["bytes"] / kernel_ms / 1e6 if kernel_ms else None,
+                "end_to_end_ms": sum(v for v in (out["ms"]["malloc_memset"], out["ms"]["trace_h2d_kernel_d2h"], out["ms"]["free"])),
+                "end_to_end_gbs": out["gbs_end_to_end"],
+                "note": "GPU_Malloc_Memory + GPU_TraceTable + GPU_Free_memory of master_kernel.cu (tex1Dfetch -> __ldg), "
+                        "dense result of 4*max_pat_len bytes per input byte copied back; host-side sift not included"}
+    except Exception:
+        return None
 
 
 def main():
