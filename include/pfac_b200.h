@@ -83,6 +83,10 @@ int pfac_tables_from_arrays(const int32_t *s0, const int32_t *r, int32_t n_r, co
                             const int32_t *val, int32_t ht_size, int32_t width, int32_t state_num,
                             int32_t n_final, const int32_t *idmap, int32_t max_pat_len,
                             pfac_tables **out);
+/* On-disk cache of the canonical arrays of every partition (checksummed; the reference rebuilds its
+ * tables on every run, main.cc:100-126).  A loaded set scans exactly like the set that was saved. */
+int pfac_tables_save(const pfac_tables *t, const char *path);
+int pfac_tables_load(const char *path, pfac_tables **out);
 void pfac_tables_destroy(pfac_tables *t);
 
 int pfac_tables_n_parts(const pfac_tables *t);

@@ -82,6 +82,16 @@ class Tables:
                                           a[4].ctypes.data, max_pat_len, C.byref(h)))
         return cls(h)
 
+    @classmethod
+    def load(cls, path):
+        """A table set saved with save() (checksummed cache of the canonical arrays)."""
+        h = C.c_void_p()
+        check(lib.pfac_tables_load(str(path).encode(), C.byref(h)))
+        return cls(h)
+
+    def save(self, path):
+        check(lib.pfac_tables_save(self._h, str(path).encode()))
+
     def part(self, g=0):
         return PartView(self, g)
 

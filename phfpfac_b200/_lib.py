@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(PKG_DIR, "_build", "libpfac_b200.so")
 # every symbol include/pfac_b200.h and include/pfac_synth.h declare
 ABI_SYMBOLS = [
     "pfac_last_error", "pfac_abi_version",
-    "pfac_tables_build_file", "pfac_tables_build_mem", "pfac_tables_build_file_ext", "pfac_tables_build_mem_ext", "pfac_tables_from_arrays", "pfac_tables_destroy",
+    "pfac_tables_build_file", "pfac_tables_build_mem", "pfac_tables_build_file_ext", "pfac_tables_build_mem_ext", "pfac_tables_from_arrays", "pfac_tables_save", "pfac_tables_load", "pfac_tables_destroy",
     "pfac_tables_n_parts", "pfac_tables_n_patterns", "pfac_tables_max_pat_len", "pfac_tables_width",
     "pfac_tables_part_info", "pfac_tables_s0", "pfac_tables_r", "pfac_tables_HT", "pfac_tables_val",
     "pfac_tables_idmap", "pfac_tables_lookup", "pfac_tables_derive_check", "pfac_tables_filter_profile",
@@ -52,6 +52,8 @@ def _load():
     lib.pfac_tables_build_mem.argtypes = [_vp, C.c_size_t, C.c_int, C.c_int, C.POINTER(_vp)]
     lib.pfac_tables_build_file_ext.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_uint, C.POINTER(_vp)]
     lib.pfac_tables_build_mem_ext.argtypes = [_vp, C.c_size_t, C.c_int, C.c_int, C.c_uint, C.POINTER(_vp)]
+    lib.pfac_tables_save.argtypes = [_vp, C.c_char_p]
+    lib.pfac_tables_load.argtypes = [C.c_char_p, C.POINTER(_vp)]
     lib.pfac_tables_from_arrays.argtypes = [_vp, _vp, C.c_int32, _vp, _vp, C.c_int32, C.c_int32, C.c_int32,
                                             C.c_int32, _vp, C.c_int32, C.POINTER(_vp)]
     lib.pfac_tables_destroy.argtypes = [_vp]

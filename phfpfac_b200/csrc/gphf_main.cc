@@ -48,7 +48,27 @@ int main(int argc, char **argv)
     pfac_tables *tables = nullptr;
     // GPHF_ESCAPES=1: read the patterns through the reference's (unused) escape reader, read_pattern_ext
     const unsigned pflags = getenv("GPHF_ESCAPES") && atoi(getenv("GPHF_ESCAPES")) ? PFAC_PATTERNS_ESCAPES : 0u;
-    if (pfac_tables_build_file_ext(argv[1], 1, width, pflags, &tables)) return fail("create PFAC/PHF tables");
+    // GPHF_TABLE_CACHE=<file>: load the tables from it if it exists (the caller vouches that it belongs
+    // to this pattern file and width), else build them and write it
+    const char *cache = getenv("GPHF_TABLE_CACHE");
+    bool from_cache = false;
+    if (cache && *cache) {
+        FILE *probe = fopen(cache, "rb");
+        if (probe) {
+            fclose(probe);
+            if (pfac_tables_load(cache, &tables)) return fail("load the table cache");
+            if (pfac_tables_width(tables) != width || pfac_tables_n_parts(tables) != 1) {
+                fprintf(stderr, "%s holds tables of width %d in %d partition(s), not width %d\n", cache,
+                        pfac_tables_width(tables), pfac_tables_n_parts(tables), width);
+                return 1;
+            }
+            from_cache = true;
+        }
+    }
+    if (!from_cache) {
+        if (pfac_tables_build_file_ext(argv[1], 1, width, pflags, &tables)) return fail("create PFAC/PHF tables");
+        if (cache && *cache && pfac_tables_save(tables, cache)) return fail("write the table cache");
+    }
     double t1 = now();
     int32_t info[9];
     pfac_tables_part_info(tables, 0, info);

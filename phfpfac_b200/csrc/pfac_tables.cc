@@ -575,6 +575,117 @@ int pfac_tables_from_arrays(const int32_t *s0, const int32_t *r, int32_t n_r, co
     }
 }
 
+// ---- on-disk cache of the canonical arrays (the reference serialises nothing: it rebuilds the trie
+// and the PHF on every run, main.cc:100-126).  Little-endian int32 fields:
+//   "PFACTBL1", n_parts, n_patterns, max_pat_len, width,
+//   per partition: state_num, n_final, max_len, min_len, width, n_keys, max_key, max_row, max_offset,
+//                  ht_size, n_r, then s0[256], r[n_r], HT[ht_size], val[ht_size], idmap[n_final],
+//   FNV-1a 64 of everything before it.
+namespace {
+struct Fnv {
+    uint64_t h = 1469598103934665603ull;
+    void add(const void *p, size_t n)
+    {
+        const unsigned char *b = (const unsigned char *)p;
+        for (size_t i = 0; i < n; i++) h = (h ^ b[i]) * 1099511628211ull;
+    }
+};
+bool put(FILE *f, Fnv &h, const void *p, size_t n)
+{
+    h.add(p, n);
+    return n == 0 || fwrite(p, 1, n, f) == n;
+}
+bool get(FILE *f, Fnv &h, void *p, size_t n)
+{
+    if (n && fread(p, 1, n, f) != n) return false;
+    h.add(p, n);
+    return true;
+}
+}  // namespace
+
+int pfac_tables_save(const pfac_tables *t, const char *path)
+{
+    if (!t || !path) return set_error(PFAC_ERR_ARG, "bad arguments to pfac_tables_save");
+    FILE *f = fopen(path, "wb");
+    if (!f) return set_error(PFAC_ERR_IO, "cannot create %s", path);
+    Fnv h;
+    bool ok = put(f, h, "PFACTBL1", 8);
+    const int32_t head[4] = {(int32_t)t->parts.size(), t->n_patterns, t->max_pat_len, t->width};
+    ok = ok && put(f, h, head, sizeof head);
+    for (const Partition &P : t->parts) {
+        const int32_t ph[11] = {P.state_num, P.n_final, P.max_len, P.min_len, P.width, P.n_keys, P.max_key, P.max_row,
+                                P.max_offset, P.ht_size, (int32_t)P.r.size()};
+        std::vector<int32_t> s0 = P.s0;
+        s0.resize(kCharSet, -1);
+        ok = ok && put(f, h, ph, sizeof ph) && put(f, h, s0.data(), kCharSet * 4) && put(f, h, P.r.data(), P.r.size() * 4) &&
+             put(f, h, P.HT.data(), (size_t)P.ht_size * 4) && put(f, h, P.val.data(), (size_t)P.ht_size * 4) &&
+             put(f, h, P.idmap.data(), (size_t)P.n_final * 4);
+    }
+    const uint64_t sum = h.h;
+    ok = ok && fwrite(&sum, 1, 8, f) == 8;
+    ok = (fclose(f) == 0) && ok;
+    return ok ? PFAC_OK : set_error(PFAC_ERR_IO, "short write to %s", path);
+}
+
+int pfac_tables_load(const char *path, pfac_tables **out)
+{
+    if (!path || !out) return set_error(PFAC_ERR_ARG, "bad arguments to pfac_tables_load");
+    FILE *f = fopen(path, "rb");
+    if (!f) return set_error(PFAC_ERR_IO, "Open input file failed: %s", path);
+    auto bad = [&](const char *why) {
+        fclose(f);
+        return set_error(PFAC_ERR_IO, "%s is not a table cache this library wrote (%s)", path, why);
+    };
+    try {
+        Fnv h;
+        char magic[8];
+        int32_t head[4];
+        if (!get(f, h, magic, 8) || memcmp(magic, "PFACTBL1", 8) != 0) return bad("magic");
+        if (!get(f, h, head, sizeof head) || head[0] < 1 || head[0] > (1 << 20) || head[1] < 0 || head[2] < 0 ||
+            width_bits(head[3]) < 0)
+            return bad("header");
+        std::unique_ptr<pfac_tables> t(new pfac_tables);
+        t->n_patterns = head[1];
+        t->max_pat_len = head[2];
+        t->width = head[3];
+        t->parts.resize((size_t)head[0]);
+        for (Partition &P : t->parts) {
+            int32_t ph[11];
+            if (!get(f, h, ph, sizeof ph)) return bad("truncated");
+            if (ph[0] < 0 || ph[1] < 0 || ph[1] > ph[0] + 1 || ph[9] < 0 || ph[10] < 1 || ph[4] != head[3] ||
+                (int64_t)ph[10] != ((int64_t)ph[0] * kCharSet) / ph[4] + 1)
+                return bad("partition header");
+            P.state_num = ph[0];
+            P.n_final = ph[1];
+            P.max_len = ph[2];
+            P.min_len = ph[3];
+            P.width = ph[4];
+            P.n_keys = ph[5];
+            P.max_key = ph[6];
+            P.max_row = ph[7];
+            P.max_offset = ph[8];
+            P.ht_size = ph[9];
+            P.s0.resize(kCharSet);
+            P.r.resize((size_t)ph[10]);
+            P.HT.resize((size_t)ph[9]);
+            P.val.resize((size_t)ph[9]);
+            P.idmap.resize((size_t)ph[1]);
+            if (!get(f, h, P.s0.data(), kCharSet * 4) || !get(f, h, P.r.data(), P.r.size() * 4) ||
+                !get(f, h, P.HT.data(), P.HT.size() * 4) || !get(f, h, P.val.data(), P.val.size() * 4) ||
+                !get(f, h, P.idmap.data(), P.idmap.size() * 4))
+                return bad("truncated");
+        }
+        uint64_t sum = 0;
+        if (fread(&sum, 1, 8, f) != 8 || sum != h.h) return bad("checksum");
+        fclose(f);
+        *out = t.release();
+        return PFAC_OK;
+    } catch (const std::bad_alloc &) {
+        fclose(f);
+        return set_error(PFAC_ERR_NOMEM, "out of memory loading %s", path);
+    }
+}
+
 void pfac_tables_destroy(pfac_tables *t) { delete t; }
 int pfac_tables_n_parts(const pfac_tables *t) { return t ? (int)t->parts.size() : 0; }
 int pfac_tables_n_patterns(const pfac_tables *t) { return t ? t->n_patterns : 0; }

@@ -246,3 +246,37 @@ def test_escape_front_end_fuzz(tmp_path):
             assert same(t.part(0), RefBuild(str(f), width=256, escapes=True).part(0)), (trial, blob)
         agreed += 1
     assert agreed > 50
+
+
+def test_table_cache_roundtrip(tmp_path, fixtures):
+    """pfac_tables_save / pfac_tables_load: every canonical array of every partition comes back bit
+    for bit, the derived filter tables are the same, and damaged files are refused."""
+    for blob, parts, width in ((fixtures["dictionary"], 4, 64), (pf.synth_patterns(1, 3000, 3, 4, 64), 1, 256),
+                               (b"a\n", 1, 4096)):
+        t = pf.Tables.from_bytes(blob, parts, width)
+        f = tmp_path / "cache.bin"
+        t.save(f)
+        u = pf.Tables.load(f)
+        assert (u.n_parts, u.n_patterns, u.max_pat_len) == (t.n_parts, t.n_patterns, t.max_pat_len)
+        for g in range(parts):
+            a, b = t.part(g), u.part(g)
+            assert same(a, b) and (a.n_keys, a.max_key, a.max_offset) == (b.n_keys, b.max_key, b.max_offset)
+        assert u.derive_check() == t.derive_check()
+        assert u.lookup(int(t.part(0).s0[blob[0]]), blob[1] if blob[1] != 10 else 0) == \
+            t.lookup(int(t.part(0).s0[blob[0]]), blob[1] if blob[1] != 10 else 0)
+    raw = bytearray(f.read_bytes())
+    for damage in ("flip", "truncate", "magic"):
+        bad = bytearray(raw)
+        if damage == "flip":
+            bad[len(bad) // 2] ^= 1
+        elif damage == "truncate":
+            bad = bad[:-9]
+        else:
+            bad[0] = ord("X")
+        g = tmp_path / "bad.bin"
+        g.write_bytes(bytes(bad))
+        with pytest.raises(pf.PfacError) as e:
+            pf.Tables.load(g)
+        assert e.value.code == -1
+    with pytest.raises(pf.PfacError):
+        pf.Tables.load(tmp_path / "missing.bin")
