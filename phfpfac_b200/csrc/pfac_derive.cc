@@ -132,6 +132,61 @@ bool place_all(std::vector<Key> &keys, uint32_t bits, std::vector<uint16_t> &tab
     return true;
 }
 
+// Hash-and-displace placement (pfac_derive.h: ph_lookup) of every key into its own slot: buckets in
+// order of decreasing size, each takes the first displacement that puts all its keys on free slots.
+// `premixed`: the keys are hashes already (level 2).  false if no 16-bit displacement works.
+bool ph_build(const std::vector<Key> &keys, bool premixed, uint32_t nb, uint32_t ns, std::vector<uint16_t> &D,
+              std::vector<uint16_t> &E)
+{
+    D.assign(nb, 0);
+    E.assign(ns, 0);
+    if (keys.empty()) return true;
+    if (keys.size() > ns) return false;
+    std::vector<std::vector<uint32_t>> bucket(nb);
+    for (uint32_t i = 0; i < keys.size(); i++) {
+        const uint32_t x = premixed ? keys[i].key : ph_mix(keys[i].key);
+        bucket[mulhi32(x, nb)].push_back(i);
+    }
+    std::vector<uint32_t> order(nb);
+    std::iota(order.begin(), order.end(), 0u);
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return bucket[a].size() > bucket[b].size(); });
+    std::vector<uint8_t> used(ns, 0);
+    std::vector<uint32_t> slots;
+    for (uint32_t b : order) {
+        const auto &ks = bucket[b];
+        if (ks.empty()) break;
+        bool placed = false;
+        for (uint32_t d = 0; d < 65536 && !placed; d++) {
+            slots.clear();
+            bool ok = true;
+            for (uint32_t i : ks) {
+                const uint32_t sl = ph_slot(keys[i].key, d, ns);
+                if (used[sl] || std::find(slots.begin(), slots.end(), sl) != slots.end()) { ok = false; break; }
+                slots.push_back(sl);
+            }
+            if (!ok) continue;
+            D[b] = (uint16_t)d;
+            for (size_t j = 0; j < ks.size(); j++) {
+                const uint32_t x = premixed ? keys[ks[j]].key : ph_mix(keys[ks[j]].key);
+                used[slots[j]] = 1;
+                E[slots[j]] = (uint16_t)(((x & 255u) << 8) | keys[ks[j]].m);
+            }
+            placed = true;
+        }
+        if (!placed) return false;
+    }
+    return true;
+}
+// sizes of a perfect-hash table for n keys: about three keys per bucket, slots 80 % full
+inline void ph_sizes(size_t n, uint32_t &nb, uint32_t &ns)
+{
+    nb = (uint32_t)std::max<size_t>(8, (n + 2) / 3);
+    ns = (uint32_t)std::max<size_t>(16, n * 5 / 4 + 8);
+    nb = (nb + 63u) & ~63u;   // sections stay 128-byte aligned
+    ns = (ns + 63u) & ~63u;
+}
+constexpr uint32_t kPh1MaxBytes = 24576;   // level 1 beyond this: the set goes to global mode
+
 inline uint32_t le32(const uint8_t *q)
 {
     return (uint32_t)q[0] | ((uint32_t)q[1] << 8) | ((uint32_t)q[2] << 16) | ((uint32_t)q[3] << 24);
@@ -155,12 +210,13 @@ void derive_tables(const Partition &P, uint32_t t2_bytes, uint32_t t3_bytes, uin
     std::vector<uint32_t> t2(t2_bits / 32, 0);
     const uint32_t t2_shift = t2_bits ? 32u - log2u(t2_bits) : 32u;
     std::vector<std::pair<uint32_t, int32_t>> prefix4;   // (4-byte prefix as a little-endian word, state after it)
-    bool any_short = false, too_many = false;
+    bool any_short = false, too_many = false, all_shortc = false;
     for (int b0 = 0; b0 < kCharSet; b0++) {
         const int32_t s1 = s0(b0);
         if (s1 < 0) continue;
         if (g.is_final(s1)) {   // a 1-byte pattern: every pair starting with b0 reports a match
             any_short = true;
+            all_shortc = true;   // ... and as bytes 1-2 of a start every window may follow it
             for (int b1 = 0; b1 < kCharSet; b1++) t1[t1_index((uint32_t)b0, (uint32_t)b1)] |= kT1P01 | kT1Short;
         }
         for (uint32_t e1 = g.begin(s1); e1 < g.end(s1); e1++) {
@@ -168,12 +224,23 @@ void derive_tables(const Partition &P, uint32_t t2_bytes, uint32_t t3_bytes, uin
             const uint32_t pair = (uint32_t)b0 | ((uint32_t)b1 << 8);
             t1[t1_index((uint32_t)b0, (uint32_t)b1)] |= kT1P01;
             bool shortp = g.is_final(s2);
+            if (shortp)   // a 2-byte pattern (b0, b1): bytes 1-2 of its start are (b1, anything)
+                for (int b2 = 0; b2 < kCharSet; b2++) t1[t1_index((uint32_t)b1, (uint32_t)b2)] |= kT1ShortC;
             for (uint32_t e2 = g.begin(s2); e2 < g.end(s2); e2++) {
                 const int32_t b2 = g.edges[e2].byte, s3 = g.edges[e2].next;
-                if (g.is_final(s3)) shortp = true;
+                if (g.is_final(s3)) {
+                    shortp = true;
+                    t1[t1_index((uint32_t)b1, (uint32_t)b2)] |= kT1ShortC;
+                }
                 t1[t1_index((uint32_t)b1, (uint32_t)b2)] |= kT1P12;
                 for (uint32_t e3 = g.begin(s3); e3 < g.end(s3); e3++) {
                     t1[t1_index((uint32_t)b2, (uint32_t)g.edges[e3].byte)] |= kT1P23;
+                    {   // bytes 3-4 of the paths that go on; a pattern of 4 bytes is settled by its bytes 1-2
+                        const int32_t s4 = g.edges[e3].next;
+                        if (g.is_final(s4)) t1[t1_index((uint32_t)b1, (uint32_t)b2)] |= kT1ShortC;
+                        for (uint32_t e4 = g.begin(s4); e4 < g.end(s4); e4++)
+                            t1[t1_index((uint32_t)g.edges[e3].byte, (uint32_t)g.edges[e4].byte)] |= kT1P34;
+                    }
                     if (too_many) continue;
                     const uint32_t w = pair | ((uint32_t)b2 << 16) | ((uint32_t)g.edges[e3].byte << 24);
                     if (t2_bits) {
@@ -192,7 +259,11 @@ void derive_tables(const Partition &P, uint32_t t2_bytes, uint32_t t3_bytes, uin
         }
     }
     if (too_many) std::fill(t2.begin(), t2.end(), 0xFFFFFFFFu);   // not a tree: T2 filters nothing
+    if (all_shortc)
+        for (auto &b : t1) b |= kT1ShortC;
     out.has_short = any_short ? 1u : 0u;
+    for (uint8_t b : t1)
+        if (b & kT1ShortC) out.has_shortc = 1;
     out.n_prefix4 = (uint32_t)std::min<size_t>(prefix4.size(), 0xFFFFFFFFu);
 
     // ---- Tm / Tm2 / T3: two-point checks (pfac_derive.h).  First with the shared-memory sizes; if the
@@ -200,6 +271,8 @@ void derive_tables(const Partition &P, uint32_t t2_bytes, uint32_t t3_bytes, uin
     // sized for the key counts, to live in global memory (L2-resident).
     uint32_t t3_bits = too_many ? 0 : pow2_bits_for_bytes(t3_bytes);
     std::vector<uint16_t> tm, tm2;
+    std::vector<uint16_t> d1, e1, d2, e2;   // mode 0: perfect-hash tables of the two key levels
+    uint32_t nb1 = 0, ns1 = 0, nb2 = 0, ns2 = 0;
     std::vector<uint32_t> t3;
     uint32_t tm2_bits = 0, tm_bits = kTmSlotBits;
     bool global_mode = false;
@@ -216,6 +289,7 @@ void derive_tables(const Partition &P, uint32_t t2_bytes, uint32_t t3_bytes, uin
         tm.clear();
         tm2.clear();
         tm2_bits = 0;
+        nb1 = ns1 = nb2 = ns2 = 0;
         out.t3_shift = 32u - log2u(t3_bits);
         // shortest distance from every state to a final state (reverse breadth-first search)
         const uint32_t kInf = 0xFFFFFFFFu;
@@ -264,7 +338,13 @@ void derive_tables(const Partition &P, uint32_t t2_bytes, uint32_t t3_bytes, uin
             }
             i = j;
         }
-        bool ok = place_all(k1, tm_bits, tm);
+        bool ok;
+        if (global_mode) {
+            ok = place_all(k1, tm_bits, tm);
+        } else {
+            ph_sizes(k1.size(), nb1, ns1);
+            ok = (nb1 + ns1) * 2u <= kPh1MaxBytes && ph_build(k1, false, nb1, ns1, d1, e1);
+        }
 
         // every string of exactly `len` bytes that continues (state, str); str holds the bytes so far
         uint64_t visited = 0;
@@ -288,6 +368,7 @@ void derive_tables(const Partition &P, uint32_t t2_bytes, uint32_t t3_bytes, uin
             std::string str;
         };
         std::vector<Member> members;
+        std::vector<uint32_t> l1_bits;   // T3 indices of the level-1 windows
         for (size_t i = 0; i < k1.size() && ok; i++) {
             Level level;
             std::string pre(4, '\0');
@@ -297,8 +378,7 @@ void derive_tables(const Partition &P, uint32_t t2_bytes, uint32_t t3_bytes, uin
             for (auto &it : level) {
                 if (dist(it.first) == kInf) continue;   // no pattern below
                 const uint32_t w1 = le32(it.second, k1[i].m - 4u);
-                const uint32_t h = hash_t3(k1[i].key, w1) >> out.t3_shift;
-                t3[h >> 5] |= 1u << (h & 31);
+                l1_bits.push_back(hash_t3(k1[i].key, w1) >> out.t3_shift);
                 members.push_back({hash_key2(k1[i].key, w1), it.first, std::move(it.second)});
             }
         }
@@ -323,8 +403,16 @@ void derive_tables(const Partition &P, uint32_t t2_bytes, uint32_t t3_bytes, uin
                 while ((4ull << (bits + 1)) <= tm2_bytes) bits++;   // 2^bits buckets x 2 slots x 2 bytes <= tm2_bytes
             else
                 while ((size_t)(2u << bits) * 7 / 10 < k2.size()) bits++;
-            if (place_all(k2, bits, tm2)) {
-                tm2_bits = bits;
+            bool placed2;
+            if (global_mode) {
+                placed2 = place_all(k2, bits, tm2);
+            } else {
+                ph_sizes(k2.size(), nb2, ns2);
+                placed2 = (uint64_t)(nb2 + ns2) * 2u <= tm2_bytes && ph_build(k2, true, nb2, ns2, d2, e2);
+                if (!placed2) nb2 = ns2 = 0;
+            }
+            if (placed2) {
+                tm2_bits = global_mode ? bits : 1u;
                 for (size_t i = 0; i < k2.size() && ok; i++)
                     for (size_t j = k2_range[i].first; j < k2_range[i].second; j++) {
                         Level level(1, {members[j].state, members[j].str});
@@ -339,6 +427,10 @@ void derive_tables(const Partition &P, uint32_t t2_bytes, uint32_t t3_bytes, uin
                 tm2.clear();
             }
         }
+        // T3 holds the windows of the last level only when the level before it is verified by a
+        // tagged perfect-hash look-up (mode 0 with level 2); otherwise the level-1 windows as well
+        if (ok && (global_mode || !ns2))
+            for (uint32_t h : l1_bits) t3[h >> 5] |= 1u << (h & 31);
         if (ok) {
             out.has_t3 = 1;
             out.tm_bits = tm_bits;
@@ -372,18 +464,33 @@ void derive_tables(const Partition &P, uint32_t t2_bytes, uint32_t t3_bytes, uin
         off = align128(off + 65536);
         out.off_t2 = off;
         off = align128(off + t2_bits / 8);
-        out.off_tm = off;
-        off = align128(off + tm_bytes);
-        out.off_tm2 = off;
-        off = align128(off + tm2_bytes_used);
+        out.off_tm = out.off_tm2 = off;   // (cuckoo tables exist in global mode only)
+        if (out.has_t3) {
+            out.nb1 = nb1;
+            out.ns1 = ns1;
+            out.nb2 = nb2;
+            out.ns2 = ns2;
+            out.off_d1 = off;
+            off = align128(off + nb1 * 2);
+            out.off_e1 = off;
+            off = align128(off + ns1 * 2);
+            out.off_d2 = off;
+            off = align128(off + nb2 * 2);
+            out.off_e2 = off;
+            off = align128(off + ns2 * 2);
+        }
         out.off_t3 = off;
         off = align128(off + t3_bits / 8);
         out.image.assign(off, 0);
         memcpy(out.image.data() + out.off_t1, t1.data(), 65536);
         if (t2_bits) memcpy(out.image.data() + out.off_t2, t2.data(), t2_bits / 8);
         if (out.has_t3) {
-            memcpy(out.image.data() + out.off_tm, tm.data(), tm_bytes);
-            if (tm2_bits) memcpy(out.image.data() + out.off_tm2, tm2.data(), tm2_bytes_used);
+            memcpy(out.image.data() + out.off_d1, d1.data(), nb1 * 2);
+            memcpy(out.image.data() + out.off_e1, e1.data(), ns1 * 2);
+            if (ns2) {
+                memcpy(out.image.data() + out.off_d2, d2.data(), nb2 * 2);
+                memcpy(out.image.data() + out.off_e2, e2.data(), ns2 * 2);
+            }
             memcpy(out.image.data() + out.off_t3, t3.data(), t3_bits / 8);
         }
     } else {
@@ -408,6 +515,11 @@ void derive_tables(const Partition &P, uint32_t t2_bytes, uint32_t t3_bytes, uin
         for (uint32_t w : t3) out.t3_set += (uint32_t)__builtin_popcount(w);
         for (uint16_t e : tm) out.tm_set += e ? 1u : 0u;
         for (uint16_t e : tm2) out.tm2_set += e ? 1u : 0u;
+        if (!global_mode) {
+            for (uint16_t e : e1) out.tm_set += e ? 1u : 0u;
+            if (ns2)
+                for (uint16_t e : e2) out.tm2_set += e ? 1u : 0u;
+        }
     }
     for (uint8_t b : t1) out.t1_set += b & kT1P01;
     if (t2_bits)
@@ -418,7 +530,7 @@ namespace {
 
 // The detector's stage 1 on the bytes t[0, len) (bytes past len read as 0, like stale shared memory
 // may read as anything): P01 of the first pair, and either the short plane or P12 and P23 further on.
-bool stage1_pass(const Derived &d, const uint8_t *t, size_t len)
+bool stage1_pass(const Derived &d, const uint8_t *t, size_t len, bool odd)
 {
     if (d.mode == 2) {   // global mode: stage 1 is T2 over the 4-byte prefix (no pattern is shorter than 4)
         if (len < 4) return false;
@@ -427,6 +539,16 @@ bool stage1_pass(const Derived &d, const uint8_t *t, size_t len)
     }
     const uint8_t *t1 = d.image.data() + d.off_t1;
     auto at = [&](size_t i) { return i < len ? (uint32_t)t[i] : 0u; };
+    if (d.mode == 0) {
+        // mode 0 probes T1 at even offsets of the (16-byte aligned) input stream only.  A start at an
+        // even offset sees its bytes 0-1 and 2-3, one at an odd offset its bytes 1-2 and 3-4.
+        if (!odd) {
+            const uint32_t v0 = t1[t1_index(at(0), at(1))];
+            return (v0 & kT1P01) && ((v0 & kT1Short) || (t1[t1_index(at(2), at(3))] & kT1P23));
+        }
+        const uint32_t v1 = t1[t1_index(at(1), at(2))];
+        return (v1 & kT1ShortC) || ((v1 & kT1P12) && (t1[t1_index(at(3), at(4))] & kT1P34));
+    }
     const uint32_t v0 = t1[t1_index(at(0), at(1))];
     if (!(v0 & kT1P01)) return false;
     if (v0 & kT1Short) return true;
@@ -436,7 +558,7 @@ bool stage1_pass(const Derived &d, const uint8_t *t, size_t len)
 // The detector's stage 2 on the bytes t[0, len): may a pattern start here?  (stage 1 = T1 passed)
 // `stage` (optional) receives how far the start got: 1 bypass, 2 T2/Tm pass, 3 level-1 window pass,
 // 4 level-2 pass.
-bool stage2_pass(const Derived &d, const uint8_t *t, size_t len, int *stage)
+bool stage2_pass(const Derived &d, const uint8_t *t, size_t len, bool odd, int *stage)
 {
     const uint8_t *img = d.mode == 2 ? d.gimage.data() : d.image.data();   // where T1/Tm/Tm2/T3 live
     const uint8_t *t1 = img + d.off_t1;
@@ -447,6 +569,31 @@ bool stage2_pass(const Derived &d, const uint8_t *t, size_t len, int *stage)
     if (stage) *stage = 1;
     if (len < 4) return true;   // fewer than 4 readable bytes: the emit kernel decides
     const uint32_t w4 = le32(t);
+    if (d.mode == 0) {
+        // short patterns (<= 3 bytes) are not in the prefix tables: their starts go to the emit kernel
+        if (d.has_short) {
+            if (!odd && (t1[t1_index(w4 & 255u, (w4 >> 8) & 255u)] & kT1Short)) return true;
+            if (odd && (t1[t1_index((w4 >> 8) & 255u, (w4 >> 16) & 255u)] & kT1ShortC)) return true;
+        }
+        const uint16_t *D1 = reinterpret_cast<const uint16_t *>(img + d.off_d1), *E1 = reinterpret_cast<const uint16_t *>(img + d.off_e1);
+        const uint32_t m1 = ph_lookup(D1, E1, d.nb1, d.ns1, w4, ph_mix(w4));
+        if (!m1 || m1 > len) return false;
+        if (stage) *stage = 2;
+        const uint32_t w1 = le32(t + m1 - 4);
+        if (!d.ns2) {
+            if (!bit(t3, hash_t3(w4, w1) >> d.t3_shift)) return false;
+            if (stage) *stage = 3;
+            return true;
+        }
+        const uint16_t *D2 = reinterpret_cast<const uint16_t *>(img + d.off_d2), *E2 = reinterpret_cast<const uint16_t *>(img + d.off_e2);
+        const uint32_t key2 = hash_key2(w4, w1);
+        const uint32_t m2 = ph_lookup(D2, E2, d.nb2, d.ns2, key2, key2);
+        if (!m2 || m2 > len) return false;
+        if (stage) *stage = 3;
+        if (!bit(t3, hash_t3(key2 ^ kT3Seed2, le32(t + m2 - 4)) >> d.t3_shift)) return false;
+        if (stage) *stage = 4;
+        return true;
+    }
     if (d.has_short && (t1[t1_index(w4 & 255u, (w4 >> 8) & 255u)] & kT1Short)) return true;
     if (!d.has_t3) {
         if (d.t2_shift < 32 && !(bit(t2, (w4 * kHash4Mul) >> d.t2_shift) && bit(t2, (w4 * kHash4Mul2) >> d.t2_shift))) return false;
@@ -478,10 +625,10 @@ void derive_profile(const Partition &P, const Derived &d, const uint8_t *text, s
     size_t last_slice = (size_t)-1;
     for (size_t i = 0; i < n; i++) {
         out[0]++;
-        if (!stage1_pass(d, text + i, n - i)) continue;
+        if (!stage1_pass(d, text + i, n - i, (i & 1) != 0)) continue;
         out[1]++;   // stage 1 survivors
         int stage = 0;
-        const bool pass = stage2_pass(d, text + i, std::min(n - i, maxlen), &stage);
+        const bool pass = stage2_pass(d, text + i, std::min(n - i, maxlen), (i & 1) != 0, &stage);
         if (stage >= 2) out[2]++;   // T2 / Tm found the prefix
         if (stage >= 3) out[3]++;   // level-1 window passed
         if (stage >= 4) out[4]++;   // level-2 window passed
@@ -546,9 +693,15 @@ int derive_selfcheck(const Partition &P, const Derived &d)
         str.clear();
         for (int32_t x = f; x >= 0; x = par[(size_t)x]) str.push_back(pbyte[(size_t)x]);
         std::reverse(str.begin(), str.end());
-        int stage = 0;
-        if (!stage1_pass(d, str.data(), str.size())) return 8;
-        if (!stage2_pass(d, str.data(), str.size(), &stage)) return 10 + stage;
+        // at either alignment, and whatever follows the pattern in the input
+        for (int odd = 0; odd < 2; odd++)
+            for (uint8_t fill : {(uint8_t)0x00, (uint8_t)0xFF, (uint8_t)0x5A}) {
+                std::vector<uint8_t> padded(str);
+                padded.resize(str.size() + 8, fill);
+                int stage = 0;
+                if (!stage1_pass(d, padded.data(), padded.size(), odd != 0)) return 8;
+                if (!stage2_pass(d, padded.data(), str.size(), odd != 0, &stage)) return 10 + stage;
+            }
     }
     return 0;
 }

@@ -89,7 +89,37 @@ PFAC_HD inline uint32_t rot2(uint32_t c) { return ((c << 2) | (c >> 6)) & 0xFFu;
 PFAC_HD inline uint32_t rot2(uint32_t c) { return c; }
 #endif
 PFAC_HD inline uint32_t t1_index(uint32_t c0, uint32_t c1) { return rot2(c0) | (rot2(c1) << 8); }
-constexpr uint8_t kT1P01 = 1, kT1P12 = 2, kT1P23 = 4, kT1Short = 8;
+constexpr uint8_t kT1P01 = 1, kT1P12 = 2, kT1P23 = 4, kT1Short = 8, kT1P34 = 16, kT1ShortC = 32;
+
+// ---- perfect-hash tables of the mode-0 detector (hash-and-displace, one slot per key).
+// bucket = mulhi(x, nb) with x = a mixed hash of the key, d = D[bucket], slot = mulhi(key * c3 + d *
+// (key * c4 | 1), ns), entry E[slot] = tag << 8 | m with tag = x & 255.  A key of the set finds its
+// own entry; any other word finds m = 0 or, once in 256, some other key's m.
+PFAC_HD inline uint32_t mulhi32(uint32_t a, uint32_t b)
+{
+#if defined(__CUDA_ARCH__)
+    return __umulhi(a, b);
+#else
+    return (uint32_t)(((uint64_t)a * b) >> 32);
+#endif
+}
+PFAC_HD inline uint32_t ph_mix(uint32_t key)
+{
+    uint32_t x = key * 0x9E3779B1u;
+    x ^= x >> 15;
+    return x * 0x85EBCA77u;
+}
+PFAC_HD inline uint32_t ph_slot(uint32_t key, uint32_t d, uint32_t ns)
+{
+    return mulhi32(key * 0xC2B2AE3Du + d * ((key * 0x27D4EB2Fu) | 1u), ns);
+}
+// x = ph_mix(key) for raw keys (level 1: the 4-byte prefix), x = key for keys that are hashes already (level 2)
+PFAC_HD inline uint32_t ph_lookup(const uint16_t *D, const uint16_t *E, uint32_t nb, uint32_t ns, uint32_t key, uint32_t x)
+{
+    const uint32_t d = D[mulhi32(x, nb)];
+    const uint32_t e = E[ph_slot(key, d, ns)];
+    return (e >> 8) == (x & 255u) ? (e & 255u) : 0u;
+}
 
 struct Derived {
     // shared-memory image, copied verbatim by the detector kernel (sections 128-byte aligned)
@@ -97,9 +127,13 @@ struct Derived {
     uint32_t off_t1 = 0, off_t2 = 0, off_tm = 0, off_tm2 = 0, off_t3 = 0;
     uint32_t t2_shift = 32;      // indices = (w * kHash4Mul) >> t2_shift and (w * kHash4Mul2) >> t2_shift   (32: no T2)
     uint32_t has_short = 0;      // patterns of length <= 3 exist (T1's Short plane is not empty)
+    uint32_t has_shortc = 0;     // patterns of length <= 4 exist (T1's ShortC plane is not empty)
     uint32_t has_t3 = 0;         // Tm + T3 present (then no T2)
     uint32_t t3_shift = 32;
-    uint32_t tm_bits = 0, tm2_bits = 0;   // log2 buckets of Tm / Tm2 (0: absent)
+    uint32_t tm_bits = 0, tm2_bits = 0;   // log2 buckets of Tm / Tm2 (0: absent; mode 2 only)
+    // mode 0: perfect-hash tables of the 4-byte prefixes (level 1) and the (prefix, window) groups (level 2)
+    uint32_t off_d1 = 0, off_e1 = 0, nb1 = 0, ns1 = 0;
+    uint32_t off_d2 = 0, off_e2 = 0, nb2 = 0, ns2 = 0;   // ns2 = 0: no level 2
     // mode 0: two-point checks from shared memory; 1: T2 alone; 2: stage 1 = T2 (the whole shared
     // image), Tm/Tm2/T3 sized for the key counts in `gimage` (global memory, L2-resident) -- offsets
     // off_t1/off_tm/off_tm2/off_t3 then refer to gimage, which starts with a copy of T1

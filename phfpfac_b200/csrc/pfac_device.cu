@@ -207,6 +207,14 @@ int launch_scan(pfac_ctx *ctx, Slot &slot, const void *d_in, uint64_t n_starts, 
     p.t3_shift = ctx->dv.t3_shift;
     p.tm_bits = ctx->dv.tm_bits;
     p.tm2_bits = ctx->dv.tm2_bits;
+    p.off_d1 = ctx->dv.off_d1;
+    p.off_e1 = ctx->dv.off_e1;
+    p.nb1 = ctx->dv.nb1;
+    p.ns1 = ctx->dv.ns1;
+    p.off_d2 = ctx->dv.off_d2;
+    p.off_e2 = ctx->dv.off_e2;
+    p.nb2 = ctx->dv.nb2;
+    p.ns2 = ctx->dv.ns2;
     p.gimage = ctx->d_gimage;
     if (ctx->n_stages < (uint32_t)min_stages((int)ctx->dv.mode))
         return set_error(PFAC_ERR_INTERNAL, "input ring of %u stages is too shallow for the slot scheme", ctx->n_stages);
@@ -222,6 +230,7 @@ int launch_scan(pfac_ctx *ctx, Slot &slot, const void *d_in, uint64_t n_starts, 
     p.ctrl = slot.d_ctrl;
     p.debug = ctx->debug;
     const uint32_t grid = (uint32_t)std::min<uint64_t>(p.n_tiles, (uint64_t)ctx->sm_count);
+    p.ticket_batch = std::max<uint32_t>(1u, std::min<uint32_t>((uint32_t)kTicketBatch, p.n_tiles / (4u * grid)));
     cudaEvent_t ev_after = nullptr;
     if (ctx->timing && !ctx->ev.empty()) {
         const size_t slot_i = ctx->ev_next;
@@ -231,7 +240,10 @@ int launch_scan(pfac_ctx *ctx, Slot &slot, const void *d_in, uint64_t n_starts, 
         ev_after = ctx->ev[slot_i + 1];
     }
     if (ctx->dv.mode == 2) pfac_scan_kernel<2><<<grid, kThreads, ctx->smem_bytes, stream>>>(p);
-    else pfac_scan_kernel<0><<<grid, kThreads, ctx->smem_bytes, stream>>>(p);
+    else if (ctx->dv.mode == 1) pfac_scan_kernel<0><<<grid, kThreads, ctx->smem_bytes, stream>>>(p);
+    else if (ctx->dv.has_short) pfac_scan2_kernel<true, true><<<grid, kThreads, ctx->smem_bytes, stream>>>(p);
+    else if (ctx->dv.has_shortc) pfac_scan2_kernel<false, true><<<grid, kThreads, ctx->smem_bytes, stream>>>(p);
+    else pfac_scan2_kernel<false, false><<<grid, kThreads, ctx->smem_bytes, stream>>>(p);
     CU_TRY(cudaGetLastError());
     if (ev_after) CU_TRY(cudaEventRecord(ev_after, stream));
 
@@ -373,8 +385,12 @@ int pfac_ctx_create(int device, const pfac_tables *t, int part, int n_streams, s
         const size_t fit = smem_max > fixed ? (smem_max - fixed) / stride : 0;
         const bool minimal = t2_bytes < 2048 && (ctx->dv.mode == 2 || (t3_bytes < 2048 && tm2_bytes < 2048));
         const size_t need = (size_t)min_stages((int)ctx->dv.mode);   // 2 (shared-memory mode) or 4 (global mode)
-        if (fit >= std::max<size_t>(3, need) || (fit >= need && minimal)) {
+        // mode 0 wants a deep ring (bytes in flight hide the HBM latency): T3 gives way down to 16 KiB
+        const bool deepen = ctx->dv.mode == 0 && fit < 9 && t3_bytes > 16384 && !getenv("PFAC_T3_BYTES");
+        if (!deepen && (fit >= std::max<size_t>(3, need) || (fit >= need && minimal))) {
             ctx->n_stages = (uint32_t)std::min<size_t>(fit, kMaxStages);
+            if (const char *v = getenv("PFAC_RING_STAGES"))   // tests: a ring as shallow as the slot scheme allows
+                ctx->n_stages = (uint32_t)std::max<size_t>(need, std::min<size_t>(ctx->n_stages, (size_t)atoi(v)));
             ctx->smem_bytes = scan_smem_bytes(ctx->image_bytes, ctx->halo, ctx->n_stages, ctx->dv.mode);
             break;
         }
@@ -426,11 +442,16 @@ int pfac_ctx_create(int device, const pfac_tables *t, int part, int n_streams, s
     // the attribute is per function and device, not per context: always allow the device maximum
     CU_TRY(cudaFuncSetAttribute(pfac_scan_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
     CU_TRY(cudaFuncSetAttribute(pfac_scan_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
+    CU_TRY(cudaFuncSetAttribute(pfac_scan2_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
+    CU_TRY(cudaFuncSetAttribute(pfac_scan2_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
+    CU_TRY(cudaFuncSetAttribute(pfac_scan2_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
     int bps = 0;
     if (ctx->dv.mode == 2)
         CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, pfac_scan_kernel<2>, kThreads, ctx->smem_bytes));
-    else
+    else if (ctx->dv.mode == 1)
         CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, pfac_scan_kernel<0>, kThreads, ctx->smem_bytes));
+    else
+        CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, pfac_scan2_kernel<true, true>, kThreads, ctx->smem_bytes));
     if (bps < 1) return set_error(PFAC_ERR_CUDA, "scan kernel does not fit on an SM (smem %zu B)", ctx->smem_bytes);
 
     CU_TRY(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));

@@ -60,7 +60,9 @@ struct ScanParams {
     const uint4 *image;
     uint32_t image_bytes, off_t2, off_tm, off_tm2, off_t3;
     uint32_t t2_shift, has_short, has_t3, t3_shift, tm_bits, tm2_bits;
+    uint32_t off_d1, off_e1, nb1, ns1, off_d2, off_e2, nb2, ns2;   // mode 0: perfect-hash tables (pfac_derive.h)
     const uint8_t *gimage;            // mode 2: T1 | Tm | Tm2 | T3 in global memory (offsets above refer to it)
+    uint32_t ticket_batch;            // tiles a producer claims with one atomic (1 for small inputs: balance first)
     uint32_t n_stages, stage_magic;   // depth of the input ring (as many as shared memory holds); floor(2^32 / n_stages) + 1
     // output
     unsigned int *tile_cnt;           // [n_tiles] 0 from the detector; the emit kernel writes the tile's match count
@@ -92,7 +94,7 @@ constexpr int kConsumerWarps = 31;
 constexpr int kThreads = (kConsumerWarps + 1) * 32;   // + the producer warp
 constexpr int kSlice = 512;           // start positions per stage-1 step of a warp (32 lanes x 16 B)
 #ifndef PFAC_TILE_SLICES
-#define PFAC_TILE_SLICES 32
+#define PFAC_TILE_SLICES 16
 #endif
 constexpr int kSlicesPerTile = PFAC_TILE_SLICES;    // one bit each in tile_mask (<= 32)
 constexpr int kTile = kSlicesPerTile * kSlice;   // 16,384 start positions per tile
@@ -117,12 +119,16 @@ __host__ __device__ constexpr int min_stages(int mode)
     return (kConsumerWarps + kSlicesPerTile / slot_slices(mode) - 1) / (kSlicesPerTile / slot_slices(mode));
 }
 static_assert(kSlicesPerTile % PFAC_SLOT_SLICES == 0 && kSlicesPerTile % PFAC_SLOT_SLICES_GLOBAL == 0, "slots tile the tile");
-constexpr int kMaxStages = 8;
-constexpr int kCtrlBytes = 1024;
+constexpr int kMaxStages = 16;
+constexpr int kCtrlBytes = 1536;          // CtlView below
 constexpr int kMaxParts = 1024;           // tile ranges of the ordering pass (one per finalize CTA)
 constexpr int kCandPerTile = 32;          // candidate starts the detector hands over per tile (more: whole slices)
 constexpr unsigned kCandOverflow = 0xFFFFFFFFu;
 constexpr unsigned kSpinLimit = 1u << 21;
+#ifndef PFAC_TICKET_BATCH
+#define PFAC_TICKET_BATCH 4
+#endif
+constexpr int kTicketBatch = PFAC_TICKET_BATCH;   // tiles a producer claims with one atomic
 
 __host__ __device__ inline uint32_t scan_buf_stride(uint32_t halo) { return (kTile + halo + 32 + 127) & ~127u; }
 __host__ inline size_t scan_smem_bytes(uint32_t image_bytes, uint32_t halo, uint32_t n_stages, int mode)
@@ -208,7 +214,9 @@ __device__ __forceinline__ uint64_t policy_evict_first()
 __device__ __forceinline__ uint32_t rot2x4(uint32_t w)
 {
 #ifndef PFAC_NO_ROT2
-    return ((w << 2) & 0xFCFCFCFCu) | ((w >> 6) & 0x03030303u);
+    uint32_t r;   // one LOP3: bitwise select between the two shifted copies
+    asm("lop3.b32 %0, %1, %2, %3, 0xE4;" : "=r"(r) : "r"(w << 2), "r"(w >> 6), "r"(0xFCFCFCFCu));
+    return r;
 #else
     return w;
 #endif
@@ -314,8 +322,364 @@ __device__ __forceinline__ void add_candidate(uint32_t *n, uint16_t *list, uint3
     if (i < (uint32_t)kCandPerTile) list[i] = (uint16_t)tpos;
 }
 
-// MODE 0: all filter tables in shared memory (stage 1 = T1).  MODE 2: stage 1 = T2 (the whole
-// shared image), Tm / Tm2 / T3 in global memory.
+// The control block of the detector kernels (kCtrlBytes of shared memory after the image).
+struct CtlView {
+    uint64_t *full, *empty;     // [kMaxStages] mbarriers of the input ring
+    uint32_t *tile;             // [kMaxStages] tile id of the stage
+    uint32_t *tflag;            // [kMaxStages] flagged slices of the tile
+    uint32_t *ncand;            // [kMaxStages] candidates (bit 31: a dense slot, hand the slices over whole)
+    uint32_t *grab;             // next (tile, slice) slot of this CTA
+    uint32_t *kend;             // sequence number of the CTA's sentinel tile
+    uint64_t *imgbar;           // mbarrier of the image copy
+    uint16_t *cand;             // [kMaxStages][kCandPerTile]
+};
+__device__ __forceinline__ CtlView ctl_view(uint8_t *ctl)
+{
+    CtlView c;
+    c.full = reinterpret_cast<uint64_t *>(ctl);
+    c.empty = reinterpret_cast<uint64_t *>(ctl + 128);
+    c.tile = reinterpret_cast<uint32_t *>(ctl + 256);
+    c.tflag = reinterpret_cast<uint32_t *>(ctl + 320);
+    c.ncand = reinterpret_cast<uint32_t *>(ctl + 384);
+    c.grab = reinterpret_cast<uint32_t *>(ctl + 448);
+    c.kend = reinterpret_cast<uint32_t *>(ctl + 452);
+    c.imgbar = reinterpret_cast<uint64_t *>(ctl + 456);
+    c.cand = reinterpret_cast<uint16_t *>(ctl + 512);
+    return c;
+}
+static_assert(512 + kMaxStages * kCandPerTile * 2 <= kCtrlBytes, "control block");
+
+__device__ __forceinline__ void bulk_g2s_plain(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+        ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+// Prologue shared by the detector kernels: barriers, control words, and the filter image, which one
+// thread brings in with TMA bulk copies (the other warps meanwhile start on their roles; consumers wait
+// for the image in image_wait()).
+__device__ __forceinline__ void detector_init(const ScanParams &p, const CtlView &c, int slots_per_tile)
+{
+    const int tid = threadIdx.x;
+    if (blockIdx.x == 0)
+        for (int i = tid; i < kMaxParts; i += kThreads) p.partial[i] = 0ull;
+    if (tid == 0) {
+        for (uint32_t s = 0; s < p.n_stages; s++) {
+            mbar_init(&c.full[s], 1);
+            mbar_init(&c.empty[s], (uint32_t)slots_per_tile);   // one arrival per slot
+            c.tflag[s] = 0;
+            c.ncand[s] = 0;
+        }
+        mbar_init(c.imgbar, 1);
+        *c.grab = 0;
+        *c.kend = 0xFFFFFFFFu;
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        mbar_expect_tx(c.imgbar, p.image_bytes);
+        const uint8_t *src = reinterpret_cast<const uint8_t *>(p.image);
+        for (uint32_t o = 0; o < p.image_bytes; o += 32768u)
+            bulk_g2s_plain(smem + o, src + o, min(32768u, p.image_bytes - o), c.imgbar);
+    }
+    __syncthreads();
+}
+__device__ __forceinline__ void image_wait(const ScanParams &p, const CtlView &c)
+{
+    mbar_wait<32>(c.imgbar, 0u, &p.ctrl->error_flag, 5u);
+}
+
+// The producer role (one lane): streams tiles into the ring and, once every consumer warp has
+// released a stage, publishes that tile's result (flag mask, candidate list) before the stage is
+// refilled.
+__device__ __forceinline__ void producer_role(const ScanParams &p, const CtlView &c, uint8_t *s_in, uint32_t stride)
+{
+    const uint32_t n_stages = p.n_stages;
+    const uint64_t policy = policy_evict_first();
+    uint32_t held[kMaxStages];   // tile held by each stage (0xFFFFFFFF: none)
+    for (int i = 0; i < kMaxStages; i++) held[i] = 0xFFFFFFFFu;
+    auto publish = [&](uint32_t st, uint32_t tile) {
+        const uint32_t flags = c.tflag[st];
+        uint32_t nc = c.ncand[st];
+        if (nc > (uint32_t)kCandPerTile) nc = kCandOverflow;   // too many (or the overflow bit is set)
+        p.tile_cnt[tile] = 0u;
+        p.tile_nc[tile] = flags ? nc : 0u;
+        p.tile_mask[tile] = flags;
+        if (flags) {
+            if (nc != kCandOverflow)
+                for (uint32_t i = 0; i < nc; i++) p.cand[(size_t)tile * kCandPerTile + i] = c.cand[st * kCandPerTile + i];
+            c.tflag[st] = 0;
+            c.ncand[st] = 0;
+        }
+    };
+    uint32_t s = 0, round = 0;
+    // Tiles are claimed p.ticket_batch at a time and one batch ahead: the claim is one global atomic
+    // whose round trip (about a microsecond when every SM asks) then hides behind a whole batch of
+    // tiles instead of stalling every tile.
+    const uint32_t batch = p.ticket_batch;
+    uint32_t t = atomicAdd(&p.ctrl->ticket, batch), t_left = batch;
+    uint32_t b_next = t < p.n_tiles ? atomicAdd(&p.ctrl->ticket, batch) : t;
+    bool ok = true;
+    while (true) {
+        if (t_left == 0) {   // on to the batch claimed while the last one was streamed; claim the one after it
+            t = b_next;
+            t_left = batch;
+            b_next = t < p.n_tiles ? atomicAdd(&p.ctrl->ticket, batch) : t;
+        }
+        if (held[s] != 0xFFFFFFFFu) {
+            if (!mbar_wait<PFAC_PROD_SLEEP_NS>(&c.empty[s], (round - 1) & 1u, &p.ctrl->error_flag, 3u)) { ok = false; break; }
+            publish(s, held[s]);
+            held[s] = 0xFFFFFFFFu;
+        }
+        c.tile[s] = t;
+        if (t >= p.n_tiles) {
+            // sentinel: consumers leave when they see it; kend releases the warps whose slot
+            // lies past the sentinel tile (its stage is never filled)
+            *reinterpret_cast<volatile uint32_t *>(c.kend) = round * n_stages + s;
+            mbar_arrive(&c.full[s]);   // release: orders the store above
+            break;
+        }
+        uint8_t *buf = s_in + s * stride;
+        const uint32_t a0 = t * (uint32_t)kTile;
+        uint32_t nbytes = p.a_valid_end - a0;
+        const uint32_t want = (uint32_t)kTile + p.halo;
+        if (nbytes > want) nbytes = want;
+        const uint32_t nb16 = nbytes & ~15u;
+        // last bytes of the input: not a whole 16-byte block, copied by hand
+        for (uint32_t i = nb16; i < nbytes; i++) buf[i] = p.in_al[(size_t)a0 + i];
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_expect_tx(&c.full[s], nb16);
+        if (nb16) bulk_g2s(buf, p.in_al + a0, nb16, &c.full[s], policy);
+        held[s] = t;
+        t++;
+        t_left--;
+        if (++s == n_stages) { s = 0; round++; }
+    }
+    if (!ok) *reinterpret_cast<volatile uint32_t *>(c.kend) = 0u;   // watchdog tripped: let the consumers go
+    // drain: the tiles still in the ring were filled in this round (stages < s) or the previous one
+    for (uint32_t k = 1; ok && k < n_stages; k++) {
+        const uint32_t st = (s + n_stages - k) % n_stages;
+        if (held[st] == 0xFFFFFFFFu) continue;
+        const uint32_t fill_round = st < s ? round : round - 1;
+        if (!mbar_wait<PFAC_PROD_SLEEP_NS>(&c.empty[st], fill_round & 1u, &p.ctrl->error_flag, 4u)) break;
+        publish(st, held[st]);
+    }
+}
+
+// A consumer warp takes the next slot of the CTA's tile sequence and waits for its tile.  Returns
+// false when the work has ended.  Slot g belongs to the CTA's k-th tile, k = g / slots per tile:
+// stage k % n_stages, phase k / n_stages; a warp leaves on a slot of the sentinel tile or, told by
+// kend, on one past it.
+template <int SLOTS_PER_TILE>
+__device__ __forceinline__ bool take_slot(const ScanParams &p, const CtlView &c, int lane, uint32_t &s, uint32_t &slot_in_tile,
+                                          uint32_t &tile)
+{
+    uint32_t g = 0;
+    if (lane == 0) g = atomicAdd(c.grab, 1u);
+    g = __shfl_sync(0xffffffffu, g, 0);
+    const uint32_t k = g / (uint32_t)SLOTS_PER_TILE;
+    slot_in_tile = g - k * (uint32_t)SLOTS_PER_TILE;
+    const uint32_t round = __umulhi(k, p.stage_magic);   // k / n_stages, exact for k < 2^32 / n_stages
+    s = k - round * p.n_stages;
+    for (unsigned spins = 0; !mbar_try_wait(&c.full[s], round & 1u);) {
+        if (*reinterpret_cast<volatile uint32_t *>(c.kend) < k) return false;   // a slot past the end of the work
+        if (++spins > kSpinLimit) {
+            atomicExch(&p.ctrl->error_flag, 2u);
+            return false;
+        }
+        if (PFAC_CONS_SLEEP_NS) __nanosleep(PFAC_CONS_SLEEP_NS);
+    }
+    tile = c.tile[s];
+    return tile < p.n_tiles;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Mode 0 detector: all filter tables in shared memory.
+//
+// Stage 1 probes T1 at EVEN offsets of the input stream only -- 8 LDS.U8 per lane and 16 start
+// positions instead of 16.  An even start 2k is judged by the windows at 2k (its bytes 0-1: plane P01)
+// and 2k+2 (bytes 2-3: P23); an odd start 2k+1 by the windows at 2k+2 (its bytes 1-2: P12) and 2k+4
+// (bytes 3-4: P34).  Patterns too short for the second window pass on the planes Short (<= 3 bytes,
+// even starts) and ShortC (<= 4 bytes, odd starts).  The eight T1 bytes of a lane are packed four to
+// a register and the two rules evaluated for all of them with funnel shifts.
+//
+// Stage 2 (per slot, lane-parallel over the compacted survivors): the 4-byte prefix in the
+// perfect-hash table of level 1 -> m1; the window that ends the shortest pattern below it keys level 2
+// -> m2; the window that ends the shortest pattern of that group in T3.
+template <bool HAS_SHORT, bool HAS_SC>
+__device__ __forceinline__ uint32_t s1_combine(uint32_t X, uint32_t Xn)
+{
+    // X = T1 bytes of windows k..k+3, Xn = of the four after them.  Result: bit 0 of byte k = even
+    // start 2k passes, bit 1 = odd start 2k+1 passes.
+    uint32_t b = __funnelshift_r(X, Xn, 10);                       // P23 of window k+1 -> bit 0
+    if (HAS_SHORT) b |= X >> 3;                                    // Short of window k -> bit 0
+    uint32_t o = __funnelshift_r(X, Xn, 8) & __funnelshift_r(X, Xn, 19);   // P12 of k+1, P34 of k+2 -> bit 1
+    if (HAS_SC) o |= __funnelshift_r(X, Xn, 12);                   // ShortC of window k+1 -> bit 1
+    return (X & b & 0x01010101u) | (o & 0x02020202u);
+}
+// the T1 bytes of the 8 even windows of a lane's 16 bytes, four to a register
+__device__ __forceinline__ void s1_probe(const uint4 v, uint32_t &X0, uint32_t &X1)
+{
+    const uint8_t *t1 = smem;
+    const uint32_t r0 = rot2x4(v.x), r1 = rot2x4(v.y), r2 = rot2x4(v.z), r3 = rot2x4(v.w);
+    const uint32_t e0 = t1[r0 & 0xffffu], e1 = t1[r0 >> 16], e2 = t1[r1 & 0xffffu], e3 = t1[r1 >> 16];
+    const uint32_t e4 = t1[r2 & 0xffffu], e5 = t1[r2 >> 16], e6 = t1[r3 & 0xffffu], e7 = t1[r3 >> 16];
+    X0 = e0 + (e1 << 8) + (e2 << 16) + (e3 << 24);
+    X1 = e4 + (e5 << 8) + (e6 << 16) + (e7 << 24);
+}
+// unaligned 32-bit read of the staged tile
+__device__ __forceinline__ uint32_t load_w4(const uint8_t *buf, uint32_t pos)
+{
+    const uint32_t *wp = reinterpret_cast<const uint32_t *>(buf + (pos & ~3u));
+    return __funnelshift_r(wp[0], wp[1], (pos & 3u) * 8u);
+}
+
+template <bool HAS_SHORT, bool HAS_SC>
+__global__ void __launch_bounds__(kThreads, 1) pfac_scan2_kernel(const ScanParams p)
+{
+    constexpr int kSlotSlices = slot_slices(0), kSlotsPerTile = kSlicesPerTile / kSlotSlices;
+    constexpr int kQ1Cap = q1_cap(0), kQueueBytes = queue_bytes(0);
+    static_assert(kSlotSlices == 2, "the survivor masks of a slot share one 32-bit word");
+    uint8_t *ctl = smem + p.image_bytes;
+    const CtlView c = ctl_view(ctl);
+    uint8_t *qbase = ctl + kCtrlBytes;
+    uint8_t *s_in = qbase + kConsumerWarps * kQueueBytes;
+    const uint32_t stride = scan_buf_stride(p.halo);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    detector_init(p, c, kSlotsPerTile);
+    if (warp == kConsumerWarps) {
+        if (lane == 0) producer_role(p, c, s_in, stride);
+        return;
+    }
+    image_wait(p, c);
+
+    const uint16_t *s_d1 = reinterpret_cast<const uint16_t *>(smem + p.off_d1);
+    const uint16_t *s_e1 = reinterpret_cast<const uint16_t *>(smem + p.off_e1);
+    const uint16_t *s_d2 = reinterpret_cast<const uint16_t *>(smem + p.off_d2);
+    const uint16_t *s_e2 = reinterpret_cast<const uint16_t *>(smem + p.off_e2);
+    const uint32_t *s_t3 = reinterpret_cast<const uint32_t *>(smem + p.off_t3);
+    uint16_t *wq = reinterpret_cast<uint16_t *>(qbase + warp * kQueueBytes);   // stage-1 survivors of the slot
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    const uint32_t next_lane = (lane + 1) & 31;
+
+    for (;;) {
+        uint32_t s, slot_in_tile, tile;
+        if (!take_slot<kSlotsPerTile>(p, c, lane, s, slot_in_tile, tile)) break;
+        const uint32_t slice0 = slot_in_tile * (uint32_t)kSlotSlices;
+        const uint8_t *buf = s_in + s * stride;
+        const uint32_t a0 = tile * (uint32_t)kTile;
+        const uint32_t valid_t = p.a_valid_end - a0;   // tile-relative end of readable input (may exceed the buffer)
+        // an interior tile: every start of it is a start position and none can reach the end of the
+        // input or a reference walk bound
+        const bool interior = !p.use_ref_bound && a0 >= p.mis && valid_t >= (uint32_t)kTile + p.max_pat_len &&
+                              a0 + (uint32_t)kTile <= p.a_start_end;
+        const uint32_t base = slice0 * kSlice + lane * 16;   // tile-relative position of the lane's first start
+        // ---- stage 1, the slot's two slices from the upper one down: the T1 bytes of the two windows
+        // after a lane's 16 bytes are the next lane's first two -- for lane 31 those of lane 0 in the
+        // slice above, which is why that one goes first (its lane 31 looks them up itself)
+        uint32_t m;   // bit 16 h + j: start j of this lane in slice slice0 + h passed stage 1
+        {
+            const uint4 v1 = *reinterpret_cast<const uint4 *>(buf + base + kSlice);
+            const uint4 v0 = *reinterpret_cast<const uint4 *>(buf + base);
+            uint32_t X0, X1, Y0, Y1;
+            s1_probe(v1, Y0, Y1);
+            s1_probe(v0, X0, X1);
+            uint32_t ey = __shfl_sync(0xffffffffu, Y0, next_lane);
+            if (lane == 31) {
+                const uint32_t r = rot2x4(*reinterpret_cast<const uint32_t *>(buf + base + kSlice + 16));
+                ey = (uint32_t)smem[r & 0xffffu] | ((uint32_t)smem[r >> 16] << 8);
+            }
+            const uint32_t ex = __shfl_sync(0xffffffffu, lane == 0 ? Y0 : X0, next_lane);
+            const uint32_t q0 = s1_combine<HAS_SHORT, HAS_SC>(X0, X1) * 0x01041040u;
+            const uint32_t q1 = s1_combine<HAS_SHORT, HAS_SC>(X1, ex) * 0x01041040u;
+            const uint32_t q2 = s1_combine<HAS_SHORT, HAS_SC>(Y0, Y1) * 0x01041040u;
+            const uint32_t q3 = s1_combine<HAS_SHORT, HAS_SC>(Y1, ey) * 0x01041040u;
+            // byte 3 of each product = the 8 results in start order
+            m = __byte_perm(__byte_perm(q0, q1, 0x0073), __byte_perm(q2, q3, 0x0073), 0x5410);
+        }
+        if (!interior) {   // start positions are [mis, a_start_end) in aligned coordinates
+#pragma unroll
+            for (int h = 0; h < kSlotSlices; h++) {
+                const uint32_t a = a0 + base + h * kSlice;
+                const uint32_t first = p.mis > a ? p.mis - a : 0u;
+                const uint32_t last = p.a_start_end > a ? p.a_start_end - a : 0u;
+                uint32_t keep = last >= 16u ? 0xffffu : ((1u << last) - 1u);
+                keep &= first >= 16u ? 0u : (0xffffu << first);
+                m &= ~(0xffffu << (16 * h)) | ((keep & 0xffffu) << (16 * h));
+            }
+        }
+        // ---- compaction into the warp queue: every round, each lane that still has survivors hands
+        // over its lowest one (rank by ballot); the order of the queue does not matter
+        uint32_t nq = 0, anym = 0;
+        while (true) {
+            const uint32_t bal = __ballot_sync(0xffffffffu, m != 0u);
+            if (!bal) break;
+            if (m) {
+                const uint32_t b = __ffs(m) - 1;
+                m &= m - 1;
+                const uint32_t idx = nq + __popc(bal & lt_mask);
+                if (idx < (uint32_t)kQ1Cap) wq[idx] = (uint16_t)(base + (b & 15u) + (b >> 4) * kSlice);
+            }
+            nq += __popc(bal);
+        }
+        if (nq > (uint32_t)kQ1Cap) {   // dense slot: the emit kernel looks at all of it
+            anym = (1u << kSlotSlices) - 1u;
+            if (lane == 0) atomicOr(c.ncand + s, 0x80000000u);
+            nq = 0;
+        }
+        __syncwarp();
+        // ---- stage 2
+        for (uint32_t e0 = 0; e0 < nq; e0 += 32) {
+            const uint32_t e = e0 + lane;
+            if (e >= nq) continue;
+            const uint32_t tpos = wq[e];
+            bool keep = true;
+            if (tpos + 4u <= valid_t) {   // else: the emit kernel decides
+                const uint32_t w4 = load_w4(buf, tpos);
+                bool shortp = false;
+                if (HAS_SHORT) {   // starts of patterns that are not in the prefix tables
+                    const uint32_t r = rot2x4(w4);
+                    shortp = (tpos & 1u) ? (smem[(r >> 8) & 0xffffu] & kT1ShortC) != 0 : (smem[r & 0xffffu] & kT1Short) != 0;
+                }
+                if (!shortp) {
+                    const uint32_t m1 = ph_lookup(s_d1, s_e1, p.nb1, p.ns1, w4, ph_mix(w4));   // 0 = no pattern has this prefix
+                    const uint32_t lim = interior ? tpos + p.max_pat_len : walk_limit(p, a0, tpos);   // never past the staged halo
+                    keep = m1 != 0 && tpos + m1 <= lim;
+                    if (keep) {
+                        const uint32_t w1 = load_w4(buf, tpos + m1 - 4u);
+                        if (!p.ns2) {
+                            const uint32_t h3 = hash_t3(w4, w1) >> p.t3_shift;
+                            keep = (s_t3[h3 >> 5] >> (h3 & 31u)) & 1u;
+                        } else {
+                            const uint32_t key2 = hash_key2(w4, w1);
+                            const uint32_t m2 = ph_lookup(s_d2, s_e2, p.nb2, p.ns2, key2, key2);   // 0 = no such group
+                            keep = m2 != 0 && tpos + m2 <= lim;
+                            if (keep) {
+                                const uint32_t w2 = load_w4(buf, tpos + m2 - 4u);
+                                const uint32_t h4 = hash_t3(key2 ^ kT3Seed2, w2) >> p.t3_shift;
+                                keep = (s_t3[h4 >> 5] >> (h4 & 31u)) & 1u;
+                            }
+                        }
+                    }
+                }
+            }
+            if (keep) {
+                anym |= 1u << (tpos / (uint32_t)kSlice - slice0);
+                add_candidate(c.ncand + s, c.cand + s * kCandPerTile, tpos);
+            }
+        }
+        // ---- done with the slot: flag the slices in which a start survived, release the stage
+        anym = __reduce_or_sync(0xffffffffu, anym);
+        if (lane == 0) {
+            if (anym) atomicOr(&c.tflag[s], anym << slice0);
+            mbar_arrive(&c.empty[s]);   // release: orders the shared-memory updates above before the producer's reads
+        }
+    }
+}
+
+// The detector of the modes without shared-memory two-point tables.  MODE 0 here: stage 1 = T1 (one
+// probe per start), stage 2 = T2 (mode 1 of pfac_derive.h: sets whose automaton is not a tree, or
+// with short patterns and too many prefixes).  MODE 2: stage 1 = T2 (the whole shared image),
+// Tm / Tm2 / T3 in global memory.
 template <int MODE>
 __global__ void __launch_bounds__(kThreads, 1) pfac_scan_kernel(const ScanParams p)
 {
@@ -325,16 +689,10 @@ __global__ void __launch_bounds__(kThreads, 1) pfac_scan_kernel(const ScanParams
     const uint16_t *s_tm2 = reinterpret_cast<const uint16_t *>(tab + p.off_tm2);
     const uint32_t *s_t3 = reinterpret_cast<const uint32_t *>(tab + p.off_t3);
     uint8_t *ctl = smem + p.image_bytes;
-    uint64_t *s_full = reinterpret_cast<uint64_t *>(ctl);               // [kMaxStages]
-    uint64_t *s_empty = reinterpret_cast<uint64_t *>(ctl + 64);         // [kMaxStages]
-    uint32_t *s_tile = reinterpret_cast<uint32_t *>(ctl + 128);         // [kMaxStages] tile id of the stage
-    uint32_t *s_grab = reinterpret_cast<uint32_t *>(ctl + 192);         // next (tile, slice) slot of this CTA
-    uint32_t *s_kend = reinterpret_cast<uint32_t *>(ctl + 196);         // sequence number of the CTA's sentinel tile
-    uint32_t *s_tflag = reinterpret_cast<uint32_t *>(ctl + 224);        // [kMaxStages] flagged slices of the tile
-    uint32_t *s_ncand = reinterpret_cast<uint32_t *>(ctl + 256);        // [kMaxStages] candidates (or kCandOverflow)
-    uint16_t *s_cand = reinterpret_cast<uint16_t *>(ctl + 512);         // [kMaxStages][kCandPerTile]
+    const CtlView c = ctl_view(ctl);
+    uint32_t *s_tflag = c.tflag, *s_ncand = c.ncand;
+    uint16_t *s_cand = c.cand;
     uint8_t *qbase = ctl + kCtrlBytes;
-    const uint32_t n_stages = p.n_stages;
     constexpr int kSlotSlices = slot_slices(MODE), kSlotsPerTile = kSlicesPerTile / kSlotSlices;
     constexpr int kQ1Cap = q1_cap(MODE), kQueueBytes = queue_bytes(MODE);
     uint8_t *s_in = qbase + kConsumerWarps * kQueueBytes;
@@ -342,96 +700,12 @@ __global__ void __launch_bounds__(kThreads, 1) pfac_scan_kernel(const ScanParams
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
-    if (blockIdx.x == 0)
-        for (int i = tid; i < kMaxParts; i += kThreads) p.partial[i] = 0ull;
-    {   // shared-memory image: T1, T2 or Tm/Tm2/T3
-        uint4 *dst = reinterpret_cast<uint4 *>(smem);
-        const uint32_t n16 = p.image_bytes >> 4;
-        for (uint32_t i = tid; i < n16; i += kThreads) dst[i] = __ldg(&p.image[i]);
-    }
-    if (tid == 0) {
-        for (uint32_t s = 0; s < n_stages; s++) {
-            mbar_init(&s_full[s], 1);
-            mbar_init(&s_empty[s], kSlotsPerTile);   // one arrival per slot
-            s_tflag[s] = 0;
-            s_ncand[s] = 0;
-        }
-        *s_grab = 0;
-        *s_kend = 0xFFFFFFFFu;
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-
+    detector_init(p, c, kSlotsPerTile);
     if (warp == kConsumerWarps) {
-        // ------------------------------------------------------------------ producer
-        // Streams tiles into the ring and, once every consumer warp has released a stage, publishes
-        // that tile's result (flag mask, candidate list) before the stage is refilled.
-        if (lane == 0) {
-            const uint64_t policy = policy_evict_first();
-            uint32_t held[kMaxStages];   // tile held by each stage (0xFFFFFFFF: none)
-            for (int i = 0; i < kMaxStages; i++) held[i] = 0xFFFFFFFFu;
-            auto publish = [&](uint32_t st, uint32_t tile) {
-                const uint32_t flags = s_tflag[st];
-                uint32_t nc = s_ncand[st];
-                if (nc > (uint32_t)kCandPerTile) nc = kCandOverflow;   // too many (or the overflow bit is set)
-                p.tile_cnt[tile] = 0u;
-                p.tile_nc[tile] = flags ? nc : 0u;
-                p.tile_mask[tile] = flags;
-                if (flags) {
-                    if (nc != kCandOverflow)
-                        for (uint32_t i = 0; i < nc; i++) p.cand[(size_t)tile * kCandPerTile + i] = s_cand[st * kCandPerTile + i];
-                    s_tflag[st] = 0;
-                    s_ncand[st] = 0;
-                }
-            };
-            uint32_t s = 0, round = 0;
-            uint32_t t = atomicAdd(&p.ctrl->ticket, 1u);
-            uint32_t t_next = t < p.n_tiles ? atomicAdd(&p.ctrl->ticket, 1u) : t;
-            bool ok = true;
-            while (true) {
-                // tickets are claimed two tiles ahead: the atomic's latency hides behind a whole tile
-                const uint32_t t_next2 = t_next < p.n_tiles ? atomicAdd(&p.ctrl->ticket, 1u) : t_next;
-                if (held[s] != 0xFFFFFFFFu) {
-                    if (!mbar_wait<PFAC_PROD_SLEEP_NS>(&s_empty[s], (round - 1) & 1u, &p.ctrl->error_flag, 3u)) { ok = false; break; }
-                    publish(s, held[s]);
-                    held[s] = 0xFFFFFFFFu;
-                }
-                s_tile[s] = t;
-                if (t >= p.n_tiles) {
-                    // sentinel: consumers leave when they see it; s_kend releases the warps whose slot
-                    // lies past the sentinel tile (its stage is never filled)
-                    *reinterpret_cast<volatile uint32_t *>(s_kend) = round * n_stages + s;
-                    mbar_arrive(&s_full[s]);   // release: orders the store above
-                    break;
-                }
-                uint8_t *buf = s_in + s * stride;
-                const uint32_t a0 = t * (uint32_t)kTile;
-                uint32_t nbytes = p.a_valid_end - a0;
-                const uint32_t want = (uint32_t)kTile + p.halo;
-                if (nbytes > want) nbytes = want;
-                const uint32_t nb16 = nbytes & ~15u;
-                // last bytes of the input: not a whole 16-byte block, copied by hand
-                for (uint32_t i = nb16; i < nbytes; i++) buf[i] = p.in_al[(size_t)a0 + i];
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                mbar_expect_tx(&s_full[s], nb16);
-                if (nb16) bulk_g2s(buf, p.in_al + a0, nb16, &s_full[s], policy);
-                held[s] = t;
-                t = t_next;
-                t_next = t_next2;
-                if (++s == n_stages) { s = 0; round++; }
-            }
-            if (!ok) *reinterpret_cast<volatile uint32_t *>(s_kend) = 0u;   // watchdog tripped: let the consumers go
-            // drain: the tiles still in the ring were filled in this round (stages < s) or the previous one
-            for (uint32_t k = 1; ok && k < n_stages; k++) {
-                const uint32_t st = (s + n_stages - k) % n_stages;
-                if (held[st] == 0xFFFFFFFFu) continue;
-                const uint32_t fill_round = st < s ? round : round - 1;
-                if (!mbar_wait<PFAC_PROD_SLEEP_NS>(&s_empty[st], fill_round & 1u, &p.ctrl->error_flag, 4u)) break;
-                publish(st, held[st]);
-            }
-        }
+        if (lane == 0) producer_role(p, c, s_in, stride);
         return;
     }
+    image_wait(p, c);
 
     // ---------------------------------------------------------------------- consumers
     // Slots (kSlotSlices consecutive slices) are not bound to warps: the CTA's tiles form one sequence
@@ -444,26 +718,9 @@ __global__ void __launch_bounds__(kThreads, 1) pfac_scan_kernel(const ScanParams
     const uint32_t lt_mask = (1u << lane) - 1u;
 
     for (;;) {
-        uint32_t g = 0;
-        if (lane == 0) g = atomicAdd(s_grab, 1u);
-        g = __shfl_sync(0xffffffffu, g, 0);
-        const uint32_t k = g / (uint32_t)kSlotsPerTile;
-        const uint32_t slice0 = (g - k * (uint32_t)kSlotsPerTile) * (uint32_t)kSlotSlices;   // first slice of the slot
-        const uint32_t round = __umulhi(k, p.stage_magic);   // k / n_stages, exact for k < 2^32 / n_stages
-        const uint32_t s = k - round * n_stages;
-        bool leave = false;
-        for (unsigned spins = 0; !mbar_try_wait(&s_full[s], round & 1u);) {
-            if (*reinterpret_cast<volatile uint32_t *>(s_kend) < k) { leave = true; break; }   // a slot past the end of the work
-            if (++spins > kSpinLimit) {
-                atomicExch(&p.ctrl->error_flag, 2u);
-                leave = true;
-                break;
-            }
-            if (PFAC_CONS_SLEEP_NS) __nanosleep(PFAC_CONS_SLEEP_NS);
-        }
-        if (leave) break;
-        const uint32_t tile = s_tile[s];
-        if (tile >= p.n_tiles) break;
+        uint32_t s, slot_in_tile, tile;
+        if (!take_slot<kSlotsPerTile>(p, c, lane, s, slot_in_tile, tile)) break;
+        const uint32_t slice0 = slot_in_tile * (uint32_t)kSlotSlices;   // first slice of the slot
         const uint8_t *buf = s_in + s * stride;
         const uint32_t a0 = tile * (uint32_t)kTile;
         const uint32_t valid_t = p.a_valid_end - a0;   // tile-relative end of readable input (may exceed the buffer)
@@ -586,7 +843,7 @@ __global__ void __launch_bounds__(kThreads, 1) pfac_scan_kernel(const ScanParams
         anym = __reduce_or_sync(0xffffffffu, anym);
         if (lane == 0) {
             if (anym) atomicOr(&s_tflag[s], anym << slice0);
-            mbar_arrive(&s_empty[s]);   // release: orders the shared-memory updates above before the producer's reads
+            mbar_arrive(&c.empty[s]);   // release: orders the shared-memory updates above before the producer's reads
         }
     }
 }

@@ -393,20 +393,21 @@ def test_job_multi_segment_64bit_positions():
 
 
 def test_shallow_ring(monkeypatch):
-    """A larger level-2 table leaves the input ring 3 stages instead of 4: the slot scheme (warps
-    taking slots from a counter, sentinel + s_kend at the end) must not depend on the depth."""
+    """The shallowest input ring the slot scheme allows (4 stages of 8 KiB for 31 consumer warps) instead
+    of all that fits: the scheme (warps taking slots from a counter, sentinel + kend at the end) must
+    not depend on the depth."""
     torch = torch_cuda()
-    monkeypatch.setenv("PFAC_TM2_BYTES", "65536")
+    monkeypatch.setenv("PFAC_RING_STAGES", "1")
     pats = pf.synth_patterns(1, 3000, 3, 4, 64)
     t = pf.Tables.from_bytes(pats, 1, 256)
     m = pf.Matcher(t)
-    assert m.derived_info()["ring_stages"] == 3
+    assert m.derived_info()["ring_stages"] == 4
     text = pf.synth_text(1, 9, 3 << 20, patterns=pats)
     got = m.scan_host(text)
     m.close()
-    monkeypatch.delenv("PFAC_TM2_BYTES")
+    monkeypatch.delenv("PFAC_RING_STAGES")
     m2 = pf.Matcher(t)
-    assert m2.derived_info()["ring_stages"] >= 4
+    assert m2.derived_info()["ring_stages"] > 4
     want = m2.scan_host(text)
     m2.close()
     assert len(want) > 0 and np.array_equal(got, want)
