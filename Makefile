@@ -29,6 +29,12 @@ $(B)/gphf: $(SRC)/gphf_main.cc $(B)/libpfac_b200.so
 oracle:
 	$(MAKE) -C oracle all
 
+# development: a variant of the library under another name, e.g.
+#   make variant NAME=w23 EXTRA=-DPFAC_CONSUMER_WARPS=23   ->  $(B)/libpfac_b200_w23.so  (PFAC_B200_LIB=... selects it)
+variant:
+	@mkdir -p $(B)
+	$(NVCC) $(NVFLAGS) -shared -cudart static -o $(B)/libpfac_b200_$(NAME).so $(CUDA_SRCS) $(HOST_SRCS) 2> $(B)/ptxas_$(NAME).log || (cat $(B)/ptxas_$(NAME).log; false)
+
 clean:
 	rm -rf $(B)
 	$(MAKE) -C oracle clean

@@ -8,7 +8,8 @@ import os
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG_DIR)
-LIB_PATH = os.path.join(PKG_DIR, "_build", "libpfac_b200.so")
+# PFAC_B200_LIB: another build of the same library (development: kernel variants side by side)
+LIB_PATH = os.environ.get("PFAC_B200_LIB") or os.path.join(PKG_DIR, "_build", "libpfac_b200.so")
 
 # every symbol include/pfac_b200.h and include/pfac_synth.h declare
 ABI_SYMBOLS = [

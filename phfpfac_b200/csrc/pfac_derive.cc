@@ -169,7 +169,7 @@ bool ph_build(const std::vector<Key> &keys, bool premixed, uint32_t nb, uint32_t
             for (size_t j = 0; j < ks.size(); j++) {
                 const uint32_t x = premixed ? keys[ks[j]].key : ph_mix(keys[ks[j]].key);
                 used[slots[j]] = 1;
-                E[slots[j]] = (uint16_t)(((x & 255u) << 8) | keys[ks[j]].m);
+                E[slots[j]] = (uint16_t)((keys[ks[j]].m << 8) | (x & 255u));
             }
             placed = true;
         }
@@ -516,9 +516,9 @@ void derive_tables(const Partition &P, uint32_t t2_bytes, uint32_t t3_bytes, uin
         for (uint16_t e : tm) out.tm_set += e ? 1u : 0u;
         for (uint16_t e : tm2) out.tm2_set += e ? 1u : 0u;
         if (!global_mode) {
-            for (uint16_t e : e1) out.tm_set += e ? 1u : 0u;
+            for (uint16_t e : e1) out.tm_set += (e >> 8) ? 1u : 0u;
             if (ns2)
-                for (uint16_t e : e2) out.tm2_set += e ? 1u : 0u;
+                for (uint16_t e : e2) out.tm2_set += (e >> 8) ? 1u : 0u;
         }
     }
     for (uint8_t b : t1) out.t1_set += b & kT1P01;

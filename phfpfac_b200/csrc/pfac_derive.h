@@ -93,7 +93,7 @@ constexpr uint8_t kT1P01 = 1, kT1P12 = 2, kT1P23 = 4, kT1Short = 8, kT1P34 = 16,
 
 // ---- perfect-hash tables of the mode-0 detector (hash-and-displace, one slot per key).
 // bucket = mulhi(x, nb) with x = a mixed hash of the key, d = D[bucket], slot = mulhi(key * c3 + d *
-// (key * c4 | 1), ns), entry E[slot] = tag << 8 | m with tag = x & 255.  A key of the set finds its
+// (key * c4 | 1), ns), entry E[slot] = m << 8 | tag with tag = x & 255.  A key of the set finds its
 // own entry; any other word finds m = 0 or, once in 256, some other key's m.
 PFAC_HD inline uint32_t mulhi32(uint32_t a, uint32_t b)
 {
@@ -118,7 +118,7 @@ PFAC_HD inline uint32_t ph_lookup(const uint16_t *D, const uint16_t *E, uint32_t
 {
     const uint32_t d = D[mulhi32(x, nb)];
     const uint32_t e = E[ph_slot(key, d, ns)];
-    return (e >> 8) == (x & 255u) ? (e & 255u) : 0u;
+    return ((e ^ x) & 255u) ? 0u : (e >> 8);   // entry = m << 8 | tag
 }
 
 struct Derived {

@@ -240,7 +240,7 @@ int launch_scan(pfac_ctx *ctx, Slot &slot, const void *d_in, uint64_t n_starts, 
         ev_after = ctx->ev[slot_i + 1];
     }
     if (ctx->dv.mode == 2) pfac_scan_kernel<2><<<grid, kThreads, ctx->smem_bytes, stream>>>(p);
-    else if (ctx->dv.mode == 1) pfac_scan_kernel<0><<<grid, kThreads, ctx->smem_bytes, stream>>>(p);
+    else if (ctx->dv.mode == 1) pfac_scan_kernel<1><<<grid, kThreads, ctx->smem_bytes, stream>>>(p);
     else if (ctx->dv.has_short) pfac_scan2_kernel<true, true><<<grid, kThreads, ctx->smem_bytes, stream>>>(p);
     else if (ctx->dv.has_shortc) pfac_scan2_kernel<false, true><<<grid, kThreads, ctx->smem_bytes, stream>>>(p);
     else pfac_scan2_kernel<false, false><<<grid, kThreads, ctx->smem_bytes, stream>>>(p);
@@ -440,7 +440,7 @@ int pfac_ctx_create(int device, const pfac_tables *t, int part, int n_streams, s
     ctx->dv.gimage.shrink_to_fit();
 
     // the attribute is per function and device, not per context: always allow the device maximum
-    CU_TRY(cudaFuncSetAttribute(pfac_scan_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
+    CU_TRY(cudaFuncSetAttribute(pfac_scan_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
     CU_TRY(cudaFuncSetAttribute(pfac_scan_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
     CU_TRY(cudaFuncSetAttribute(pfac_scan2_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
     CU_TRY(cudaFuncSetAttribute(pfac_scan2_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
@@ -449,7 +449,7 @@ int pfac_ctx_create(int device, const pfac_tables *t, int part, int n_streams, s
     if (ctx->dv.mode == 2)
         CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, pfac_scan_kernel<2>, kThreads, ctx->smem_bytes));
     else if (ctx->dv.mode == 1)
-        CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, pfac_scan_kernel<0>, kThreads, ctx->smem_bytes));
+        CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, pfac_scan_kernel<1>, kThreads, ctx->smem_bytes));
     else
         CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, pfac_scan2_kernel<true, true>, kThreads, ctx->smem_bytes));
     if (bps < 1) return set_error(PFAC_ERR_CUDA, "scan kernel does not fit on an SM (smem %zu B)", ctx->smem_bytes);

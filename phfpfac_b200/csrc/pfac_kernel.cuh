@@ -90,7 +90,10 @@ struct FinalizeParams {
     unsigned long long *count_out;    // caller's device counter (may be null)
 };
 
-constexpr int kConsumerWarps = 31;
+#ifndef PFAC_CONSUMER_WARPS
+#define PFAC_CONSUMER_WARPS 31
+#endif
+constexpr int kConsumerWarps = PFAC_CONSUMER_WARPS;
 constexpr int kThreads = (kConsumerWarps + 1) * 32;   // + the producer warp
 constexpr int kSlice = 512;           // start positions per stage-1 step of a warp (32 lanes x 16 B)
 #ifndef PFAC_TILE_SLICES
@@ -107,7 +110,11 @@ constexpr int kTile = kSlicesPerTile * kSlice;   // 16,384 start positions per t
 #ifndef PFAC_SLOT_SLICES_GLOBAL
 #define PFAC_SLOT_SLICES_GLOBAL 4
 #endif
-__host__ __device__ constexpr int slot_slices(int mode) { return mode == 2 ? PFAC_SLOT_SLICES_GLOBAL : PFAC_SLOT_SLICES; }
+#ifndef PFAC_SLOT_SLICES2
+#define PFAC_SLOT_SLICES2 4
+#endif
+// mode (pfac_derive.h): 0 = pfac_scan2_kernel, 1 = pfac_scan_kernel<1> (T1 + T2), 2 = pfac_scan_kernel<2> (global tables)
+__host__ __device__ constexpr int slot_slices(int mode) { return mode == 2 ? PFAC_SLOT_SLICES_GLOBAL : mode == 1 ? PFAC_SLOT_SLICES : PFAC_SLOT_SLICES2; }
 __host__ __device__ constexpr int q1_cap(int mode) { return 64 * slot_slices(mode); }   // per consumer warp: starts of one slot that passed stage 1 (u16)
 __host__ __device__ constexpr int queue_bytes(int mode) { return q1_cap(mode) * 2; }     // a slot with more survivors is handed over whole
 // Ring depth the slot scheme needs.  Each warp holds one slot; when the ring is exhausted (or the
@@ -118,13 +125,17 @@ __host__ __device__ constexpr int min_stages(int mode)
 {
     return (kConsumerWarps + kSlicesPerTile / slot_slices(mode) - 1) / (kSlicesPerTile / slot_slices(mode));
 }
-static_assert(kSlicesPerTile % PFAC_SLOT_SLICES == 0 && kSlicesPerTile % PFAC_SLOT_SLICES_GLOBAL == 0, "slots tile the tile");
+static_assert(kSlicesPerTile % PFAC_SLOT_SLICES == 0 && kSlicesPerTile % PFAC_SLOT_SLICES_GLOBAL == 0 && kSlicesPerTile % PFAC_SLOT_SLICES2 == 0, "slots tile the tile");
 constexpr int kMaxStages = 16;
-constexpr int kCtrlBytes = 1536;          // CtlView below
+constexpr int kCtrlBytes = 1664;          // CtlView below
 constexpr int kMaxParts = 1024;           // tile ranges of the ordering pass (one per finalize CTA)
 constexpr int kCandPerTile = 32;          // candidate starts the detector hands over per tile (more: whole slices)
 constexpr unsigned kCandOverflow = 0xFFFFFFFFu;
 constexpr unsigned kSpinLimit = 1u << 21;
+#ifndef PFAC_WAIT_NS
+#define PFAC_WAIT_NS 1000
+#endif
+constexpr unsigned kWaitNs = PFAC_WAIT_NS;   // suspend-time hint of the consumers' wait for a tile
 #ifndef PFAC_TICKET_BATCH
 #define PFAC_TICKET_BATCH 4
 #endif
@@ -180,6 +191,19 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity)
 #endif
     return ok != 0;
 }
+// The same with a suspend-time hint: the warp sleeps inside the instruction until the phase completes
+// or about `ns` nanoseconds have passed -- a waiting warp issues nothing in between (a poll loop with
+// nanosleep costs issue slots and, for its exit conditions, shared-memory wavefronts).
+__device__ __forceinline__ bool mbar_try_wait_for(uint64_t *bar, uint32_t parity, uint32_t ns)
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity), "r"(ns) : "memory");
+    return ok != 0;
+}
 // returns false if the watchdog tripped (never expected).  SLEEP_NS > 0: back off between polls so
 // that a waiting warp does not burn the issue slots of the warps that work.
 template <unsigned SLEEP_NS>
@@ -194,6 +218,14 @@ __device__ __forceinline__ bool mbar_wait(uint64_t *bar, uint32_t parity, unsign
         if (SLEEP_NS) __nanosleep(SLEEP_NS);
     }
     return true;
+}
+// shared-memory atomic add of ONE lane (the caller has elected it): plain ATOMS, without the
+// warp-aggregation preamble the compiler wraps around atomicAdd in possibly divergent code
+__device__ __forceinline__ uint32_t atoms_add(uint32_t *addr, uint32_t v)
+{
+    uint32_t old;
+    asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(smem_u32(addr)), "r"(v) : "memory");
+    return old;
 }
 // TMA bulk copy global -> shared with an L2 evict-first policy: the input is streamed once and
 // must not push the PHF tables out of L2.  Completion is counted in bytes on the mbarrier.
@@ -320,14 +352,15 @@ __device__ __forceinline__ void add_candidate(uint32_t *n, uint16_t *list, uint3
 {
     const uint32_t i = atomicAdd(n, 1u);
     if (i < (uint32_t)kCandPerTile) list[i] = (uint16_t)tpos;
+    __threadfence_block();   // rare path: the list entry is visible before this warp reports the slot finished
 }
 
 // The control block of the detector kernels (kCtrlBytes of shared memory after the image).
 struct CtlView {
     uint64_t *full, *empty;     // [kMaxStages] mbarriers of the input ring
     uint32_t *tile;             // [kMaxStages] tile id of the stage
-    uint32_t *tflag;            // [kMaxStages] flagged slices of the tile
     uint32_t *ncand;            // [kMaxStages] candidates (bit 31: a dense slot, hand the slices over whole)
+    uint32_t *done;             // [kMaxStages] low byte: slots of the tile that are finished; bits 8..: flagged slices
     uint32_t *grab;             // next (tile, slice) slot of this CTA
     uint32_t *kend;             // sequence number of the CTA's sentinel tile
     uint64_t *imgbar;           // mbarrier of the image copy
@@ -339,15 +372,15 @@ __device__ __forceinline__ CtlView ctl_view(uint8_t *ctl)
     c.full = reinterpret_cast<uint64_t *>(ctl);
     c.empty = reinterpret_cast<uint64_t *>(ctl + 128);
     c.tile = reinterpret_cast<uint32_t *>(ctl + 256);
-    c.tflag = reinterpret_cast<uint32_t *>(ctl + 320);
     c.ncand = reinterpret_cast<uint32_t *>(ctl + 384);
-    c.grab = reinterpret_cast<uint32_t *>(ctl + 448);
-    c.kend = reinterpret_cast<uint32_t *>(ctl + 452);
-    c.imgbar = reinterpret_cast<uint64_t *>(ctl + 456);
-    c.cand = reinterpret_cast<uint16_t *>(ctl + 512);
+    c.done = reinterpret_cast<uint32_t *>(ctl + 448);
+    c.grab = reinterpret_cast<uint32_t *>(ctl + 512);
+    c.kend = reinterpret_cast<uint32_t *>(ctl + 516);
+    c.imgbar = reinterpret_cast<uint64_t *>(ctl + 520);
+    c.cand = reinterpret_cast<uint16_t *>(ctl + 640);
     return c;
 }
-static_assert(512 + kMaxStages * kCandPerTile * 2 <= kCtrlBytes, "control block");
+static_assert(640 + kMaxStages * kCandPerTile * 2 <= kCtrlBytes, "control block");
 
 __device__ __forceinline__ void bulk_g2s_plain(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
 {
@@ -359,7 +392,7 @@ __device__ __forceinline__ void bulk_g2s_plain(void *dst, const void *src, uint3
 // Prologue shared by the detector kernels: barriers, control words, and the filter image, which one
 // thread brings in with TMA bulk copies (the other warps meanwhile start on their roles; consumers wait
 // for the image in image_wait()).
-__device__ __forceinline__ void detector_init(const ScanParams &p, const CtlView &c, int slots_per_tile)
+__device__ __forceinline__ void detector_init(const ScanParams &p, const CtlView &c)
 {
     const int tid = threadIdx.x;
     if (blockIdx.x == 0)
@@ -367,9 +400,9 @@ __device__ __forceinline__ void detector_init(const ScanParams &p, const CtlView
     if (tid == 0) {
         for (uint32_t s = 0; s < p.n_stages; s++) {
             mbar_init(&c.full[s], 1);
-            mbar_init(&c.empty[s], (uint32_t)slots_per_tile);   // one arrival per slot
-            c.tflag[s] = 0;
+            mbar_init(&c.empty[s], 1);   // one arrival per tile: the warp that finishes its last slot (finish_slot)
             c.ncand[s] = 0;
+            c.done[s] = 0;
         }
         mbar_init(c.imgbar, 1);
         *c.grab = 0;
@@ -387,80 +420,90 @@ __device__ __forceinline__ void image_wait(const ScanParams &p, const CtlView &c
     mbar_wait<32>(c.imgbar, 0u, &p.ctrl->error_flag, 5u);
 }
 
-// The producer role (one lane): streams tiles into the ring and, once every consumer warp has
-// released a stage, publishes that tile's result (flag mask, candidate list) before the stage is
-// refilled.
+// The producer role (one lane): streams the CTA's tiles -- blockIdx.x, + gridDim.x, ... : consecutive
+// tiles are in flight on different SMs at the same time, a sequential sweep for the DRAM pages, and
+// no atomic is needed to hand them out -- into the ring.  Its loop is kept short on purpose: one thread
+// runs it, and at 8 KiB per tile every hundred cycles of it cost bandwidth.  A stage is free again when
+// the consumer warp that finished the tile's last slot has published the tile's result and arrived on
+// its `empty` barrier (finish_slot).
 __device__ __forceinline__ void producer_role(const ScanParams &p, const CtlView &c, uint8_t *s_in, uint32_t stride)
 {
     const uint32_t n_stages = p.n_stages;
     const uint64_t policy = policy_evict_first();
-    uint32_t held[kMaxStages];   // tile held by each stage (0xFFFFFFFF: none)
-    for (int i = 0; i < kMaxStages; i++) held[i] = 0xFFFFFFFFu;
-    auto publish = [&](uint32_t st, uint32_t tile) {
-        const uint32_t flags = c.tflag[st];
-        uint32_t nc = c.ncand[st];
-        if (nc > (uint32_t)kCandPerTile) nc = kCandOverflow;   // too many (or the overflow bit is set)
-        p.tile_cnt[tile] = 0u;
-        p.tile_nc[tile] = flags ? nc : 0u;
-        p.tile_mask[tile] = flags;
-        if (flags) {
-            if (nc != kCandOverflow)
-                for (uint32_t i = 0; i < nc; i++) p.cand[(size_t)tile * kCandPerTile + i] = c.cand[st * kCandPerTile + i];
-            c.tflag[st] = 0;
-            c.ncand[st] = 0;
-        }
-    };
+    const uint32_t want = (uint32_t)kTile + p.halo;
+    // interior tiles [t_lo, t_hi): every start of them is a start position and no walk from them can
+    // reach the end of the input or a reference walk bound (bit 31 of the tile word: the consumers then
+    // skip those checks)
+    uint32_t t_lo = 0xFFFFFFFFu, t_hi = 0;
+    if (!p.use_ref_bound) {
+        t_lo = (p.mis + (uint32_t)kTile - 1u) / (uint32_t)kTile;
+        const uint32_t by_valid = p.a_valid_end >= (uint32_t)kTile + p.max_pat_len
+                                      ? (p.a_valid_end - (uint32_t)kTile - p.max_pat_len) / (uint32_t)kTile + 1u : 0u;
+        t_hi = min(by_valid, p.a_start_end / (uint32_t)kTile);
+    }
     uint32_t s = 0, round = 0;
-    // Tiles are claimed p.ticket_batch at a time and one batch ahead: the claim is one global atomic
-    // whose round trip (about a microsecond when every SM asks) then hides behind a whole batch of
-    // tiles instead of stalling every tile.
-    const uint32_t batch = p.ticket_batch;
-    uint32_t t = atomicAdd(&p.ctrl->ticket, batch), t_left = batch;
-    uint32_t b_next = t < p.n_tiles ? atomicAdd(&p.ctrl->ticket, batch) : t;
-    bool ok = true;
-    while (true) {
-        if (t_left == 0) {   // on to the batch claimed while the last one was streamed; claim the one after it
-            t = b_next;
-            t_left = batch;
-            b_next = t < p.n_tiles ? atomicAdd(&p.ctrl->ticket, batch) : t;
+    for (uint32_t t = blockIdx.x;; t += gridDim.x) {
+        // the stage's previous tile (one round ago) must be consumed and published
+        if (round > 0 && !mbar_wait<PFAC_PROD_SLEEP_NS>(&c.empty[s], (round - 1) & 1u, &p.ctrl->error_flag, 3u)) {
+            *reinterpret_cast<volatile uint32_t *>(c.kend) = 0u;   // watchdog tripped: let the consumers go
+            return;
         }
-        if (held[s] != 0xFFFFFFFFu) {
-            if (!mbar_wait<PFAC_PROD_SLEEP_NS>(&c.empty[s], (round - 1) & 1u, &p.ctrl->error_flag, 3u)) { ok = false; break; }
-            publish(s, held[s]);
-            held[s] = 0xFFFFFFFFu;
-        }
-        c.tile[s] = t;
         if (t >= p.n_tiles) {
             // sentinel: consumers leave when they see it; kend releases the warps whose slot
             // lies past the sentinel tile (its stage is never filled)
+            c.tile[s] = t;
             *reinterpret_cast<volatile uint32_t *>(c.kend) = round * n_stages + s;
-            mbar_arrive(&c.full[s]);   // release: orders the store above
-            break;
+            mbar_arrive(&c.full[s]);   // release: orders the stores above
+            return;
         }
+        c.tile[s] = t | ((t >= t_lo && t < t_hi) ? 0x80000000u : 0u);
         uint8_t *buf = s_in + s * stride;
         const uint32_t a0 = t * (uint32_t)kTile;
-        uint32_t nbytes = p.a_valid_end - a0;
-        const uint32_t want = (uint32_t)kTile + p.halo;
-        if (nbytes > want) nbytes = want;
+        const uint32_t avail = p.a_valid_end - a0;
+        const uint32_t nbytes = avail < want ? avail : want;
         const uint32_t nb16 = nbytes & ~15u;
-        // last bytes of the input: not a whole 16-byte block, copied by hand
-        for (uint32_t i = nb16; i < nbytes; i++) buf[i] = p.in_al[(size_t)a0 + i];
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        mbar_expect_tx(&c.full[s], nb16);
+        // last bytes of the input: not a whole 16-byte block, copied by hand and ordered before the
+        // barrier's completion with a proxy fence
+        if (nb16 < nbytes) {
+            for (uint32_t i = nb16; i < nbytes; i++) buf[i] = p.in_al[(size_t)a0 + i];
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        }
+        mbar_expect_tx(&c.full[s], nb16);   // release: orders the tile word before the consumers' reads
         if (nb16) bulk_g2s(buf, p.in_al + a0, nb16, &c.full[s], policy);
-        held[s] = t;
-        t++;
-        t_left--;
         if (++s == n_stages) { s = 0; round++; }
     }
-    if (!ok) *reinterpret_cast<volatile uint32_t *>(c.kend) = 0u;   // watchdog tripped: let the consumers go
-    // drain: the tiles still in the ring were filled in this round (stages < s) or the previous one
-    for (uint32_t k = 1; ok && k < n_stages; k++) {
-        const uint32_t st = (s + n_stages - k) % n_stages;
-        if (held[st] == 0xFFFFFFFFu) continue;
-        const uint32_t fill_round = st < s ? round : round - 1;
-        if (!mbar_wait<PFAC_PROD_SLEEP_NS>(&c.empty[st], fill_round & 1u, &p.ctrl->error_flag, 4u)) break;
-        publish(st, held[st]);
+}
+
+// End of a slot.  One shared-memory atomic per slot counts the tile's finished slots (low byte) and
+// collects the flagged slices (bits 8..): the warp that finishes the tile's last slot publishes the
+// tile's result (flag mask, candidate list) to global memory, resets the stage's words and hands the
+// stage back to the producer.
+template <int SLOTS_PER_TILE>
+__device__ __forceinline__ void finish_slot(const ScanParams &p, const CtlView &c, int lane, uint32_t s, uint32_t tile,
+                                            uint32_t anym, uint32_t slice0)
+{
+    anym = __reduce_or_sync(0xffffffffu, anym);   // (a warp barrier: the lanes' candidate stores precede lane 0's atomic)
+    uint32_t old = 0;
+    if (lane == 0) old = atoms_add(&c.done[s], 1u + ((anym << slice0) << 8));   // each slot owns its slices' bits
+    old = __shfl_sync(0xffffffffu, old, 0);
+    if ((old & 255u) != (uint32_t)SLOTS_PER_TILE - 1u) return;
+    const uint32_t flags = (old >> 8) | (anym << slice0);
+    uint32_t nc = 0;
+    if (flags) {   // rare: some start of the tile survived every filter
+        __threadfence_block();
+        nc = *reinterpret_cast<volatile uint32_t *>(&c.ncand[s]);
+        if (nc > (uint32_t)kCandPerTile) nc = kCandOverflow;   // too many (or the overflow bit is set)
+        if (nc != kCandOverflow && (uint32_t)lane < nc)
+            p.cand[(size_t)tile * kCandPerTile + lane] = *reinterpret_cast<volatile uint16_t *>(&c.cand[s * kCandPerTile + lane]);
+        __syncwarp();
+    }
+    if (lane == 0) {
+        p.tile_cnt[tile] = 0u;
+        p.tile_nc[tile] = nc;
+        p.tile_mask[tile] = flags;
+        if (flags) c.ncand[s] = 0;
+        c.done[s] = 0;
+        mbar_arrive(&c.empty[s]);   // release: orders the shared-memory reads and resets above before the refill
     }
 }
 
@@ -473,22 +516,22 @@ __device__ __forceinline__ bool take_slot(const ScanParams &p, const CtlView &c,
                                           uint32_t &tile)
 {
     uint32_t g = 0;
-    if (lane == 0) g = atomicAdd(c.grab, 1u);
+    if (lane == 0) g = atoms_add(c.grab, 1u);
     g = __shfl_sync(0xffffffffu, g, 0);
     const uint32_t k = g / (uint32_t)SLOTS_PER_TILE;
     slot_in_tile = g - k * (uint32_t)SLOTS_PER_TILE;
     const uint32_t round = __umulhi(k, p.stage_magic);   // k / n_stages, exact for k < 2^32 / n_stages
     s = k - round * p.n_stages;
-    for (unsigned spins = 0; !mbar_try_wait(&c.full[s], round & 1u);) {
+    // the wait suspends the warp in hardware; only when it times out is the end of the work checked
+    for (unsigned spins = 0; !mbar_try_wait_for(&c.full[s], round & 1u, kWaitNs);) {
         if (*reinterpret_cast<volatile uint32_t *>(c.kend) < k) return false;   // a slot past the end of the work
         if (++spins > kSpinLimit) {
             atomicExch(&p.ctrl->error_flag, 2u);
             return false;
         }
-        if (PFAC_CONS_SLEEP_NS) __nanosleep(PFAC_CONS_SLEEP_NS);
     }
-    tile = c.tile[s];
-    return tile < p.n_tiles;
+    tile = c.tile[s];   // bit 31 = interior flag (producer_role)
+    return (tile & 0x7FFFFFFFu) < p.n_tiles;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -532,12 +575,44 @@ __device__ __forceinline__ uint32_t load_w4(const uint8_t *buf, uint32_t pos)
     return __funnelshift_r(wp[0], wp[1], (pos & 3u) * 8u);
 }
 
+// Stage 1 over two consecutive slices (1 KiB, `pair` = tile-relative offset of the lane's 16 bytes in
+// the lower one): bit 16 h + j of the result = start j of this lane in slice h passed.  The upper
+// slice goes first: the T1 bytes of the two windows after a lane's 16 bytes are the next lane's first
+// two -- for lane 31 those of lane 0 in the slice above (lane 31 of the upper slice looks them up itself).
+template <bool HAS_SHORT, bool HAS_SC>
+__device__ __forceinline__ uint32_t s1_pair(const uint8_t *buf, uint32_t pair, int lane, uint32_t next_lane)
+{
+    const uint4 v1 = *reinterpret_cast<const uint4 *>(buf + pair + kSlice);
+    const uint4 v0 = *reinterpret_cast<const uint4 *>(buf + pair);
+#ifdef PFAC_EXP_NO_S1   // timing experiment: the streaming skeleton alone
+    return ((v0.x ^ v1.y) + (v0.z ^ v1.w)) == 0x12345679u ? 1u : 0u;
+#endif
+    uint32_t X0, X1, Y0, Y1;
+    s1_probe(v1, Y0, Y1);
+    s1_probe(v0, X0, X1);
+    uint32_t ey = __shfl_sync(0xffffffffu, Y0, next_lane);
+    if (lane == 31) {
+        const uint32_t r = rot2x4(*reinterpret_cast<const uint32_t *>(buf + pair + kSlice + 16));
+        ey = (uint32_t)smem[r & 0xffffu] | ((uint32_t)smem[r >> 16] << 8);
+    }
+    const uint32_t ex = __shfl_sync(0xffffffffu, lane == 0 ? Y0 : X0, next_lane);
+    const uint32_t q0 = s1_combine<HAS_SHORT, HAS_SC>(X0, X1) * 0x01041040u;
+    const uint32_t q1 = s1_combine<HAS_SHORT, HAS_SC>(X1, ex) * 0x01041040u;
+    const uint32_t q2 = s1_combine<HAS_SHORT, HAS_SC>(Y0, Y1) * 0x01041040u;
+    const uint32_t q3 = s1_combine<HAS_SHORT, HAS_SC>(Y1, ey) * 0x01041040u;
+    // byte 3 of each product = the 8 results in start order
+    return __byte_perm(__byte_perm(q0, q1, 0x0073), __byte_perm(q2, q3, 0x0073), 0x5410);
+}
+
+constexpr int kSlotSlices2 = slot_slices(0);   // slices per slot of the mode-0 detector (2 or 4)
+static_assert(kSlotSlices2 % 2 == 0 && kSlicesPerTile % kSlotSlices2 == 0, "slots are made of slice pairs");
+constexpr int kQ2Cap = q1_cap(0);              // survivors a slot's queue holds; a slot with more is handed over whole
+
 template <bool HAS_SHORT, bool HAS_SC>
 __global__ void __launch_bounds__(kThreads, 1) pfac_scan2_kernel(const ScanParams p)
 {
-    constexpr int kSlotSlices = slot_slices(0), kSlotsPerTile = kSlicesPerTile / kSlotSlices;
-    constexpr int kQ1Cap = q1_cap(0), kQueueBytes = queue_bytes(0);
-    static_assert(kSlotSlices == 2, "the survivor masks of a slot share one 32-bit word");
+    constexpr int kSlotSlices = kSlotSlices2, kSlotsPerTile = kSlicesPerTile / kSlotSlices;
+    constexpr int kQueueBytes = kQ2Cap * 2;
     uint8_t *ctl = smem + p.image_bytes;
     const CtlView c = ctl_view(ctl);
     uint8_t *qbase = ctl + kCtrlBytes;
@@ -545,7 +620,7 @@ __global__ void __launch_bounds__(kThreads, 1) pfac_scan2_kernel(const ScanParam
     const uint32_t stride = scan_buf_stride(p.halo);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
-    detector_init(p, c, kSlotsPerTile);
+    detector_init(p, c);
     if (warp == kConsumerWarps) {
         if (lane == 0) producer_role(p, c, s_in, stride);
         return;
@@ -558,44 +633,24 @@ __global__ void __launch_bounds__(kThreads, 1) pfac_scan2_kernel(const ScanParam
     const uint16_t *s_e2 = reinterpret_cast<const uint16_t *>(smem + p.off_e2);
     const uint32_t *s_t3 = reinterpret_cast<const uint32_t *>(smem + p.off_t3);
     uint16_t *wq = reinterpret_cast<uint16_t *>(qbase + warp * kQueueBytes);   // stage-1 survivors of the slot
-    const uint32_t lt_mask = (1u << lane) - 1u;
     const uint32_t next_lane = (lane + 1) & 31;
 
     for (;;) {
-        uint32_t s, slot_in_tile, tile;
-        if (!take_slot<kSlotsPerTile>(p, c, lane, s, slot_in_tile, tile)) break;
+        uint32_t s, slot_in_tile, tinfo;
+        if (!take_slot<kSlotsPerTile>(p, c, lane, s, slot_in_tile, tinfo)) break;
+        const uint32_t tile = tinfo & 0x7FFFFFFFu;
+        const bool interior = (tinfo >> 31) != 0;   // every start of the tile counts, no walk reaches the end of the input
         const uint32_t slice0 = slot_in_tile * (uint32_t)kSlotSlices;
         const uint8_t *buf = s_in + s * stride;
         const uint32_t a0 = tile * (uint32_t)kTile;
         const uint32_t valid_t = p.a_valid_end - a0;   // tile-relative end of readable input (may exceed the buffer)
-        // an interior tile: every start of it is a start position and none can reach the end of the
-        // input or a reference walk bound
-        const bool interior = !p.use_ref_bound && a0 >= p.mis && valid_t >= (uint32_t)kTile + p.max_pat_len &&
-                              a0 + (uint32_t)kTile <= p.a_start_end;
+        // ---- stage 1 of all the slot's slice pairs (their T1 probes overlap), then the compaction: the
+        // lanes' survivor counts are scanned across the warp and every lane writes its own into the queue
+        constexpr int kPairs = kSlotSlices / 2;
+        uint32_t m[kPairs];
         const uint32_t base = slice0 * kSlice + lane * 16;   // tile-relative position of the lane's first start
-        // ---- stage 1, the slot's two slices from the upper one down: the T1 bytes of the two windows
-        // after a lane's 16 bytes are the next lane's first two -- for lane 31 those of lane 0 in the
-        // slice above, which is why that one goes first (its lane 31 looks them up itself)
-        uint32_t m;   // bit 16 h + j: start j of this lane in slice slice0 + h passed stage 1
-        {
-            const uint4 v1 = *reinterpret_cast<const uint4 *>(buf + base + kSlice);
-            const uint4 v0 = *reinterpret_cast<const uint4 *>(buf + base);
-            uint32_t X0, X1, Y0, Y1;
-            s1_probe(v1, Y0, Y1);
-            s1_probe(v0, X0, X1);
-            uint32_t ey = __shfl_sync(0xffffffffu, Y0, next_lane);
-            if (lane == 31) {
-                const uint32_t r = rot2x4(*reinterpret_cast<const uint32_t *>(buf + base + kSlice + 16));
-                ey = (uint32_t)smem[r & 0xffffu] | ((uint32_t)smem[r >> 16] << 8);
-            }
-            const uint32_t ex = __shfl_sync(0xffffffffu, lane == 0 ? Y0 : X0, next_lane);
-            const uint32_t q0 = s1_combine<HAS_SHORT, HAS_SC>(X0, X1) * 0x01041040u;
-            const uint32_t q1 = s1_combine<HAS_SHORT, HAS_SC>(X1, ex) * 0x01041040u;
-            const uint32_t q2 = s1_combine<HAS_SHORT, HAS_SC>(Y0, Y1) * 0x01041040u;
-            const uint32_t q3 = s1_combine<HAS_SHORT, HAS_SC>(Y1, ey) * 0x01041040u;
-            // byte 3 of each product = the 8 results in start order
-            m = __byte_perm(__byte_perm(q0, q1, 0x0073), __byte_perm(q2, q3, 0x0073), 0x5410);
-        }
+#pragma unroll
+        for (int pr = 0; pr < kPairs; pr++) m[pr] = s1_pair<HAS_SHORT, HAS_SC>(buf, base + pr * 2 * kSlice, lane, next_lane);
         if (!interior) {   // start positions are [mis, a_start_end) in aligned coordinates
 #pragma unroll
             for (int h = 0; h < kSlotSlices; h++) {
@@ -604,29 +659,41 @@ __global__ void __launch_bounds__(kThreads, 1) pfac_scan2_kernel(const ScanParam
                 const uint32_t last = p.a_start_end > a ? p.a_start_end - a : 0u;
                 uint32_t keep = last >= 16u ? 0xffffu : ((1u << last) - 1u);
                 keep &= first >= 16u ? 0u : (0xffffu << first);
-                m &= ~(0xffffu << (16 * h)) | ((keep & 0xffffu) << (16 * h));
+                m[h >> 1] &= ~(0xffffu << (16 * (h & 1))) | ((keep & 0xffffu) << (16 * (h & 1)));
             }
         }
-        // ---- compaction into the warp queue: every round, each lane that still has survivors hands
-        // over its lowest one (rank by ballot); the order of the queue does not matter
-        uint32_t nq = 0, anym = 0;
-        while (true) {
-            const uint32_t bal = __ballot_sync(0xffffffffu, m != 0u);
-            if (!bal) break;
-            if (m) {
-                const uint32_t b = __ffs(m) - 1;
-                m &= m - 1;
-                const uint32_t idx = nq + __popc(bal & lt_mask);
-                if (idx < (uint32_t)kQ1Cap) wq[idx] = (uint16_t)(base + (b & 15u) + (b >> 4) * kSlice);
-            }
-            nq += __popc(bal);
+        uint32_t cnt = 0;
+#pragma unroll
+        for (int pr = 0; pr < kPairs; pr++) cnt += __popc(m[pr]);
+        uint32_t incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t n = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += n;
         }
-        if (nq > (uint32_t)kQ1Cap) {   // dense slot: the emit kernel looks at all of it
+        uint32_t nq = __shfl_sync(0xffffffffu, incl, 31), anym = 0;
+        if (nq <= (uint32_t)kQ2Cap) {
+            uint16_t *wp = wq + (incl - cnt);
+#pragma unroll
+            for (int pr = 0; pr < kPairs; pr++) {
+                uint32_t mm = m[pr];
+                const uint32_t pb = base + pr * 2 * kSlice;
+                while (mm) {
+                    const uint32_t b = __ffs(mm) - 1;
+                    mm &= mm - 1;
+                    *wp++ = (uint16_t)(pb + b + (b >> 4) * (kSlice - 16));
+                }
+            }
+        }
+        if (nq > (uint32_t)kQ2Cap) {   // dense slot: the emit kernel looks at all of it
             anym = (1u << kSlotSlices) - 1u;
             if (lane == 0) atomicOr(c.ncand + s, 0x80000000u);
             nq = 0;
         }
         __syncwarp();
+#ifdef PFAC_EXP_NO_S2   // timing experiment: stage 1 and the compaction alone
+        if (nq < 100000u) nq = 0;
+#endif
         // ---- stage 2
         for (uint32_t e0 = 0; e0 < nq; e0 += 32) {
             const uint32_t e = e0 + lane;
@@ -667,12 +734,7 @@ __global__ void __launch_bounds__(kThreads, 1) pfac_scan2_kernel(const ScanParam
                 add_candidate(c.ncand + s, c.cand + s * kCandPerTile, tpos);
             }
         }
-        // ---- done with the slot: flag the slices in which a start survived, release the stage
-        anym = __reduce_or_sync(0xffffffffu, anym);
-        if (lane == 0) {
-            if (anym) atomicOr(&c.tflag[s], anym << slice0);
-            mbar_arrive(&c.empty[s]);   // release: orders the shared-memory updates above before the producer's reads
-        }
+        finish_slot<kSlotsPerTile>(p, c, lane, s, tile, anym, slice0);
     }
 }
 
@@ -690,7 +752,7 @@ __global__ void __launch_bounds__(kThreads, 1) pfac_scan_kernel(const ScanParams
     const uint32_t *s_t3 = reinterpret_cast<const uint32_t *>(tab + p.off_t3);
     uint8_t *ctl = smem + p.image_bytes;
     const CtlView c = ctl_view(ctl);
-    uint32_t *s_tflag = c.tflag, *s_ncand = c.ncand;
+    uint32_t *s_ncand = c.ncand;
     uint16_t *s_cand = c.cand;
     uint8_t *qbase = ctl + kCtrlBytes;
     constexpr int kSlotSlices = slot_slices(MODE), kSlotsPerTile = kSlicesPerTile / kSlotSlices;
@@ -700,7 +762,7 @@ __global__ void __launch_bounds__(kThreads, 1) pfac_scan_kernel(const ScanParams
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
-    detector_init(p, c, kSlotsPerTile);
+    detector_init(p, c);
     if (warp == kConsumerWarps) {
         if (lane == 0) producer_role(p, c, s_in, stride);
         return;
@@ -720,6 +782,7 @@ __global__ void __launch_bounds__(kThreads, 1) pfac_scan_kernel(const ScanParams
     for (;;) {
         uint32_t s, slot_in_tile, tile;
         if (!take_slot<kSlotsPerTile>(p, c, lane, s, slot_in_tile, tile)) break;
+        tile &= 0x7FFFFFFFu;
         const uint32_t slice0 = slot_in_tile * (uint32_t)kSlotSlices;   // first slice of the slot
         const uint8_t *buf = s_in + s * stride;
         const uint32_t a0 = tile * (uint32_t)kTile;
@@ -839,12 +902,7 @@ __global__ void __launch_bounds__(kThreads, 1) pfac_scan_kernel(const ScanParams
                 add_candidate(s_ncand + s, s_cand + s * kCandPerTile, tpos);
             }
         }
-        // ---- done with the slot: flag the slices in which a start survived, release the stage
-        anym = __reduce_or_sync(0xffffffffu, anym);
-        if (lane == 0) {
-            if (anym) atomicOr(&s_tflag[s], anym << slice0);
-            mbar_arrive(&c.empty[s]);   // release: orders the shared-memory updates above before the producer's reads
-        }
+        finish_slot<kSlotsPerTile>(p, c, lane, s, tile, anym, slice0);
     }
 }
 

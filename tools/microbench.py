@@ -34,6 +34,12 @@ for n in sizes:
         m.scan_device_raw(d.data_ptr(), n, n, 0, out.data_ptr(), cap, cntd.data_ptr(), st.cuda_stream)
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / a.iters
+    m.set_timing(True)
+    for _ in range(a.iters):
+        m.scan_device_raw(d.data_ptr(), n, n, 0, out.data_ptr(), cap, cntd.data_ptr(), st.cuda_stream)
+    kms, kn = m.kernel_time()
+    m.set_timing(False)
+    print(f"detector {kms / max(kn, 1):.3f} ms = {n / (kms / max(kn, 1)) / 1e6:.1f} GB/s;", end=" ")
     print(f"{a.workload} debug={os.environ.get('PFAC_DEBUG','0')} n={n>>20}MiB {ms:.3f} ms {n/ms/1e6:.1f} GB/s matches={int(cntd.item())} info={m.last_info()}", flush=True)
 import ctypes as C
 cnt = C.c_uint64(0)
