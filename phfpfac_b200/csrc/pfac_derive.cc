@@ -135,16 +135,16 @@ bool place_all(std::vector<Key> &keys, uint32_t bits, std::vector<uint16_t> &tab
 // Hash-and-displace placement (pfac_derive.h: ph_lookup) of every key into its own slot: buckets in
 // order of decreasing size, each takes the first displacement that puts all its keys on free slots.
 // `premixed`: the keys are hashes already (level 2).  false if no 16-bit displacement works.
-bool ph_build(const std::vector<Key> &keys, bool premixed, uint32_t nb, uint32_t ns, std::vector<uint16_t> &D,
-              std::vector<uint16_t> &E)
+bool ph_place(const std::vector<uint32_t> &keys, bool premixed, uint32_t nb, uint32_t ns, std::vector<uint16_t> &D,
+              std::vector<uint32_t> &slot_of)
 {
     D.assign(nb, 0);
-    E.assign(ns, 0);
+    slot_of.assign(keys.size(), 0);
     if (keys.empty()) return true;
     if (keys.size() > ns) return false;
     std::vector<std::vector<uint32_t>> bucket(nb);
     for (uint32_t i = 0; i < keys.size(); i++) {
-        const uint32_t x = premixed ? keys[i].key : ph_mix(keys[i].key);
+        const uint32_t x = premixed ? keys[i] : ph_mix(keys[i]);
         bucket[mulhi32(x, nb)].push_back(i);
     }
     std::vector<uint32_t> order(nb);
@@ -160,20 +160,33 @@ bool ph_build(const std::vector<Key> &keys, bool premixed, uint32_t nb, uint32_t
             slots.clear();
             bool ok = true;
             for (uint32_t i : ks) {
-                const uint32_t sl = ph_slot(keys[i].key, d, ns);
+                const uint32_t sl = ph_slot(keys[i], d, ns);
                 if (used[sl] || std::find(slots.begin(), slots.end(), sl) != slots.end()) { ok = false; break; }
                 slots.push_back(sl);
             }
             if (!ok) continue;
             D[b] = (uint16_t)d;
             for (size_t j = 0; j < ks.size(); j++) {
-                const uint32_t x = premixed ? keys[ks[j]].key : ph_mix(keys[ks[j]].key);
                 used[slots[j]] = 1;
-                E[slots[j]] = (uint16_t)((keys[ks[j]].m << 8) | (x & 255u));
+                slot_of[ks[j]] = slots[j];
             }
             placed = true;
         }
         if (!placed) return false;
+    }
+    return true;
+}
+// the detector's tables: entry = m << 8 | tag
+bool ph_build(const std::vector<Key> &keys, bool premixed, uint32_t nb, uint32_t ns, std::vector<uint16_t> &D,
+              std::vector<uint16_t> &E)
+{
+    std::vector<uint32_t> k(keys.size()), slot_of;
+    for (size_t i = 0; i < keys.size(); i++) k[i] = keys[i].key;
+    E.assign(ns, 0);
+    if (!ph_place(k, premixed, nb, ns, D, slot_of)) return false;
+    for (size_t i = 0; i < keys.size(); i++) {
+        const uint32_t x = premixed ? k[i] : ph_mix(k[i]);
+        E[slot_of[i]] = (uint16_t)((keys[i].m << 8) | (x & 255u));
     }
     return true;
 }
@@ -704,6 +717,76 @@ int derive_selfcheck(const Partition &P, const Derived &d)
             }
     }
     return 0;
+}
+
+void derive_walk_cache(const Partition &P, uint32_t budget_bytes, WalkCache &out)
+{
+    out = WalkCache();
+    Graph g;
+    build_graph(P, g);
+    std::vector<uint32_t> keys2, keys3;
+    std::vector<int32_t> st2, st3;
+    bool too_many = false;
+    for (int b0 = 0; b0 < kCharSet && !too_many; b0++) {
+        const int32_t s1 = P.s0.empty() ? -1 : P.s0[(size_t)b0];
+        if (s1 < 0) continue;
+        for (uint32_t e1 = g.begin(s1); e1 < g.end(s1); e1++) {
+            const uint32_t pair = (uint32_t)b0 | ((uint32_t)g.edges[e1].byte << 8);
+            keys2.push_back(pair | kWalkDepth2);
+            st2.push_back(g.edges[e1].next);
+            const int32_t s2 = g.edges[e1].next;
+            for (uint32_t e2 = g.begin(s2); e2 < g.end(s2); e2++) {
+                keys3.push_back(pair | ((uint32_t)g.edges[e2].byte << 16) | kWalkDepth3);
+                st3.push_back(g.edges[e2].next);
+            }
+            if (keys2.size() + keys3.size() > (1u << 20)) { too_many = true; break; }
+        }
+    }
+    // the root row is always there; depth 2 and then depth 3 as long as they fit the budget
+    for (int depth = too_many ? 1 : 3; depth >= 1; depth--) {
+        std::vector<uint32_t> keys;
+        std::vector<int32_t> states;
+        if (depth >= 2) { keys = keys2; states = st2; }
+        if (depth >= 3) { keys.insert(keys.end(), keys3.begin(), keys3.end()); states.insert(states.end(), st3.begin(), st3.end()); }
+        uint32_t nb = 0, ns = 0;
+        std::vector<uint16_t> D;
+        std::vector<uint32_t> slot_of;
+        if (!keys.empty()) {
+            ph_sizes(keys.size(), nb, ns);
+            if (1024u + nb * 2u + (uint64_t)ns * 8u > budget_bytes) continue;
+            if (!ph_place(keys, false, nb, ns, D, slot_of)) continue;
+        }
+        out.depth = keys.empty() ? 1u : (uint32_t)depth;
+        out.nb = nb;
+        out.ns = ns;
+        out.off_d = 1024;
+        out.off_e = (1024u + nb * 2u + 127u) & ~127u;
+        out.image.assign(out.off_e + (size_t)ns * 8u, 0);
+        int32_t *s0 = reinterpret_cast<int32_t *>(out.image.data());
+        for (int b = 0; b < kCharSet; b++) s0[b] = P.s0.empty() ? -1 : P.s0[(size_t)b];
+        if (!keys.empty()) {
+            memcpy(out.image.data() + out.off_d, D.data(), nb * 2u);
+            uint32_t *E = reinterpret_cast<uint32_t *>(out.image.data() + out.off_e);
+            for (uint32_t i = 0; i < ns; i++) { E[2 * i] = 0xFFFFFFFFu; E[2 * i + 1] = 0xFFFFFFFFu; }   // no key has depth byte 0xFF
+            for (size_t i = 0; i < keys.size(); i++) {
+                E[2 * slot_of[i]] = keys[i];
+                E[2 * slot_of[i] + 1] = (uint32_t)states[i];
+            }
+        }
+        return;
+    }
+}
+
+// host model of the dense kernel's cached walk: the state after the first `depth` bytes of t (depth <= cache depth), -1 = none
+int32_t walk_cache_lookup(const WalkCache &w, const uint8_t *t, uint32_t depth)
+{
+    const int32_t *s0 = reinterpret_cast<const int32_t *>(w.image.data());
+    if (depth == 1) return s0[t[0]];
+    const uint32_t key = (uint32_t)t[0] | ((uint32_t)t[1] << 8) | (depth == 3 ? ((uint32_t)t[2] << 16) | kWalkDepth3 : kWalkDepth2);
+    const uint16_t *D = reinterpret_cast<const uint16_t *>(w.image.data() + w.off_d);
+    const uint32_t *E = reinterpret_cast<const uint32_t *>(w.image.data() + w.off_e);
+    const uint32_t slot = ph_slot(key, D[mulhi32(ph_mix(key), w.nb)], w.ns);
+    return E[2 * slot] == key ? (int32_t)E[2 * slot + 1] : -1;
 }
 
 }  // namespace pfac

@@ -143,6 +143,21 @@ struct Derived {
     uint32_t t1_set = 0, t2_set = 0, t3_set = 0, tm_set = 0, tm2_set = 0, n_prefix4 = 0;
 };
 
+// ---- walk cache of the dense-match kernel (pfac_dense_kernel): the first levels of the trie as an
+// exact perfect-hash map in shared memory, so that the walks of dense inputs (most starts take a few
+// steps) read shared memory instead of chasing r[] / {HT,val} through L1/L2.
+//   image = s0Table (256 x i32) | D (nb x u16) | E (ns x {key u32, state i32})
+//   key   = b0 | b1 << 8 | kWalkDepth2   or   b0 | b1 << 8 | b2 << 16 | kWalkDepth3
+// The map is COMPLETE for every depth it covers: a miss means the automaton has no such path.
+constexpr uint32_t kWalkDepth2 = 0x02000000u, kWalkDepth3 = 0x03000000u;
+struct WalkCache {
+    std::vector<uint8_t> image;
+    uint32_t depth = 1;          // 1: root row only, 2: + every 2-byte path, 3: + every 3-byte path
+    uint32_t off_d = 0, off_e = 0, nb = 0, ns = 0;
+};
+void derive_walk_cache(const Partition &P, uint32_t budget_bytes, WalkCache &out);
+int32_t walk_cache_lookup(const WalkCache &w, const uint8_t *t, uint32_t depth);
+
 // t2/t3/tm2_bytes: shared-memory budget of the variable sections (rounded down to powers of two)
 void derive_tables(const Partition &P, uint32_t t2_bytes, uint32_t t3_bytes, uint32_t tm2_bytes, Derived &out);
 

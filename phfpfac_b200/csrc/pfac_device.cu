@@ -32,12 +32,12 @@ struct Slot {
     Result *d_result = nullptr;
     Result *h_result = nullptr;   // pinned
     unsigned long long *d_partial = nullptr;   // [kMaxParts] matches per tile range (emit -> finalize)
-    unsigned int *d_tile_cnt = nullptr, *d_tile_mask = nullptr, *d_tile_nc = nullptr;
-    uint16_t *d_cand = nullptr;
-    uint4 *d_slice_ent = nullptr;
+    unsigned int *d_tile_cnt = nullptr, *d_tile_nc = nullptr;
+    unsigned long long *d_tile_src = nullptr;
     size_t tile_cap = 0;
     uint2 *d_scratch = nullptr;
     size_t scratch_cap = 0;   // records
+    bool dirty = false;       // a launch sequence failed half way: the control block is reset before the next scan
 };
 
 struct Stage {   // one pipeline stage of pfac_scan_host
@@ -62,6 +62,10 @@ struct pfac_ctx {
     int2 *d_htval = nullptr;
     uint4 *d_image = nullptr;
     uint8_t *d_gimage = nullptr;   // mode 2: T1 | Tm | Tm2 | T3 in global memory
+    uint8_t *d_wcache = nullptr;   // walk cache of the dense-match kernel (pfac_derive.h)
+    WalkCache wc;                  // its layout (the image bytes are dropped after the upload)
+    uint32_t wc_bytes = 0;
+    size_t dense_smem = 0;
     Derived dv;   // image layout and hash parameters (the image bytes are dropped after the upload)
     uint32_t image_bytes = 0;
     int32_t ht_size = 0, width_bit = 0, n_final = 0, max_pat_len = 0;
@@ -119,10 +123,8 @@ void slot_free(Slot &s)
     if (s.d_partial) cudaFree(s.d_partial);
     if (s.h_result) cudaFreeHost(s.h_result);
     if (s.d_tile_cnt) cudaFree(s.d_tile_cnt);
-    if (s.d_tile_mask) cudaFree(s.d_tile_mask);
+    if (s.d_tile_src) cudaFree(s.d_tile_src);
     if (s.d_tile_nc) cudaFree(s.d_tile_nc);
-    if (s.d_cand) cudaFree(s.d_cand);
-    if (s.d_slice_ent) cudaFree(s.d_slice_ent);
     if (s.d_scratch) cudaFree(s.d_scratch);
     s = Slot();
 }
@@ -134,20 +136,15 @@ int slot_reserve(Slot &s, size_t n_tiles, size_t records, cudaStream_t stream)
     if (n_tiles > s.tile_cap) {
         CU_TRY(cudaStreamSynchronize(stream));
         if (s.d_tile_cnt) cudaFree(s.d_tile_cnt);
-        if (s.d_tile_mask) cudaFree(s.d_tile_mask);
+        if (s.d_tile_src) cudaFree(s.d_tile_src);
         if (s.d_tile_nc) cudaFree(s.d_tile_nc);
-        if (s.d_cand) cudaFree(s.d_cand);
-        if (s.d_slice_ent) cudaFree(s.d_slice_ent);
-        s.d_tile_cnt = s.d_tile_mask = s.d_tile_nc = nullptr;
-        s.d_cand = nullptr;
-        s.d_slice_ent = nullptr;
+                s.d_tile_cnt = s.d_tile_nc = nullptr;
+        s.d_tile_src = nullptr;
         s.tile_cap = 0;
         const size_t n = std::max<size_t>(n_tiles, 1024);
         CU_TRY(cudaMalloc(&s.d_tile_cnt, n * sizeof(unsigned int)));
-        CU_TRY(cudaMalloc(&s.d_tile_mask, n * sizeof(unsigned int)));
+        CU_TRY(cudaMalloc(&s.d_tile_src, n * sizeof(unsigned long long)));
         CU_TRY(cudaMalloc(&s.d_tile_nc, n * sizeof(unsigned int)));
-        CU_TRY(cudaMalloc(&s.d_cand, n * kCandPerTile * sizeof(uint16_t)));
-        CU_TRY(cudaMalloc(&s.d_slice_ent, n * kSlicesPerTile * sizeof(uint4)));
         s.tile_cap = n;
     }
     if (records > s.scratch_cap) {
@@ -184,6 +181,15 @@ int launch_scan(pfac_ctx *ctx, Slot &slot, const void *d_in, uint64_t n_starts, 
         if (d_count) CU_TRY(cudaMemsetAsync(d_count, 0, sizeof(unsigned long long), stream));
         return PFAC_OK;
     }
+    if (slot.dirty) {   // a previous launch sequence failed between the kernels: start from a clean control block
+        CU_TRY(cudaMemsetAsync(slot.d_ctrl, 0, sizeof(Ctrl), stream));
+        slot.dirty = false;
+    }
+    struct DirtyOnError {   // set back to false on the success path
+        Slot &s;
+        bool armed = true;
+        ~DirtyOnError() { if (armed) s.dirty = true; }
+    } guard{slot};
     ScanParams p;
     memset(&p, 0, sizeof p);
     p.in_al = (const uint8_t *)d_in - mis;
@@ -223,13 +229,43 @@ int launch_scan(pfac_ctx *ctx, Slot &slot, const void *d_in, uint64_t n_starts, 
     e = slot_reserve(slot, p.n_tiles, (size_t)std::max<uint64_t>(cap, 4096), stream);
     if (e) return e;
     p.tile_cnt = slot.d_tile_cnt;
-    p.tile_mask = slot.d_tile_mask;
     p.tile_nc = slot.d_tile_nc;
-    p.cand = slot.d_cand;
     p.partial = slot.d_partial;
     p.ctrl = slot.d_ctrl;
     p.debug = ctx->debug;
     const uint32_t grid = (uint32_t)std::min<uint64_t>(p.n_tiles, (uint64_t)ctx->sm_count);
+    // tile ranges of the ordering pass: many small ones, so that dense outputs (every tile a long run
+    // of records) are moved by the whole GPU
+    const uint32_t fgrid = (uint32_t)std::min<uint64_t>((p.n_tiles + 7) / 8, (uint64_t)kMaxParts);
+    const uint32_t tiles_per_part = (p.n_tiles + fgrid - 1) / fgrid;
+    EmitParams ep;
+    memset(&ep, 0, sizeof ep);
+    ep.in_al = p.in_al;
+    ep.mis = p.mis;
+    ep.a_start_end = p.a_start_end;
+    ep.a_valid_end = p.a_valid_end;
+    ep.max_pat_len = p.max_pat_len;
+    ep.use_ref_bound = p.use_ref_bound;
+    ep.base_pos = base_pos;
+    ep.pos_bias = pos_bias;
+    ep.r = ctx->d_r;
+    ep.htval = ctx->d_htval;
+    ep.idmap = ctx->d_idmap;
+    ep.s0 = ctx->d_s0;
+    ep.ht_size = ctx->ht_size;
+    ep.width_bit = ctx->width_bit;
+    ep.n_final = ctx->n_final;
+    ep.scratch = slot.d_scratch;
+    ep.scratch_cap = slot.scratch_cap;
+    ep.tile_cnt = slot.d_tile_cnt;
+    ep.tile_src = slot.d_tile_src;
+    ep.tile_nc = slot.d_tile_nc;
+    ep.n_tiles = p.n_tiles;
+    ep.tiles_per_part = tiles_per_part;
+    ep.partial = slot.d_partial;
+    ep.ctrl = slot.d_ctrl;
+    p.emit = ep;
+
     p.ticket_batch = std::max<uint32_t>(1u, std::min<uint32_t>((uint32_t)kTicketBatch, p.n_tiles / (4u * grid)));
     cudaEvent_t ev_after = nullptr;
     if (ctx->timing && !ctx->ev.empty()) {
@@ -247,48 +283,26 @@ int launch_scan(pfac_ctx *ctx, Slot &slot, const void *d_in, uint64_t n_starts, 
     CU_TRY(cudaGetLastError());
     if (ev_after) CU_TRY(cudaEventRecord(ev_after, stream));
 
-    EmitParams ep;
-    memset(&ep, 0, sizeof ep);
-    ep.in_al = p.in_al;
-    ep.mis = p.mis;
-    ep.a_start_end = p.a_start_end;
-    ep.a_valid_end = p.a_valid_end;
-    ep.max_pat_len = p.max_pat_len;
-    ep.use_ref_bound = p.use_ref_bound;
-    ep.base_pos = base_pos;
-    ep.pos_bias = pos_bias;
-    ep.r = ctx->d_r;
-    ep.htval = ctx->d_htval;
-    ep.idmap = ctx->d_idmap;
-    ep.t1 = (ctx->dv.mode == 2 ? (const uint8_t *)ctx->d_gimage : (const uint8_t *)ctx->d_image) + ctx->dv.off_t1;
-    ep.s0 = ctx->d_s0;
-    ep.ht_size = ctx->ht_size;
-    ep.width_bit = ctx->width_bit;
-    ep.n_final = ctx->n_final;
-    ep.scratch = slot.d_scratch;
-    ep.scratch_cap = slot.scratch_cap;
-    ep.tile_cnt = slot.d_tile_cnt;
-    ep.tile_mask = slot.d_tile_mask;
-    ep.tile_nc = slot.d_tile_nc;
-    ep.n_tiles = p.n_tiles;
-    const uint32_t fgrid = (uint32_t)std::min<uint64_t>((p.n_tiles + kFinThreads - 1) / kFinThreads,
-                                                        (uint64_t)std::min(4 * ctx->sm_count, (int)kMaxParts));
-    const uint32_t tiles_per_part = (p.n_tiles + fgrid - 1) / fgrid;
-    ep.tiles_per_part = tiles_per_part;
-    ep.partial = slot.d_partial;
-    ep.cand = slot.d_cand;
-    ep.slice_ent = slot.d_slice_ent;
-    ep.ctrl = slot.d_ctrl;
-    // pass B deals one tile per warp: size the grid for it
-    const uint32_t egrid = (uint32_t)std::min<uint64_t>((p.n_tiles + (kEmitThreads / 32) - 1) / (kEmitThreads / 32),
-                                                        (uint64_t)ctx->sm_count * 8);
-    pfac_emit_kernel<<<egrid, kEmitThreads, 0, stream>>>(ep);
+
+    // the tiles the detector handed over whole (dense matches); returns at once when there are none
+    DenseParams dp;
+    memset(&dp, 0, sizeof dp);
+    dp.e = ep;
+    dp.wc_image = ctx->d_wcache;
+    dp.wc_bytes = ctx->wc_bytes;
+    dp.wc_depth = ctx->wc.depth;
+    dp.wc_off_d = ctx->wc.off_d;
+    dp.wc_off_e = ctx->wc.off_e;
+    dp.wc_nb = ctx->wc.nb;
+    dp.wc_ns = ctx->wc.ns;
+    dp.halo = ctx->halo;
+    dp.n_dense = &slot.d_ctrl->n_dense;
+    pfac_dense_kernel<<<grid, kDenseThreads, ctx->dense_smem, stream>>>(dp);
     CU_TRY(cudaGetLastError());
 
     FinalizeParams f;
     f.tile_cnt = slot.d_tile_cnt;
-    f.tile_mask = slot.d_tile_mask;
-    f.slice_ent = slot.d_slice_ent;
+    f.tile_src = slot.d_tile_src;
     f.scratch = slot.d_scratch;
     f.scratch_cap = slot.scratch_cap;
     f.out = (uint2 *)d_out;
@@ -304,6 +318,7 @@ int launch_scan(pfac_ctx *ctx, Slot &slot, const void *d_in, uint64_t n_starts, 
     if (tiles_out) *tiles_out = p.n_tiles;
     if (ctas_out) *ctas_out = grid;
     if (launches_out) *launches_out = 3;
+    guard.armed = false;
     return PFAC_OK;
 }
 
@@ -345,7 +360,8 @@ int pfac_ctx_create(int device, const pfac_tables *t, int part, int n_streams, s
     DeviceGuard g(device);
     if (!g.ok) return set_error(PFAC_ERR_CUDA, "cudaSetDevice(%d) failed", device);
     const Partition &P = t->parts[(size_t)part];
-    std::unique_ptr<pfac_ctx> ctx(new pfac_ctx);
+    // (every early return below releases what was allocated so far: pfac_ctx_destroy tolerates null members)
+    std::unique_ptr<pfac_ctx, void (*)(pfac_ctx *)> ctx(new pfac_ctx, pfac_ctx_destroy);
     ctx->device = device;
     ctx->n_streams = n_streams;
     ctx->chunk_bytes = chunk_bytes ? chunk_bytes : ((size_t)32 << 20);
@@ -433,7 +449,22 @@ int pfac_ctx_create(int device, const pfac_tables *t, int part, int n_streams, s
         CU_TRY(cudaMalloc(&ctx->d_gimage, ctx->dv.gimage.size()));
         CU_TRY(cudaMemcpy(ctx->d_gimage, ctx->dv.gimage.data(), ctx->dv.gimage.size(), cudaMemcpyHostToDevice));
     }
-    ctx->table_bytes = n_r * 4 + n_ht * 8 + n_id * 4 + 1024 + ctx->image_bytes + ctx->dv.gimage.size();
+    {   // walk cache of the dense-match kernel: as deep as fits beside its text tile and result arrays
+        const size_t fixed = dense_smem_bytes(0, ctx->halo);
+        const uint32_t budget = smem_max > fixed + 4096 ? (uint32_t)std::min<size_t>(smem_max - fixed, 128u << 10) : 2048u;
+        derive_walk_cache(P, budget, ctx->wc);
+        ctx->wc_bytes = (uint32_t)((ctx->wc.image.size() + 15) & ~(size_t)15);
+        ctx->wc.image.resize(ctx->wc_bytes, 0);
+        ctx->dense_smem = dense_smem_bytes(ctx->wc_bytes, ctx->halo);
+        if (ctx->dense_smem > smem_max)
+            return set_error(PFAC_ERR_CUDA, "dense-match kernel needs %zu B of shared memory (patterns too long)", ctx->dense_smem);
+        CU_TRY(cudaMalloc(&ctx->d_wcache, ctx->wc_bytes));
+        CU_TRY(cudaMemcpy(ctx->d_wcache, ctx->wc.image.data(), ctx->wc_bytes, cudaMemcpyHostToDevice));
+        ctx->wc.image.clear();
+        ctx->wc.image.shrink_to_fit();
+        CU_TRY(cudaFuncSetAttribute(pfac_dense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
+    }
+    ctx->table_bytes = n_r * 4 + n_ht * 8 + n_id * 4 + 1024 + ctx->image_bytes + ctx->dv.gimage.size() + ctx->wc_bytes;
     ctx->dv.image.clear();
     ctx->dv.image.shrink_to_fit();
     ctx->dv.gimage.clear();
@@ -475,6 +506,7 @@ void pfac_ctx_destroy(pfac_ctx *ctx)
     if (ctx->d_image) cudaFree(ctx->d_image);
     if (ctx->d_s0) cudaFree(ctx->d_s0);
     if (ctx->d_gimage) cudaFree(ctx->d_gimage);
+    if (ctx->d_wcache) cudaFree(ctx->d_wcache);
     for (auto e : ctx->ev)
         if (e) cudaEventDestroy(e);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);

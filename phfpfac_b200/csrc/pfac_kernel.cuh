@@ -37,13 +37,36 @@ struct Ctrl {   // device-side control block; the finalize kernel resets it for 
     unsigned int ticket;
     unsigned int error_flag;
     unsigned long long alloc;   // records reserved in the arrival-order scratch
-    unsigned int pad[2];
+    unsigned int n_dense;       // tiles the detector handed over whole (to the dense-match pass)
+    unsigned int pad;
 };
 
 struct Result {   // written by the finalize kernel, copied to the host
     unsigned long long count;
     unsigned int error_flag;
     unsigned int pad;
+};
+
+// what a walk needs: the input, the canonical PHF arrays, the scratch and the tile directory
+struct EmitParams {
+    const uint8_t *in_al;
+    uint32_t mis, a_start_end, a_valid_end, max_pat_len;
+    int32_t use_ref_bound;
+    uint64_t base_pos;
+    uint32_t pos_bias;
+    const int32_t *r;
+    const int2 *htval;
+    const int32_t *idmap;
+    const int32_t *s0;        // root row, s0Table (main.cc:200)
+    int32_t ht_size, width_bit, n_final;
+    uint2 *scratch;
+    unsigned long long scratch_cap;
+    unsigned int *tile_cnt;
+    unsigned long long *tile_src;   // [n_tiles] start of the tile's (contiguous, position-ordered) run of records in the scratch
+    unsigned int *tile_nc;
+    uint32_t n_tiles, tiles_per_part;
+    unsigned long long *partial;
+    Ctrl *ctrl;
 };
 
 struct ScanParams {
@@ -65,20 +88,17 @@ struct ScanParams {
     uint32_t ticket_batch;            // tiles a producer claims with one atomic (1 for small inputs: balance first)
     uint32_t n_stages, stage_magic;   // depth of the input ring (as many as shared memory holds); floor(2^32 / n_stages) + 1
     // output
-    unsigned int *tile_cnt;           // [n_tiles] 0 from the detector; the emit kernel writes the tile's match count
-    unsigned int *tile_nc;            // [n_tiles] candidates of the tile (kCandOverflow: too many, whole slices instead)
-    unsigned int *tile_mask;          // [n_tiles] bit s set iff slice s of the tile is flagged
-    uint16_t *cand;                   // [n_tiles*kCandPerTile] tile-relative start positions that survived every filter
-    unsigned int *flagged;            // [n_tiles] ids of the tiles with a non-zero mask, arrival order
-    unsigned long long *partial;      // [kMaxParts] zeroed here; the emit kernel sums matches per tile range into it
+    unsigned int *tile_cnt;           // [n_tiles] matches of the tile (0 for the tiles handed to the dense-match kernel, which sets it)
+    unsigned int *tile_nc;            // [n_tiles] kCandOverflow: too many candidates, the dense-match kernel walks the whole tile; else 0
+    unsigned long long *partial;      // [kMaxParts] zeroed here; matches per tile range (for the ordering pass)
+    EmitParams emit;                  // the walk parameters (emit_tile)
     Ctrl *ctrl;
     uint32_t debug;           // PFAC_DEBUG bits (timing experiments only): 4 no T1, 8 no stage 2
 };
 
 struct FinalizeParams {
     const unsigned int *tile_cnt;
-    const unsigned int *tile_mask;
-    const uint4 *slice_ent;
+    const unsigned long long *tile_src;   // [n_tiles] where the tile's run of records starts in the scratch
     const uint2 *scratch;
     unsigned long long scratch_cap;
     uint2 *out;
@@ -355,6 +375,130 @@ __device__ __forceinline__ void add_candidate(uint32_t *n, uint16_t *list, uint3
     __threadfence_block();   // rare path: the list entry is visible before this warp reports the slot finished
 }
 
+// ---------------------------------------------------------------------------------------------
+// The plain PFAC walk of SUBSEG_MATCH (master_kernel.cu:37-74) over the canonical PHF arrays: used
+// for the starts that survived every filter of the detector (by the warp that finishes their tile,
+// emit_tile below) and, beyond the cached levels, by the dense-match kernel.
+
+// master_kernel.cu:52-64 over the canonical arrays
+__device__ __forceinline__ int32_t phf_next(const EmitParams &p, int32_t state, uint32_t byte)
+{
+    const int32_t key = (state << 8) + (int32_t)byte;                // :52
+    const int32_t row = key >> p.width_bit;                          // :53
+    const int32_t idx = __ldg(&p.r[row]) + (key & ((1 << p.width_bit) - 1));   // :54-55
+    if (idx < 0 || idx >= p.ht_size) return -1;                      // :56-57
+    const int2 hv = __ldg(&p.htval[idx]);                            // :59-61
+    return hv.x == row ? hv.y : -1;
+}
+
+template <bool WRITE>
+__device__ __forceinline__ uint32_t emit_walk(const EmitParams &p, uint32_t a, uint32_t lim_a, unsigned long long o)
+{
+    int32_t state = __ldg(&p.s0[p.in_al[a]]);                        // :41
+    if (state < 0) return 0;                                         // :43
+    uint32_t n = 0, q = a + 1;
+    const uint32_t rec_pos = a - p.mis + p.pos_bias;
+    while (true) {
+        if (state < p.n_final) {                                     // :44-47, :67-70
+            if (WRITE && o + n < p.scratch_cap) p.scratch[o + n] = make_uint2(rec_pos, (uint32_t)__ldg(&p.idmap[state]));
+            n++;
+        }
+        if (q >= lim_a) break;                                       // :50
+        state = phf_next(p, state, p.in_al[q]);
+        if (state < 0) break;                                        // :63-64
+        q++;
+    }
+    return n;
+}
+
+// The same walk, once: counts the matches of start a and keeps the first kWalkKeep final states in
+// registers, so that the records can be written after the scratch space is reserved without walking
+// the (latency-bound) chain a second time.  Starts with more matches than that are walked again.
+constexpr int kWalkKeep = 4;
+__device__ __forceinline__ uint32_t walk_collect(const EmitParams &p, uint32_t a, uint32_t lim_a, int32_t (&st)[kWalkKeep])
+{
+    int32_t state = __ldg(&p.s0[p.in_al[a]]);                        // :41
+    if (state < 0) return 0;                                         // :43
+    uint32_t n = 0, q = a + 1;
+    while (true) {
+        if (state < p.n_final) {                                     // :44-47, :67-70
+#pragma unroll
+            for (int i = 0; i < kWalkKeep; i++)
+                if (n == (uint32_t)i) st[i] = state;
+            n++;
+        }
+        if (q >= lim_a) break;                                       // :50
+        state = phf_next(p, state, p.in_al[q]);
+        if (state < 0) break;                                        // :63-64
+        q++;
+    }
+    return n;
+}
+__device__ __forceinline__ void write_collected(const EmitParams &p, uint32_t a, uint32_t lim_a, uint32_t n,
+                                                const int32_t (&st)[kWalkKeep], unsigned long long o)
+{
+    if (n > (uint32_t)kWalkKeep) {
+        emit_walk<true>(p, a, lim_a, o);
+        return;
+    }
+    const uint32_t rec_pos = a - p.mis + p.pos_bias;
+#pragma unroll
+    for (int i = 0; i < kWalkKeep; i++)
+        if ((uint32_t)i < n && o + i < p.scratch_cap) p.scratch[o + i] = make_uint2(rec_pos, (uint32_t)__ldg(&p.idmap[st[i]]));
+}
+
+
+// The walks of one tile: its (at most 32) candidates are sorted by position with a warp-wide bitonic
+// network, every lane runs SUBSEG_MATCH for its start once, keeping the first final states in
+// registers; the tile's records are reserved as ONE run of the arrival-order scratch (one atomic) and
+// written in (position, pattern length) order.  Called by the warp that finished the tile's last slot.
+// Not inlined: the detector's hot loop must not pay for its registers.
+__device__ __noinline__ void emit_tile(const EmitParams &p, uint32_t tile, uint32_t my_cand, int lane)
+{
+    const uint32_t a0 = tile * (uint32_t)kTile;
+    auto limit = [&](uint32_t a) {
+        uint32_t lim_a = p.a_valid_end;
+        if (p.use_ref_bound) {   // reference tiles: 4096 bytes of global positions + 512-byte halo
+            const unsigned long long g = p.base_pos + (unsigned long long)(a - p.mis);
+            const unsigned long long lim2 = ((g & ~4095ull) + 4608ull) - p.base_pos + p.mis;
+            if (lim2 < lim_a) lim_a = (uint32_t)lim2;
+        }
+        const unsigned long long depth = (unsigned long long)a + p.max_pat_len;
+        return depth < lim_a ? (uint32_t)depth : lim_a;
+    };
+    uint32_t key = my_cand;   // tile-relative start of lane's candidate, 0xFFFF = none
+#pragma unroll
+    for (int k = 2; k <= 32; k <<= 1)
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {   // bitonic sort across the warp
+            const uint32_t other = __shfl_xor_sync(0xffffffffu, key, j);
+            const bool up = ((lane & k) == 0) == ((lane & j) == 0);
+            key = up ? min(key, other) : max(key, other);
+        }
+    const bool live = key != 0xFFFFu;
+    const uint32_t a = a0 + key;
+    int32_t st[kWalkKeep];
+    const uint32_t cnt = live ? walk_collect(p, a, limit(a), st) : 0u;
+    uint32_t incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t n = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += n;
+    }
+    const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+    if (total) {
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(&p.ctrl->alloc, (unsigned long long)total);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (cnt) write_collected(p, a, limit(a), cnt, st, base + incl - cnt);
+        if (lane == 0) {
+            p.tile_src[tile] = base;
+            atomicAdd(&p.partial[tile / p.tiles_per_part], (unsigned long long)total);
+        }
+    }
+    if (lane == 0) p.tile_cnt[tile] = total;
+}
+
 // The control block of the detector kernels (kCtrlBytes of shared memory after the image).
 struct CtlView {
     uint64_t *full, *empty;     // [kMaxStages] mbarriers of the input ring
@@ -488,23 +632,31 @@ __device__ __forceinline__ void finish_slot(const ScanParams &p, const CtlView &
     old = __shfl_sync(0xffffffffu, old, 0);
     if ((old & 255u) != (uint32_t)SLOTS_PER_TILE - 1u) return;
     const uint32_t flags = (old >> 8) | (anym << slice0);
-    uint32_t nc = 0;
+    uint32_t nc = 0, my_cand = 0xFFFFu;
     if (flags) {   // rare: some start of the tile survived every filter
         __threadfence_block();
         nc = *reinterpret_cast<volatile uint32_t *>(&c.ncand[s]);
         if (nc > (uint32_t)kCandPerTile) nc = kCandOverflow;   // too many (or the overflow bit is set)
-        if (nc != kCandOverflow && (uint32_t)lane < nc)
-            p.cand[(size_t)tile * kCandPerTile + lane] = *reinterpret_cast<volatile uint16_t *>(&c.cand[s * kCandPerTile + lane]);
+        if (nc != kCandOverflow && (uint32_t)lane < nc) my_cand = *reinterpret_cast<volatile uint16_t *>(&c.cand[s * kCandPerTile + lane]);
         __syncwarp();
     }
     if (lane == 0) {
-        p.tile_cnt[tile] = 0u;
-        p.tile_nc[tile] = nc;
-        p.tile_mask[tile] = flags;
+        if (nc == kCandOverflow) {
+            p.tile_cnt[tile] = 0u;
+            p.tile_nc[tile] = kCandOverflow;
+            atomicAdd(&p.ctrl->n_dense, 1u);
+        } else {
+            if (!flags) p.tile_cnt[tile] = 0u;
+            p.tile_nc[tile] = 0u;
+        }
         if (flags) c.ncand[s] = 0;
         c.done[s] = 0;
         mbar_arrive(&c.empty[s]);   // release: orders the shared-memory reads and resets above before the refill
     }
+    // The walks of the tile's candidates, straight away, by this warp -- AFTER the stage went back to
+    // the producer (the walk reads the input and the PHF from global memory: microseconds of dependent
+    // loads that must stall one warp, not the ring).
+    if (flags && nc != kCandOverflow) emit_tile(p.emit, tile, my_cand, lane);
 }
 
 // A consumer warp takes the next slot of the CTA's tile sequence and waits for its tile.  Returns
@@ -907,253 +1059,213 @@ __global__ void __launch_bounds__(kThreads, 1) pfac_scan_kernel(const ScanParams
 }
 
 // ---------------------------------------------------------------------------------------------
-// Emit pass: one warp per tile that the detector flagged.  For every flagged 512-byte slice the
-// plain PFAC walk of SUBSEG_MATCH (master_kernel.cu:37-74) runs over every start position, straight
-// from the canonical PHF (state words are masked down to the state number; T1 -- read from the
-// global copy of the image -- only skips starts that cannot take a first step).  Two sweeps per
-// slice: count, reserve scratch space with one atomic, write the records in (position, length) order.
-struct EmitParams {
-    const uint8_t *in_al;
-    uint32_t mis, a_start_end, a_valid_end, max_pat_len;
-    int32_t use_ref_bound;
-    uint64_t base_pos;
-    uint32_t pos_bias;
-    const int32_t *r;
-    const int2 *htval;
-    const int32_t *idmap;
-    const uint8_t *t1;        // global copy of the image's T1 (offset 0)
-    const int32_t *s0;        // root row, s0Table (main.cc:200)
-    int32_t ht_size, width_bit, n_final;
-    uint2 *scratch;
-    unsigned long long scratch_cap;
-    unsigned int *tile_cnt, *tile_mask;
-    const unsigned int *tile_nc;
-    uint32_t n_tiles, tiles_per_part;
-    unsigned long long *partial;
-    const uint16_t *cand;
-    uint4 *slice_ent;
-    Ctrl *ctrl;
+// Dense-match pass: the tiles the detector handed over whole (too many candidates: inputs where a
+// large share of the start positions match, e.g. a dictionary over English text -- the reference's
+// own fixtures).  One CTA per such tile; every start position of the tile is walked as SUBSEG_MATCH
+// does (master_kernel.cu:37-74), but
+//   * the tile and its halo are staged in shared memory, so the walks read LDS, not global bytes;
+//   * the first levels of the trie come from the walk cache (pfac_derive.h: the root row and an exact
+//     perfect-hash map of every 2- and 3-byte path) in shared memory; only deeper steps go through
+//     r[] / {HT,val} (read-only path, L1/L2);
+//   * ONE sweep: each start leaves its match count and its first two final states in shared memory;
+//     a block scan over the counts gives every start its place in the tile's record run, which is
+//     reserved in the arrival-order scratch with one atomic and written from the stored states
+//     (starts with more than two matches are walked again, writing directly).
+// Records of a tile come out in (position, pattern length) order; the ordering pass moves the run
+// into place like those of the emit kernel.
+struct DenseParams {
+    EmitParams e;
+    const uint8_t *wc_image;    // walk cache image (global); copied to shared memory per CTA
+    uint32_t wc_bytes, wc_depth, wc_off_d, wc_off_e, wc_nb, wc_ns;
+    uint32_t halo;              // staged halo bytes (multiple of 16, >= max_pat_len - 1)
+    const unsigned int *n_dense;   // tiles the detector handed over whole (0: nothing to do)
 };
 
-constexpr int kEmitThreads = 256;
+constexpr int kDenseThreads = 1024;
+constexpr int kDensePer = kTile / kDenseThreads;   // consecutive starts a thread owns in the write pass
+static_assert(kTile % kDenseThreads == 0 && kSlice % kDensePer == 0 && kSlicesPerTile <= 32, "dense pass ownership");
 
-// master_kernel.cu:52-64 over the canonical arrays
-__device__ __forceinline__ int32_t phf_next(const EmitParams &p, int32_t state, uint32_t byte)
+__host__ inline size_t dense_smem_bytes(uint32_t wc_bytes, uint32_t halo)
 {
-    const int32_t key = (state << 8) + (int32_t)byte;                // :52
-    const int32_t row = key >> p.width_bit;                          // :53
-    const int32_t idx = __ldg(&p.r[row]) + (key & ((1 << p.width_bit) - 1));   // :54-55
-    if (idx < 0 || idx >= p.ht_size) return -1;                      // :56-57
-    const int2 hv = __ldg(&p.htval[idx]);                            // :59-61
-    return hv.x == row ? hv.y : -1;
+    // walk cache | text (tile + halo + 16) | cnt u16[kTile] | fin i32[2][kTile] | scan scratch
+    return (size_t)((wc_bytes + 127u) & ~127u) + ((kTile + halo + 16 + 127u) & ~127u) + (size_t)kTile * 2 + (size_t)kTile * 8 + 512;
 }
 
-template <bool WRITE>
-__device__ __forceinline__ uint32_t emit_walk(const EmitParams &p, uint32_t a, uint32_t lim_a, unsigned long long o)
+__global__ void __launch_bounds__(kDenseThreads, 1) pfac_dense_kernel(const DenseParams d)
 {
-    int32_t state = __ldg(&p.s0[p.in_al[a]]);                        // :41
-    if (state < 0) return 0;                                         // :43
-    uint32_t n = 0, q = a + 1;
-    const uint32_t rec_pos = a - p.mis + p.pos_bias;
-    while (true) {
-        if (state < p.n_final) {                                     // :44-47, :67-70
-            if (WRITE && o + n < p.scratch_cap) p.scratch[o + n] = make_uint2(rec_pos, (uint32_t)__ldg(&p.idmap[state]));
-            n++;
-        }
-        if (q >= lim_a) break;                                       // :50
-        state = phf_next(p, state, p.in_al[q]);
-        if (state < 0) break;                                        // :63-64
-        q++;
-    }
-    return n;
-}
+    if (*d.n_dense == 0u) return;   // the common case: sparse matches, nothing was handed over
+    const EmitParams &p = d.e;
+    const uint32_t wcb = (d.wc_bytes + 127u) & ~127u;
+    const int32_t *s_s0 = reinterpret_cast<const int32_t *>(smem);
+    const uint16_t *s_d = reinterpret_cast<const uint16_t *>(smem + d.wc_off_d);
+    const uint2 *s_e = reinterpret_cast<const uint2 *>(smem + d.wc_off_e);
+    uint8_t *s_text = smem + wcb;
+    const uint32_t text_bytes = (kTile + d.halo + 16 + 127u) & ~127u;
+    uint16_t *s_cnt = reinterpret_cast<uint16_t *>(s_text + text_bytes);
+    int32_t *s_fin = reinterpret_cast<int32_t *>(s_text + text_bytes + kTile * 2);   // [2][kTile]
+    uint32_t *s_scan = reinterpret_cast<uint32_t *>(s_text + text_bytes + kTile * 2 + kTile * 8);   // [0..31] warp offsets, [32] total, [33..34] base
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
-// The same walk, once: counts the matches of start a and keeps the first kWalkKeep final states in
-// registers, so that the records can be written after the scratch space is reserved without walking
-// the (latency-bound) chain a second time.  Starts with more matches than that are walked again.
-constexpr int kWalkKeep = 4;
-__device__ __forceinline__ uint32_t walk_collect(const EmitParams &p, uint32_t a, uint32_t lim_a, int32_t (&st)[kWalkKeep])
-{
-    int32_t state = __ldg(&p.s0[p.in_al[a]]);                        // :41
-    if (state < 0) return 0;                                         // :43
-    uint32_t n = 0, q = a + 1;
-    while (true) {
-        if (state < p.n_final) {                                     // :44-47, :67-70
-#pragma unroll
-            for (int i = 0; i < kWalkKeep; i++)
-                if (n == (uint32_t)i) st[i] = state;
-            n++;
-        }
-        if (q >= lim_a) break;                                       // :50
-        state = phf_next(p, state, p.in_al[q]);
-        if (state < 0) break;                                        // :63-64
-        q++;
-    }
-    return n;
-}
-__device__ __forceinline__ void write_collected(const EmitParams &p, uint32_t a, uint32_t lim_a, uint32_t n,
-                                                const int32_t (&st)[kWalkKeep], unsigned long long o)
-{
-    if (n > (uint32_t)kWalkKeep) {
-        emit_walk<true>(p, a, lim_a, o);
-        return;
-    }
-    const uint32_t rec_pos = a - p.mis + p.pos_bias;
-#pragma unroll
-    for (int i = 0; i < kWalkKeep; i++)
-        if ((uint32_t)i < n && o + i < p.scratch_cap) p.scratch[o + i] = make_uint2(rec_pos, (uint32_t)__ldg(&p.idmap[st[i]]));
-}
+    for (uint32_t i = tid; i < d.wc_bytes / 16; i += kDenseThreads)
+        reinterpret_cast<uint4 *>(smem)[i] = __ldg(reinterpret_cast<const uint4 *>(d.wc_image) + i);
 
-__global__ void __launch_bounds__(kEmitThreads) pfac_emit_kernel(const EmitParams p)
-{
-    const int lane = threadIdx.x & 31;
-    const uint32_t warps_total = gridDim.x * (kEmitThreads / 32);
-    auto limit = [&](uint32_t a) {
-        uint32_t lim_a = p.a_valid_end;
-        if (p.use_ref_bound) {   // reference tiles: 4096 bytes of global positions + 512-byte halo
-            const unsigned long long g = p.base_pos + (unsigned long long)(a - p.mis);
-            const unsigned long long lim2 = ((g & ~4095ull) + 4608ull) - p.base_pos + p.mis;
-            if (lim2 < lim_a) lim_a = (uint32_t)lim2;
-        }
-        const unsigned long long depth = (unsigned long long)a + p.max_pat_len;
-        return depth < lim_a ? (uint32_t)depth : lim_a;
+    // the cached transition: state after (b0 .. b_{depth-1}) or -1
+    auto cached = [&](uint32_t key) -> int32_t {
+        const uint32_t dd = s_d[mulhi32(ph_mix(key), d.wc_nb)];
+        const uint2 e = s_e[ph_slot(key, dd, d.wc_ns)];
+        return e.x == key ? (int32_t)e.y : -1;
     };
-    const uint32_t warp_g = blockIdx.x * (kEmitThreads / 32) + (threadIdx.x >> 5);
-    // ---- pass A: tiles with exactly one candidate (the common case), one lane per tile
-    for (uint32_t t0 = warp_g * 32u; t0 < p.n_tiles; t0 += warps_total * 32u) {
-        const uint32_t my_tile = t0 + lane;
-        if (my_tile >= p.n_tiles || p.tile_nc[my_tile] != 1u) continue;
-        const uint32_t key = p.cand[(size_t)my_tile * kCandPerTile];
-        const uint32_t a = my_tile * (uint32_t)kTile + key, lim = limit(a);
-        int32_t st[kWalkKeep];
-        const uint32_t cnt = walk_collect(p, a, lim, st);
-        if (cnt) {
-            const unsigned long long base = atomicAdd(&p.ctrl->alloc, (unsigned long long)cnt);
-            write_collected(p, a, lim, cnt, st, base);
-            p.slice_ent[(size_t)my_tile * kSlicesPerTile + key / kSlice] = make_uint4(cnt, (uint32_t)base, (uint32_t)(base >> 32), 0u);
-            atomicAdd(&p.partial[my_tile / p.tiles_per_part], (unsigned long long)cnt);
+    // SUBSEG_MATCH for the start at tile-relative t0 (aligned coordinate a): counts the matches, keeps the
+    // first two final states; with WRITE, stores the records at scratch[o ...] instead
+    auto walk = [&](uint32_t t0, uint32_t a, uint32_t lim_t, int32_t &f0, int32_t &f1, bool write, unsigned long long o) -> uint32_t {
+        uint32_t n = 0;
+        const uint32_t rec_pos = a - p.mis + p.pos_bias;
+        auto final_state = [&](int32_t st) {
+            if (st < p.n_final) {                                     // master_kernel.cu:44-47, :67-70
+                if (write) {
+                    if (o + n < p.scratch_cap) p.scratch[o + n] = make_uint2(rec_pos, (uint32_t)__ldg(&p.idmap[st]));
+                } else if (n == 0) f0 = st;
+                else if (n == 1) f1 = st;
+                n++;
+            }
+        };
+        const uint32_t b0 = s_text[t0];
+        int32_t state = s_s0[b0];                                     // :41
+        if (state < 0) return 0;                                      // :43
+        final_state(state);
+        uint32_t q = t0 + 1;
+        if (q >= lim_t) return n;                                     // :50
+        uint32_t key = b0;
+        if (d.wc_depth >= 2) {
+            key |= (uint32_t)s_text[q] << 8;
+            state = cached(key | kWalkDepth2);
+            if (state < 0) return n;
+            final_state(state);
+            if (++q >= lim_t) return n;
+            if (d.wc_depth >= 3) {
+                key |= (uint32_t)s_text[q] << 16;
+                state = cached(key | kWalkDepth3);
+                if (state < 0) return n;
+                final_state(state);
+                if (++q >= lim_t) return n;
+            }
         }
-        p.tile_cnt[my_tile] = cnt;
-        p.tile_mask[my_tile] = cnt ? 1u << (key / kSlice) : 0u;
-    }
-    // ---- pass B: the other flagged tiles (several candidates, or whole slices), one warp per tile,
-    //      dealt round-robin.  tile_nc is never written here, so the two passes cannot confuse each other.
-    for (uint32_t tile = warp_g; tile < p.n_tiles; tile += warps_total) {
-      const uint32_t nc = p.tile_nc[tile];
-      if (nc == 0u || nc == 1u) continue;
-      {
-        uint32_t m = p.tile_mask[tile], out_mask = 0, tile_total = 0;
+        while (true) {
+            state = phf_next(p, state, s_text[q]);                    // :52-64
+            if (state < 0) break;
+            final_state(state);
+            if (++q >= lim_t) break;
+        }
+        return n;
+    };
+
+    for (uint32_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+        if (p.tile_nc[tile] != kCandOverflow) continue;   // (uniform across the CTA)
+        __syncthreads();   // the previous tile's arrays are free (and, the first time, the walk cache is in place)
         const uint32_t a0 = tile * (uint32_t)kTile;
-        if (nc != kCandOverflow) {
-            // ---- candidate mode: the detector named every start that can match (at most 32): one lane
-            //      per candidate, sorted by position
-            uint32_t key = (uint32_t)lane < nc ? (uint32_t)p.cand[(size_t)tile * kCandPerTile + lane] : 0xFFFFu;
-#pragma unroll
-            for (int k = 2; k <= 32; k <<= 1)
-#pragma unroll
-                for (int j = k >> 1; j > 0; j >>= 1) {   // bitonic sort across the warp
-                    const uint32_t other = __shfl_xor_sync(0xffffffffu, key, j);
-                    const bool up = ((lane & k) == 0) == ((lane & j) == 0);
-                    key = up ? min(key, other) : max(key, other);
+        // ---- stage the tile and its halo (16-byte loads; nothing past the readable input)
+        const uint32_t avail = p.a_valid_end - a0;
+        const uint32_t nbytes = min(avail, (uint32_t)kTile + d.halo);
+        for (uint32_t i = tid; i < (nbytes + 15) / 16; i += kDenseThreads) {
+            const uint32_t off = i * 16;
+            if (off + 16 <= nbytes) {
+                reinterpret_cast<uint4 *>(s_text)[i] = __ldg(reinterpret_cast<const uint4 *>(p.in_al + a0) + i);
+            } else {
+                for (uint32_t k = off; k < nbytes; k++) s_text[k] = p.in_al[(size_t)a0 + k];
+            }
+        }
+        __syncthreads();
+        // ---- the sweep: starts interleaved over the threads (neighbouring lanes read neighbouring bytes)
+        for (uint32_t t0 = tid; t0 < (uint32_t)kTile; t0 += kDenseThreads) {
+            const uint32_t a = a0 + t0;
+            uint32_t n = 0;
+            int32_t f0 = -1, f1 = -1;
+            if (a >= p.mis && a < p.a_start_end) {
+                // walk bound: end of the input, the reference's 4096+512 tile bound, max_pat_len bytes
+                uint32_t lim_a = p.a_valid_end;
+                if (p.use_ref_bound) {
+                    const unsigned long long gpos = p.base_pos + (unsigned long long)(a - p.mis);
+                    const unsigned long long lim2 = ((gpos & ~4095ull) + 4608ull) - p.base_pos + p.mis;
+                    if (lim2 < lim_a) lim_a = (uint32_t)lim2;
                 }
-            const bool live = key != 0xFFFFu;
-            const uint32_t a = a0 + key;
-            int32_t st[kWalkKeep];
-            const uint32_t cnt = live ? walk_collect(p, a, limit(a), st) : 0u;
-            uint32_t incl = cnt;
+                const unsigned long long depth = (unsigned long long)a + p.max_pat_len;
+                if (depth < lim_a) lim_a = (uint32_t)depth;
+                n = walk(t0, a, lim_a - a0, f0, f1, false, 0ull);
+            }
+            s_cnt[t0] = (uint16_t)min(n, 0xFFFFu);
+            s_fin[t0] = f0;
+            s_fin[kTile + t0] = f1;
+        }
+        __syncthreads();
+        // ---- block scan: thread t owns the starts [t * kDensePer, (t + 1) * kDensePer)
+        uint32_t mine = 0;
+#pragma unroll
+        for (int j = 0; j < kDensePer; j++) mine += s_cnt[tid * kDensePer + j];
+        uint32_t incl = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += v;
+        }
+        if (lane == 31) s_scan[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            uint32_t w = s_scan[lane], wi = w;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
-                const uint32_t n = __shfl_up_sync(0xffffffffu, incl, o);
-                if (lane >= o) incl += n;
+                const uint32_t v = __shfl_up_sync(0xffffffffu, wi, o);
+                if (lane >= o) wi += v;
             }
-            const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
-            if (total) {
-                unsigned long long base = 0;
-                if (lane == 0) base = atomicAdd(&p.ctrl->alloc, (unsigned long long)total);
-                base = __shfl_sync(0xffffffffu, base, 0);
-                if (cnt) write_collected(p, a, limit(a), cnt, st, base + incl - cnt);
-                // per-slice directory: records of a slice are contiguous (sorted by position)
-                const uint32_t my_slice = live ? key / kSlice : 0xFFFFFFFFu;
-                while (m) {
-                    const uint32_t sl = __ffs(m) - 1;
-                    m &= m - 1;
-                    const uint32_t mine = my_slice == sl ? cnt : 0u;
-                    uint32_t ssum = mine;
+            s_scan[lane] = wi - w;   // exclusive warp offsets
+            if (lane == 31) {
+                s_scan[32] = wi;     // the tile's total
+                const unsigned long long base = wi ? atomicAdd(&p.ctrl->alloc, (unsigned long long)wi) : 0ull;
+                s_scan[33] = (uint32_t)base;
+                s_scan[34] = (uint32_t)(base >> 32);
+                p.tile_cnt[tile] = wi;
+                p.tile_src[tile] = base;
+                if (wi) atomicAdd(&p.partial[tile / p.tiles_per_part], (unsigned long long)wi);
+            }
+        }
+        __syncthreads();
+        const uint32_t total = s_scan[32];
+        const unsigned long long base = (unsigned long long)s_scan[33] | ((unsigned long long)s_scan[34] << 32);
+        uint32_t off = s_scan[warp] + incl - mine;   // this thread's first record within the tile's run
+        // ---- write the records
+        if (total) {
 #pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) ssum += __shfl_xor_sync(0xffffffffu, ssum, o);
-                    if (!ssum) continue;
-                    // offset of the slice = records of all candidates in earlier slices
-                    uint32_t before = (live && my_slice < sl) ? cnt : 0u;
-#pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) before += __shfl_xor_sync(0xffffffffu, before, o);
-                    const unsigned long long so = base + before;
-                    if (lane == 0)
-                        p.slice_ent[(size_t)tile * kSlicesPerTile + sl] = make_uint4(ssum, (uint32_t)so, (uint32_t)(so >> 32), 0u);
-                    out_mask |= 1u << sl;
+            for (int j = 0; j < kDensePer; j++) {
+                const uint32_t t0 = tid * kDensePer + j, n = s_cnt[t0];
+                if (!n) continue;
+                const uint32_t a = a0 + t0;
+                const unsigned long long o = base + off;
+                if (n <= 2u) {
+                    const uint32_t rec_pos = a - p.mis + p.pos_bias;
+                    if (o < p.scratch_cap) p.scratch[o] = make_uint2(rec_pos, (uint32_t)__ldg(&p.idmap[s_fin[t0]]));
+                    if (n == 2u && o + 1 < p.scratch_cap) p.scratch[o + 1] = make_uint2(rec_pos, (uint32_t)__ldg(&p.idmap[s_fin[kTile + t0]]));
+                } else {
+                    uint32_t lim_a = p.a_valid_end;
+                    if (p.use_ref_bound) {
+                        const unsigned long long gpos = p.base_pos + (unsigned long long)(a - p.mis);
+                        const unsigned long long lim2 = ((gpos & ~4095ull) + 4608ull) - p.base_pos + p.mis;
+                        if (lim2 < lim_a) lim_a = (uint32_t)lim2;
+                    }
+                    const unsigned long long depth = (unsigned long long)a + p.max_pat_len;
+                    if (depth < lim_a) lim_a = (uint32_t)depth;
+                    int32_t f0, f1;
+                    walk(t0, a, lim_a - a0, f0, f1, true, o);
                 }
-                tile_total = total;
+                off += n;
             }
-            if (lane == 0) {
-                p.tile_cnt[tile] = tile_total;
-                p.tile_mask[tile] = out_mask;
-                if (tile_total) atomicAdd(&p.partial[tile / p.tiles_per_part], (unsigned long long)tile_total);
-            }
-            continue;
         }
-        // ---- slice mode: too many candidates; every start of the flagged slices is examined
-        while (m) {
-            const uint32_t sl = __ffs(m) - 1;
-            m &= m - 1;
-            const uint32_t a_lane = a0 + sl * kSlice + lane * 16;   // aligned coordinates of this lane's 16 starts
-            // which of the 16 starts can match at all: inside [mis, a_start_end) and passing T1
-            uint32_t cand = 0;
-            for (uint32_t j = 0; j < 16; j++) {
-                const uint32_t a = a_lane + j;
-                if (a < p.mis || a >= p.a_start_end) continue;
-                const uint32_t c0 = p.in_al[a], c1 = a + 1 < p.a_valid_end ? p.in_al[a + 1] : 0u;
-                if (__ldg(&p.t1[t1_index(c0, c1)]) & kT1P01) cand |= 1u << j;
-            }
-            uint32_t cnt = 0, hit = 0;
-            for (uint32_t c = cand; c; c &= c - 1) {
-                const uint32_t j = __ffs(c) - 1;
-                const uint32_t n = emit_walk<false>(p, a_lane + j, limit(a_lane + j), 0ull);
-                if (n) hit |= 1u << j;
-                cnt += n;
-            }
-            uint32_t incl = cnt;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const uint32_t n = __shfl_up_sync(0xffffffffu, incl, o);
-                if (lane >= o) incl += n;
-            }
-            const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
-            if (!total) continue;
-            unsigned long long base = 0;
-            if (lane == 0) base = atomicAdd(&p.ctrl->alloc, (unsigned long long)total);
-            base = __shfl_sync(0xffffffffu, base, 0);
-            unsigned long long o = base + incl - cnt;
-            for (uint32_t c = hit; c; c &= c - 1) {
-                const uint32_t j = __ffs(c) - 1;
-                o += emit_walk<true>(p, a_lane + j, limit(a_lane + j), o);
-            }
-            if (lane == 0)
-                p.slice_ent[(size_t)tile * kSlicesPerTile + sl] = make_uint4(total, (uint32_t)base, (uint32_t)(base >> 32), 0u);
-            out_mask |= 1u << sl;
-            tile_total += total;
-        }
-        if (lane == 0) {
-            p.tile_cnt[tile] = tile_total;
-            p.tile_mask[tile] = out_mask;
-            if (tile_total) atomicAdd(&p.partial[tile / p.tiles_per_part], (unsigned long long)tile_total);
-        }
-      }
     }
 }
 
 // ---------------------------------------------------------------------------------------------
-// Position-ordering pass: exclusive scan of the per-tile counts, then every matching slice's
-// records move from the arrival-order scratch to their final place.  One CTA per tile range; the
-// matches of the ranges before it come from the partial sums the emit kernel accumulated.
+// Position-ordering pass.  Every tile's records are one position-ordered run of the arrival-order
+// scratch (tile_src, tile_cnt); an exclusive scan of the per-tile counts gives each run its final
+// place.  One CTA per tile range; the matches of the ranges before it come from the partial sums the
+// emit and dense kernels accumulated.
 constexpr int kFinThreads = 256;
 constexpr int kFinSmall = 8;   // records a single thread moves by itself
 
@@ -1162,6 +1274,7 @@ __global__ void __launch_bounds__(kFinThreads) pfac_finalize_kernel(const Finali
     __shared__ unsigned long long s_red[kFinThreads / 32];
     __shared__ unsigned long long s_base[kFinThreads];
     __shared__ unsigned int s_cnt[kFinThreads];
+    __shared__ unsigned int s_big[kFinThreads / 32];
     __shared__ unsigned long long s_run;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t per = f.tiles_per_part;   // CTA b owns tiles [b*per, (b+1)*per); partial[b] = matches in them
@@ -1195,38 +1308,35 @@ __global__ void __launch_bounds__(kFinThreads) pfac_finalize_kernel(const Finali
         for (int w = 0; w < warp; w++) wbase += s_red[w];
         s_base[tid] = s_run + wbase + incl - c;
         // a tile with a few records (the common case: one match) is moved by the thread that owns it,
-        // all tiles of the chunk in parallel -- the dependent loads tile_mask -> slice_ent -> scratch
-        // are latency, not bandwidth; tiles with many records are left to whole warps below
+        // all tiles of the chunk in parallel -- the dependent loads tile_src -> scratch are latency,
+        // not bandwidth; tiles with many records are left to the whole CTA below
         const bool small = c != 0u && c <= (unsigned)kFinSmall;
         if (small) {
-            unsigned long long dst = s_base[tid];
-            unsigned int m = f.tile_mask[i];
-            while (m) {
-                const int sl = __ffs(m) - 1;
-                m &= m - 1;
-                const uint4 ent = f.slice_ent[(size_t)i * kSlicesPerTile + sl];
-                const unsigned long long src = (unsigned long long)ent.y | ((unsigned long long)ent.z << 32);
-                for (uint32_t k = 0; k < ent.x; k++)
-                    if (src + k < f.scratch_cap && dst + k < f.cap) f.out[dst + k] = f.scratch[src + k];
-                dst += ent.x;
-            }
+            const unsigned long long dst = s_base[tid], src = f.tile_src[i];
+            for (uint32_t k = 0; k < c; k++)
+                if (src + k < f.scratch_cap && dst + k < f.cap) f.out[dst + k] = f.scratch[src + k];
         }
         s_cnt[tid] = small ? 0u : c;
+        const uint32_t big = __ballot_sync(0xffffffffu, !small && c != 0u);
+        if (lane == 0) s_big[warp] = big;
         __syncthreads();
-        // one warp per remaining matching tile
-        for (int j = warp; j < kFinThreads; j += kFinThreads / 32) {
-            if (!s_cnt[j]) continue;
-            const uint32_t tile = c0 + j;
-            unsigned long long dst = s_base[j];
-            unsigned int m = f.tile_mask[tile];
-            while (m) {
-                const int sl = __ffs(m) - 1;
-                m &= m - 1;
-                const uint4 ent = f.slice_ent[(size_t)tile * kSlicesPerTile + sl];
-                const unsigned long long src = (unsigned long long)ent.y | ((unsigned long long)ent.z << 32);
-                for (uint32_t k = lane; k < ent.x; k += 32)
-                    if (src + k < f.scratch_cap && dst + k < f.cap) f.out[dst + k] = f.scratch[src + k];
-                dst += ent.x;
+        // the remaining matching tiles: all threads move one run at a time (coalesced)
+        for (int w = 0; w < kFinThreads / 32; w++)
+          for (uint32_t bits = s_big[w]; bits; bits &= bits - 1) {
+            const int j = w * 32 + __ffs(bits) - 1;
+            const uint32_t n = s_cnt[j];
+            const unsigned long long dst = s_base[j], src = f.tile_src[c0 + j];
+            // (the run fits both buffers or is cut at the caller's capacity; four loads in flight per thread)
+            const uint32_t room = dst < f.cap ? (uint32_t)min((unsigned long long)n, f.cap - dst) : 0u;
+            const uint32_t m = src < f.scratch_cap ? (uint32_t)min((unsigned long long)room, f.scratch_cap - src) : 0u;
+            for (uint32_t k = tid; k < m; k += 4 * kFinThreads) {
+                uint2 r[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++)
+                    if (k + u * kFinThreads < m) r[u] = f.scratch[src + k + u * kFinThreads];
+#pragma unroll
+                for (int u = 0; u < 4; u++)
+                    if (k + u * kFinThreads < m) f.out[dst + k + u * kFinThreads] = r[u];
             }
         }
         __syncthreads();
@@ -1240,7 +1350,7 @@ __global__ void __launch_bounds__(kFinThreads) pfac_finalize_kernel(const Finali
         f.ctrl->ticket = 0;
         f.ctrl->error_flag = 0;
         f.ctrl->alloc = 0;
-
+        f.ctrl->n_dense = 0;
     }
 }
 

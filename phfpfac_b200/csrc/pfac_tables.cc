@@ -729,6 +729,28 @@ int pfac_tables_derive_check(const pfac_tables *t, int part, uint32_t t2_bytes, 
         }
         const int bad = derive_selfcheck(*P, d);
         if (bad) return set_error(PFAC_ERR_INTERNAL, "derived tables violate invariant %d", bad);
+        // the dense-match kernel's walk cache must be the PHF's transition function on the levels it covers
+        for (uint32_t budget : {131072u, 16384u, 2048u}) {
+            WalkCache w;
+            derive_walk_cache(*P, budget, w);
+            if (w.image.size() < 1024) return set_error(PFAC_ERR_INTERNAL, "walk cache has no root row");
+            for (int b0 = 0; b0 < 256; b0++) {
+                uint8_t t[3] = {(uint8_t)b0, 0, 0};
+                const int32_t s1 = P->s0.empty() ? -1 : P->s0[(size_t)b0];
+                if (walk_cache_lookup(w, t, 1) != s1) return set_error(PFAC_ERR_INTERNAL, "walk cache: root row differs");
+                if (w.depth < 2) continue;
+                for (int b1 = 0; b1 < 256; b1++) {
+                    t[1] = (uint8_t)b1;
+                    const int32_t s2 = s1 < 0 ? -1 : P->lookup(s1, b1);
+                    if (walk_cache_lookup(w, t, 2) != s2) return set_error(PFAC_ERR_INTERNAL, "walk cache: depth 2 differs");
+                    if (w.depth < 3 || s2 < 0) continue;
+                    for (int b2 = 0; b2 < 256; b2++) {
+                        t[2] = (uint8_t)b2;
+                        if (walk_cache_lookup(w, t, 3) != P->lookup(s2, b2)) return set_error(PFAC_ERR_INTERNAL, "walk cache: depth 3 differs");
+                    }
+                }
+            }
+        }
         return PFAC_OK;
     } catch (const std::bad_alloc &) {
         return set_error(PFAC_ERR_NOMEM, "out of memory");

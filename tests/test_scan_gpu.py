@@ -393,7 +393,7 @@ def test_job_multi_segment_64bit_positions():
 
 
 def test_shallow_ring(monkeypatch):
-    """The shallowest input ring the slot scheme allows (4 stages of 8 KiB for 31 consumer warps) instead
+    """The shallowest input ring the slot scheme allows (one 8 KiB stage per slot the consumer warps can hold) instead
     of all that fits: the scheme (warps taking slots from a counter, sentinel + kend at the end) must
     not depend on the depth."""
     torch = torch_cuda()
@@ -401,13 +401,13 @@ def test_shallow_ring(monkeypatch):
     pats = pf.synth_patterns(1, 3000, 3, 4, 64)
     t = pf.Tables.from_bytes(pats, 1, 256)
     m = pf.Matcher(t)
-    assert m.derived_info()["ring_stages"] == 4
+    shallow = m.derived_info()["ring_stages"]
     text = pf.synth_text(1, 9, 3 << 20, patterns=pats)
     got = m.scan_host(text)
     m.close()
     monkeypatch.delenv("PFAC_RING_STAGES")
     m2 = pf.Matcher(t)
-    assert m2.derived_info()["ring_stages"] > 4
+    assert m2.derived_info()["ring_stages"] > shallow >= 4
     want = m2.scan_host(text)
     m2.close()
     assert len(want) > 0 and np.array_equal(got, want)
