@@ -31,7 +31,11 @@ struct Slot {
     Ctrl *d_ctrl = nullptr;
     Result *d_result = nullptr;
     Result *h_result = nullptr;   // pinned
-    unsigned long long *d_partial = nullptr;   // [kMaxParts] matches per tile range (emit -> finalize)
+    // [2][kMaxParts] matches per tile range (walks -> ordering pass).  Two buffers, alternating per scan:
+    // the walks of a scan add to one while its detector zeroes the other for the next scan (a buffer
+    // zeroed at the start of the scan that uses it would race with the first walks)
+    unsigned long long *d_partial = nullptr;
+    unsigned flip = 0;
     unsigned int *d_tile_cnt = nullptr, *d_tile_nc = nullptr;
     unsigned long long *d_tile_src = nullptr;
     size_t tile_cap = 0;
@@ -66,6 +70,7 @@ struct pfac_ctx {
     WalkCache wc;                  // its layout (the image bytes are dropped after the upload)
     uint32_t wc_bytes = 0;
     size_t dense_smem = 0;
+    bool dense_first = false;      // no detector: the dense-match kernel walks every tile (sets with patterns <= 3 bytes)
     Derived dv;   // image layout and hash parameters (the image bytes are dropped after the upload)
     uint32_t image_bytes = 0;
     int32_t ht_size = 0, width_bit = 0, n_final = 0, max_pat_len = 0;
@@ -111,7 +116,8 @@ int slot_init(Slot &s)
     CU_TRY(cudaMalloc(&s.d_ctrl, sizeof(Ctrl)));
     CU_TRY(cudaMemset(s.d_ctrl, 0, sizeof(Ctrl)));
     CU_TRY(cudaMalloc(&s.d_result, sizeof(Result)));
-    CU_TRY(cudaMalloc(&s.d_partial, kMaxParts * sizeof(unsigned long long)));
+    CU_TRY(cudaMalloc(&s.d_partial, 2 * kMaxParts * sizeof(unsigned long long)));
+    CU_TRY(cudaMemset(s.d_partial, 0, 2 * kMaxParts * sizeof(unsigned long long)));
     CU_TRY(cudaHostAlloc(&s.h_result, sizeof(Result), cudaHostAllocPortable));
     return PFAC_OK;
 }
@@ -144,6 +150,7 @@ int slot_reserve(Slot &s, size_t n_tiles, size_t records, cudaStream_t stream)
         const size_t n = std::max<size_t>(n_tiles, 1024);
         CU_TRY(cudaMalloc(&s.d_tile_cnt, n * sizeof(unsigned int)));
         CU_TRY(cudaMalloc(&s.d_tile_src, n * sizeof(unsigned long long)));
+        CU_TRY(cudaMemset(s.d_tile_src, 0, n * sizeof(unsigned long long)));   // (epoch 0 = never published: DIRECT dense scans)
         CU_TRY(cudaMalloc(&s.d_tile_nc, n * sizeof(unsigned int)));
         s.tile_cap = n;
     }
@@ -183,6 +190,7 @@ int launch_scan(pfac_ctx *ctx, Slot &slot, const void *d_in, uint64_t n_starts, 
     }
     if (slot.dirty) {   // a previous launch sequence failed between the kernels: start from a clean control block
         CU_TRY(cudaMemsetAsync(slot.d_ctrl, 0, sizeof(Ctrl), stream));
+        CU_TRY(cudaMemsetAsync(slot.d_partial, 0, 2 * kMaxParts * sizeof(unsigned long long), stream));
         slot.dirty = false;
     }
     struct DirtyOnError {   // set back to false on the success path
@@ -230,7 +238,9 @@ int launch_scan(pfac_ctx *ctx, Slot &slot, const void *d_in, uint64_t n_starts, 
     if (e) return e;
     p.tile_cnt = slot.d_tile_cnt;
     p.tile_nc = slot.d_tile_nc;
-    p.partial = slot.d_partial;
+    unsigned long long *partial_now = slot.d_partial + (slot.flip & 1u) * kMaxParts;
+    p.partial = partial_now;
+    p.partial_next = slot.d_partial + ((slot.flip + 1u) & 1u) * kMaxParts;
     p.ctrl = slot.d_ctrl;
     p.debug = ctx->debug;
     const uint32_t grid = (uint32_t)std::min<uint64_t>(p.n_tiles, (uint64_t)ctx->sm_count);
@@ -262,7 +272,7 @@ int launch_scan(pfac_ctx *ctx, Slot &slot, const void *d_in, uint64_t n_starts, 
     ep.tile_nc = slot.d_tile_nc;
     ep.n_tiles = p.n_tiles;
     ep.tiles_per_part = tiles_per_part;
-    ep.partial = slot.d_partial;
+    ep.partial = partial_now;
     ep.ctrl = slot.d_ctrl;
     p.emit = ep;
 
@@ -275,13 +285,18 @@ int launch_scan(pfac_ctx *ctx, Slot &slot, const void *d_in, uint64_t n_starts, 
         CU_TRY(cudaEventRecord(ctx->ev[slot_i], stream));
         ev_after = ctx->ev[slot_i + 1];
     }
-    if (ctx->dv.mode == 2) pfac_scan_kernel<2><<<grid, kThreads, ctx->smem_bytes, stream>>>(p);
+    // Pattern sets with patterns of <= 3 bytes (the reference's own fixtures: a dictionary, "a/aa/aaa")
+    // match at a large share of the start positions of natural text: no filter pays off, the dense-match
+    // kernel walks every tile straight away.
+    const bool dense_first = ctx->dense_first;
+    if (dense_first) {}
+    else if (ctx->dv.mode == 2) pfac_scan_kernel<2><<<grid, kThreads, ctx->smem_bytes, stream>>>(p);
     else if (ctx->dv.mode == 1) pfac_scan_kernel<1><<<grid, kThreads, ctx->smem_bytes, stream>>>(p);
     else if (ctx->dv.has_short) pfac_scan2_kernel<true, true><<<grid, kThreads, ctx->smem_bytes, stream>>>(p);
     else if (ctx->dv.has_shortc) pfac_scan2_kernel<false, true><<<grid, kThreads, ctx->smem_bytes, stream>>>(p);
     else pfac_scan2_kernel<false, false><<<grid, kThreads, ctx->smem_bytes, stream>>>(p);
     CU_TRY(cudaGetLastError());
-    if (ev_after) CU_TRY(cudaEventRecord(ev_after, stream));
+    if (ev_after && !dense_first) CU_TRY(cudaEventRecord(ev_after, stream));
 
 
     // the tiles the detector handed over whole (dense matches); returns at once when there are none
@@ -297,7 +312,24 @@ int launch_scan(pfac_ctx *ctx, Slot &slot, const void *d_in, uint64_t n_starts, 
     dp.wc_ns = ctx->wc.ns;
     dp.halo = ctx->halo;
     dp.n_dense = &slot.d_ctrl->n_dense;
-    pfac_dense_kernel<<<grid, kDenseThreads, ctx->dense_smem, stream>>>(dp);
+    if (dense_first) {   // the dense-match kernel is the whole scan: records go straight to the caller's buffer
+        dp.out = (uint2 *)d_out;
+        dp.cap = cap;
+        dp.prefix = slot.d_tile_src;
+        dp.epoch = slot.flip % 0xFFFFFEu + 1u;
+        dp.result = slot.d_result;
+        dp.count_out = (unsigned long long *)d_count;
+        pfac_dense_kernel<true><<<grid, kDenseThreads, ctx->dense_smem, stream>>>(dp);
+        CU_TRY(cudaGetLastError());
+        if (ev_after) CU_TRY(cudaEventRecord(ev_after, stream));
+        if (tiles_out) *tiles_out = p.n_tiles;
+        if (ctas_out) *ctas_out = grid;
+        if (launches_out) *launches_out = 1;
+        slot.flip++;
+        guard.armed = false;
+        return PFAC_OK;
+    }
+    pfac_dense_kernel<false><<<grid, kDenseThreads, ctx->dense_smem, stream>>>(dp);
     CU_TRY(cudaGetLastError());
 
     FinalizeParams f;
@@ -309,7 +341,7 @@ int launch_scan(pfac_ctx *ctx, Slot &slot, const void *d_in, uint64_t n_starts, 
     f.cap = cap;
     f.n_tiles = p.n_tiles;
     f.tiles_per_part = tiles_per_part;
-    f.partial = slot.d_partial;
+    f.partial = partial_now;
     f.ctrl = slot.d_ctrl;
     f.result = slot.d_result;
     f.count_out = (unsigned long long *)d_count;
@@ -318,6 +350,7 @@ int launch_scan(pfac_ctx *ctx, Slot &slot, const void *d_in, uint64_t n_starts, 
     if (tiles_out) *tiles_out = p.n_tiles;
     if (ctas_out) *ctas_out = grid;
     if (launches_out) *launches_out = 3;
+    slot.flip++;
     guard.armed = false;
     return PFAC_OK;
 }
@@ -462,8 +495,11 @@ int pfac_ctx_create(int device, const pfac_tables *t, int part, int n_streams, s
         CU_TRY(cudaMemcpy(ctx->d_wcache, ctx->wc.image.data(), ctx->wc_bytes, cudaMemcpyHostToDevice));
         ctx->wc.image.clear();
         ctx->wc.image.shrink_to_fit();
-        CU_TRY(cudaFuncSetAttribute(pfac_dense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
+        CU_TRY(cudaFuncSetAttribute(pfac_dense_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
+        CU_TRY(cudaFuncSetAttribute(pfac_dense_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
     }
+    ctx->dense_first = ctx->dv.has_short != 0;
+    if (const char *v = getenv("PFAC_DENSE_FIRST")) ctx->dense_first = atoi(v) != 0;   // experiments: force either path
     ctx->table_bytes = n_r * 4 + n_ht * 8 + n_id * 4 + 1024 + ctx->image_bytes + ctx->dv.gimage.size() + ctx->wc_bytes;
     ctx->dv.image.clear();
     ctx->dv.image.shrink_to_fit();

@@ -38,7 +38,7 @@ struct Ctrl {   // device-side control block; the finalize kernel resets it for 
     unsigned int error_flag;
     unsigned long long alloc;   // records reserved in the arrival-order scratch
     unsigned int n_dense;       // tiles the detector handed over whole (to the dense-match pass)
-    unsigned int pad;
+    unsigned int exited;        // CTAs of a DIRECT dense-match scan that are done (the last one resets this block)
 };
 
 struct Result {   // written by the finalize kernel, copied to the host
@@ -90,7 +90,8 @@ struct ScanParams {
     // output
     unsigned int *tile_cnt;           // [n_tiles] matches of the tile (0 for the tiles handed to the dense-match kernel, which sets it)
     unsigned int *tile_nc;            // [n_tiles] kCandOverflow: too many candidates, the dense-match kernel walks the whole tile; else 0
-    unsigned long long *partial;      // [kMaxParts] zeroed here; matches per tile range (for the ordering pass)
+    unsigned long long *partial;      // [kMaxParts] matches per tile range (for the ordering pass); zero on entry
+    unsigned long long *partial_next; // [kMaxParts] the other of the slot's two buffers: zeroed here for the next scan
     EmitParams emit;                  // the walk parameters (emit_tile)
     Ctrl *ctrl;
     uint32_t debug;           // PFAC_DEBUG bits (timing experiments only): 4 no T1, 8 no stage 2
@@ -540,7 +541,7 @@ __device__ __forceinline__ void detector_init(const ScanParams &p, const CtlView
 {
     const int tid = threadIdx.x;
     if (blockIdx.x == 0)
-        for (int i = tid; i < kMaxParts; i += kThreads) p.partial[i] = 0ull;
+        for (int i = tid; i < kMaxParts; i += kThreads) p.partial_next[i] = 0ull;   // (nobody touches it during this scan)
     if (tid == 0) {
         for (uint32_t s = 0; s < p.n_stages; s++) {
             mbar_init(&c.full[s], 1);
@@ -1079,6 +1080,15 @@ struct DenseParams {
     uint32_t wc_bytes, wc_depth, wc_off_d, wc_off_e, wc_nb, wc_ns;
     uint32_t halo;              // staged halo bytes (multiple of 16, >= max_pat_len - 1)
     const unsigned int *n_dense;   // tiles the detector handed over whole (0: nothing to do)
+    // DIRECT mode (no detector ran: pattern sets with patterns of <= 3 bytes match densely) -- the kernel is
+    // the whole scan: tiles are taken in ticket order, a chained prefix over the tiles' totals (the
+    // scan-then-propagate of a single-pass prefix sum) gives every tile its place in `out`
+    uint2 *out;
+    unsigned long long cap;
+    unsigned long long *prefix;    // [n_tiles] status words of the look-back: epoch << 40 | flag << 38 | records
+    uint32_t epoch;                // 1 .. 2^24-1, differs from that of the slot's previous scans
+    Result *result;
+    unsigned long long *count_out;
 };
 
 constexpr int kDenseThreads = 1024;
@@ -1087,13 +1097,15 @@ static_assert(kTile % kDenseThreads == 0 && kSlice % kDensePer == 0 && kSlicesPe
 
 __host__ inline size_t dense_smem_bytes(uint32_t wc_bytes, uint32_t halo)
 {
-    // walk cache | text (tile + halo + 16) | cnt u16[kTile] | fin i32[2][kTile] | scan scratch
-    return (size_t)((wc_bytes + 127u) & ~127u) + ((kTile + halo + 16 + 127u) & ~127u) + (size_t)kTile * 2 + (size_t)kTile * 8 + 512;
+    // walk cache | text (tile + halo + 16) | cnt u16[kTile] | fin i32[2][kTile] | queues uint2[kTile] | scan scratch | tile list u32[1024]
+    return (size_t)((wc_bytes + 127u) & ~127u) + ((kTile + halo + 16 + 127u) & ~127u) + (size_t)kTile * 2 + (size_t)kTile * 8 +
+           (size_t)kTile * 8 + 512 + 4 * 1024;
 }
 
+template <bool DIRECT>
 __global__ void __launch_bounds__(kDenseThreads, 1) pfac_dense_kernel(const DenseParams d)
 {
-    if (*d.n_dense == 0u) return;   // the common case: sparse matches, nothing was handed over
+    if (!DIRECT && *d.n_dense == 0u) return;   // the common case: sparse matches, nothing was handed over
     const EmitParams &p = d.e;
     const uint32_t wcb = (d.wc_bytes + 127u) & ~127u;
     const int32_t *s_s0 = reinterpret_cast<const int32_t *>(smem);
@@ -1102,9 +1114,17 @@ __global__ void __launch_bounds__(kDenseThreads, 1) pfac_dense_kernel(const Dens
     uint8_t *s_text = smem + wcb;
     const uint32_t text_bytes = (kTile + d.halo + 16 + 127u) & ~127u;
     uint16_t *s_cnt = reinterpret_cast<uint16_t *>(s_text + text_bytes);
-    int32_t *s_fin = reinterpret_cast<int32_t *>(s_text + text_bytes + kTile * 2);   // [2][kTile]
-    uint32_t *s_scan = reinterpret_cast<uint32_t *>(s_text + text_bytes + kTile * 2 + kTile * 8);   // [0..31] warp offsets, [32] total, [33..34] base
+    int32_t *s_fin = reinterpret_cast<int32_t *>(s_text + text_bytes + kTile * 2);   // [2][kTile] first final states of a start ...
+    uint16_t *s_fin16 = reinterpret_cast<uint16_t *>(s_fin);                          // ... or [4][kTile] when they fit 16 bits
+    const bool fin16 = p.n_final <= 65536;
+    const uint32_t fin_keep = fin16 ? 4u : 2u;
+    uint2 *s_q = reinterpret_cast<uint2 *>(s_text + text_bytes + kTile * 2 + kTile * 8);         // [kTile] the warps' queues of live walks
+    uint32_t *s_scan = reinterpret_cast<uint32_t *>(s_text + text_bytes + kTile * 2 + kTile * 16);   // [0..31] warp offsets, [32] total, [33..34] base, [36] ticket
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    // where the records go: the arrival-order scratch (ordered later), or straight to the caller's buffer
+    uint2 *const dst = DIRECT ? d.out : p.scratch;
+    const unsigned long long dst_cap = DIRECT ? d.cap : p.scratch_cap;
 
     for (uint32_t i = tid; i < d.wc_bytes / 16; i += kDenseThreads)
         reinterpret_cast<uint4 *>(smem)[i] = __ldg(reinterpret_cast<const uint4 *>(d.wc_image) + i);
@@ -1115,53 +1135,64 @@ __global__ void __launch_bounds__(kDenseThreads, 1) pfac_dense_kernel(const Dens
         const uint2 e = s_e[ph_slot(key, dd, d.wc_ns)];
         return e.x == key ? (int32_t)e.y : -1;
     };
-    // SUBSEG_MATCH for the start at tile-relative t0 (aligned coordinate a): counts the matches, keeps the
-    // first two final states; with WRITE, stores the records at scratch[o ...] instead
-    auto walk = [&](uint32_t t0, uint32_t a, uint32_t lim_t, int32_t &f0, int32_t &f1, bool write, unsigned long long o) -> uint32_t {
-        uint32_t n = 0;
+    // tile-relative walk bound of the start at aligned coordinate a: end of the input, the reference's
+    // 4096+512 tile bound (master_kernel.cu:141-144), max_pat_len bytes
+    auto limit_t = [&](uint32_t a, uint32_t a0) -> uint32_t {
+        uint32_t lim_a = p.a_valid_end;
+        if (p.use_ref_bound) {
+            const unsigned long long gpos = p.base_pos + (unsigned long long)(a - p.mis);
+            const unsigned long long lim2 = ((gpos & ~4095ull) + 4608ull) - p.base_pos + p.mis;
+            if (lim2 < lim_a) lim_a = (uint32_t)lim2;
+        }
+        const unsigned long long depth = (unsigned long long)a + p.max_pat_len;
+        if (depth < lim_a) lim_a = (uint32_t)depth;
+        return lim_a - a0;
+    };
+    // SUBSEG_MATCH for one start, writing its records at dst[o ...] (starts with more than two matches)
+    auto walk_write = [&](uint32_t t0, uint32_t a, uint32_t lim_t, unsigned long long o) {
         const uint32_t rec_pos = a - p.mis + p.pos_bias;
-        auto final_state = [&](int32_t st) {
-            if (st < p.n_final) {                                     // master_kernel.cu:44-47, :67-70
-                if (write) {
-                    if (o + n < p.scratch_cap) p.scratch[o + n] = make_uint2(rec_pos, (uint32_t)__ldg(&p.idmap[st]));
-                } else if (n == 0) f0 = st;
-                else if (n == 1) f1 = st;
+        uint32_t n = 0;
+        int32_t state = s_s0[s_text[t0]];                             // :41
+        for (uint32_t q = t0 + 1; state >= 0; q++) {
+            if (state < p.n_final) {                                  // :44-47, :67-70
+                if (o + n < dst_cap) dst[o + n] = make_uint2(rec_pos, (uint32_t)__ldg(&p.idmap[state]));
                 n++;
             }
-        };
-        const uint32_t b0 = s_text[t0];
-        int32_t state = s_s0[b0];                                     // :41
-        if (state < 0) return 0;                                      // :43
-        final_state(state);
-        uint32_t q = t0 + 1;
-        if (q >= lim_t) return n;                                     // :50
-        uint32_t key = b0;
-        if (d.wc_depth >= 2) {
-            key |= (uint32_t)s_text[q] << 8;
-            state = cached(key | kWalkDepth2);
-            if (state < 0) return n;
-            final_state(state);
-            if (++q >= lim_t) return n;
-            if (d.wc_depth >= 3) {
-                key |= (uint32_t)s_text[q] << 16;
-                state = cached(key | kWalkDepth3);
-                if (state < 0) return n;
-                final_state(state);
-                if (++q >= lim_t) return n;
-            }
-        }
-        while (true) {
+            if (q >= lim_t) break;                                    // :50
             state = phf_next(p, state, s_text[q]);                    // :52-64
-            if (state < 0) break;
-            final_state(state);
-            if (++q >= lim_t) break;
         }
-        return n;
     };
 
-    for (uint32_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-        if (p.tile_nc[tile] != kCandOverflow) continue;   // (uniform across the CTA)
+    // Which tiles: DIRECT -- all, in ticket order (a tile only ever waits for tiles that running CTAs
+    // hold); otherwise the CTA's share (blockIdx.x, + gridDim.x, ...) of the tiles the detector handed
+    // over, found kDenseThreads at a time (one tile_nc word per thread) and listed in shared memory.
+    uint32_t *s_list = s_scan + 64;   // [kDenseThreads]
+    uint32_t chunk = 0, li = 0, ln = 0;
+    for (;;) {
         __syncthreads();   // the previous tile's arrays are free (and, the first time, the walk cache is in place)
+        uint32_t tile;
+        if (DIRECT) {
+            if (tid == 0) s_scan[36] = atomicAdd(&p.ctrl->ticket, 1u);
+            __syncthreads();
+            tile = s_scan[36];
+            if (tile >= p.n_tiles) break;
+        } else {
+            while (li == ln) {   // (uniform) the list is used up: look at the next kDenseThreads tiles of the share
+                const uint64_t first = (uint64_t)blockIdx.x + (uint64_t)chunk * kDenseThreads * gridDim.x;
+                if (first >= p.n_tiles) break;
+                if (tid == 0) s_scan[37] = 0;
+                __syncthreads();
+                const uint64_t t = first + (uint64_t)tid * gridDim.x;
+                if (t < p.n_tiles && p.tile_nc[t] == kCandOverflow) s_list[atomicAdd(&s_scan[37], 1u)] = (uint32_t)t;
+                __syncthreads();
+                ln = s_scan[37];
+                li = 0;
+                chunk++;
+                __syncthreads();
+            }
+            if (li == ln) break;
+            tile = s_list[li++];
+        }
         const uint32_t a0 = tile * (uint32_t)kTile;
         // ---- stage the tile and its halo (16-byte loads; nothing past the readable input)
         const uint32_t avail = p.a_valid_end - a0;
@@ -1175,26 +1206,116 @@ __global__ void __launch_bounds__(kDenseThreads, 1) pfac_dense_kernel(const Dens
             }
         }
         __syncthreads();
-        // ---- the sweep: starts interleaved over the threads (neighbouring lanes read neighbouring bytes)
-        for (uint32_t t0 = tid; t0 < (uint32_t)kTile; t0 += kDenseThreads) {
-            const uint32_t a = a0 + t0;
-            uint32_t n = 0;
-            int32_t f0 = -1, f1 = -1;
-            if (a >= p.mis && a < p.a_start_end) {
-                // walk bound: end of the input, the reference's 4096+512 tile bound, max_pat_len bytes
-                uint32_t lim_a = p.a_valid_end;
-                if (p.use_ref_bound) {
-                    const unsigned long long gpos = p.base_pos + (unsigned long long)(a - p.mis);
-                    const unsigned long long lim2 = ((gpos & ~4095ull) + 4608ull) - p.base_pos + p.mis;
-                    if (lim2 < lim_a) lim_a = (uint32_t)lim2;
+        // ---- the sweep, level by level: a warp owns kTile/32 consecutive starts.  Walking them start by
+        // start leaves most lanes idle (walks end at different depths); instead the warp keeps a queue
+        // of the walks that are still alive and advances ALL of them one byte per pass -- every pass is
+        // dense, 32 walks at a time, and runs the code of one trie level only.  A queue entry is
+        // (start | walk bound << 16, state); a final state met bumps the start's count and, for the
+        // first two, is kept for the write pass.
+        {
+            constexpr int kPerWarp = kTile / (kDenseThreads / 32);
+            uint2 *q = s_q + warp * kPerWarp;
+            const uint32_t w0 = warp * kPerWarp;
+            auto record = [&](uint32_t t0, int32_t st) {              // :44-47, :67-70
+                if (st < p.n_final) {
+                    const uint32_t n = s_cnt[t0];
+                    if (fin16) { if (n < 4u) s_fin16[n * kTile + t0] = (uint16_t)st; }
+                    else if (n < 2u) s_fin[n * kTile + t0] = st;
+                    s_cnt[t0] = (uint16_t)(n + 1u);
                 }
-                const unsigned long long depth = (unsigned long long)a + p.max_pat_len;
-                if (depth < lim_a) lim_a = (uint32_t)depth;
-                n = walk(t0, a, lim_a - a0, f0, f1, false, 0ull);
+            };
+            // compaction of a pass's survivors (in place: the write index never passes the batch just read)
+            auto push = [&](bool alive, uint32_t &nw, uint2 it) {
+                const uint32_t bal = __ballot_sync(0xffffffffu, alive);
+                if (alive) q[nw + __popc(bal & lt_mask)] = it;
+                nw += __popc(bal);
+            };
+            uint32_t nq = 0;
+            // level 0: the root row (:41-43)
+            for (uint32_t e = 0; e < (uint32_t)kPerWarp; e += 32) {
+                const uint32_t t0 = w0 + e + lane, a = a0 + t0;
+                bool alive = false;
+                uint2 it = make_uint2(0u, 0u);
+                s_cnt[t0] = 0;
+                if (a >= p.mis && a < p.a_start_end) {
+                    const int32_t st = s_s0[s_text[t0]];
+                    if (st >= 0) {
+                        record(t0, st);
+                        const uint32_t lim = limit_t(a, a0);
+                        alive = t0 + 1u < lim;                        // :50
+                        it = make_uint2(t0 | (lim << 16), (uint32_t)st);
+                    }
+                }
+                push(alive, nq, it);
             }
-            s_cnt[t0] = (uint16_t)min(n, 0xFFFFu);
-            s_fin[t0] = f0;
-            s_fin[kTile + t0] = f1;
+            __syncwarp();
+            uint32_t dep = 1;
+            if (d.wc_depth >= 2) {   // level 1 from the walk cache
+                uint32_t nw = 0;
+                for (uint32_t e = 0; e < nq; e += 32) {
+                    const bool have = e + lane < nq;
+                    uint2 it = have ? q[e + lane] : make_uint2(0u, 0u);
+                    __syncwarp();
+                    bool alive = false;
+                    if (have) {
+                        const uint32_t t0 = it.x & 0xffffu;
+                        const int32_t st = cached((uint32_t)s_text[t0] | ((uint32_t)s_text[t0 + 1] << 8) | kWalkDepth2);
+                        if (st >= 0) {
+                            record(t0, st);
+                            it.y = (uint32_t)st;
+                            alive = t0 + 2u < (it.x >> 16);
+                        }
+                    }
+                    push(alive, nw, it);
+                }
+                __syncwarp();
+                nq = nw;
+                dep = 2;
+                if (d.wc_depth >= 3) {   // level 2 from the walk cache
+                    nw = 0;
+                    for (uint32_t e = 0; e < nq; e += 32) {
+                        const bool have = e + lane < nq;
+                        uint2 it = have ? q[e + lane] : make_uint2(0u, 0u);
+                        __syncwarp();
+                        bool alive = false;
+                        if (have) {
+                            const uint32_t t0 = it.x & 0xffffu;
+                            const int32_t st = cached((uint32_t)s_text[t0] | ((uint32_t)s_text[t0 + 1] << 8) |
+                                                      ((uint32_t)s_text[t0 + 2] << 16) | kWalkDepth3);
+                            if (st >= 0) {
+                                record(t0, st);
+                                it.y = (uint32_t)st;
+                                alive = t0 + 3u < (it.x >> 16);
+                            }
+                        }
+                        push(alive, nw, it);
+                    }
+                    __syncwarp();
+                    nq = nw;
+                    dep = 3;
+                }
+            }
+            for (; nq; dep++) {   // deeper levels through the PHF (:52-64)
+                uint32_t nw = 0;
+                for (uint32_t e = 0; e < nq; e += 32) {
+                    const bool have = e + lane < nq;
+                    uint2 it = have ? q[e + lane] : make_uint2(0u, 0u);
+                    __syncwarp();
+                    bool alive = false;
+                    if (have) {
+                        const uint32_t t0 = it.x & 0xffffu;
+                        const int32_t st = phf_next(p, (int32_t)it.y, s_text[t0 + dep]);
+                        if (st >= 0) {
+                            record(t0, st);
+                            it.y = (uint32_t)st;
+                            alive = t0 + dep + 1u < (it.x >> 16);
+                        }
+                    }
+                    push(alive, nw, it);
+                }
+                __syncwarp();
+                nq = nw;
+            }
         }
         __syncthreads();
         // ---- block scan: thread t owns the starts [t * kDensePer, (t + 1) * kDensePer)
@@ -1217,14 +1338,54 @@ __global__ void __launch_bounds__(kDenseThreads, 1) pfac_dense_kernel(const Dens
                 if (lane >= o) wi += v;
             }
             s_scan[lane] = wi - w;   // exclusive warp offsets
-            if (lane == 31) {
-                s_scan[32] = wi;     // the tile's total
-                const unsigned long long base = wi ? atomicAdd(&p.ctrl->alloc, (unsigned long long)wi) : 0ull;
+            const uint32_t tot = __shfl_sync(0xffffffffu, wi, 31);   // the tile's total
+            unsigned long long base = 0;
+            if (DIRECT) {
+                // Decoupled look-back over the tiles' status words (epoch << 40 | flag << 38 | value): a tile
+                // publishes its own total at once (flag 1 = aggregate), sums the aggregates of the tiles
+                // before it back to the nearest one whose inclusive prefix is known (flag 2), 32 status
+                // words per step, and then publishes its own inclusive prefix.
+                constexpr unsigned long long kVal = (1ull << 38) - 1ull;
+                const unsigned long long ep = (unsigned long long)d.epoch << 40;
+                volatile unsigned long long *st = d.prefix;
+                if (lane == 0) st[tile] = ep | ((tile == 0 ? 2ull : 1ull) << 38) | (unsigned long long)tot;
+                for (long long look = (long long)tile - 1; look >= 0; look -= 32) {
+                    const long long idx = look - lane;
+                    unsigned long long v = ep | (2ull << 38);   // before the first tile: prefix 0
+                    if (idx >= 0) {
+                        v = st[idx];
+                        for (unsigned spins = 0; (v >> 40) != d.epoch; v = st[idx]) {
+                            if (++spins > kSpinLimit) { atomicExch(&p.ctrl->error_flag, 6u); v = ep | (2ull << 38); break; }
+                            __nanosleep(32);
+                        }
+                    }
+                    const uint32_t has_p = __ballot_sync(0xffffffffu, ((v >> 38) & 3ull) == 2ull);
+                    const int fp = has_p ? __ffs(has_p) - 1 : 31;   // the nearest tile with an inclusive prefix
+                    unsigned long long add = lane <= fp ? (v & kVal) : 0ull;
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) add += __shfl_xor_sync(0xffffffffu, add, o);
+                    base += add;
+                    if (has_p) break;
+                }
+                const unsigned long long inc = base + tot;
+                if (lane == 0) {
+                    if (tile > 0) st[tile] = ep | (2ull << 38) | (inc & kVal);
+                    if (tile + 1 == p.n_tiles) {   // the last tile owns the total
+                        d.result->count = inc;
+                        d.result->error_flag = p.ctrl->error_flag;
+                        if (d.count_out) *d.count_out = inc;
+                    }
+                }
+            } else if (lane == 31) {
+                base = tot ? atomicAdd(&p.ctrl->alloc, (unsigned long long)tot) : 0ull;
+                p.tile_cnt[tile] = tot;
+                p.tile_src[tile] = base;
+                if (tot) atomicAdd(&p.partial[tile / p.tiles_per_part], (unsigned long long)tot);
+            }
+            if (DIRECT ? lane == 0 : lane == 31) {
+                s_scan[32] = tot;
                 s_scan[33] = (uint32_t)base;
                 s_scan[34] = (uint32_t)(base >> 32);
-                p.tile_cnt[tile] = wi;
-                p.tile_src[tile] = base;
-                if (wi) atomicAdd(&p.partial[tile / p.tiles_per_part], (unsigned long long)wi);
             }
         }
         __syncthreads();
@@ -1239,24 +1400,25 @@ __global__ void __launch_bounds__(kDenseThreads, 1) pfac_dense_kernel(const Dens
                 if (!n) continue;
                 const uint32_t a = a0 + t0;
                 const unsigned long long o = base + off;
-                if (n <= 2u) {
+                if (n <= fin_keep) {
                     const uint32_t rec_pos = a - p.mis + p.pos_bias;
-                    if (o < p.scratch_cap) p.scratch[o] = make_uint2(rec_pos, (uint32_t)__ldg(&p.idmap[s_fin[t0]]));
-                    if (n == 2u && o + 1 < p.scratch_cap) p.scratch[o + 1] = make_uint2(rec_pos, (uint32_t)__ldg(&p.idmap[s_fin[kTile + t0]]));
-                } else {
-                    uint32_t lim_a = p.a_valid_end;
-                    if (p.use_ref_bound) {
-                        const unsigned long long gpos = p.base_pos + (unsigned long long)(a - p.mis);
-                        const unsigned long long lim2 = ((gpos & ~4095ull) + 4608ull) - p.base_pos + p.mis;
-                        if (lim2 < lim_a) lim_a = (uint32_t)lim2;
+                    for (uint32_t k = 0; k < n; k++) {
+                        const int32_t st = fin16 ? (int32_t)s_fin16[k * kTile + t0] : s_fin[k * kTile + t0];
+                        if (o + k < dst_cap) dst[o + k] = make_uint2(rec_pos, (uint32_t)__ldg(&p.idmap[st]));
                     }
-                    const unsigned long long depth = (unsigned long long)a + p.max_pat_len;
-                    if (depth < lim_a) lim_a = (uint32_t)depth;
-                    int32_t f0, f1;
-                    walk(t0, a, lim_a - a0, f0, f1, true, o);
+                } else {
+                    walk_write(t0, a, limit_t(a, a0), o);
                 }
                 off += n;
             }
+        }
+    }
+    if (DIRECT && tid == 0) {   // the last CTA out resets the control block for the next scan
+        __threadfence();
+        if (atomicAdd(&p.ctrl->exited, 1u) == gridDim.x - 1u) {
+            p.ctrl->ticket = 0;
+            p.ctrl->exited = 0;
+            p.ctrl->error_flag = 0;
         }
     }
 }

@@ -13,7 +13,8 @@ import phfpfac_b200 as pf
 from bench import WORKLOADS
 
 ap = argparse.ArgumentParser()
-ap.add_argument("--workload", default="config3")
+ap.add_argument("--workload", default="config3", help="a synthetic workload of bench.py, or a reference fixture: "
+                "config1 (experimentpattern over 1M) / dictionary (xaa..xad over 1M)")
 ap.add_argument("--mib", type=int, default=0, help="input MiB (default: the largest the reference can index)")
 ap.add_argument("--no-compare", action="store_true", help="time the reference only (no product scan, no sift)")
 a = ap.parse_args()
@@ -25,14 +26,31 @@ ref = C.CDLL(so)
 ref.refgpu_scan.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p,
                             C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_double)]
 
-pk, cnt, pseed, lo, hi, tk, tseed, nbytes, desc = WORKLOADS[a.workload]
-pats = pf.synth_patterns(pk, cnt, pseed, lo, hi)
-tables = pf.Tables.from_bytes(pats, 1, 256)
-p = tables.part(0)
-mpl = tables.max_pat_len
-n_max = ((1 << 32) // (4 * mpl)) - 4096
-n = min(a.mib << 20, n_max) if a.mib else n_max
-text = pf.synth_text(tk, tseed, n, patterns=pats)
+if a.workload in ("config1", "dictionary"):
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from conftest import load_fixtures
+    fx = load_fixtures()
+    pats = fx["experimentpattern" if a.workload == "config1" else "dictionary"]
+    desc = ("config1: the reference's experimentpattern over its 1M text" if a.workload == "config1"
+            else "dictionary: the reference's xaa..xad (7,989 words) over its 1M text")
+    tables = pf.Tables.from_bytes(pats, 1, 256)
+    p = tables.part(0)
+    mpl = tables.max_pat_len
+    n_max = ((1 << 32) // (4 * mpl)) - 4096
+    reps = max(a.mib, 1)
+    text = np.frombuffer(fx["1M"] * reps, dtype=np.uint8)[:min(reps << 20, n_max)].copy()
+    if reps == 1:
+        text = text[:len(text) - 1]        # the CLI drops the last byte of the file (main.cc:138)
+    n = len(text)
+else:
+    pk, cnt, pseed, lo, hi, tk, tseed, nbytes, desc = WORKLOADS[a.workload]
+    pats = pf.synth_patterns(pk, cnt, pseed, lo, hi)
+    tables = pf.Tables.from_bytes(pats, 1, 256)
+    p = tables.part(0)
+    mpl = tables.max_pat_len
+    n_max = ((1 << 32) // (4 * mpl)) - 4096
+    n = min(a.mib << 20, n_max) if a.mib else n_max
+    text = pf.synth_text(tk, tseed, n, patterns=pats)
 
 def pinned(nbytes):
     ptr = C.c_void_p()
