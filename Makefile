@@ -8,12 +8,18 @@ B := phfpfac_b200/_build
 SRC := phfpfac_b200/csrc
 NVFLAGS := $(EXTRA) $(ARCH) -lineinfo -O3 -std=c++17 -ccbin $(HOSTCXX) -Iinclude -I$(SRC) \
            -Xcompiler -fPIC,-Wall,-Wextra,-pthread -Xptxas -v
-HOST_SRCS := $(SRC)/pfac_tables.cc $(SRC)/pfac_writer.cc $(SRC)/pfac_job.cc $(SRC)/pfac_synth.cc $(SRC)/pfac_derive.cc
+HOST_SRCS := $(SRC)/pfac_tables.cc $(SRC)/pfac_writer.cc $(SRC)/pfac_job.cc $(SRC)/pfac_derive.cc
 CUDA_SRCS := $(SRC)/pfac_device.cu
-HDRS := include/pfac_b200.h include/pfac_synth.h $(SRC)/pfac_internal.h $(SRC)/pfac_kernel.cuh $(SRC)/pfac_derive.h
+HDRS := include/pfac_b200.h $(SRC)/pfac_internal.h $(SRC)/pfac_kernel.cuh $(SRC)/pfac_derive.h
 
-.PHONY: all lib cli oracle clean
-all: lib cli oracle
+.PHONY: all lib cli oracle synth clean
+all: lib cli oracle synth
+
+# workload generators of the tests and bench.py: a tools library, not part of the product ABI
+synth: tools/_build/libpfac_synth.so
+tools/_build/libpfac_synth.so: tools/synth/pfac_synth.cc tools/synth/pfac_synth.h
+	@mkdir -p tools/_build
+	$(HOSTCXX) -O2 -std=c++17 -Wall -Wextra -fPIC -shared -pthread -Itools/synth -o $@ tools/synth/pfac_synth.cc
 
 lib: $(B)/libpfac_b200.so
 cli: $(B)/gphf
@@ -36,5 +42,5 @@ variant:
 	$(NVCC) $(NVFLAGS) -shared -cudart static -o $(B)/libpfac_b200_$(NAME).so $(CUDA_SRCS) $(HOST_SRCS) 2> $(B)/ptxas_$(NAME).log || (cat $(B)/ptxas_$(NAME).log; false)
 
 clean:
-	rm -rf $(B)
+	rm -rf $(B) tools/_build
 	$(MAKE) -C oracle clean

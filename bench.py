@@ -25,6 +25,8 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+import pfac_synth as synth  # noqa: E402  (workload generators: a tools library, not the product)
 
 WORKLOADS = {
     # name: (pattern kind, count, seed, min_len, max_len, text kind, text seed, default bytes, description)
@@ -55,7 +57,7 @@ def make_workload(args, rank):
     import phfpfac_b200 as pf
     pk, cnt, pseed, lo, hi, tk, tseed, nbytes, desc = WORKLOADS[args.workload]
     n = args.bytes or nbytes
-    pats = pf.synth_patterns(pk, cnt, pseed, lo, hi)
+    pats = synth.synth_patterns(pk, cnt, pseed, lo, hi)
     tables = pf.Tables.from_bytes(pats, n_parts=1, width=256)
     return pf, pats, tables, n, tk, tseed, desc
 
@@ -67,9 +69,9 @@ def make_shard(pf, pats, mpl, tk, tseed, n, rank, world, out=None):
     [r*n, (r+1)*n).  Returns (buffer of n + halo bytes, n_valid)."""
     halo = max(mpl - 1, 0)
     buf = np.empty(n + halo, dtype=np.uint8) if out is None else out
-    pf.synth_text(tk, tseed + 1000 * rank, n, patterns=pats, out=buf[:n])
+    synth.synth_text(tk, tseed + 1000 * rank, n, patterns=pats, out=buf[:n])
     if rank + 1 < world and halo:
-        buf[n:] = pf.synth_text(tk, tseed + 1000 * (rank + 1), min(n, 65536), patterns=pats)[:halo]
+        buf[n:] = synth.synth_text(tk, tseed + 1000 * (rank + 1), min(n, 65536), patterns=pats)[:halo]
         return buf, n + halo
     buf[n:] = 0
     return buf, n
@@ -187,7 +189,7 @@ def run_reference(args):
     part = tables.part(0)
     # bounded sample per step so K+W steps end within a few minutes
     cal_n = 4 << 20
-    text = pf.synth_text(tk, tseed, min(n, 256 << 20), patterns=pats)
+    text = synth.synth_text(tk, tseed, min(n, 256 << 20), patterns=pats)
     t0 = time.perf_counter()
     scan_tables_cpu(part, part.idmap, tables.max_pat_len, text[:cal_n], nthreads=cores, count_only=True)
     rate = cal_n / max(time.perf_counter() - t0, 1e-6)

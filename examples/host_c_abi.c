@@ -10,7 +10,6 @@
 #include <stdlib.h>
 
 #include "pfac_b200.h"
-#include "pfac_synth.h"
 
 int main(int argc, char **argv)
 {

@@ -294,21 +294,3 @@ def write_result(path, segments):
             check(lib.pfac_write_records(w, base, rec.ctypes.data if len(rec) else None, len(rec)))
     finally:
         check(lib.pfac_write_end(w))
-
-
-def synth_patterns(kind, count, seed, min_len, max_len):
-    n = lib.pfac_synth_patterns(kind, count, seed, min_len, max_len, None, 0)
-    if n < 0:
-        raise ValueError(f"pfac_synth_patterns failed: {n}")
-    buf = C.create_string_buffer(int(n))
-    lib.pfac_synth_patterns(kind, count, seed, min_len, max_len, buf, n)
-    return buf.raw[:n]
-
-
-def synth_text(kind, seed, n, patterns=None, n_threads=0, out=None):
-    a = np.empty(n, dtype=np.uint8) if out is None else out
-    pb = bytes(patterns) if patterns is not None else None
-    rc = lib.pfac_synth_text(kind, seed, a.ctypes.data if n else None, n, pb, len(pb) if pb else 0, n_threads)
-    if rc:
-        raise ValueError(f"pfac_synth_text failed: {rc}")
-    return a

@@ -11,7 +11,7 @@ ROOT = os.path.dirname(PKG_DIR)
 # PFAC_B200_LIB: another build of the same library (development: kernel variants side by side)
 LIB_PATH = os.environ.get("PFAC_B200_LIB") or os.path.join(PKG_DIR, "_build", "libpfac_b200.so")
 
-# every symbol include/pfac_b200.h and include/pfac_synth.h declare
+# every symbol include/pfac_b200.h declares
 ABI_SYMBOLS = [
     "pfac_last_error", "pfac_abi_version",
     "pfac_tables_build_file", "pfac_tables_build_mem", "pfac_tables_build_file_ext", "pfac_tables_build_mem_ext", "pfac_tables_from_arrays", "pfac_tables_save", "pfac_tables_load", "pfac_tables_destroy",
@@ -24,7 +24,6 @@ ABI_SYMBOLS = [
     "pfac_job_create", "pfac_job_destroy", "pfac_job_run", "pfac_job_n_segments", "pfac_job_segment",
     "pfac_job_last_timing", "pfac_job_plan",
     "pfac_write_begin", "pfac_write_records", "pfac_write_end", "pfac_format_records",
-    "pfac_synth_patterns", "pfac_synth_text",
 ]
 
 PFAC_OK = 0
@@ -104,9 +103,6 @@ def _load():
     lib.pfac_write_end.argtypes = [_vp]
     lib.pfac_format_records.argtypes = [C.c_uint64, _vp, C.c_uint64, _vp, C.c_size_t]
     lib.pfac_format_records.restype = C.c_size_t
-    lib.pfac_synth_patterns.argtypes = [C.c_int, C.c_int, C.c_uint64, C.c_int, C.c_int, _vp, C.c_size_t]
-    lib.pfac_synth_patterns.restype = C.c_longlong
-    lib.pfac_synth_text.argtypes = [C.c_int, C.c_uint64, _vp, C.c_size_t, _vp, C.c_size_t, C.c_int]
     return lib
 
 

@@ -13,7 +13,7 @@ import pytest
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 GOLDEN = os.path.join(HERE, "golden")
-for p in (ROOT, HERE):
+for p in (ROOT, HERE, os.path.join(ROOT, "tools")):
     if p not in sys.path:
         sys.path.insert(0, p)
 
@@ -24,6 +24,8 @@ def pytest_configure(config):
     lib = os.path.join(ROOT, "phfpfac_b200", "_build", "libpfac_b200.so")
     if not os.path.exists(lib):
         subprocess.run(["make", "-s", "-C", ROOT, "lib", "cli"], check=True)
+    if not os.path.exists(os.path.join(ROOT, "tools", "_build", "libpfac_synth.so")):
+        subprocess.run(["make", "-s", "-C", ROOT, "synth"], check=True)
     if not os.path.exists(os.path.join(ROOT, "oracle", "_build", "libpfac_oracle.so")):
         subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "oracle"], check=True)
 

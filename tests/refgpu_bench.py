@@ -10,6 +10,8 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import phfpfac_b200 as pf
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+import pfac_synth as synth
 from bench import WORKLOADS
 
 ap = argparse.ArgumentParser()
@@ -44,13 +46,13 @@ if a.workload in ("config1", "dictionary"):
     n = len(text)
 else:
     pk, cnt, pseed, lo, hi, tk, tseed, nbytes, desc = WORKLOADS[a.workload]
-    pats = pf.synth_patterns(pk, cnt, pseed, lo, hi)
+    pats = synth.synth_patterns(pk, cnt, pseed, lo, hi)
     tables = pf.Tables.from_bytes(pats, 1, 256)
     p = tables.part(0)
     mpl = tables.max_pat_len
     n_max = ((1 << 32) // (4 * mpl)) - 4096
     n = min(a.mib << 20, n_max) if a.mib else n_max
-    text = pf.synth_text(tk, tseed, n, patterns=pats)
+    text = synth.synth_text(tk, tseed, n, patterns=pats)
 
 def pinned(nbytes):
     ptr = C.c_void_p()

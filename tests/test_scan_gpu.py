@@ -9,6 +9,7 @@ import numpy as np
 import pytest
 
 import phfpfac_b200 as pf
+import pfac_synth as synth
 from _oracle import Oracle, render_result
 
 pytestmark = pytest.mark.gpu
@@ -171,7 +172,7 @@ def test_candidate_list_boundaries(n_plants):
     candidates; beyond that (or when a slice has too many stage-1 survivors) whole slices are handed
     over.  Plant 1..3000 matches inside one 16,384-byte tile and across its borders."""
     torch = torch_cuda()
-    pats = pf.synth_patterns(1, 3000, 3, 4, 64)
+    pats = synth.synth_patterns(1, 3000, 3, 4, 64)
     lines = pats.split(b"\n")[:-1]
     n = 100000
     rng = np.random.default_rng(n_plants)
@@ -262,8 +263,8 @@ def test_long_patterns_reference_tile_bound():
     (0, 30000, 5, 8, 32, 0, 6, 3 << 20),       # config 4 shape, reduced (the oracle keeps the reference's O(R^2) sort)
 ])
 def test_baseline_config_shapes_small(kind, count, seed, lo, hi, tkind, tseed, n):
-    pats = pf.synth_patterns(kind, count, seed, lo, hi)
-    text = pf.synth_text(tkind, tseed, n + 1, patterns=pats)[:n]
+    pats = synth.synth_patterns(kind, count, seed, lo, hi)
+    text = synth.synth_text(tkind, tseed, n + 1, patterns=pats)[:n]
     # results do not depend on partition count / width: the oracle uses 8 partitions
     # at width 4096 to keep its quadratic SortRows short; the product uses one automaton at width 256
     pos, ids, got = check_both_paths(pats, text, n_streams=4, chunk_bytes=1 << 20, oracle_parts=8, oracle_width=4096)
@@ -276,9 +277,9 @@ def test_full_size_properties_config2():
     shard-invariance, and exact oracle parity on sampled 1 MiB windows."""
     torch = torch_cuda()
     n = 256 << 20
-    pats = pf.synth_patterns(0, 1000, 1, 8, 32)
+    pats = synth.synth_patterns(0, 1000, 1, 8, 32)
     lines = pats.split(b"\n")[:-1]
-    text = pf.synth_text(0, 2, n + 1, patterns=pats)[:n]
+    text = synth.synth_text(0, 2, n + 1, patterns=pats)[:n]
     t = pf.Tables.from_bytes(pats, 1, 256)
     m = pf.Matcher(t, device=0, n_streams=4)
     d = torch.from_numpy(text).cuda()
@@ -308,9 +309,9 @@ def test_full_size_properties_config4_tables():
     and completeness checked by an independent brute-force (Python set of patterns) on windows."""
     torch = torch_cuda()
     n = 64 << 20
-    pats = pf.synth_patterns(0, 100000, 5, 8, 32)
+    pats = synth.synth_patterns(0, 100000, 5, 8, 32)
     lines = pats.split(b"\n")[:-1]
-    text = pf.synth_text(0, 6, n + 1, patterns=pats)[:n]
+    text = synth.synth_text(0, 6, n + 1, patterns=pats)[:n]
     # a few extra plants of overlapping/prefix-sharing patterns at awkward places
     for i, at in enumerate((0, 16383 - 5, 16384 * 3 - 1, n - len(lines[7]))):
         p = lines[7 * i]
@@ -345,9 +346,9 @@ def test_full_size_properties_config4_tables():
 def test_job_all_gpus_and_segments():
     """pfac_job over every visible GPU: segments concatenate to the oracle's list."""
     torch = torch_cuda()
-    pats = pf.synth_patterns(1, 2000, 3, 4, 64)
+    pats = synth.synth_patterns(1, 2000, 3, 4, 64)
     n = 5 * (1 << 20) + 12345
-    text = pf.synth_text(1, 4, n, patterns=pats)
+    text = synth.synth_text(1, 4, n, patterns=pats)
     o = Oracle(pats, 1, 256)
     pos, ids = o.scan(text)
     t = pf.Tables.from_bytes(pats, 1, 256)
@@ -367,10 +368,10 @@ def test_job_multi_segment_64bit_positions():
     sorted, every record re-verified against its pattern, a match planted across the segment
     border is found, and the rendered lines carry positions > 2^30."""
     torch = torch_cuda()
-    pats = pf.synth_patterns(0, 1000, 1, 8, 32)
+    pats = synth.synth_patterns(0, 1000, 1, 8, 32)
     lines = pats.split(b"\n")[:-1]
     n = (1 << 30) + (3 << 20) + 17
-    text = pf.synth_text(0, 2, n, patterns=pats)
+    text = synth.synth_text(0, 2, n, patterns=pats)
     border = 1 << 30
     p0 = lines[5]
     text[border - 3:border - 3 + len(p0)] = np.frombuffer(p0, dtype=np.uint8)      # straddles the segment border
@@ -398,11 +399,11 @@ def test_shallow_ring(monkeypatch):
     not depend on the depth."""
     torch = torch_cuda()
     monkeypatch.setenv("PFAC_RING_STAGES", "1")
-    pats = pf.synth_patterns(1, 3000, 3, 4, 64)
+    pats = synth.synth_patterns(1, 3000, 3, 4, 64)
     t = pf.Tables.from_bytes(pats, 1, 256)
     m = pf.Matcher(t)
     shallow = m.derived_info()["ring_stages"]
-    text = pf.synth_text(1, 9, 3 << 20, patterns=pats)
+    text = synth.synth_text(1, 9, 3 << 20, patterns=pats)
     got = m.scan_host(text)
     m.close()
     monkeypatch.delenv("PFAC_RING_STAGES")

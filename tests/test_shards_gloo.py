@@ -1,6 +1,8 @@
-"""N>1 host logic on CPU: two gloo ranks cut their shards exactly as bench.py does (own text +
-halo from the next rank), scan them with the oracle and all-gather the results; rank 0 checks the
-concatenation against one scan of the whole input.  No collective is on the data path itself."""
+"""N>1 host logic on CPU: two gloo ranks cut ONE input with the product's own sharding rule
+(pfac_job_plan through pf.plan_shard -- what pfac_job_run and bench.py --scaling strong apply: a
+contiguous range of start positions per rank plus a halo of max_pat_len-1 readable bytes), scan
+their shards with the oracle and all-gather the results; rank 0 checks the concatenation against
+one scan of the whole input.  No collective is on the data path itself."""
 import os
 import socket
 import sys
@@ -15,25 +17,25 @@ ROOT = os.path.dirname(HERE)
 
 
 def _worker(rank, world, port, n, q):
-    sys.path.insert(0, ROOT)
-    sys.path.insert(0, HERE)
-    import bench
+    for p in (ROOT, HERE, os.path.join(ROOT, "tools")):
+        sys.path.insert(0, p)
+    import pfac_synth as synth
     import phfpfac_b200 as pf
     from _oracle import Oracle
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    pats = pf.synth_patterns(1, 400, 3, 4, 64) + b"GET /\nHost: www.\n"
+    pats = synth.synth_patterns(1, 400, 3, 4, 64) + b"GET /\nHost: www.\n"
     o = Oracle(pats, 1, 256)
     mpl = o.max_pat_len
-    buf, n_valid = bench.make_shard(pf, pats, mpl, 1, 4, n, rank, world)
-    # force a match that straddles the rank boundary: the tail of rank 0 + the head of rank 1
+    whole = synth.synth_text(1, 4, n, patterns=pats)          # every rank generates the same seeded input
+    start, n_starts, n_valid = pf.plan_shard(n, world, mpl, rank)
+    # force a match that straddles the rank boundary: it starts in rank 0's range, ends in rank 1's
+    b0 = pf.plan_shard(n, world, mpl, 0)[1]
     straddle = b"Host: www."
-    if rank == 0:
-        buf[n - 4:n] = np.frombuffer(straddle[:4], dtype=np.uint8)
-        buf[n:n + 6] = np.frombuffer(straddle[4:], dtype=np.uint8)
-    pos, ids = o.scan(buf[:n_valid])
-    keep = pos < n
-    pos, ids = pos[keep] + rank * n, ids[keep]
+    whole[b0 - 4:b0 + 6] = np.frombuffer(straddle, dtype=np.uint8)
+    pos, ids = o.scan(whole[start:start + n_valid])
+    keep = pos < n_starts                                       # a shard reports the matches that START in it
+    pos, ids = pos[keep] + start, ids[keep]
     cnt = torch.tensor([len(pos)], dtype=torch.int64)
     counts = [torch.zeros(1, dtype=torch.int64) for _ in range(world)]
     dist.all_gather(counts, cnt)
@@ -43,15 +45,17 @@ def _worker(rank, world, port, n, q):
     pad[1, :len(ids)] = torch.from_numpy(ids.astype(np.int64))
     gathered = [torch.zeros_like(pad) for _ in range(world)]
     dist.all_gather(gathered, pad)
-    ok = True
     if rank == 0:
-        whole = np.concatenate([bench.make_shard(pf, pats, mpl, 1, 4, n, r, world)[0][:n] for r in range(world)])
-        whole[n - 4:n + 6] = np.frombuffer(straddle, dtype=np.uint8)
         wpos, wids = o.scan(whole)
         gp = np.concatenate([g[0, :int(c.item())].numpy() for g, c in zip(gathered, counts)])
         gi = np.concatenate([g[1, :int(c.item())].numpy() for g, c in zip(gathered, counts)])
         ok = bool(np.array_equal(gp, wpos) and np.array_equal(gi, wids.astype(np.int64)))
-        ok = ok and bool(((wpos == n - 4)).any())
+        ok = ok and bool((wpos == b0 - 4).any())
+        # the plan itself: the shards tile [0, n) and every halo is max_pat_len-1 bytes (clipped to n)
+        plan = [pf.plan_shard(n, world, mpl, r) for r in range(world)]
+        ok = ok and plan[0][0] == 0 and all(plan[r][0] + plan[r][1] == plan[r + 1][0] for r in range(world - 1))
+        ok = ok and plan[-1][0] + plan[-1][1] == n
+        ok = ok and all(p[2] == min(p[1] + mpl - 1, n - p[0]) for p in plan)
         q.put((ok, len(wpos)))
     dist.barrier()
     dist.destroy_process_group()
@@ -64,7 +68,7 @@ def test_two_rank_sharding_gloo():
     s.close()
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, 3 * 65536 + 123, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, 5 * 65536 + 123, q)) for r in range(2)]
     for p in procs:
         p.start()
     ok, n = q.get(timeout=240)

@@ -7,6 +7,7 @@ import numpy as np
 import pytest
 
 import phfpfac_b200 as pf
+import pfac_synth as synth
 from _oracle import Oracle, RefBuild, ref_available
 from conftest import digest, parse_key
 
@@ -115,7 +116,7 @@ def test_error_behaviour(tmp_path):
 def test_large_set_beyond_reference_limits():
     """100k patterns at width 256 exceed ROW_MAX (phf.c:7): the builder has dynamic limits; the PHF
     must still be a perfect hash of the trie (every edge found, nothing else)."""
-    blob = pf.synth_patterns(0, 30000, 5, 8, 32)
+    blob = synth.synth_patterns(0, 30000, 5, 8, 32)
     t = pf.Tables.from_bytes(blob, n_parts=1, width=256)
     p = t.part(0)
     assert p.n_final == 30000 and p.n_r == p.state_num * 256 // 256 + 1
@@ -155,7 +156,7 @@ def test_derived_device_tables_selfcheck(fixtures, case):
     """The kernel's shared-memory accelerators (pfac_derive.cc), built and verified on the host:
     T1 exact over 2-byte prefixes, T1s/T2 supersets, hot rows == master_kernel.cu:52-64 lookups."""
     blob = {"short": b"a\nab\nabc\nabcd\nb\nbcdef\nxyzxyzxyz\n",
-            "config3": pf.synth_patterns(1, 3000, 3, 4, 64),
+            "config3": synth.synth_patterns(1, 3000, 3, 4, 64),
             "binary": b"".join(bytes([i, (i * 7) % 256 or 1, 200, 201, 202]).replace(b"\n", b"\x0b") + b"\n" for i in range(256) if i != 10),
             }.get(case) or fixtures[case]
     for width in (256, 64, 4096):
@@ -251,7 +252,7 @@ def test_escape_front_end_fuzz(tmp_path):
 def test_table_cache_roundtrip(tmp_path, fixtures):
     """pfac_tables_save / pfac_tables_load: every canonical array of every partition comes back bit
     for bit, the derived filter tables are the same, and damaged files are refused."""
-    for blob, parts, width in ((fixtures["dictionary"], 4, 64), (pf.synth_patterns(1, 3000, 3, 4, 64), 1, 256),
+    for blob, parts, width in ((fixtures["dictionary"], 4, 64), (synth.synth_patterns(1, 3000, 3, 4, 64), 1, 256),
                                (b"a\n", 1, 4096)):
         t = pf.Tables.from_bytes(blob, parts, width)
         f = tmp_path / "cache.bin"

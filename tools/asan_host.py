@@ -3,7 +3,7 @@
 AddressSanitizer + UBSan.  No GPU, no CUDA: the four host translation units are built on their own.
 
     g++ -std=c++17 -O1 -g -fsanitize=address,undefined -fPIC -shared -Iinclude -Iphfpfac_b200/csrc -pthread \
-        -o /tmp/libpfac_host_asan.so phfpfac_b200/csrc/pfac_{tables,writer,synth,derive}.cc
+        -o /tmp/libpfac_host_asan.so phfpfac_b200/csrc/pfac_{tables,writer,derive}.cc tools/synth/pfac_synth.cc
     LD_PRELOAD=$(gcc -print-file-name=libasan.so):$(gcc -print-file-name=libubsan.so) ASAN_OPTIONS=detect_leaks=0 \
         python tools/asan_host.py /tmp/libpfac_host_asan.so
 Development tool; last run clean (round 1)."""

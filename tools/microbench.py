@@ -6,6 +6,8 @@ import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import phfpfac_b200 as pf
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+import pfac_synth as synth
 from bench import WORKLOADS
 
 ap = argparse.ArgumentParser()
@@ -14,10 +16,10 @@ ap.add_argument("--sizes", default="32,256,1024")
 ap.add_argument("--iters", type=int, default=5)
 a = ap.parse_args()
 pk, cnt, pseed, lo, hi, tk, tseed, nbytes, desc = WORKLOADS[a.workload]
-pats = pf.synth_patterns(pk, cnt, pseed, lo, hi)
+pats = synth.synth_patterns(pk, cnt, pseed, lo, hi)
 tables = pf.Tables.from_bytes(pats)
 sizes = [int(s) << 20 for s in a.sizes.split(",")]
-text = pf.synth_text(tk, tseed, max(sizes), patterns=pats)
+text = synth.synth_text(tk, tseed, max(sizes), patterns=pats)
 d = torch.from_numpy(text).cuda()
 m = pf.Matcher(tables, device=0)
 print("derived:", m.derived_info(), flush=True)

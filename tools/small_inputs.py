@@ -5,11 +5,13 @@ import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch, numpy as np
 import phfpfac_b200 as pf
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+import pfac_synth as synth
 from bench import WORKLOADS
 pk, cnt, pseed, lo, hi, tk, tseed, nbytes, desc = WORKLOADS["config3"]
-pats = pf.synth_patterns(pk, cnt, pseed, lo, hi)
+pats = synth.synth_patterns(pk, cnt, pseed, lo, hi)
 tables = pf.Tables.from_bytes(pats)
-text = pf.synth_text(tk, tseed, 64 << 20, patterns=pats)
+text = synth.synth_text(tk, tseed, 64 << 20, patterns=pats)
 d = torch.from_numpy(text).cuda()
 m = pf.Matcher(tables, device=0)
 m.set_timing(True)

@@ -6,6 +6,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import torch
 import phfpfac_b200 as pf
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+import pfac_synth as synth
 from bench import WORKLOADS
 
 ap = argparse.ArgumentParser()
@@ -14,12 +16,12 @@ ap.add_argument("--streams", default="1,2,4,8")
 ap.add_argument("--workload", default="config3")
 a = ap.parse_args()
 pk, cnt, pseed, lo, hi, tk, tseed, nbytes, desc = WORKLOADS[a.workload]
-pats = pf.synth_patterns(pk, cnt, pseed, lo, hi)
+pats = synth.synth_patterns(pk, cnt, pseed, lo, hi)
 tables = pf.Tables.from_bytes(pats)
 sizes = [int(x) << 20 for x in a.mib.split(",")]
 nmax = max(sizes)
 h_text = torch.empty(nmax, dtype=torch.uint8, pin_memory=True)
-pf.synth_text(tk, tseed, nmax, patterns=pats, out=h_text.numpy())
+synth.synth_text(tk, tseed, nmax, patterns=pats, out=h_text.numpy())
 d_text = h_text.cuda()
 cap = max(nmax // 8, 1 << 16)
 d_out = torch.empty((cap, 2), dtype=torch.int32, device="cuda")

@@ -1,7 +1,8 @@
 /*
  * pfac_synth.h -- seeded synthetic pattern sets and texts of BASELINE.json's configs
- * (SURVEY.md section 8(d)).  Workload generation for tests and bench.py; the reference ships
- * only fixed files (regex_GPU_PHF/bytefile/, xaa..xad), no generator.
+ * (SURVEY.md section 8(d)).  Workload generation for tests and bench.py -- a tools library
+ * (tools/_build/libpfac_synth.so), NOT part of the product ABI; the reference ships only fixed files
+ * (regex_GPU_PHF/bytefile/, xaa..xad), no generator.
  */
 #ifndef PFAC_SYNTH_H
 #define PFAC_SYNTH_H
