@@ -705,6 +705,67 @@ long long oracle_scan_tables_omp(const int *s0, const int *r, const int *HT, con
     return total;
 }
 
+/* The same scan in ONE pass over the input (the timed CPU legs of bench.py): every thread walks its
+ * position range once, appending its records to a buffer of its own; the buffers are then copied,
+ * in range order, into pos_out / id_out (up to cap records).  Returns the total number of matches. */
+long long oracle_scan_tables_omp_1pass(const int *s0, const int *r, const int *HT, const int *val,
+                                       int ht_size, int width, int n_final, const int *idmap,
+                                       int max_pat_len, int ref_tile_bound,
+                                       const unsigned char *input, long long n, int nthreads,
+                                       int64_t *pos_out, int32_t *id_out, long long cap)
+{
+    if (n <= 0 || max_pat_len <= 0) return 0;
+    otab t = { s0, r, HT, val, ht_size, log2_shift(width), n_final };
+    if (nthreads < 1) nthreads = 1;
+    long long *counts = (long long *)calloc((size_t)nthreads + 1, sizeof(long long));
+    int64_t **lpos = (int64_t **)calloc((size_t)nthreads, sizeof(int64_t *));
+    int32_t **lid = (int32_t **)calloc((size_t)nthreads, sizeof(int32_t *));
+    long long chunk = (n + nthreads - 1) / nthreads;
+#ifdef _OPENMP
+#pragma omp parallel for num_threads(nthreads) schedule(static, 1)
+#endif
+    for (int k = 0; k < nthreads; k++) {
+        long long lo = (long long)k * chunk, hi = lo + chunk;
+        if (hi > n) hi = n;
+        int *tmp = (int *)malloc((size_t)(max_pat_len + 1) * sizeof(int));
+        long long c = 0, room = 4096;
+        int64_t *bp = (int64_t *)malloc((size_t)room * sizeof(int64_t));
+        int32_t *bi = (int32_t *)malloc((size_t)room * sizeof(int32_t));
+        for (long long i = lo; i < hi; i++) {
+            long long b = ref_tile_bound ? walk_bound(i, n) : n;
+            int m = walk_start(&t, input, i, b, tmp, max_pat_len);
+            if (c + m > room) {
+                while (c + m > room) room *= 2;
+                bp = (int64_t *)realloc(bp, (size_t)room * sizeof(int64_t));
+                bi = (int32_t *)realloc(bi, (size_t)room * sizeof(int32_t));
+            }
+            for (int q = 0; q < m; q++) { bp[c + q] = i; bi[c + q] = idmap[tmp[q]]; }
+            c += m;
+        }
+        counts[k] = c;
+        lpos[k] = bp;
+        lid[k] = bi;
+        free(tmp);
+    }
+    long long acc = 0;
+    for (int k = 0; k < nthreads; k++) { long long c = counts[k]; counts[k] = acc; acc += c; }
+#ifdef _OPENMP
+#pragma omp parallel for num_threads(nthreads) schedule(static, 1)
+#endif
+    for (int k = 0; k < nthreads; k++) {
+        long long base = counts[k], c = (k + 1 < nthreads ? counts[k + 1] : acc) - base;
+        if (pos_out && base < cap) {
+            long long m = c < cap - base ? c : cap - base;
+            memcpy(pos_out + base, lpos[k], (size_t)m * sizeof(int64_t));
+            memcpy(id_out + base, lid[k], (size_t)m * sizeof(int32_t));
+        }
+        free(lpos[k]);
+        free(lid[k]);
+    }
+    free(counts); free(lpos); free(lid);
+    return acc;
+}
+
 int oracle_max_threads(void)
 {
 #ifdef _OPENMP

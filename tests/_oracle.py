@@ -58,6 +58,8 @@ def _load_oracle():
     lib.oracle_scan_tables_omp.argtypes = [
         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p,
         C.c_int, C.c_int, C.c_void_p, C.c_longlong, C.c_int, C.c_void_p, C.c_void_p, C.c_longlong]
+    lib.oracle_scan_tables_omp_1pass.restype = C.c_longlong
+    lib.oracle_scan_tables_omp_1pass.argtypes = lib.oracle_scan_tables_omp.argtypes
     lib.oracle_max_threads.restype = C.c_int
     lib.oracle_write_result.restype = C.c_int
     lib.oracle_write_result.argtypes = [C.c_char_p, C.c_void_p, C.c_void_p, C.c_longlong]
@@ -174,6 +176,28 @@ def scan_tables_cpu(t, idmap, max_pat_len, data, nthreads=1, ref_tile_bound=True
     if cnt:
         lib.oracle_scan_tables_omp(*args, pos.ctypes.data, ids.ctypes.data, cnt)
     return pos, ids
+
+
+def scan_tables_cpu_1pass(t, idmap, max_pat_len, data, nthreads=1, ref_tile_bound=True, cap=None):
+    """oracle_scan_tables_omp_1pass: the input is walked ONCE and the records written (the timed CPU
+    legs of bench.py).  cap = record capacity (default: one per 8 input bytes, grown if exceeded)."""
+    lib = oracle_lib()
+    buf = data if isinstance(data, np.ndarray) else np.frombuffer(bytes(data), dtype=np.uint8)
+    s0 = np.ascontiguousarray(t.s0, dtype=np.int32)
+    r = np.ascontiguousarray(t.r, dtype=np.int32)
+    HT = np.ascontiguousarray(t.HT, dtype=np.int32)
+    val = np.ascontiguousarray(t.val, dtype=np.int32)
+    im = np.ascontiguousarray(idmap, dtype=np.int32)
+    args = [s0.ctypes.data, r.ctypes.data, HT.ctypes.data, val.ctypes.data, t.ht_size, t.width,
+            t.n_final, im.ctypes.data, max_pat_len, int(ref_tile_bound), buf.ctypes.data, len(buf), nthreads]
+    cap = cap or max(len(buf) // 8, 65536)
+    while True:
+        pos = np.empty(cap, dtype=np.int64)
+        ids = np.empty(cap, dtype=np.int32)
+        cnt = lib.oracle_scan_tables_omp_1pass(*args, pos.ctypes.data, ids.ctypes.data, cap)
+        if cnt <= cap:
+            return pos[:cnt], ids[:cnt]
+        cap = cnt
 
 
 def render_result(pos, ids):

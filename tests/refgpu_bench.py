@@ -9,10 +9,12 @@ import argparse, ctypes as C, json, os, sys, time
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-import phfpfac_b200 as pf
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
 import pfac_synth as synth
 from bench import WORKLOADS
+from _oracle import Oracle
+import torch
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--workload", default="config3", help="a synthetic workload of bench.py, or a reference fixture: "
@@ -35,7 +37,7 @@ if a.workload in ("config1", "dictionary"):
     pats = fx["experimentpattern" if a.workload == "config1" else "dictionary"]
     desc = ("config1: the reference's experimentpattern over its 1M text" if a.workload == "config1"
             else "dictionary: the reference's xaa..xad (7,989 words) over its 1M text")
-    tables = pf.Tables.from_bytes(pats, 1, 256)
+    tables = Oracle(pats, 1, 256)       # the oracle's restatement of CreateTable + FFDM (bit-identical to the reference's)
     p = tables.part(0)
     mpl = tables.max_pat_len
     n_max = ((1 << 32) // (4 * mpl)) - 4096
@@ -47,17 +49,18 @@ if a.workload in ("config1", "dictionary"):
 else:
     pk, cnt, pseed, lo, hi, tk, tseed, nbytes, desc = WORKLOADS[a.workload]
     pats = synth.synth_patterns(pk, cnt, pseed, lo, hi)
-    tables = pf.Tables.from_bytes(pats, 1, 256)
+    tables = Oracle(pats, 1, 256)
     p = tables.part(0)
     mpl = tables.max_pat_len
     n_max = ((1 << 32) // (4 * mpl)) - 4096
     n = min(a.mib << 20, n_max) if a.mib else n_max
     text = synth.synth_text(tk, tseed, n, patterns=pats)
 
-def pinned(nbytes):
-    ptr = C.c_void_p()
-    pf.check(pf.lib.pfac_host_alloc(C.byref(ptr), nbytes))
-    return ptr
+_keep = []
+def pinned(nbytes):      # pinned host memory as main.cc:147,161 (cudaHostAlloc), through torch
+    t = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+    _keep.append(t)
+    return C.c_void_p(t.data_ptr())
 
 h_in = pinned(n + 4096)
 C.memmove(h_in, text.ctypes.data, n)
@@ -80,7 +83,8 @@ if not a.no_compare:
     states = res[rows, cols]
     ids = np.asarray(p.idmap)[states]
     sift_s = time.perf_counter() - t0
-    m = pf.Matcher(tables)
+    import phfpfac_b200 as pf            # the product, only for the cross-check
+    m = pf.Matcher(pf.Tables.from_bytes(pats, 1, 256))
     ours = m.scan_host(text)
     same = bool(len(ours) == len(rows) and np.array_equal(ours["pos"].astype(np.int64), rows)
                 and np.array_equal(ours["id"].astype(np.int64), ids.astype(np.int64)))

@@ -88,6 +88,12 @@ def test_scan_tables_cpu_equals_partition_merge(fixtures):
         pos2, ids2 = scan_tables_cpu(p, p.idmap, o.max_pat_len, data, nthreads=nt)
         assert np.array_equal(pos, pos2) and np.array_equal(ids, ids2)
     assert scan_tables_cpu(p, p.idmap, o.max_pat_len, data, nthreads=2, count_only=True) == len(pos)
+    # the single-pass variant timed by bench.py (thread-local buffers, concatenated in range order),
+    # also when the first capacity guess is too small
+    from _oracle import scan_tables_cpu_1pass
+    for nt, cap in ((1, None), (4, None), (3, 1000)):
+        pos3, ids3 = scan_tables_cpu_1pass(p, p.idmap, o.max_pat_len, data, nthreads=nt, cap=cap)
+        assert np.array_equal(pos, pos3) and np.array_equal(ids, ids3)
 
 
 def test_oracle_error_cases():
