@@ -376,6 +376,28 @@ __device__ __forceinline__ void add_candidate(uint32_t *n, uint16_t *list, uint3
     __threadfence_block();   // rare path: the list entry is visible before this warp reports the slot finished
 }
 
+// Read-only loads of the PHF tables with an L2 evict-last policy: the tables are a megabyte or a few
+// that every walk chases through dependent loads, next to a gigabyte of input streamed with
+// evict-first -- they are to stay in the 126 MB L2.
+__device__ __forceinline__ uint64_t policy_evict_last()
+{
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ int32_t ldg_keep(const int32_t *ptr)
+{
+    int32_t v;
+    asm volatile("ld.global.nc.L2::cache_hint.b32 %0, [%1], %2;" : "=r"(v) : "l"(ptr), "l"(policy_evict_last()));
+    return v;
+}
+__device__ __forceinline__ int2 ldg_keep(const int2 *ptr)
+{
+    int2 v;
+    asm volatile("ld.global.nc.L2::cache_hint.v2.b32 {%0, %1}, [%2], %3;" : "=r"(v.x), "=r"(v.y) : "l"(ptr), "l"(policy_evict_last()));
+    return v;
+}
+
 // ---------------------------------------------------------------------------------------------
 // The plain PFAC walk of SUBSEG_MATCH (master_kernel.cu:37-74) over the canonical PHF arrays: used
 // for the starts that survived every filter of the detector (by the warp that finishes their tile,
@@ -386,22 +408,22 @@ __device__ __forceinline__ int32_t phf_next(const EmitParams &p, int32_t state, 
 {
     const int32_t key = (state << 8) + (int32_t)byte;                // :52
     const int32_t row = key >> p.width_bit;                          // :53
-    const int32_t idx = __ldg(&p.r[row]) + (key & ((1 << p.width_bit) - 1));   // :54-55
+    const int32_t idx = ldg_keep(&p.r[row]) + (key & ((1 << p.width_bit) - 1));   // :54-55
     if (idx < 0 || idx >= p.ht_size) return -1;                      // :56-57
-    const int2 hv = __ldg(&p.htval[idx]);                            // :59-61
+    const int2 hv = ldg_keep(&p.htval[idx]);                            // :59-61
     return hv.x == row ? hv.y : -1;
 }
 
 template <bool WRITE>
 __device__ __forceinline__ uint32_t emit_walk(const EmitParams &p, uint32_t a, uint32_t lim_a, unsigned long long o)
 {
-    int32_t state = __ldg(&p.s0[p.in_al[a]]);                        // :41
+    int32_t state = ldg_keep(&p.s0[p.in_al[a]]);                        // :41
     if (state < 0) return 0;                                         // :43
     uint32_t n = 0, q = a + 1;
     const uint32_t rec_pos = a - p.mis + p.pos_bias;
     while (true) {
         if (state < p.n_final) {                                     // :44-47, :67-70
-            if (WRITE && o + n < p.scratch_cap) p.scratch[o + n] = make_uint2(rec_pos, (uint32_t)__ldg(&p.idmap[state]));
+            if (WRITE && o + n < p.scratch_cap) p.scratch[o + n] = make_uint2(rec_pos, (uint32_t)ldg_keep(&p.idmap[state]));
             n++;
         }
         if (q >= lim_a) break;                                       // :50
@@ -418,7 +440,7 @@ __device__ __forceinline__ uint32_t emit_walk(const EmitParams &p, uint32_t a, u
 constexpr int kWalkKeep = 4;
 __device__ __forceinline__ uint32_t walk_collect(const EmitParams &p, uint32_t a, uint32_t lim_a, int32_t (&st)[kWalkKeep])
 {
-    int32_t state = __ldg(&p.s0[p.in_al[a]]);                        // :41
+    int32_t state = ldg_keep(&p.s0[p.in_al[a]]);                        // :41
     if (state < 0) return 0;                                         // :43
     uint32_t n = 0, q = a + 1;
     while (true) {
@@ -445,7 +467,7 @@ __device__ __forceinline__ void write_collected(const EmitParams &p, uint32_t a,
     const uint32_t rec_pos = a - p.mis + p.pos_bias;
 #pragma unroll
     for (int i = 0; i < kWalkKeep; i++)
-        if ((uint32_t)i < n && o + i < p.scratch_cap) p.scratch[o + i] = make_uint2(rec_pos, (uint32_t)__ldg(&p.idmap[st[i]]));
+        if ((uint32_t)i < n && o + i < p.scratch_cap) p.scratch[o + i] = make_uint2(rec_pos, (uint32_t)ldg_keep(&p.idmap[st[i]]));
 }
 
 
@@ -555,8 +577,9 @@ __device__ __forceinline__ void detector_init(const ScanParams &p, const CtlView
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         mbar_expect_tx(c.imgbar, p.image_bytes);
         const uint8_t *src = reinterpret_cast<const uint8_t *>(p.image);
+        const uint64_t keep = policy_evict_last();   // every CTA of every scan reads it: it is to stay in L2
         for (uint32_t o = 0; o < p.image_bytes; o += 32768u)
-            bulk_g2s_plain(smem + o, src + o, min(32768u, p.image_bytes - o), c.imgbar);
+            bulk_g2s(smem + o, src + o, min(32768u, p.image_bytes - o), c.imgbar, keep);
     }
     __syncthreads();
 }
@@ -657,7 +680,9 @@ __device__ __forceinline__ void finish_slot(const ScanParams &p, const CtlView &
     // The walks of the tile's candidates, straight away, by this warp -- AFTER the stage went back to
     // the producer (the walk reads the input and the PHF from global memory: microseconds of dependent
     // loads that must stall one warp, not the ring).
+#ifndef PFAC_EXP_NO_EMIT   // (timing experiment: no walks, no records)
     if (flags && nc != kCandOverflow) emit_tile(p.emit, tile, my_cand, lane);
+#endif
 }
 
 // A consumer warp takes the next slot of the CTA's tile sequence and waits for its tile.  Returns
@@ -1155,7 +1180,7 @@ __global__ void __launch_bounds__(kDenseThreads, 1) pfac_dense_kernel(const Dens
         int32_t state = s_s0[s_text[t0]];                             // :41
         for (uint32_t q = t0 + 1; state >= 0; q++) {
             if (state < p.n_final) {                                  // :44-47, :67-70
-                if (o + n < dst_cap) dst[o + n] = make_uint2(rec_pos, (uint32_t)__ldg(&p.idmap[state]));
+                if (o + n < dst_cap) dst[o + n] = make_uint2(rec_pos, (uint32_t)ldg_keep(&p.idmap[state]));
                 n++;
             }
             if (q >= lim_t) break;                                    // :50
@@ -1404,7 +1429,7 @@ __global__ void __launch_bounds__(kDenseThreads, 1) pfac_dense_kernel(const Dens
                     const uint32_t rec_pos = a - p.mis + p.pos_bias;
                     for (uint32_t k = 0; k < n; k++) {
                         const int32_t st = fin16 ? (int32_t)s_fin16[k * kTile + t0] : s_fin[k * kTile + t0];
-                        if (o + k < dst_cap) dst[o + k] = make_uint2(rec_pos, (uint32_t)__ldg(&p.idmap[st]));
+                        if (o + k < dst_cap) dst[o + k] = make_uint2(rec_pos, (uint32_t)ldg_keep(&p.idmap[st]));
                     }
                 } else {
                     walk_write(t0, a, limit_t(a, a0), o);

@@ -11,14 +11,14 @@ from bench import WORKLOADS
 pk, cnt, pseed, lo, hi, tk, tseed, nbytes, desc = WORKLOADS["config3"]
 pats = synth.synth_patterns(pk, cnt, pseed, lo, hi)
 tables = pf.Tables.from_bytes(pats)
-text = synth.synth_text(tk, tseed, 64 << 20, patterns=pats)
+text = synth.synth_text(tk, tseed, 128 << 20, patterns=pats)
 d = torch.from_numpy(text).cuda()
 m = pf.Matcher(tables, device=0)
 m.set_timing(True)
 st = torch.cuda.Stream(); torch.cuda.set_stream(st)
 cap = 1 << 20
 out = torch.empty((cap, 2), dtype=torch.int32, device="cuda"); cntd = torch.zeros(1, dtype=torch.int64, device="cuda")
-for mib in (1, 4, 16, 64):
+for mib in (1, 4, 16, 64, 128):
     n = mib << 20
     for _ in range(3):
         m.scan_device_raw(d.data_ptr(), n, n, 0, out.data_ptr(), cap, cntd.data_ptr(), st.cuda_stream)
