@@ -85,6 +85,11 @@ int pfac_tables_from_arrays(const int32_t *s0, const int32_t *r, int32_t n_r, co
                             pfac_tables **out);
 /* On-disk cache of the canonical arrays of every partition (checksummed; the reference rebuilds its
  * tables on every run, main.cc:100-126).  A loaded set scans exactly like the set that was saved. */
+/* What a table set was built from: a 64-bit hash of the pattern file image and the front-end flags
+ * (0 for sets wrapped from arrays).  It travels with pfac_tables_save/_load, so that a cache can be
+ * checked against the pattern file it is about to stand in for (pfac_pattern_file_hash). */
+uint64_t pfac_tables_source_hash(const pfac_tables *t);
+int pfac_pattern_file_hash(const char *pattern_file, unsigned flags, uint64_t *hash);
 int pfac_tables_save(const pfac_tables *t, const char *path);
 int pfac_tables_load(const char *path, pfac_tables **out);
 void pfac_tables_destroy(pfac_tables *t);

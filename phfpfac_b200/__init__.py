@@ -92,6 +92,10 @@ class Tables:
     def save(self, path):
         check(lib.pfac_tables_save(self._h, str(path).encode()))
 
+    def source_hash(self):
+        """Hash of the pattern file image + reader flags the set was built from (0: wrapped from arrays)."""
+        return int(lib.pfac_tables_source_hash(self._h))
+
     def part(self, g=0):
         return PartView(self, g)
 
@@ -122,6 +126,12 @@ class Tables:
 
     def __del__(self):
         self.close()
+
+
+def pattern_file_hash(path, escapes=False):
+    h = C.c_uint64(0)
+    check(lib.pfac_pattern_file_hash(str(path).encode(), 1 if escapes else 0, C.byref(h)))
+    return h.value
 
 
 def device_count():
@@ -185,8 +195,12 @@ class Matcher:
         while True:
             out = torch.empty((max(cap, 1), 2), dtype=torch.int32, device=t_in.device)
             cnt = C.c_uint64(0)
+            # on torch's current stream: ordered after whatever produced t_in (and allocated `out`) there
+            stream = torch.cuda.current_stream(t_in.device).cuda_stream
+            if stream == 0:     # the legacy default stream: 0 means "the library's own stream" to the C ABI
+                torch.cuda.current_stream(t_in.device).synchronize()
             rc = lib.pfac_scan_device_sync(self._h, t_in.data_ptr() + offset, n_starts, n_valid, base_pos,
-                                           out.data_ptr(), cap, C.byref(cnt), None)
+                                           out.data_ptr(), cap, C.byref(cnt), stream or None)
             if rc == PFAC_ERR_OUTPUT_FULL:
                 cap = cnt.value
                 continue

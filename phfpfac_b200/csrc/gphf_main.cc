@@ -48,8 +48,8 @@ int main(int argc, char **argv)
     pfac_tables *tables = nullptr;
     // GPHF_ESCAPES=1: read the patterns through the reference's (unused) escape reader, read_pattern_ext
     const unsigned pflags = getenv("GPHF_ESCAPES") && atoi(getenv("GPHF_ESCAPES")) ? PFAC_PATTERNS_ESCAPES : 0u;
-    // GPHF_TABLE_CACHE=<file>: load the tables from it if it exists (the caller vouches that it belongs
-    // to this pattern file and width), else build them and write it
+    // GPHF_TABLE_CACHE=<file>: load the tables from it if it exists and was built from this pattern file
+    // (hash of the file image + escape flag in the cache header) at this width, else build them and write it
     const char *cache = getenv("GPHF_TABLE_CACHE");
     bool from_cache = false;
     if (cache && *cache) {
@@ -57,12 +57,17 @@ int main(int argc, char **argv)
         if (probe) {
             fclose(probe);
             if (pfac_tables_load(cache, &tables)) return fail("load the table cache");
-            if (pfac_tables_width(tables) != width || pfac_tables_n_parts(tables) != 1) {
-                fprintf(stderr, "%s holds tables of width %d in %d partition(s), not width %d\n", cache,
-                        pfac_tables_width(tables), pfac_tables_n_parts(tables), width);
-                return 1;
+            uint64_t want = 0;
+            if (pfac_pattern_file_hash(argv[1], pflags, &want)) return fail("read the pattern file");
+            if (pfac_tables_width(tables) != width || pfac_tables_n_parts(tables) != 1 ||
+                pfac_tables_source_hash(tables) != want) {
+                // built from another pattern file, width or escape setting: rebuild (and rewrite the cache)
+                fprintf(stderr, "%s does not belong to this pattern file / width: rebuilding the tables\n", cache);
+                pfac_tables_destroy(tables);
+                tables = nullptr;
+            } else {
+                from_cache = true;
             }
-            from_cache = true;
         }
     }
     if (!from_cache) {

@@ -746,6 +746,17 @@ int pfac_scan_host(pfac_ctx *ctx, const void *h_in, uint64_t n_starts, uint64_t 
             st.d_out_cap = need_out;
         }
     }
+    // Whatever path leaves this function: no copy from h_in or into h_out may still be in flight (the
+    // caller is free to release its buffers on an error).
+    struct DrainOnExit {
+        pfac_ctx *ctx;
+        int S;
+        ~DrainOnExit()
+        {
+            for (int s = 0; s < S; s++)
+                if (ctx->stages[(size_t)s].stream) cudaStreamSynchronize(ctx->stages[(size_t)s].stream);
+        }
+    } drain{ctx, S};
     uint64_t h2d = 0, d2h = 0, launches = 0, tiles_total = 0, ctas_max = 0;
     auto enqueue = [&](uint64_t c) -> int {
         Stage &st = ctx->stages[(size_t)(c % (uint64_t)S)];
@@ -786,6 +797,8 @@ int pfac_scan_host(pfac_ctx *ctx, const void *h_in, uint64_t n_starts, uint64_t 
             st.d_out_cap = (size_t)m;
             if ((rc = enqueue(c)) != PFAC_OK) return rc;
             CU_TRY(cudaEventSynchronize(st.done));
+            if (st.slot.h_result->error_flag)
+                return set_error(PFAC_ERR_INTERNAL, "device watchdog tripped (code %u)", st.slot.h_result->error_flag);
             m = st.slot.h_result->count;
         }
         // records already carry positions relative to h_in[0] (pos_bias = sub-chunk offset)

@@ -45,4 +45,5 @@ struct pfac_tables {
     int max_pat_len = 0;
     int width = 256;
     std::vector<pfac::Partition> parts;
+    uint64_t source_hash = 0;   // FNV-1a of the pattern file image + flags the set was built from (0: unknown)
 };

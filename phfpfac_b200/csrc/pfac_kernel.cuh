@@ -152,7 +152,26 @@ constexpr int kCtrlBytes = 1664;          // CtlView below
 constexpr int kMaxParts = 1024;           // tile ranges of the ordering pass (one per finalize CTA)
 constexpr int kCandPerTile = 32;          // candidate starts the detector hands over per tile (more: whole slices)
 constexpr unsigned kCandOverflow = 0xFFFFFFFFu;
-constexpr unsigned kSpinLimit = 1u << 21;
+// Device-side watchdog of the waits (never expected to trip): a TIME limit on the GPU's global timer, not a
+// spin count -- under MPS / time slicing / a profiler's replay a correct scan may poll any number of times.
+constexpr unsigned long long kWatchdogNs = 20ull * 1000ull * 1000ull * 1000ull;
+__device__ __forceinline__ unsigned long long gtime_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+struct Watchdog {   // checks the clock every 1024 polls only
+    unsigned spins = 0;
+    unsigned long long t0 = 0;
+    __device__ __forceinline__ bool expired()
+    {
+        if ((++spins & 1023u) != 0u) return false;
+        const unsigned long long now = gtime_ns();
+        if (!t0) { t0 = now; return false; }
+        return now - t0 > kWatchdogNs;
+    }
+};
 #ifndef PFAC_WAIT_NS
 #define PFAC_WAIT_NS 1000
 #endif
@@ -230,9 +249,9 @@ __device__ __forceinline__ bool mbar_try_wait_for(uint64_t *bar, uint32_t parity
 template <unsigned SLEEP_NS>
 __device__ __forceinline__ bool mbar_wait(uint64_t *bar, uint32_t parity, unsigned int *error_flag, unsigned code)
 {
-    unsigned spins = 0;
+    Watchdog wd;
     while (!mbar_try_wait(bar, parity)) {
-        if (++spins > kSpinLimit) {
+        if (wd.expired()) {
             atomicExch(error_flag, code);
             return false;
         }
@@ -701,9 +720,9 @@ __device__ __forceinline__ bool take_slot(const ScanParams &p, const CtlView &c,
     const uint32_t round = __umulhi(k, p.stage_magic);   // k / n_stages, exact for k < 2^32 / n_stages
     s = k - round * p.n_stages;
     // the wait suspends the warp in hardware; only when it times out is the end of the work checked
-    for (unsigned spins = 0; !mbar_try_wait_for(&c.full[s], round & 1u, kWaitNs);) {
+    for (Watchdog wd; !mbar_try_wait_for(&c.full[s], round & 1u, kWaitNs);) {
         if (*reinterpret_cast<volatile uint32_t *>(c.kend) < k) return false;   // a slot past the end of the work
-        if (++spins > kSpinLimit) {
+        if (wd.expired()) {
             atomicExch(&p.ctrl->error_flag, 2u);
             return false;
         }
@@ -1379,8 +1398,8 @@ __global__ void __launch_bounds__(kDenseThreads, 1) pfac_dense_kernel(const Dens
                     unsigned long long v = ep | (2ull << 38);   // before the first tile: prefix 0
                     if (idx >= 0) {
                         v = st[idx];
-                        for (unsigned spins = 0; (v >> 40) != d.epoch; v = st[idx]) {
-                            if (++spins > kSpinLimit) { atomicExch(&p.ctrl->error_flag, 6u); v = ep | (2ull << 38); break; }
+                        for (Watchdog wd; (v >> 40) != d.epoch; v = st[idx]) {
+                            if (wd.expired()) { atomicExch(&p.ctrl->error_flag, 6u); v = ep | (2ull << 38); break; }
                             __nanosleep(32);
                         }
                     }

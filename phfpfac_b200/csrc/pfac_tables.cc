@@ -507,6 +507,41 @@ extern "C" {
 const char *pfac_last_error(void) { return g_last_error.c_str(); }
 int pfac_abi_version(void) { return PFAC_B200_ABI_VERSION; }
 
+}  // extern "C"  (helpers)
+
+namespace {
+// FNV-1a 64 of the pattern file image and the front-end flags: identifies what a table set was built from
+uint64_t source_hash_of(const void *bytes, size_t len, unsigned flags)
+{
+    uint64_t h = 1469598103934665603ull;
+    const unsigned char *b = (const unsigned char *)bytes;
+    for (size_t i = 0; i < len; i++) h = (h ^ b[i]) * 1099511628211ull;
+    for (int i = 0; i < 4; i++) h = (h ^ ((flags >> (8 * i)) & 255u)) * 1099511628211ull;
+    return h ? h : 1;   // 0 = unknown (tables wrapped from arrays)
+}
+// The kernels index r[] / {HT,val} / s0 / idmap with what these arrays hold, unchecked (as the
+// reference does): a table set that did not come out of the builder is checked once, here.
+const char *validate_partition(const pfac::Partition &P)
+{
+    using pfac::kCharSet;
+    if (P.state_num < 0 || P.n_final < 0 || P.max_len < 0 || P.ht_size < 0) return "negative size";
+    if (pfac::width_bits(P.width) < 0) return "width";
+    if ((int64_t)P.r.size() != ((int64_t)P.state_num * kCharSet) / P.width + 1) return "r[] size is not state_num*256/width + 1";
+    if ((int64_t)P.HT.size() != P.ht_size || (int64_t)P.val.size() != P.ht_size) return "HT/val size";
+    if ((int64_t)P.idmap.size() != P.n_final || P.s0.size() != (size_t)kCharSet) return "idmap/s0 size";
+    if (P.n_final > P.state_num + 1) return "more final states than states";
+    for (int32_t v : P.s0)
+        if (v < -1 || v >= P.state_num) return "s0Table entry out of range";
+    for (int32_t v : P.val)
+        if (v < -1 || v >= P.state_num) return "val entry out of range";
+    for (int32_t v : P.HT)
+        if (v < -1 || v >= (int32_t)P.r.size()) return "HT entry out of range";
+    return nullptr;
+}
+}  // namespace
+
+extern "C" {
+
 int pfac_tables_build_mem(const void *pattern_bytes, size_t len, int n_parts, int width, pfac_tables **out)
 {
     return pfac_tables_build_mem_ext(pattern_bytes, len, n_parts, width, 0u, out);
@@ -517,10 +552,28 @@ int pfac_tables_build_mem_ext(const void *pattern_bytes, size_t len, int n_parts
 {
     if (!pattern_bytes && len) return set_error(PFAC_ERR_ARG, "null pattern buffer");
     try {
-        return build((const unsigned char *)pattern_bytes, len, n_parts, width, flags, out);
+        const int rc = build((const unsigned char *)pattern_bytes, len, n_parts, width, flags, out);
+        if (rc == PFAC_OK && out && *out) (*out)->source_hash = source_hash_of(pattern_bytes, len, flags);
+        return rc;
     } catch (const std::bad_alloc &) {
         return set_error(PFAC_ERR_NOMEM, "out of memory building tables");
     }
+}
+
+uint64_t pfac_tables_source_hash(const pfac_tables *t) { return t ? t->source_hash : 0; }
+
+int pfac_pattern_file_hash(const char *pattern_file, unsigned flags, uint64_t *hash)
+{
+    if (!hash) return set_error(PFAC_ERR_ARG, "null hash");
+    FILE *f = pattern_file ? fopen(pattern_file, "rb") : nullptr;
+    if (!f) return set_error(PFAC_ERR_IO, "Open input file failed: %s", pattern_file ? pattern_file : "(null)");
+    std::vector<unsigned char> buf;
+    unsigned char tmp[1 << 16];
+    size_t got;
+    while ((got = fread(tmp, 1, sizeof tmp, f)) > 0) buf.insert(buf.end(), tmp, tmp + got);
+    fclose(f);
+    *hash = source_hash_of(buf.data(), buf.size(), flags);
+    return PFAC_OK;
 }
 
 int pfac_tables_build_file(const char *pattern_file, int n_parts, int width, pfac_tables **out)
@@ -568,6 +621,7 @@ int pfac_tables_from_arrays(const int32_t *s0, const int32_t *r, int32_t n_r, co
         P.idmap.assign(idmap, idmap + n_final);
         for (int32_t i = 0; i < ht_size; i++)
             if (P.HT[(size_t)i] >= 0) P.n_keys++;
+        if (const char *why = validate_partition(P)) return set_error(PFAC_ERR_ARG, "inconsistent tables: %s", why);
         *out = t.release();
         return PFAC_OK;
     } catch (const std::bad_alloc &) {
@@ -577,7 +631,7 @@ int pfac_tables_from_arrays(const int32_t *s0, const int32_t *r, int32_t n_r, co
 
 // ---- on-disk cache of the canonical arrays (the reference serialises nothing: it rebuilds the trie
 // and the PHF on every run, main.cc:100-126).  Little-endian int32 fields:
-//   "PFACTBL1", n_parts, n_patterns, max_pat_len, width,
+//   "PFACTBL2", n_parts, n_patterns, max_pat_len, width, source hash (u64: pattern file image + flags),
 //   per partition: state_num, n_final, max_len, min_len, width, n_keys, max_key, max_row, max_offset,
 //                  ht_size, n_r, then s0[256], r[n_r], HT[ht_size], val[ht_size], idmap[n_final],
 //   FNV-1a 64 of everything before it.
@@ -609,9 +663,9 @@ int pfac_tables_save(const pfac_tables *t, const char *path)
     FILE *f = fopen(path, "wb");
     if (!f) return set_error(PFAC_ERR_IO, "cannot create %s", path);
     Fnv h;
-    bool ok = put(f, h, "PFACTBL1", 8);
+    bool ok = put(f, h, "PFACTBL2", 8);
     const int32_t head[4] = {(int32_t)t->parts.size(), t->n_patterns, t->max_pat_len, t->width};
-    ok = ok && put(f, h, head, sizeof head);
+    ok = ok && put(f, h, head, sizeof head) && put(f, h, &t->source_hash, 8);
     for (const Partition &P : t->parts) {
         const int32_t ph[11] = {P.state_num, P.n_final, P.max_len, P.min_len, P.width, P.n_keys, P.max_key, P.max_row,
                                 P.max_offset, P.ht_size, (int32_t)P.r.size()};
@@ -640,11 +694,13 @@ int pfac_tables_load(const char *path, pfac_tables **out)
         Fnv h;
         char magic[8];
         int32_t head[4];
-        if (!get(f, h, magic, 8) || memcmp(magic, "PFACTBL1", 8) != 0) return bad("magic");
-        if (!get(f, h, head, sizeof head) || head[0] < 1 || head[0] > (1 << 20) || head[1] < 0 || head[2] < 0 ||
-            width_bits(head[3]) < 0)
+        if (!get(f, h, magic, 8) || memcmp(magic, "PFACTBL2", 8) != 0) return bad("magic");
+        uint64_t src_hash = 0;
+        if (!get(f, h, head, sizeof head) || !get(f, h, &src_hash, 8) || head[0] < 1 || head[0] > (1 << 20) || head[1] < 0 ||
+            head[2] < 0 || width_bits(head[3]) < 0)
             return bad("header");
         std::unique_ptr<pfac_tables> t(new pfac_tables);
+        t->source_hash = src_hash;
         t->n_patterns = head[1];
         t->max_pat_len = head[2];
         t->width = head[3];
@@ -677,6 +733,8 @@ int pfac_tables_load(const char *path, pfac_tables **out)
         }
         uint64_t sum = 0;
         if (fread(&sum, 1, 8, f) != 8 || sum != h.h) return bad("checksum");
+        for (const Partition &P : t->parts)
+            if (const char *why = validate_partition(P)) return bad(why);
         fclose(f);
         *out = t.release();
         return PFAC_OK;

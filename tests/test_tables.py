@@ -96,6 +96,32 @@ def test_from_arrays_roundtrip(fixtures):
     assert same(p, q) and t2.max_pat_len == t.max_pat_len and t2.n_parts == 1
 
 
+def test_from_arrays_rejects_inconsistent_tables(fixtures):
+    """The kernels index r[] / {HT,val} / s0 with what the arrays hold, unchecked (as the reference does):
+    arrays that did not come out of the builder are checked once, at the boundary."""
+    t = pf.Tables.from_bytes(fixtures["xad"], n_parts=1, width=128)
+    p = t.part(0)
+
+    def wrap(**kw):
+        a = dict(s0=p.s0.copy(), r=p.r.copy(), HT=p.HT.copy(), val=p.val.copy(), width=128, state_num=p.state_num,
+                 n_final=p.n_final, idmap=p.idmap.copy(), max_len=p.max_len)
+        a.update(kw)
+        return pf.Tables.from_arrays(a["s0"], a["r"], a["HT"], a["val"], a["width"], a["state_num"], a["n_final"],
+                                     a["idmap"], a["max_len"])
+
+    wrap()
+    bad_val = p.val.copy()
+    bad_val[np.argmax(bad_val >= 0)] = p.state_num + 7            # a next state that does not exist
+    bad_s0 = p.s0.copy()
+    bad_s0[65] = p.state_num
+    bad_ht = p.HT.copy()
+    bad_ht[np.argmax(bad_ht >= 0)] = len(p.r) + 3                 # a row id past r[]
+    for kw in (dict(val=bad_val), dict(s0=bad_s0), dict(HT=bad_ht), dict(r=p.r[:-1].copy()), dict(max_len=-1),
+               dict(state_num=p.state_num + 1)):
+        with pytest.raises(pf.PfacError):
+            wrap(**kw)
+
+
 def test_error_behaviour(tmp_path):
     """Library errors instead of the reference's exit()/UB (create_table_reorder.c:71-77,:362; phf.c:161)."""
     cases = [(b"abc\n\nabd\n", 256, -3), (b"abc\nabd", 256, -2), (b"x" * 1023 + b"\n", 256, -2),
@@ -281,3 +307,15 @@ def test_table_cache_roundtrip(tmp_path, fixtures):
         assert e.value.code == -1
     with pytest.raises(pf.PfacError):
         pf.Tables.load(tmp_path / "missing.bin")
+    # the cache remembers what it was built from: a hash of the pattern file image and the reader flags
+    pat = tmp_path / "pat"
+    pat.write_bytes(fixtures["xad"])
+    t = pf.Tables.from_file(str(pat), 1, 256)
+    t.save(tmp_path / "c2.bin")
+    u = pf.Tables.load(tmp_path / "c2.bin")
+    assert u.source_hash() == t.source_hash() == pf.pattern_file_hash(str(pat)) != 0
+    assert pf.pattern_file_hash(str(pat), escapes=True) != t.source_hash()
+    pat.write_bytes(fixtures["xad"] + b"zzz\n")
+    assert pf.pattern_file_hash(str(pat)) != u.source_hash()
+    p0 = t.part(0)
+    assert pf.Tables.from_arrays(p0.s0, p0.r, p0.HT, p0.val, 256, p0.state_num, p0.n_final, p0.idmap, p0.max_len).source_hash() == 0
