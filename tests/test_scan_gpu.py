@@ -490,9 +490,15 @@ def test_cli_byte_identical_result_file(fixtures, golden, tmp_path):
         assert r.returncode == 0 and cache.exists(), r.stderr
         out = (tmp_path / "GPU_match_result.txt").read_bytes()
         assert hashlib.md5(out).hexdigest() == golden["results"]["dictionary_x_1M"]["md5"]
+    # a cache built from another width or another pattern file is not trusted: the tables are rebuilt
     r = subprocess.run([GPHF, str(dic), "2", "64", str(inp)], cwd=tmp_path, capture_output=True, text=True,
                        env=dict(os.environ, GPHF_TABLE_CACHE=str(cache)))
-    assert r.returncode == 1 and "width" in r.stderr
+    assert r.returncode == 0 and "rebuilding" in r.stderr
+    assert hashlib.md5((tmp_path / "GPU_match_result.txt").read_bytes()).hexdigest() == golden["results"]["dictionary_x_1M"]["md5"]
+    r = subprocess.run([GPHF, str(pat), "2", "64", str(inp)], cwd=tmp_path, capture_output=True, text=True,
+                       env=dict(os.environ, GPHF_TABLE_CACHE=str(cache)))
+    assert r.returncode == 0 and "rebuilding" in r.stderr
+    assert hashlib.md5((tmp_path / "GPU_match_result.txt").read_bytes()).hexdigest() == g["md5"]
     # usage / error behaviour (main.cc:93-96, :131-135)
     assert subprocess.run([GPHF, str(pat)], cwd=tmp_path, capture_output=True).returncode == 255
     assert subprocess.run([GPHF, str(pat), "1", "256", str(tmp_path / "nope")], cwd=tmp_path, capture_output=True).returncode == 1
