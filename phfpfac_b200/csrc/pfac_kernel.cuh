@@ -892,7 +892,53 @@ __global__ void __launch_bounds__(kThreads, 1) pfac_scan2_kernel(const ScanParam
         if (nq < 100000u) nq = 0;
 #endif
         // ---- stage 2
-        for (uint32_t e0 = 0; e0 < nq; e0 += 32) {
+        uint32_t e0 = 0;
+#ifndef PFAC_S2_BRANCHY
+        // The common case -- an interior tile of a set without short patterns and with both key levels --
+        // as straight-line, predicated code: a lane whose start is already rejected runs on with harmless
+        // addresses instead of branching out (some lane of the warp goes the whole way anyway), and two
+        // queue entries per lane are judged at a time, so that the two chains of dependent look-ups
+        // (prefix -> m1 -> window -> m2 -> window -> T3) overlap.
+        if (!HAS_SHORT && interior && p.ns2) {
+            auto judge = [&](const uint32_t (&tp)[2], const bool (&live)[2], int K) {
+                uint32_t w4[2], m1[2], w1[2], key2[2], m2[2], w2[2];
+                bool ok[2];
+#pragma unroll
+                for (int k = 0; k < 2; k++) if (k < K) w4[k] = load_w4(buf, tp[k]);
+#pragma unroll
+                for (int k = 0; k < 2; k++) if (k < K) m1[k] = ph_lookup(s_d1, s_e1, p.nb1, p.ns1, w4[k], ph_mix(w4[k]));
+#pragma unroll
+                for (int k = 0; k < 2; k++) if (k < K) {
+                    ok[k] = live[k] && m1[k] != 0u;          // (interior: tpos + m <= tpos + max_pat_len always holds)
+                    w1[k] = load_w4(buf, tp[k] + (ok[k] ? m1[k] - 4u : 0u));
+                    key2[k] = hash_key2(w4[k], w1[k]);
+                }
+#pragma unroll
+                for (int k = 0; k < 2; k++) if (k < K) m2[k] = ph_lookup(s_d2, s_e2, p.nb2, p.ns2, key2[k], key2[k]);
+#pragma unroll
+                for (int k = 0; k < 2; k++) if (k < K) {
+                    ok[k] = ok[k] && m2[k] != 0u;
+                    w2[k] = load_w4(buf, tp[k] + (ok[k] ? m2[k] - 4u : 0u));
+                    const uint32_t h4 = hash_t3(key2[k] ^ kT3Seed2, w2[k]) >> p.t3_shift;
+                    ok[k] = ok[k] && ((s_t3[h4 >> 5] >> (h4 & 31u)) & 1u);
+                }
+#pragma unroll
+                for (int k = 0; k < 2; k++)
+                    if (k < K && ok[k]) {   // rare
+                        anym |= 1u << (tp[k] / (uint32_t)kSlice - slice0);
+                        add_candidate(c.ncand + s, c.cand + s * kCandPerTile, tp[k]);
+                    }
+            };
+            for (; e0 < nq; e0 += 64) {
+                const uint32_t ea = e0 + lane, eb = e0 + 32 + lane;
+                const bool live[2] = {ea < nq, eb < nq};
+                const uint32_t tp[2] = {live[0] ? (uint32_t)wq[ea] : base, live[1] ? (uint32_t)wq[eb] : base};
+                if (e0 + 32 < nq) judge(tp, live, 2);
+                else judge(tp, live, 1);
+            }
+        }
+#endif
+        for (; e0 < nq; e0 += 32) {
             const uint32_t e = e0 + lane;
             if (e >= nq) continue;
             const uint32_t tpos = wq[e];
