@@ -52,6 +52,9 @@ FIXTURES = {
 }
 
 
+ALL_CPUS = os.sched_getaffinity(0)   # before any NUMA binding
+
+
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -323,6 +326,12 @@ def job_leg_rank0(args, pf, torch, tables, pats, part, mpl, world, n_per_gpu):
     stream pipeline per GPU), driven from ONE process over all N devices."""
     tk, tseed = WORKLOADS[args.workload][5], WORKLOADS[args.workload][6]
     total = n_per_gpu * world
+    # this process was bound to GPU 0's NUMA node for the per-rank legs; the job feeds every GPU from one
+    # buffer, so its pages are first-touched (by the generator's threads) from all the CPUs again
+    try:
+        os.sched_setaffinity(0, ALL_CPUS)
+    except Exception:
+        pass
     big = torch.empty(total, dtype=torch.uint8, pin_memory=True)
     synth.synth_text(tk, tseed + 7, total, patterns=pats, out=big.numpy())
     job = pf.Job(tables, devices=list(range(world)), streams_per_gpu=args.streams)

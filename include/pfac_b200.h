@@ -198,6 +198,12 @@ void pfac_job_destroy(pfac_job *job);
 /* Scan h_in[0, n) (n = file size - 1 for the CLI, main.cc:138).  On return *n_matches is the
  * total.  Records are kept inside the job until the next run. */
 int pfac_job_run(pfac_job *job, const void *h_in, uint64_t n, uint64_t *n_matches);
+/* The same, reading the input from a file (main.cc:131-155 reads the whole file into pinned memory
+ * before anything is scanned): per GPU a reader thread preads its shard in 64 MiB chunks (O_DIRECT
+ * where the file system allows) into a ring of pinned buffers while the chunks that are in are
+ * scanned; scanning starts with the first chunk.  `n` = bytes of the file to scan (file size - 1
+ * for the CLI). */
+int pfac_job_run_file(pfac_job *job, const char *path, uint64_t n, uint64_t *n_matches);
 int pfac_job_n_segments(const pfac_job *job);
 /* Segment i: records[count] with positions relative to *base_pos; segments are in position order. */
 int pfac_job_segment(const pfac_job *job, int i, uint64_t *base_pos, const pfac_match **records,

@@ -256,6 +256,24 @@ class Job:
             segs.append((base.value, a))
         return n.value, segs
 
+    def _segments(self):
+        segs = []
+        for i in range(lib.pfac_job_n_segments(self._h)):
+            base, cnt, ptr = C.c_uint64(0), C.c_uint64(0), C.c_void_p()
+            check(lib.pfac_job_segment(self._h, i, C.byref(base), C.byref(ptr), C.byref(cnt)))
+            if cnt.value:
+                a = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_uint32)), shape=(cnt.value, 2)).copy()
+            else:
+                a = np.zeros((0, 2), dtype=np.uint32)
+            segs.append((base.value, a))
+        return segs
+
+    def run_file(self, path, n):
+        """pfac_job_run_file: scan the first n bytes of a file, read chunk by chunk while scanning."""
+        nm = C.c_uint64(0)
+        check(lib.pfac_job_run_file(self._h, str(path).encode(), n, C.byref(nm)))
+        return nm.value, self._segments()
+
     def close(self):
         if self._h and lib is not None:
             lib.pfac_job_destroy(self._h)

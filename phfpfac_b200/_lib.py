@@ -22,7 +22,7 @@ ABI_SYMBOLS = [
     "pfac_device_count", "pfac_ctx_create", "pfac_ctx_destroy", "pfac_ctx_device",
     "pfac_scan_device", "pfac_scan_device_sync", "pfac_scan_host", "pfac_host_alloc", "pfac_host_free", "pfac_host_register", "pfac_host_unregister",
     "pfac_ctx_last_scan_info", "pfac_ctx_derived_info", "pfac_ctx_set_timing", "pfac_ctx_kernel_time",
-    "pfac_job_create", "pfac_job_destroy", "pfac_job_run", "pfac_job_n_segments", "pfac_job_segment",
+    "pfac_job_create", "pfac_job_destroy", "pfac_job_run", "pfac_job_run_file", "pfac_job_n_segments", "pfac_job_segment",
     "pfac_job_last_timing", "pfac_job_plan",
     "pfac_write_begin", "pfac_write_records", "pfac_write_end", "pfac_format_records",
 ]
@@ -97,6 +97,7 @@ def _load():
     lib.pfac_job_destroy.argtypes = [_vp]
     lib.pfac_job_destroy.restype = None
     lib.pfac_job_run.argtypes = [_vp, _vp, C.c_uint64, C.POINTER(C.c_uint64)]
+    lib.pfac_job_run_file.argtypes = [_vp, C.c_char_p, C.c_uint64, C.POINTER(C.c_uint64)]
     lib.pfac_job_n_segments.argtypes = [_vp]
     lib.pfac_job_segment.argtypes = [_vp, C.c_int, C.POINTER(C.c_uint64), C.POINTER(_vp), C.POINTER(C.c_uint64)]
     lib.pfac_job_plan.argtypes = [C.c_uint64, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64),

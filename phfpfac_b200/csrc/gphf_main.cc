@@ -103,7 +103,44 @@ int main(int argc, char **argv)
 
     void *input = nullptr, *mapped = nullptr;
     bool registered = false;
-    const bool want_mmap = !(getenv("GPHF_READER") && !strcmp(getenv("GPHF_READER"), "fread"));
+    // GPHF_READER = stream | mmap | fread.  Default: files of 256 MiB and more are streamed (reader threads
+    // fill a ring of pinned buffers chunk by chunk, O_DIRECT where possible, while the chunks that are in
+    // are scanned -- pfac_job_run_file); smaller ones are mapped and pinned in place.
+    const char *reader_env = getenv("GPHF_READER");
+    const bool want_stream = reader_env ? !strcmp(reader_env, "stream") : fsize >= (256ll << 20);
+    const bool want_mmap = !want_stream && !(reader_env && !strcmp(reader_env, "fread"));
+    if (want_stream) {
+        close(fd);
+        pfac_job *job = nullptr;
+        if (pfac_job_create(tables, nullptr, n_gpu, streamnum, 0, &job)) return fail("create GPU contexts");
+        printf("input reader: stream (reader thread per GPU, ring of pinned 64 MiB buffers)\n");
+        double t2 = now();
+        uint64_t n_matches = 0;
+        if (pfac_job_run_file(job, argv[4], input_size, &n_matches)) return fail("scan");
+        double t3 = now();
+        void *w = nullptr;
+        if (pfac_write_begin(out_name, &w)) return fail("open output");
+        for (int i = 0; i < pfac_job_n_segments(job); i++) {
+            uint64_t base, cnt;
+            const pfac_match *rec;
+            pfac_job_segment(job, i, &base, &rec, &cnt);
+            if (pfac_write_records(w, base, rec, cnt)) return fail("write output");
+        }
+        if (pfac_write_end(w)) return fail("close output");
+        double t4 = now();
+        printf("/////////////////////////////////////////////\n");
+        printf("1.Time for  create PFAC + Hashtable : %lf seconds\n", t1 - t0);
+        printf("2.Time for  %d GPU setup: %lf mseconds\n", n_gpu, (t2 - t1) * 1000);
+        printf("3.Time for  %d GPU match progress, file read included: %lf mseconds (%.3f GB/s file to records)\n", n_gpu,
+               (t3 - t2) * 1000, input_size / (t3 - t2) / 1e9);
+        printf("4.Time for  writing %llu matches: %lf mseconds\n", (unsigned long long)n_matches, (t4 - t3) * 1000);
+        printf("5.Wall time file -> %s: %lf seconds\n", out_name, t4 - t0);
+        printf("matching process finshed\n");
+        printf("/////////////////////////////////////////////\n");
+        pfac_job_destroy(job);
+        pfac_tables_destroy(tables);
+        return 0;
+    }
     if (want_mmap && fsize > 0) {
         mapped = mmap(nullptr, (size_t)fsize, PROT_READ, MAP_PRIVATE | MAP_POPULATE, fd, 0);
         if (mapped == MAP_FAILED) mapped = nullptr;
@@ -151,6 +188,7 @@ int main(int argc, char **argv)
     printf("3.Time for  %d GPU match progress: %lf mseconds (%.3f GB/s end to end)\n", n_gpu, (t3 - t2) * 1000,
            input_size / (t3 - t2) / 1e9);
     printf("4.Time for  writing %llu matches: %lf mseconds\n", (unsigned long long)n_matches, (t4 - t3) * 1000);
+    printf("5.Wall time file -> %s: %lf seconds\n", out_name, t4 - t0);
     printf("matching process finshed\n");
     printf("/////////////////////////////////////////////\n");
     pfac_job_destroy(job);

@@ -4,9 +4,19 @@
 // the per-GPU record lists in GPU order is already globally position-ordered.  One host thread
 // per GPU (the reference uses one OpenMP thread per GPU x stream, main.cc:225-241); streams
 // inside a GPU are driven asynchronously by pfac_scan_host.  No inter-GPU traffic, no NCCL.
+#ifndef _GNU_SOURCE
+#define _GNU_SOURCE   // O_DIRECT
+#endif
+#include <fcntl.h>
+#include <unistd.h>
+
 #include <algorithm>
+#include <cerrno>
 #include <chrono>
+#include <condition_variable>
+#include <cstring>
 #include <memory>
+#include <mutex>
 #include <thread>
 
 #include "pfac_internal.h"
@@ -123,6 +133,156 @@ int pfac_job_run(pfac_job *job, const void *h_in, uint64_t n, uint64_t *n_matche
                 break;
             }
         }
+    };
+    std::vector<std::thread> th;
+    for (int g = 1; g < G; g++) th.emplace_back(work, g);
+    work(0);
+    for (auto &t : th) t.join();
+    job->secs[0] = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    job->flat.clear();
+    uint64_t total = 0;
+    for (int g = 0; g < G; g++) {
+        if (rcs[(size_t)g]) return pfac::set_error(rcs[(size_t)g], "GPU %d: %s", pfac_ctx_device(job->ctxs[(size_t)g]), errs[(size_t)g].c_str());
+        for (const Segment &s : job->segs[(size_t)g]) {
+            job->flat.push_back(&s);
+            total += s.count;
+        }
+    }
+    *n_matches = total;
+    return PFAC_OK;
+}
+
+// The same job fed from a FILE instead of a host buffer that already holds it (the reference freads the
+// whole file into pinned memory before the first byte is scanned, main.cc:147-155): per GPU one reader
+// thread preads its shard chunk by chunk -- O_DIRECT where the file system allows it, so the page cache
+// is not filled with a multi-GB input -- into a ring of pinned buffers, while the GPU's host thread
+// scans the chunks that are in (pfac_scan_host: H2D, kernels, D2H).  The scan starts with the first
+// chunk; file size is bounded by the record buffers, not by host memory.
+int pfac_job_run_file(pfac_job *job, const char *path, uint64_t n, uint64_t *n_matches)
+{
+    if (!job || !path || !n_matches) return pfac::set_error(PFAC_ERR_ARG, "bad arguments to pfac_job_run_file");
+    const int G = (int)job->ctxs.size();
+    const uint64_t halo = job->max_pat_len > 0 ? (uint64_t)job->max_pat_len - 1 : 0;
+    constexpr uint64_t kChunk = 64ull << 20, kAlign = 4096;
+    constexpr int kRing = 3;
+    std::vector<int> rcs((size_t)G, PFAC_OK);
+    std::vector<std::string> errs((size_t)G);
+    const auto t0 = std::chrono::steady_clock::now();
+    auto work = [&](int g) {
+        auto fail = [&](int rc, const std::string &why) { rcs[(size_t)g] = rc; errs[(size_t)g] = why; };
+        uint64_t lo = 0, ns_all = 0, nv_all = 0;
+        pfac_job_plan(n, G, job->max_pat_len, g, &lo, &ns_all, &nv_all);
+        const uint64_t hi = lo + ns_all;
+        std::vector<Segment> &segs = job->segs[(size_t)g];
+        const size_t n_seg = (size_t)((hi - lo + kSegmentBytes - 1) / kSegmentBytes);
+        for (size_t i = n_seg; i < segs.size(); i++) pfac_host_free(segs[i].rec);
+        segs.resize(n_seg);
+        if (hi == lo) return;
+        int fd = open(path, O_RDONLY | O_DIRECT);
+        bool direct = fd >= 0;
+        if (fd < 0) fd = open(path, O_RDONLY);
+        if (fd < 0) return fail(PFAC_ERR_IO, std::string("Open input file failed: ") + path);
+        // ring of pinned chunk buffers
+        const size_t buf_bytes = (size_t)(kChunk + halo + 2 * kAlign);
+        uint8_t *bufs[kRing] = {nullptr, nullptr, nullptr};
+        for (auto &b : bufs)
+            if (pfac_host_alloc((void **)&b, buf_bytes)) { close(fd); return fail(PFAC_ERR_NOMEM, pfac_last_error()); }
+        struct Slot { uint64_t off = 0, len = 0, skip = 0; bool full = false, err = false; } slots[kRing];
+        std::mutex mu;
+        std::condition_variable cv;
+        const uint64_t n_chunks = (hi - lo + kChunk - 1) / kChunk;
+        bool stop = false;
+        std::thread reader([&] {
+            for (uint64_t c = 0; c < n_chunks; c++) {
+                Slot &sl = slots[c % kRing];
+                {
+                    std::unique_lock<std::mutex> lk(mu);
+                    cv.wait(lk, [&] { return !sl.full || stop; });
+                    if (stop) return;
+                }
+                const uint64_t off = lo + c * kChunk, want = std::min<uint64_t>(kChunk, hi - off);
+                const uint64_t end = std::min<uint64_t>(off + want + halo, n);          // readable bytes incl. halo
+                const uint64_t a_off = off & ~(kAlign - 1), a_end = (end + kAlign - 1) & ~(kAlign - 1);
+                uint8_t *dst = bufs[c % kRing];
+                uint64_t got = 0;
+                bool err = false;
+                while (a_off + got < end) {
+                    ssize_t r = pread(fd, dst + got, (size_t)(a_end - a_off - got), (off_t)(a_off + got));
+                    if (r < 0 && direct && errno == EINVAL) {   // the file system refuses O_DIRECT here: plain reads
+                        close(fd);
+                        fd = open(path, O_RDONLY);
+                        direct = false;
+                        if (fd < 0) { err = true; break; }
+                        continue;
+                    }
+                    if (r <= 0) { err = a_off + got < end; break; }
+                    got += (uint64_t)r;
+                }
+                std::lock_guard<std::mutex> lk(mu);
+                sl.off = off;
+                sl.len = want;
+                sl.skip = off - a_off;
+                sl.err = err;
+                sl.full = true;
+                cv.notify_all();
+            }
+        });
+        for (size_t i = 0; i < n_seg; i++) {
+            Segment &s = segs[i];
+            s.base = lo + (uint64_t)i * kSegmentBytes;
+            s.n_starts = std::min<uint64_t>(kSegmentBytes, hi - s.base);
+            s.count = 0;
+        }
+        for (uint64_t c = 0; c < n_chunks && rcs[(size_t)g] == PFAC_OK; c++) {
+            Slot &sl = slots[c % kRing];
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv.wait(lk, [&] { return sl.full; });
+            }
+            if (sl.err) { fail(PFAC_ERR_IO, std::string("short read on ") + path); break; }
+            Segment &s = segs[(size_t)((sl.off - lo) / kSegmentBytes)];
+            const uint64_t nv = std::min<uint64_t>(sl.len + halo, n - sl.off);
+            const uint8_t *src = bufs[c % kRing] + sl.skip;
+            for (int attempt = 0; attempt < 3; attempt++) {
+                if (!s.rec || s.cap < s.count + 4096) {   // (re)size the segment's record buffer, keeping what is in
+                    const uint64_t cap2 = std::max<uint64_t>(std::max<uint64_t>(s.cap * 2, s.count + 65536), s.n_starts / 8);
+                    pfac_match *nr = nullptr;
+                    if (pfac_host_alloc((void **)&nr, (size_t)cap2 * sizeof(pfac_match))) { fail(PFAC_ERR_NOMEM, pfac_last_error()); break; }
+                    if (s.rec) { memcpy(nr, s.rec, (size_t)s.count * sizeof(pfac_match)); pfac_host_free(s.rec); }
+                    s.rec = nr;
+                    s.cap = cap2;
+                }
+                uint64_t m = 0;
+                int rc = pfac_scan_host(job->ctxs[(size_t)g], src, sl.len, nv, sl.off, s.rec + s.count, s.cap - s.count, &m);
+                if (rc == PFAC_ERR_OUTPUT_FULL && attempt < 2) {   // dense matches: grow and scan the chunk again
+                    s.cap = std::max<uint64_t>(s.cap, s.count + m);
+                    pfac_match *nr = nullptr;
+                    if (pfac_host_alloc((void **)&nr, (size_t)(s.count + m + 4096) * sizeof(pfac_match))) { fail(PFAC_ERR_NOMEM, pfac_last_error()); break; }
+                    memcpy(nr, s.rec, (size_t)s.count * sizeof(pfac_match));
+                    pfac_host_free(s.rec);
+                    s.rec = nr;
+                    s.cap = s.count + m + 4096;
+                    continue;
+                }
+                if (rc) { fail(rc, pfac_last_error()); break; }
+                const uint32_t bias = (uint32_t)(sl.off - s.base);   // positions of a segment are relative to its base
+                if (bias)
+                    for (uint64_t k = 0; k < m; k++) s.rec[s.count + k].pos += bias;
+                s.count += m;
+                break;
+            }
+            std::lock_guard<std::mutex> lk(mu);
+            sl.full = false;
+            cv.notify_all();
+        }
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            stop = true;
+            cv.notify_all();
+        }
+        reader.join();
+        if (fd >= 0) close(fd);
+        for (auto &b : bufs) pfac_host_free(b);
     };
     std::vector<std::thread> th;
     for (int g = 1; g < G; g++) th.emplace_back(work, g);

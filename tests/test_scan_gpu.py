@@ -475,7 +475,7 @@ def test_cli_byte_identical_result_file(fixtures, golden, tmp_path):
     # dictionary, other stream counts / widths: still the same bytes; and equal to the oracle CLI
     dic = tmp_path / "dict"
     dic.write_bytes(fixtures["dictionary"])
-    for (streams, width), reader in zip(((4, 64), (2, 4096)), ("mmap", "fread")):
+    for (streams, width), reader in zip(((4, 64), (2, 4096), (3, 256)), ("mmap", "fread", "stream")):
         r = subprocess.run([GPHF, str(dic), str(streams), str(width), str(inp)], cwd=tmp_path, capture_output=True,
                            text=True, env=dict(os.environ, GPHF_READER=reader))
         assert r.returncode == 0, r.stderr
@@ -504,6 +504,29 @@ def test_cli_byte_identical_result_file(fixtures, golden, tmp_path):
     assert subprocess.run([GPHF, str(pat), "1", "256", str(tmp_path / "nope")], cwd=tmp_path, capture_output=True).returncode == 1
     assert subprocess.run([GPHF, str(tmp_path / "nope"), "1", "256", str(inp)], cwd=tmp_path, capture_output=True).returncode == 1
     assert subprocess.run([GPHF, str(pat), "1", "100", str(inp)], cwd=tmp_path, capture_output=True).returncode == 1
+
+
+def test_job_streams_a_file(tmp_path):
+    """pfac_job_run_file: reader threads fill a ring of pinned 64 MiB buffers while the chunks that are in
+    are scanned -- the same records as scanning the whole buffer, across chunk and segment borders."""
+    torch_cuda()
+    pats = synth.synth_patterns(1, 2000, 3, 4, 64)
+    n = (130 << 20) + 12345                   # three chunks, the last one ragged
+    text = synth.synth_text(1, 21, n, patterns=pats)
+    border = 64 << 20
+    text[border - 3:border + 2] = np.frombuffer(b"GET /", dtype=np.uint8)     # a match across a chunk border
+    pats += b"GET /\n"
+    f = tmp_path / "big.bin"
+    text.tofile(f)
+    t = pf.Tables.from_bytes(pats, 1, 256)
+    job = pf.Job(t, devices=[0], streams_per_gpu=3)
+    nm, segs = job.run(text)
+    nm2, segs2 = job.run_file(str(f), n)
+    assert nm == nm2 > 0
+    a = np.concatenate([np.stack([r[:, 0].astype(np.int64) + b, r[:, 1].astype(np.int64)], 1) for b, r in segs if len(r)])
+    b = np.concatenate([np.stack([r[:, 0].astype(np.int64) + b2, r[:, 1].astype(np.int64)], 1) for b2, r in segs2 if len(r)])
+    assert np.array_equal(a, b) and (a[:, 0] == border - 3).any()
+    job.close()
 
 
 def test_c_host_example_end_to_end(fixtures, golden, tmp_path):
