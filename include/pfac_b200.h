@@ -199,9 +199,9 @@ void pfac_job_destroy(pfac_job *job);
  * total.  Records are kept inside the job until the next run. */
 int pfac_job_run(pfac_job *job, const void *h_in, uint64_t n, uint64_t *n_matches);
 /* The same, reading the input from a file (main.cc:131-155 reads the whole file into pinned memory
- * before anything is scanned): per GPU a reader thread preads its shard in 64 MiB chunks (O_DIRECT
- * where the file system allows) into a ring of pinned buffers while the chunks that are in are
- * scanned; scanning starts with the first chunk.  `n` = bytes of the file to scan (file size - 1
+ * before anything is scanned): per GPU a reader thread preads its shard in 64 MiB chunks (buffered
+ * with sequential read-ahead; O_DIRECT with PFAC_READER_ODIRECT=1) into a ring of pinned buffers
+ * while the chunks that are in are scanned; scanning starts with the first chunk.  `n` = bytes of the file to scan (file size - 1
  * for the CLI). */
 int pfac_job_run_file(pfac_job *job, const char *path, uint64_t n, uint64_t *n_matches);
 int pfac_job_n_segments(const pfac_job *job);

@@ -14,6 +14,7 @@
 #include <cerrno>
 #include <chrono>
 #include <condition_variable>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <mutex>
@@ -117,7 +118,10 @@ int pfac_job_run(pfac_job *job, const void *h_in, uint64_t n, uint64_t *n_matche
             const uint64_t nv = std::min<uint64_t>(s.n_starts + halo, n - s.base);
             for (int attempt = 0; attempt < 2; attempt++) {
                 if (!s.rec) {
-                    s.cap = std::max<uint64_t>(s.cap, std::max<uint64_t>(s.n_starts / 8, 65536));
+                    // room for one match per 256 input bytes to begin with (pinning memory is not free: a
+                    // record per 8 bytes would pin as much again as the input); denser inputs report the
+                    // size they need and the segment is scanned again
+                    s.cap = std::max<uint64_t>(s.cap, std::max<uint64_t>(s.n_starts / 256, 65536));
                     int rc = pfac_host_alloc((void **)&s.rec, (size_t)s.cap * sizeof(pfac_match));
                     if (rc) { rcs[(size_t)g] = rc; errs[(size_t)g] = pfac_last_error(); return; }
                 }
@@ -154,8 +158,8 @@ int pfac_job_run(pfac_job *job, const void *h_in, uint64_t n, uint64_t *n_matche
 
 // The same job fed from a FILE instead of a host buffer that already holds it (the reference freads the
 // whole file into pinned memory before the first byte is scanned, main.cc:147-155): per GPU one reader
-// thread preads its shard chunk by chunk -- O_DIRECT where the file system allows it, so the page cache
-// is not filled with a multi-GB input -- into a ring of pinned buffers, while the GPU's host thread
+// thread preads its shard chunk by chunk (with PFAC_READER_ODIRECT=1 through O_DIRECT, so that the page
+// cache is not filled with a multi-GB input) into a ring of pinned buffers, while the GPU's host thread
 // scans the chunks that are in (pfac_scan_host: H2D, kernels, D2H).  The scan starts with the first
 // chunk; file size is bounded by the record buffers, not by host memory.
 int pfac_job_run_file(pfac_job *job, const char *path, uint64_t n, uint64_t *n_matches)
@@ -164,7 +168,7 @@ int pfac_job_run_file(pfac_job *job, const char *path, uint64_t n, uint64_t *n_m
     const int G = (int)job->ctxs.size();
     const uint64_t halo = job->max_pat_len > 0 ? (uint64_t)job->max_pat_len - 1 : 0;
     constexpr uint64_t kChunk = 64ull << 20, kAlign = 4096;
-    constexpr int kRing = 3;
+    constexpr int kRing = 6, kReaders = 3;   // (one thread copies out of the page cache at ~6 GB/s; the PCIe link takes ~55)
     std::vector<int> rcs((size_t)G, PFAC_OK);
     std::vector<std::string> errs((size_t)G);
     const auto t0 = std::chrono::steady_clock::now();
@@ -178,27 +182,38 @@ int pfac_job_run_file(pfac_job *job, const char *path, uint64_t n, uint64_t *n_m
         for (size_t i = n_seg; i < segs.size(); i++) pfac_host_free(segs[i].rec);
         segs.resize(n_seg);
         if (hi == lo) return;
-        int fd = open(path, O_RDONLY | O_DIRECT);
-        bool direct = fd >= 0;
-        if (fd < 0) fd = open(path, O_RDONLY);
-        if (fd < 0) return fail(PFAC_ERR_IO, std::string("Open input file failed: ") + path);
+        // PFAC_READER_ODIRECT=1: bypass the page cache (inputs that are read once and are larger than host
+        // memory is worth); default: buffered reads with sequential read-ahead, which also profit from a
+        // file that is still in the cache
+        const char *od = getenv("PFAC_READER_ODIRECT");
+        bool direct0 = od && atoi(od) != 0;
+        int fd0 = direct0 ? open(path, O_RDONLY | O_DIRECT) : -1;
+        if (fd0 < 0) {
+            direct0 = false;
+            fd0 = open(path, O_RDONLY);
+        }
+        if (fd0 < 0) return fail(PFAC_ERR_IO, std::string("Open input file failed: ") + path);
+        if (!direct0) posix_fadvise(fd0, (off_t)lo, (off_t)(hi - lo), POSIX_FADV_SEQUENTIAL);
         // ring of pinned chunk buffers
         const size_t buf_bytes = (size_t)(kChunk + halo + 2 * kAlign);
-        uint8_t *bufs[kRing] = {nullptr, nullptr, nullptr};
+        uint8_t *bufs[kRing] = {};
         for (auto &b : bufs)
-            if (pfac_host_alloc((void **)&b, buf_bytes)) { close(fd); return fail(PFAC_ERR_NOMEM, pfac_last_error()); }
+            if (pfac_host_alloc((void **)&b, buf_bytes)) { close(fd0); return fail(PFAC_ERR_NOMEM, pfac_last_error()); }
         struct Slot { uint64_t off = 0, len = 0, skip = 0; bool full = false, err = false; } slots[kRing];
         std::mutex mu;
         std::condition_variable cv;
         const uint64_t n_chunks = (hi - lo + kChunk - 1) / kChunk;
         bool stop = false;
-        std::thread reader([&] {
-            for (uint64_t c = 0; c < n_chunks; c++) {
+        auto read_chunks = [&](int r0) {
+            int fd = r0 == 0 ? fd0 : open(path, O_RDONLY | (direct0 ? O_DIRECT : 0));
+            bool direct = direct0;
+            if (fd < 0) fd = open(path, O_RDONLY), direct = false;
+            for (uint64_t c = (uint64_t)r0; c < n_chunks; c += kReaders) {
                 Slot &sl = slots[c % kRing];
                 {
                     std::unique_lock<std::mutex> lk(mu);
                     cv.wait(lk, [&] { return !sl.full || stop; });
-                    if (stop) return;
+                    if (stop) { if (fd >= 0) close(fd); return; }
                 }
                 const uint64_t off = lo + c * kChunk, want = std::min<uint64_t>(kChunk, hi - off);
                 const uint64_t end = std::min<uint64_t>(off + want + halo, n);          // readable bytes incl. halo
@@ -226,7 +241,10 @@ int pfac_job_run_file(pfac_job *job, const char *path, uint64_t n, uint64_t *n_m
                 sl.full = true;
                 cv.notify_all();
             }
-        });
+            if (fd >= 0) close(fd);
+        };
+        std::vector<std::thread> readers;
+        for (int r0 = 0; r0 < kReaders; r0++) readers.emplace_back(read_chunks, r0);
         for (size_t i = 0; i < n_seg; i++) {
             Segment &s = segs[i];
             s.base = lo + (uint64_t)i * kSegmentBytes;
@@ -245,7 +263,7 @@ int pfac_job_run_file(pfac_job *job, const char *path, uint64_t n, uint64_t *n_m
             const uint8_t *src = bufs[c % kRing] + sl.skip;
             for (int attempt = 0; attempt < 3; attempt++) {
                 if (!s.rec || s.cap < s.count + 4096) {   // (re)size the segment's record buffer, keeping what is in
-                    const uint64_t cap2 = std::max<uint64_t>(std::max<uint64_t>(s.cap * 2, s.count + 65536), s.n_starts / 8);
+                    const uint64_t cap2 = std::max<uint64_t>(std::max<uint64_t>(s.cap * 2, s.count + 65536), s.n_starts / 256);
                     pfac_match *nr = nullptr;
                     if (pfac_host_alloc((void **)&nr, (size_t)cap2 * sizeof(pfac_match))) { fail(PFAC_ERR_NOMEM, pfac_last_error()); break; }
                     if (s.rec) { memcpy(nr, s.rec, (size_t)s.count * sizeof(pfac_match)); pfac_host_free(s.rec); }
@@ -280,8 +298,7 @@ int pfac_job_run_file(pfac_job *job, const char *path, uint64_t n, uint64_t *n_m
             stop = true;
             cv.notify_all();
         }
-        reader.join();
-        if (fd >= 0) close(fd);
+        for (auto &t : readers) t.join();
         for (auto &b : bufs) pfac_host_free(b);
     };
     std::vector<std::thread> th;
