@@ -257,9 +257,8 @@ void derive_tables(const Partition &P, uint32_t t2_bytes, uint32_t t3_bytes, uin
                     if (too_many) continue;
                     const uint32_t w = pair | ((uint32_t)b2 << 16) | ((uint32_t)g.edges[e3].byte << 24);
                     if (t2_bits) {
-                        const uint32_t h = (w * kHash4Mul) >> t2_shift, h2 = (w * kHash4Mul2) >> t2_shift;
-                        t2[h >> 5] |= 1u << (h & 31);
-                        t2[h2 >> 5] |= 1u << (h2 & 31);
+                        const uint32_t h = w * kHash4Mul;
+                        t2[t2_word(h, t2_shift)] |= t2_mask(h, t2_shift);
                     }
                     prefix4.push_back({w, g.edges[e3].next});
                     if (prefix4.size() > kPathLimit) too_many = true;
@@ -548,7 +547,7 @@ bool stage1_pass(const Derived &d, const uint8_t *t, size_t len, bool odd)
     if (d.mode == 2) {   // global mode: stage 1 is T2 over the 4-byte prefix (no pattern is shorter than 4)
         if (len < 4) return false;
         const uint32_t *t2 = reinterpret_cast<const uint32_t *>(d.image.data() + d.off_t2);
-        return d.t2_shift >= 32 || (bit(t2, (le32(t) * kHash4Mul) >> d.t2_shift) && bit(t2, (le32(t) * kHash4Mul2) >> d.t2_shift));
+        return d.t2_shift >= 32 || t2_pass(t2, le32(t), d.t2_shift);
     }
     const uint8_t *t1 = d.image.data() + d.off_t1;
     auto at = [&](size_t i) { return i < len ? (uint32_t)t[i] : 0u; };
@@ -609,7 +608,7 @@ bool stage2_pass(const Derived &d, const uint8_t *t, size_t len, bool odd, int *
     }
     if (d.has_short && (t1[t1_index(w4 & 255u, (w4 >> 8) & 255u)] & kT1Short)) return true;
     if (!d.has_t3) {
-        if (d.t2_shift < 32 && !(bit(t2, (w4 * kHash4Mul) >> d.t2_shift) && bit(t2, (w4 * kHash4Mul2) >> d.t2_shift))) return false;
+        if (d.t2_shift < 32 && !t2_pass(t2, w4, d.t2_shift)) return false;
         if (stage) *stage = 2;
         return true;
     }

@@ -23,7 +23,7 @@
 //                       whose text at offset m-4 is not in T3 cannot complete any pattern under
 //                       that key (Wu-Manber style two-point checks; they settle the starts that
 //                       share a long prefix with many patterns without walking it)
-//   T2    2^k2 bits   : two multiplicative hashes (Bloom pair) of every 4-byte prefix -- only for pattern sets whose
+//   T2    2^k2 bits   : blocked Bloom filter (one word, kT2KeyBits bits) of every 4-byte prefix -- only for pattern sets whose
 //                       prefixes do not fit the shared-memory Tm.  Such sets (e.g. 100,000 patterns)
 //                       get Tm/Tm2/T3 sized for their key counts in GLOBAL memory (a few MB, L2
 //                       resident) and T2, filling shared memory, becomes stage 1.
@@ -36,7 +36,13 @@
 namespace pfac {
 
 constexpr uint32_t kHash4Mul = 0x9E3779B1u;
-constexpr uint32_t kHash4Mul2 = 0x85EBCA77u;   // T2 is a two-hash Bloom filter: both bits must be set
+// T2 is a BLOCKED Bloom filter: one multiplicative hash h of the 4-byte prefix selects a 32-bit word (its top
+// bits) and kT2KeyBits bit positions inside that word (the 5-bit fields below them) -- one shared-memory load
+// and one mask compare per start position decide, instead of one probe per hash function.
+#ifndef PFAC_T2_KEY_BITS
+#define PFAC_T2_KEY_BITS 2
+#endif
+constexpr int kT2KeyBits = PFAC_T2_KEY_BITS;
 constexpr uint32_t kTmSlotBits = 12;
 constexpr uint32_t kTm1Slots = 2u << kTmSlotBits;   // level 1: 4096 buckets x 2 slots (u16: tag << 8 | m, 0 = empty)
 constexpr uint32_t kT3Seed2 = 0x5bd1e995u;
@@ -82,6 +88,23 @@ PFAC_HD inline uint32_t tm_lookup(const uint16_t *tab, uint32_t key, uint32_t bi
     if (((a >> 8) & 255u) == tag) m = a & 255u;
     return m;
 }
+// T2 of 2^(32 - shift) bits (at least 2^(5 + 5 kT2KeyBits)... the fields may overlap the word index for tiny
+// tables, which only weakens the filter): word index and bit mask of the prefix hash h = w4 * kHash4Mul
+PFAC_HD inline uint32_t t2_word(uint32_t h, uint32_t shift) { return h >> (shift + 5u); }
+PFAC_HD inline uint32_t t2_mask(uint32_t h, uint32_t shift)
+{
+    uint32_t m = 0;
+    for (int i = 0; i < kT2KeyBits; i++) {
+        const uint32_t sh = shift >= 5u * (uint32_t)i ? shift - 5u * (uint32_t)i : 0u;
+        m |= 1u << ((h >> sh) & 31u);
+    }
+    return m;
+}
+PFAC_HD inline bool t2_pass(const uint32_t *t2, uint32_t w4, uint32_t shift)
+{
+    const uint32_t h = w4 * kHash4Mul, m = t2_mask(h, shift);
+    return (t2[t2_word(h, shift)] & m) == m;
+}
 // rotl2 of a byte; T1 index of the window (c0, c1); T1 bit-planes
 #ifndef PFAC_NO_ROT2
 PFAC_HD inline uint32_t rot2(uint32_t c) { return ((c << 2) | (c >> 6)) & 0xFFu; }
@@ -125,7 +148,7 @@ struct Derived {
     // shared-memory image, copied verbatim by the detector kernel (sections 128-byte aligned)
     std::vector<uint8_t> image;
     uint32_t off_t1 = 0, off_t2 = 0, off_tm = 0, off_tm2 = 0, off_t3 = 0;
-    uint32_t t2_shift = 32;      // indices = (w * kHash4Mul) >> t2_shift and (w * kHash4Mul2) >> t2_shift   (32: no T2)
+    uint32_t t2_shift = 32;      // T2 has 2^(32 - t2_shift) bits (t2_word / t2_mask above); 32: no T2
     uint32_t has_short = 0;      // patterns of length <= 3 exist (T1's Short plane is not empty)
     uint32_t has_shortc = 0;     // patterns of length <= 4 exist (T1's ShortC plane is not empty)
     uint32_t has_t3 = 0;         // Tm + T3 present (then no T2)

@@ -336,8 +336,17 @@ __device__ __forceinline__ void filter16(const uint4 v, const uint32_t nx, const
 }
 
 // Stage 1 of the global mode (pattern sets whose prefixes do not fit the shared-memory Tm): the
-// hashed 4-byte prefix of each of the 16 starts against T2, which fills shared memory.  Same result
-// format as filter16.
+// hashed 4-byte prefix of each of the 16 starts against T2 (a blocked Bloom filter, pfac_derive.h), which
+// fills shared memory -- one LDS.32 and one mask compare per start.  Same result format as filter16.
+__device__ __forceinline__ uint32_t one_hot(uint32_t n) { return __funnelshift_l(0u, 1u, n); }   // 1 << (n & 31): SHF.L.W
+__device__ __forceinline__ bool t2_probe(const uint32_t *__restrict__ t2, uint32_t w4, uint32_t shift)
+{
+    const uint32_t h = w4 * kHash4Mul;
+    uint32_t m = one_hot(h >> shift);
+#pragma unroll
+    for (int i = 1; i < kT2KeyBits; i++) m |= one_hot(h >> (shift - 5u * i));   // (shared-memory tables have at most 2^21 bits: shift >= 11)
+    return (t2[h >> (shift + 5u)] & m) == m;
+}
 __device__ __forceinline__ void filter16_t2(const uint4 v, const uint32_t nx, const uint32_t *__restrict__ t2,
                                             uint32_t shift, uint32_t &lo, uint32_t &hi)
 {
@@ -348,26 +357,11 @@ __device__ __forceinline__ void filter16_t2(const uint4 v, const uint32_t nx, co
 #pragma unroll
         for (int j = 0; j < 4; j++) {
             const uint32_t w4 = j == 0 ? w[k] : __funnelshift_r(w[k], w[k + 1], 8 * j);
-            const uint32_t h = (w4 * kHash4Mul) >> shift;
-            acc[k >> 1] |= ((t2[h >> 5] >> (h & 31u)) & 1u) << (((k & 1) * 4 + j) * 4);
+            if (t2_probe(t2, w4, shift)) acc[k >> 1] |= 1u << (((k & 1) * 4 + j) * 4);
         }
     }
     lo = acc[0];
     hi = acc[1];
-}
-// The second hash of T2's Bloom pair, only for the starts that passed the first (about one in ten):
-// each lane walks its own survivors; their 4 bytes come from the staged tile (base = the lane's
-// 16 bytes).  Cuts the stage-1 survivors of a 100,000-pattern set from 9.4 % to about 3 %.
-__device__ __forceinline__ uint32_t refine8_t2(uint32_t m, const uint8_t *base, const uint32_t *__restrict__ t2, uint32_t shift)
-{
-    for (uint32_t c = m; c; c &= c - 1) {
-        const uint32_t b = __ffs(c) - 1, pos = b >> 2;
-        const uint32_t *wp = reinterpret_cast<const uint32_t *>(base + (pos & ~3u));
-        const uint32_t w4 = __funnelshift_r(wp[0], wp[1], (pos & 3u) * 8u);
-        const uint32_t h2 = (w4 * kHash4Mul2) >> shift;
-        if (!((t2[h2 >> 5] >> (h2 & 31u)) & 1u)) m &= ~(1u << b);
-    }
-    return m;
 }
 
 // tile-relative bound of what a start at tile-relative tpos may read (master_kernel.cu:141-144 + input end)
@@ -776,19 +770,24 @@ __device__ __forceinline__ uint32_t load_w4(const uint8_t *buf, uint32_t pos)
 // the lower one): bit 16 h + j of the result = start j of this lane in slice h passed.  The upper
 // slice goes first: the T1 bytes of the two windows after a lane's 16 bytes are the next lane's first
 // two -- for lane 31 those of lane 0 in the slice above (lane 31 of the upper slice looks them up itself).
-template <bool HAS_SHORT, bool HAS_SC>
-__device__ __forceinline__ uint32_t s1_pair(const uint8_t *buf, uint32_t pair, int lane, uint32_t next_lane)
+// `above` (HAS_ABOVE): the first T1 register of the slice after the pair, already probed by the caller (the
+// slot's pairs go top down), so that only the slot's last slice pays lane 31's own look-ups; x0_out = this
+// pair's lower slice's, for the pair below.
+template <bool HAS_SHORT, bool HAS_SC, bool HAS_ABOVE>
+__device__ __forceinline__ uint32_t s1_pair(const uint8_t *buf, uint32_t pair, int lane, uint32_t next_lane, uint32_t above, uint32_t &x0_out)
 {
     const uint4 v1 = *reinterpret_cast<const uint4 *>(buf + pair + kSlice);
     const uint4 v0 = *reinterpret_cast<const uint4 *>(buf + pair);
 #ifdef PFAC_EXP_NO_S1   // timing experiment: the streaming skeleton alone
+    x0_out = above;
     return ((v0.x ^ v1.y) + (v0.z ^ v1.w)) == 0x12345679u ? 1u : 0u;
 #endif
     uint32_t X0, X1, Y0, Y1;
     s1_probe(v1, Y0, Y1);
     s1_probe(v0, X0, X1);
-    uint32_t ey = __shfl_sync(0xffffffffu, Y0, next_lane);
-    if (lane == 31) {
+    x0_out = X0;
+    uint32_t ey = __shfl_sync(0xffffffffu, HAS_ABOVE && lane == 0 ? above : Y0, next_lane);
+    if (!HAS_ABOVE && lane == 31) {
         const uint32_t r = rot2x4(*reinterpret_cast<const uint32_t *>(buf + pair + kSlice + 16));
         ey = (uint32_t)smem[r & 0xffffu] | ((uint32_t)smem[r >> 16] << 8);
     }
@@ -846,8 +845,12 @@ __global__ void __launch_bounds__(kThreads, 1) pfac_scan2_kernel(const ScanParam
         constexpr int kPairs = kSlotSlices / 2;
         uint32_t m[kPairs];
         const uint32_t base = slice0 * kSlice + lane * 16;   // tile-relative position of the lane's first start
+        {
+            uint32_t x0 = 0;
+            m[kPairs - 1] = s1_pair<HAS_SHORT, HAS_SC, false>(buf, base + (kPairs - 1) * 2 * kSlice, lane, next_lane, 0u, x0);
 #pragma unroll
-        for (int pr = 0; pr < kPairs; pr++) m[pr] = s1_pair<HAS_SHORT, HAS_SC>(buf, base + pr * 2 * kSlice, lane, next_lane);
+            for (int pr = kPairs - 2; pr >= 0; pr--) m[pr] = s1_pair<HAS_SHORT, HAS_SC, true>(buf, base + pr * 2 * kSlice, lane, next_lane, x0, x0);
+        }
         if (!interior) {   // start positions are [mis, a_start_end) in aligned coordinates
 #pragma unroll
             for (int h = 0; h < kSlotSlices; h++) {
@@ -910,7 +913,7 @@ __global__ void __launch_bounds__(kThreads, 1) pfac_scan2_kernel(const ScanParam
 #pragma unroll
                 for (int k = 0; k < 2; k++) if (k < K) {
                     ok[k] = live[k] && m1[k] != 0u;          // (interior: tpos + m <= tpos + max_pat_len always holds)
-                    w1[k] = load_w4(buf, tp[k] + (ok[k] ? m1[k] - 4u : 0u));
+                    w1[k] = load_w4(buf, ok[k] ? tp[k] + m1[k] - 4u : 0u);   // (rejected lanes read one broadcast word: no bank conflicts from them)
                     key2[k] = hash_key2(w4[k], w1[k]);
                 }
 #pragma unroll
@@ -918,8 +921,8 @@ __global__ void __launch_bounds__(kThreads, 1) pfac_scan2_kernel(const ScanParam
 #pragma unroll
                 for (int k = 0; k < 2; k++) if (k < K) {
                     ok[k] = ok[k] && m2[k] != 0u;
-                    w2[k] = load_w4(buf, tp[k] + (ok[k] ? m2[k] - 4u : 0u));
-                    const uint32_t h4 = hash_t3(key2[k] ^ kT3Seed2, w2[k]) >> p.t3_shift;
+                    w2[k] = load_w4(buf, ok[k] ? tp[k] + m2[k] - 4u : 0u);
+                    const uint32_t h4 = ok[k] ? hash_t3(key2[k] ^ kT3Seed2, w2[k]) >> p.t3_shift : 0u;
                     ok[k] = ok[k] && ((s_t3[h4 >> 5] >> (h4 & 31u)) & 1u);
                 }
 #pragma unroll
@@ -932,7 +935,7 @@ __global__ void __launch_bounds__(kThreads, 1) pfac_scan2_kernel(const ScanParam
             for (; e0 < nq; e0 += 64) {
                 const uint32_t ea = e0 + lane, eb = e0 + 32 + lane;
                 const bool live[2] = {ea < nq, eb < nq};
-                const uint32_t tp[2] = {live[0] ? (uint32_t)wq[ea] : base, live[1] ? (uint32_t)wq[eb] : base};
+                const uint32_t tp[2] = {live[0] ? (uint32_t)wq[ea] : 0u, live[1] ? (uint32_t)wq[eb] : 0u};
                 if (e0 + 32 < nq) judge(tp, live, 2);
                 else judge(tp, live, 1);
             }
@@ -1050,8 +1053,6 @@ __global__ void __launch_bounds__(kThreads, 1) pfac_scan_kernel(const ScanParams
             if (!(p.debug & 4u)) {
                 if (MODE == 2) {
                     filter16_t2(v, nx, s_t2, p.t2_shift, lo, hi);
-                    lo = refine8_t2(lo, buf + off, s_t2, p.t2_shift);
-                    hi = refine8_t2(hi, buf + off + 8, s_t2, p.t2_shift);
                 }
                 else filter16(v, nx, lane, lo, hi);
             }
@@ -1112,8 +1113,7 @@ __global__ void __launch_bounds__(kThreads, 1) pfac_scan_kernel(const ScanParams
                 if (MODE != 2 && p.has_short) shortp = (smem[rot2x4(w4) & 0xffffu] & kT1Short) != 0;
                 if (!shortp) {
                     if (!p.has_t3) {
-                        const uint32_t h = (w4 * kHash4Mul) >> p.t2_shift, h2 = (w4 * kHash4Mul2) >> p.t2_shift;
-                        keep = (s_t2[h >> 5] >> (h & 31u)) & (s_t2[h2 >> 5] >> (h2 & 31u)) & 1u;
+                        keep = t2_pass(s_t2, w4, p.t2_shift);
                     } else {
                         const uint32_t m1 = tm_lookup(s_tm, w4, p.tm_bits);   // 0 = no pattern has this prefix
                         const uint32_t lim = interior ? tpos + p.max_pat_len : walk_limit(p, a0, tpos);   // never past the staged halo
