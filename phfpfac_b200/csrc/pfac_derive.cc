@@ -538,6 +538,84 @@ void derive_tables(const Partition &P, uint32_t t2_bytes, uint32_t t3_bytes, uin
         for (uint32_t w : t2) out.t2_set += (uint32_t)__builtin_popcount(w);
 }
 
+void derive_patdir(const Partition &P, PatDir &out)
+{
+    out = PatDir();
+    if (P.max_len < 1 || P.max_len > 64 || P.n_final < 1 || P.s0.empty()) return;
+    Graph g;
+    build_graph(P, g);
+    // depth-first over the trie; every state must be reached exactly once (a tree) and no deeper than max_len
+    struct Item { int32_t state; uint32_t depth; uint8_t byte; };
+    std::vector<Item> stack;
+    std::vector<uint8_t> path((size_t)P.max_len + 1);
+    std::vector<uint8_t> seen((size_t)g.n_states, 0);
+    std::vector<uint8_t> pool;
+    struct Ent { uint64_t h; uint32_t id, len, off; };
+    std::vector<Ent> ents;
+    for (int b = kCharSet - 1; b >= 0; b--)
+        if (P.s0[(size_t)b] >= 0) stack.push_back({P.s0[(size_t)b], 1u, (uint8_t)b});
+    while (!stack.empty()) {
+        const Item it = stack.back();
+        stack.pop_back();
+        if (it.state >= g.n_states || it.depth > (uint32_t)P.max_len || seen[(size_t)it.state]) return;   // not a tree of that depth
+        seen[(size_t)it.state] = 1;
+        path[it.depth - 1] = it.byte;
+        if (g.is_final(it.state)) {
+            uint64_t h = 0;
+            for (uint32_t i = 0; i < it.depth; i++) h = dir_hash_step(h, path[i]);
+            if (pool.size() + it.depth >= (1u << 25)) return;
+            ents.push_back({h, (uint32_t)P.idmap[(size_t)it.state], it.depth, (uint32_t)pool.size()});
+            pool.insert(pool.end(), path.begin(), path.begin() + it.depth);
+            out.len_mask |= 1ull << (it.depth - 1);
+        }
+        for (uint32_t e = g.end(it.state); e > g.begin(it.state); e--)
+            stack.push_back({g.edges[e - 1].next, it.depth + 1, (uint8_t)g.edges[e - 1].byte});
+    }
+    if ((int32_t)ents.size() != P.n_final) { out = PatDir(); return; }   // a final state nobody reaches: leave it to the walk
+    uint32_t n_slots = 64;
+    while (n_slots < 2 * ents.size()) n_slots *= 2;
+    out.n_slots = n_slots;
+    out.off_pow = n_slots * 16u;
+    out.off_pool = out.off_pow + (65u + 64u) * 8u + 8u;
+    out.image.assign((size_t)out.off_pool + ((pool.size() + 15) & ~(size_t)15), 0);
+    {
+        uint64_t kinv = 1;   // inverse of the odd K modulo 2^64 (Newton)
+        for (int i = 0; i < 6; i++) kinv *= 2 - kDirMul * kinv;
+        uint64_t *pw = reinterpret_cast<uint64_t *>(out.image.data() + out.off_pow);
+        pw[0] = 1;
+        for (int i = 1; i <= 64; i++) pw[i] = pw[i - 1] * kDirMul;
+        pw[65] = 1;
+        for (int i = 1; i < 64; i++) pw[65 + i] = pw[65 + i - 1] * kinv;
+    }
+    uint32_t *dir = reinterpret_cast<uint32_t *>(out.image.data());
+    for (uint32_t i = 0; i < n_slots; i++) dir[4 * i + 3] = 0xFFFFFFFFu;
+    for (const Ent &e : ents) {
+        uint32_t sl = dir_slot(e.h, n_slots);
+        while (dir[4 * sl + 3] != 0xFFFFFFFFu) sl = (sl + 1) & (n_slots - 1);
+        dir[4 * sl] = (uint32_t)e.h;
+        dir[4 * sl + 1] = (uint32_t)(e.h >> 32);
+        dir[4 * sl + 2] = e.id;
+        dir[4 * sl + 3] = (e.len << 25) | e.off;
+    }
+    if (!pool.empty()) memcpy(out.image.data() + out.off_pool, pool.data(), pool.size());
+}
+
+// Host model of the directory look-up (tests): id of the pattern text[0, d), -1 if it is none.
+int64_t patdir_lookup(const PatDir &pd, const uint8_t *text, uint32_t d)
+{
+    if (!pd.n_slots || d < 1 || d > 64) return -1;
+    uint64_t h = 0;
+    for (uint32_t i = 0; i < d; i++) h = dir_hash_step(h, text[i]);
+    const uint32_t *dir = reinterpret_cast<const uint32_t *>(pd.image.data());
+    for (uint32_t sl = dir_slot(h, pd.n_slots);; sl = (sl + 1) & (pd.n_slots - 1)) {
+        const uint32_t w = dir[4 * sl + 3];
+        if (w == 0xFFFFFFFFu) return -1;
+        if (dir[4 * sl] == (uint32_t)h && dir[4 * sl + 1] == (uint32_t)(h >> 32) && (w >> 25) == d &&
+            !memcmp(pd.image.data() + pd.off_pool + (w & 0x1FFFFFFu), text, d))
+            return dir[4 * sl + 2];
+    }
+}
+
 namespace {
 
 // The detector's stage 1 on the bytes t[0, len) (bytes past len read as 0, like stale shared memory
@@ -714,6 +792,58 @@ int derive_selfcheck(const Partition &P, const Derived &d)
                 if (!stage1_pass(d, padded.data(), padded.size(), odd != 0)) return 8;
                 if (!stage2_pass(d, padded.data(), str.size(), odd != 0, &stage)) return 10 + stage;
             }
+    }
+    return 0;
+}
+
+// The directory must answer like the walk: for every final state's own string, and for variations of it
+// (a byte changed, a byte dropped), "id of the pattern text[0, d)" equals what SUBSEG_MATCH's transitions say.
+int patdir_selfcheck(const Partition &P, const PatDir &pd)
+{
+    if (!pd.n_slots) return 0;
+    const int32_t n_states = std::max(P.state_num, 0);
+    auto walk_id = [&](const uint8_t *t, uint32_t d) -> int64_t {   // master_kernel.cu:41-70 over t[0, d)
+        int32_t st = P.s0.empty() ? -1 : P.s0[t[0]];
+        for (uint32_t i = 1; i < d && st >= 0; i++) st = P.lookup(st, t[i]);
+        return st >= 0 && st < P.n_final ? (int64_t)(uint32_t)P.idmap[(size_t)st] : -1;
+    };
+    std::vector<int32_t> par((size_t)n_states, -2), order;
+    std::vector<uint8_t> pbyte((size_t)n_states, 0);
+    for (int b = 0; b < kCharSet; b++) {
+        const int32_t s1 = P.s0.empty() ? -1 : P.s0[(size_t)b];
+        if (s1 >= 0 && s1 < n_states && par[(size_t)s1] == -2) {
+            par[(size_t)s1] = -1;
+            pbyte[(size_t)s1] = (uint8_t)b;
+            order.push_back(s1);
+        }
+    }
+    Graph g;
+    build_graph(P, g);
+    for (size_t i = 0; i < order.size(); i++)
+        for (uint32_t e = g.begin(order[i]); e < g.end(order[i]); e++) {
+            const int32_t y = g.edges[e].next;
+            if (y >= 0 && y < n_states && par[(size_t)y] == -2) {
+                par[(size_t)y] = order[i];
+                pbyte[(size_t)y] = (uint8_t)g.edges[e].byte;
+                order.push_back(y);
+            }
+        }
+    std::vector<uint8_t> str;
+    uint32_t k = 0;
+    for (int32_t f = 0; f < std::min(P.n_final, n_states); f++, k++) {
+        if (par[(size_t)f] == -2) return 1;   // the directory exists only when every final state is reachable
+        str.clear();
+        for (int32_t x = f; x >= 0; x = par[(size_t)x]) str.push_back(pbyte[(size_t)x]);
+        std::reverse(str.begin(), str.end());
+        const uint32_t d = (uint32_t)str.size();
+        if (d > 64) return 2;
+        if (patdir_lookup(pd, str.data(), d) != walk_id(str.data(), d)) return 3;
+        if (!((pd.len_mask >> (d - 1)) & 1ull)) return 4;
+        for (uint32_t dd = 1; dd < d; dd++)   // its proper prefixes (patterns themselves or not)
+            if (((pd.len_mask >> (dd - 1)) & 1ull) && patdir_lookup(pd, str.data(), dd) != walk_id(str.data(), dd)) return 5;
+        std::vector<uint8_t> v(str);
+        v[k % d] ^= (uint8_t)(1u << (k % 7));   // one byte changed
+        if (patdir_lookup(pd, v.data(), d) != walk_id(v.data(), d)) return 6;
     }
     return 0;
 }

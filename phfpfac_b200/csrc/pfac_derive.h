@@ -181,6 +181,32 @@ struct WalkCache {
 void derive_walk_cache(const Partition &P, uint32_t budget_bytes, WalkCache &out);
 int32_t walk_cache_lookup(const WalkCache &w, const uint8_t *t, uint32_t depth);
 
+// ---- pattern directory of the candidate walks (emit_tile_dir): every final state's own string, hashed.
+// A start that survived the detector's filters is settled by asking, for every pattern length d of the set
+// at once (one lane per length, independent loads), "is text[start, start + d) a pattern?" -- a hash probe
+// followed by an exact byte compare -- instead of chasing d dependent transitions through the PHF.  The
+// answers equal SUBSEG_MATCH's: the automaton is a trie, so text[start, start+d) reaches a final state iff
+// it IS that state's string.
+//   image = dir (n_slots x {h_lo, h_hi, id, len << 25 | pool offset}; open addressing, linear probing,
+//           0xFFFFFFFF in the last word = empty) | powers (K^0..K^64, K^-0..K^-63 as u64) | pool (the strings)
+// Built only for tree-shaped automata with max_len <= 64 and < 32 MiB of strings; otherwise empty and the
+// kernels walk.
+// Hash of a string b_0..b_{d-1}: the polynomial sum of (b_i + 1) K^(d-i) modulo 2^64 (Horner: h = (h + b + 1) K).
+// K is odd, so it has an inverse and the hashes of ALL prefixes of a text follow from one prefix sum:
+// h_d = K^d * sum_{i<d} (b_i + 1) K^-i  -- a warp scan on the device (emit_tile_dir).
+constexpr uint64_t kDirMul = 0x9E3779B97F4A7C15ull;
+PFAC_HD inline uint64_t dir_hash_step(uint64_t h, uint32_t byte) { return (h + (uint64_t)byte + 1ull) * kDirMul; }
+PFAC_HD inline uint32_t dir_slot(uint64_t h, uint32_t n_slots) { return (uint32_t)(h >> 24) & (n_slots - 1u); }
+struct PatDir {
+    std::vector<uint8_t> image;
+    uint32_t n_slots = 0;        // power of two, 0 = no directory
+    uint32_t off_pow = 0, off_pool = 0;
+    uint64_t len_mask = 0;       // bit d-1: some pattern has length d
+};
+void derive_patdir(const Partition &P, PatDir &out);
+int64_t patdir_lookup(const PatDir &pd, const uint8_t *text, uint32_t d);
+int patdir_selfcheck(const Partition &P, const PatDir &pd);   // 0 = the directory answers like the walk
+
 // t2/t3/tm2_bytes: shared-memory budget of the variable sections (rounded down to powers of two)
 void derive_tables(const Partition &P, uint32_t t2_bytes, uint32_t t3_bytes, uint32_t tm2_bytes, Derived &out);
 

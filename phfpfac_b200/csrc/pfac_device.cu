@@ -64,6 +64,10 @@ struct pfac_ctx {
     // tables (device): canonical s0Table, r, {HT, val}, idmap + the detector's shared-memory image
     int32_t *d_r = nullptr, *d_idmap = nullptr, *d_s0 = nullptr;
     int2 *d_htval = nullptr;
+    int4 *d_step = nullptr;    // {HT, val, r[row of val]}: the candidate walks' one-load layout (PHF width >= 256)
+    int2 *d_s0r = nullptr;     // {s0Table[b], r[row of it]}
+    uint8_t *d_patdir = nullptr;   // pattern directory of the candidate walks (pfac_derive.h PatDir); null: none
+    PatDir pd;                     // its layout (the image bytes are dropped after the upload)
     uint4 *d_image = nullptr;
     uint8_t *d_gimage = nullptr;   // mode 2: T1 | Tm | Tm2 | T3 in global memory
     uint8_t *d_wcache = nullptr;   // walk cache of the dense-match kernel (pfac_derive.h)
@@ -91,6 +95,7 @@ struct pfac_ctx {
     std::vector<cudaEvent_t> ev;   // pairs (before, after), used as a ring
     size_t ev_next = 0, ev_count = 0;
     uint32_t debug = 0;   // PFAC_DEBUG env (timing experiments only)
+    bool use_pdl = true;  // PFAC_NO_PDL=1: plain stream-ordered launches (timing experiments only)
     std::mutex mu;
 };
 
@@ -262,6 +267,15 @@ int launch_scan(pfac_ctx *ctx, Slot &slot, const void *d_in, uint64_t n_starts, 
     ep.htval = ctx->d_htval;
     ep.idmap = ctx->d_idmap;
     ep.s0 = ctx->d_s0;
+    ep.step = ctx->d_step;
+    ep.s0r = ctx->d_s0r;
+    if (ctx->d_patdir) {
+        ep.dir = reinterpret_cast<const uint4 *>(ctx->d_patdir);
+        ep.dir_pow = reinterpret_cast<const unsigned long long *>(ctx->d_patdir + ctx->pd.off_pow);
+        ep.pool = ctx->d_patdir + ctx->pd.off_pool;
+        ep.dir_slots = ctx->pd.n_slots;
+        ep.len_mask = ctx->pd.len_mask;
+    }
     ep.ht_size = ctx->ht_size;
     ep.width_bit = ctx->width_bit;
     ep.n_final = ctx->n_final;
@@ -329,8 +343,19 @@ int launch_scan(pfac_ctx *ctx, Slot &slot, const void *d_in, uint64_t n_starts, 
         guard.armed = false;
         return PFAC_OK;
     }
-    pfac_dense_kernel<false><<<grid, kDenseThreads, ctx->dense_smem, stream>>>(dp);
-    CU_TRY(cudaGetLastError());
+    // dense-match pass and ordering pass: programmatic dependent launches (their set-up overlaps the kernel before)
+    cudaLaunchAttribute pdl[1];
+    pdl[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    pdl[0].val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchConfig_t lc;
+    memset(&lc, 0, sizeof lc);
+    lc.stream = stream;
+    lc.attrs = pdl;
+    lc.numAttrs = ctx->use_pdl ? 1 : 0;
+    lc.gridDim = dim3(grid);
+    lc.blockDim = dim3(kDenseThreads);
+    lc.dynamicSmemBytes = ctx->dense_smem;
+    CU_TRY(cudaLaunchKernelEx(&lc, pfac_dense_kernel<false>, dp));
 
     FinalizeParams f;
     f.tile_cnt = slot.d_tile_cnt;
@@ -345,8 +370,10 @@ int launch_scan(pfac_ctx *ctx, Slot &slot, const void *d_in, uint64_t n_starts, 
     f.ctrl = slot.d_ctrl;
     f.result = slot.d_result;
     f.count_out = (unsigned long long *)d_count;
-    pfac_finalize_kernel<<<fgrid, kFinThreads, 0, stream>>>(f);
-    CU_TRY(cudaGetLastError());
+    lc.gridDim = dim3(fgrid);
+    lc.blockDim = dim3(kFinThreads);
+    lc.dynamicSmemBytes = 0;
+    CU_TRY(cudaLaunchKernelEx(&lc, pfac_finalize_kernel, f));
     if (tiles_out) *tiles_out = p.n_tiles;
     if (ctas_out) *ctas_out = grid;
     if (launches_out) *launches_out = 3;
@@ -411,6 +438,7 @@ int pfac_ctx_create(int device, const pfac_tables *t, int part, int n_streams, s
     ctx->max_pat_len = P.max_len;
     ctx->halo = (uint32_t)std::max(16, ((P.max_len > 0 ? P.max_len - 1 : 0) + 15) / 16 * 16);
     if (const char *dbg = getenv("PFAC_DEBUG")) ctx->debug = (uint32_t)atoi(dbg);
+    if (const char *v = getenv("PFAC_NO_PDL")) ctx->use_pdl = atoi(v) == 0;
 
     // shared-memory budget: T1 and the per-warp queues are fixed; T3 / Tm2 / T2 shrink until at least
     // four ring stages fit
@@ -478,6 +506,31 @@ int pfac_ctx_create(int device, const pfac_tables *t, int part, int n_streams, s
     if (P.n_final) CU_TRY(cudaMemcpy(ctx->d_idmap, P.idmap.data(), (size_t)P.n_final * sizeof(int32_t), cudaMemcpyHostToDevice));
     CU_TRY(cudaMemcpy(ctx->d_s0, s0.data(), 256 * sizeof(int32_t), cudaMemcpyHostToDevice));
     CU_TRY(cudaMemcpy(ctx->d_image, ctx->dv.image.data(), ctx->image_bytes, cudaMemcpyHostToDevice));
+    if (ctx->width_bit >= 8 && !P.r.empty()) {
+        // the one-load layout of the candidate walks: the row of a state's transitions depends on the state
+        // alone when a row holds at least 256 keys, so every entry can carry its successor's r[] value
+        const int sh = ctx->width_bit - 8;
+        auto r_of = [&](int32_t state) -> int32_t {
+            const size_t row = (size_t)state >> sh;
+            return state >= 0 && row < P.r.size() ? P.r[row] : -1;
+        };
+        std::vector<int4> step(n_ht, make_int4(-1, -1, -1, 0));
+        for (int32_t i = 0; i < P.ht_size; i++) step[(size_t)i] = make_int4(P.HT[(size_t)i], P.val[(size_t)i], r_of(P.val[(size_t)i]), 0);
+        std::vector<int2> s0r(256);
+        for (int b = 0; b < 256; b++) s0r[(size_t)b] = make_int2(s0[(size_t)b], r_of(s0[(size_t)b]));
+        CU_TRY(cudaMalloc(&ctx->d_step, n_ht * sizeof(int4)));
+        CU_TRY(cudaMalloc(&ctx->d_s0r, 256 * sizeof(int2)));
+        CU_TRY(cudaMemcpy(ctx->d_step, step.data(), n_ht * sizeof(int4), cudaMemcpyHostToDevice));
+        CU_TRY(cudaMemcpy(ctx->d_s0r, s0r.data(), 256 * sizeof(int2), cudaMemcpyHostToDevice));
+    }
+    if (!getenv("PFAC_NO_PATDIR")) derive_patdir(P, ctx->pd);
+    if (ctx->pd.n_slots) {
+        CU_TRY(cudaMalloc(&ctx->d_patdir, ctx->pd.image.size()));
+        CU_TRY(cudaMemcpy(ctx->d_patdir, ctx->pd.image.data(), ctx->pd.image.size(), cudaMemcpyHostToDevice));
+        ctx->table_bytes += ctx->pd.image.size();
+        ctx->pd.image.clear();
+        ctx->pd.image.shrink_to_fit();
+    }
     if (!ctx->dv.gimage.empty()) {
         CU_TRY(cudaMalloc(&ctx->d_gimage, ctx->dv.gimage.size()));
         CU_TRY(cudaMemcpy(ctx->d_gimage, ctx->dv.gimage.data(), ctx->dv.gimage.size(), cudaMemcpyHostToDevice));
@@ -500,7 +553,7 @@ int pfac_ctx_create(int device, const pfac_tables *t, int part, int n_streams, s
     }
     ctx->dense_first = ctx->dv.has_short != 0;
     if (const char *v = getenv("PFAC_DENSE_FIRST")) ctx->dense_first = atoi(v) != 0;   // experiments: force either path
-    ctx->table_bytes = n_r * 4 + n_ht * 8 + n_id * 4 + 1024 + ctx->image_bytes + ctx->dv.gimage.size() + ctx->wc_bytes;
+    ctx->table_bytes += n_r * 4 + n_ht * 8 + n_id * 4 + 1024 + ctx->image_bytes + ctx->dv.gimage.size() + ctx->wc_bytes + (ctx->d_step ? n_ht * 16 + 2048 : 0);
     ctx->dv.image.clear();
     ctx->dv.image.shrink_to_fit();
     ctx->dv.gimage.clear();
@@ -538,6 +591,9 @@ void pfac_ctx_destroy(pfac_ctx *ctx)
     slot_free(ctx->own);
     if (ctx->d_r) cudaFree(ctx->d_r);
     if (ctx->d_htval) cudaFree(ctx->d_htval);
+    if (ctx->d_step) cudaFree(ctx->d_step);
+    if (ctx->d_s0r) cudaFree(ctx->d_s0r);
+    if (ctx->d_patdir) cudaFree(ctx->d_patdir);
     if (ctx->d_idmap) cudaFree(ctx->d_idmap);
     if (ctx->d_image) cudaFree(ctx->d_image);
     if (ctx->d_s0) cudaFree(ctx->d_s0);

@@ -58,6 +58,17 @@ struct EmitParams {
     const int2 *htval;
     const int32_t *idmap;
     const int32_t *s0;        // root row, s0Table (main.cc:200)
+    // The same transition function in the layout of the candidate walks (null when the PHF width is below 256):
+    // step[idx] = {HT[idx], val[idx], r[row of val[idx]]}, s0r[b] = {s0Table[b], r[row of it]} -- a walk step is
+    // ONE dependent load instead of r[] then {HT,val}
+    const int4 *step;
+    const int2 *s0r;
+    // pattern directory (pfac_derive.h PatDir; null: walk instead): the strings of the final states, hashed
+    const uint4 *dir;
+    const unsigned long long *dir_pow;   // K^0..K^64, K^-0..K^-63
+    const uint8_t *pool;
+    uint32_t dir_slots;
+    unsigned long long len_mask;
     int32_t ht_size, width_bit, n_final;
     uint2 *scratch;
     unsigned long long scratch_cap;
@@ -191,6 +202,13 @@ __host__ inline size_t scan_smem_bytes(uint32_t image_bytes, uint32_t halo, uint
 #ifdef __CUDACC__
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// Programmatic dependent launch: the three kernels of a scan are enqueued back to back; the detector lets the
+// next kernel's launch proceed at once (pdl_launch_next), and that kernel's CTAs -- set up while the detector
+// still runs -- block in pdl_wait() until the whole grid before them has finished and its writes are visible.
+// Without the launch attribute both are no-ops.
+__device__ __forceinline__ void pdl_launch_next() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
 {
@@ -447,6 +465,75 @@ __device__ __forceinline__ uint32_t emit_walk(const EmitParams &p, uint32_t a, u
     return n;
 }
 
+__device__ __forceinline__ int4 ldg_keep(const int4 *ptr)
+{
+    int4 v;
+    asm volatile("ld.global.nc.L2::cache_hint.v4.b32 {%0, %1, %2, %3}, [%4], %5;"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(ptr), "l"(policy_evict_last()));
+    return v;
+}
+
+// Text bytes of a candidate walk: the input is read in aligned 32-bit words, one word AHEAD of the walk, so that
+// the byte a step needs is in a register and the step's only dependent load is the transition entry.  Words
+// that would reach past the readable input are not loaded (the last bytes come one by one).
+struct TextAhead {
+    const uint8_t *in;
+    uint32_t end;          // a_valid_end
+    uint32_t cur = 0, nxt = 0;
+    __device__ __forceinline__ uint32_t word(uint32_t a4) const   // aligned word at a4, bytes past `end` not touched
+    {
+        if (a4 + 4u <= end) return *reinterpret_cast<const uint32_t *>(in + a4);
+        uint32_t w = 0;
+        for (uint32_t i = 0; i < 4u && a4 + i < end; i++) w |= (uint32_t)in[a4 + i] << (8u * i);
+        return w;
+    }
+    __device__ __forceinline__ void start(uint32_t a)
+    {
+        cur = word(a & ~3u);
+        nxt = word((a & ~3u) + 4u);
+    }
+    __device__ __forceinline__ uint32_t at(uint32_t q)   // byte q; q only ever grows by one from start()'s a
+    {
+        const uint32_t b = (cur >> ((q & 3u) * 8u)) & 255u;
+        if ((q & 3u) == 3u) {
+            cur = nxt;
+            nxt = word((q & ~3u) + 8u);
+        }
+        return b;
+    }
+};
+
+// One walk, once, over the one-load layout (EmitParams::step): same states, same order as walk_collect below.
+__device__ __forceinline__ uint32_t walk_collect_fast(const EmitParams &p, uint32_t a, uint32_t lim_a, int32_t (&st)[4])
+{
+    TextAhead tx{p.in_al, p.a_valid_end};
+    tx.start(a);
+    const int2 s = ldg_keep(&p.s0r[tx.at(a)]);                       // :41
+    int32_t state = s.x, rcur = s.y;
+    if (state < 0) return 0;                                         // :43
+    uint32_t n = 0, q = a + 1;
+    const int32_t mask = (1 << p.width_bit) - 1;
+    while (true) {
+        if (state < p.n_final) {                                     // :44-47, :67-70
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+                if (n == (uint32_t)i) st[i] = state;
+            n++;
+        }
+        if (q >= lim_a) break;                                       // :50
+        const int32_t key = (state << 8) + (int32_t)tx.at(q);        // :52
+        const int32_t row = key >> p.width_bit;                      // :53
+        const int32_t idx = rcur + (key & mask);                     // :54-55
+        if (idx < 0 || idx >= p.ht_size) break;                      // :56-57
+        const int4 e = ldg_keep(&p.step[idx]);                       // :59-61
+        if (e.x != row || e.y < 0) break;                            // :63-64
+        state = e.y;
+        rcur = e.z;
+        q++;
+    }
+    return n;
+}
+
 // The same walk, once: counts the matches of start a and keeps the first kWalkKeep final states in
 // registers, so that the records can be written after the scratch space is reserved without walking
 // the (latency-bound) chain a second time.  Starts with more matches than that are walked again.
@@ -514,7 +601,7 @@ __device__ __noinline__ void emit_tile(const EmitParams &p, uint32_t tile, uint3
     const bool live = key != 0xFFFFu;
     const uint32_t a = a0 + key;
     int32_t st[kWalkKeep];
-    const uint32_t cnt = live ? walk_collect(p, a, limit(a), st) : 0u;
+    const uint32_t cnt = !live ? 0u : p.step ? walk_collect_fast(p, a, limit(a), st) : walk_collect(p, a, limit(a), st);
     uint32_t incl = cnt;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -533,6 +620,105 @@ __device__ __noinline__ void emit_tile(const EmitParams &p, uint32_t tile, uint3
         }
     }
     if (lane == 0) p.tile_cnt[tile] = total;
+}
+
+// The same for tiles with one or two candidates (nearly all of them when matches are sparse), without the
+// chain of dependent transitions: for every pattern length d of the set at once -- lane l asks for d = l + 1
+// and d = l + 33 -- "is text[start, start + d) a pattern?".  The start's bytes come from the staged tile
+// (copied to registers before the stage went back to the producer, lane l holds bytes l and l + 32); the
+// polynomial hashes of ALL prefixes come from one warp scan (pfac_derive.h); then one probe of the pattern
+// directory per length and, on a hit, an exact compare of the bytes by the whole warp.  Three rounds of
+// independent loads instead of up to 64 dependent ones.  The records equal the walk's: the automaton is a
+// trie, text[start, start + d) reaches a final state iff it is that state's own string, and the walk's bound
+// (end of input, reference tile bound, max_pat_len) caps d.  Returns false (nothing written) if a probe met a
+// foreign string with the same 64-bit hash and length -- the caller then walks.
+constexpr int kDirCand = 2;
+constexpr uint32_t kNoHit = 0xFFFFFFFFu;
+__device__ __noinline__ bool emit_tile_dir(const EmitParams &p, uint32_t tile, uint32_t key0, uint32_t key1, uint32_t b0_lo,
+                                           uint32_t b0_hi, uint32_t b1_lo, uint32_t b1_hi, int lane)
+{
+    const uint32_t a0 = tile * (uint32_t)kTile;
+    const uint32_t key[kDirCand] = {key0, key1};   // tile-relative starts in position order, 0xFFFF = none
+    const uint32_t blo[kDirCand] = {b0_lo, b1_lo}, bhi[kDirCand] = {b0_hi, b1_hi};
+    const unsigned long long kinv_lo = __ldg(&p.dir_pow[65 + lane]), kinv_hi = __ldg(&p.dir_pow[97 + lane]);
+    const unsigned long long kpow_lo = __ldg(&p.dir_pow[lane + 1]), kpow_hi = __ldg(&p.dir_pow[lane + 33]);
+    uint32_t hit[kDirCand][2], bal[kDirCand][2], total = 0;
+    bool clean = true;
+#pragma unroll
+    for (int c = 0; c < kDirCand; c++) {
+        hit[c][0] = hit[c][1] = kNoHit;
+        bal[c][0] = bal[c][1] = 0u;
+        if (key[c] == 0xFFFFu) continue;   // (uniform)
+        const uint32_t a = a0 + key[c];
+        uint32_t lim_a = p.a_valid_end;
+        if (p.use_ref_bound) {   // reference tiles: 4096 bytes of global positions + 512-byte halo (master_kernel.cu:141-144)
+            const unsigned long long g = p.base_pos + (unsigned long long)(a - p.mis);
+            const unsigned long long lim2 = ((g & ~4095ull) + 4608ull) - p.base_pos + p.mis;
+            if (lim2 < lim_a) lim_a = (uint32_t)lim2;
+        }
+        const uint32_t dmax = min(lim_a - a, p.max_pat_len);   // the deepest state the walk can reach (:50)
+        // prefix sums of (byte_i + 1) K^-i over i = 0..63, two elements per lane
+        unsigned long long s_lo = (unsigned long long)(blo[c] + 1u) * kinv_lo, s_hi = (unsigned long long)(bhi[c] + 1u) * kinv_hi;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned long long u = __shfl_up_sync(0xffffffffu, s_lo, o), v = __shfl_up_sync(0xffffffffu, s_hi, o);
+            if (lane >= o) { s_lo += u; s_hi += v; }
+        }
+        s_hi += __shfl_sync(0xffffffffu, s_lo, 31);
+        const unsigned long long hd[2] = {s_lo * kpow_lo, s_hi * kpow_hi};   // hash of text[a, a + d), d = lane + 1 / lane + 33
+        uint32_t ew[2] = {0xFFFFFFFFu, 0xFFFFFFFFu}, ez[2] = {0u, 0u};
+#pragma unroll
+        for (int r = 0; r < 2; r++) {
+            const uint32_t d = (uint32_t)lane + 1u + 32u * r;
+            if (d <= dmax && ((p.len_mask >> (d - 1u)) & 1ull)) {
+                const uint32_t lo = (uint32_t)hd[r], hi = (uint32_t)(hd[r] >> 32);
+                for (uint32_t sl = dir_slot(hd[r], p.dir_slots);; sl = (sl + 1u) & (p.dir_slots - 1u)) {
+                    const uint4 e = __ldg(&p.dir[sl]);
+                    if (e.w == 0xFFFFFFFFu) break;
+                    if (e.x == lo && e.y == hi && (e.w >> 25) == d) { ew[r] = e.w; ez[r] = e.z; break; }
+                }
+            }
+        }
+        // every hit is verified byte by byte, by the whole warp (lane l compares bytes l and l + 32)
+#pragma unroll
+        for (int r = 0; r < 2; r++) {
+            for (uint32_t hits = __ballot_sync(0xffffffffu, ew[r] != 0xFFFFFFFFu); hits; hits &= hits - 1u) {
+                const int src = __ffs(hits) - 1;
+                const uint32_t w = __shfl_sync(0xffffffffu, ew[r], src);
+                const uint32_t d = w >> 25;
+                const uint8_t *pat = p.pool + (w & 0x1FFFFFFu);
+                bool same = true;
+                if ((uint32_t)lane < d) same = (uint32_t)__ldg(&pat[lane]) == blo[c];
+                if ((uint32_t)lane + 32u < d) same = same && (uint32_t)__ldg(&pat[lane + 32]) == bhi[c];
+                if (__all_sync(0xffffffffu, same)) { if (lane == src) hit[c][r] = ez[r]; }
+                else clean = false;   // (uniform)
+            }
+            bal[c][r] = __ballot_sync(0xffffffffu, hit[c][r] != kNoHit);
+            total += __popc(bal[c][r]);
+        }
+    }
+    if (!clean) return false;
+    if (total) {
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(&p.ctrl->alloc, (unsigned long long)total);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        uint32_t off = 0;
+        const uint32_t lt = (1u << lane) - 1u;
+#pragma unroll
+        for (int c = 0; c < kDirCand; c++)
+#pragma unroll
+            for (int r = 0; r < 2; r++) {
+                const unsigned long long o = base + off + __popc(bal[c][r] & lt);
+                if (hit[c][r] != kNoHit && o < p.scratch_cap) p.scratch[o] = make_uint2(a0 + key[c] - p.mis + p.pos_bias, hit[c][r]);
+                off += __popc(bal[c][r]);
+            }
+        if (lane == 0) {
+            p.tile_src[tile] = base;
+            atomicAdd(&p.partial[tile / p.tiles_per_part], (unsigned long long)total);
+        }
+    }
+    if (lane == 0) p.tile_cnt[tile] = total;
+    return true;
 }
 
 // The control block of the detector kernels (kCtrlBytes of shared memory after the image).
@@ -575,6 +761,7 @@ __device__ __forceinline__ void bulk_g2s_plain(void *dst, const void *src, uint3
 __device__ __forceinline__ void detector_init(const ScanParams &p, const CtlView &c)
 {
     const int tid = threadIdx.x;
+    pdl_launch_next();
     if (blockIdx.x == 0)
         for (int i = tid; i < kMaxParts; i += kThreads) p.partial_next[i] = 0ull;   // (nobody touches it during this scan)
     if (tid == 0) {
@@ -661,7 +848,7 @@ __device__ __forceinline__ void producer_role(const ScanParams &p, const CtlView
 // stage back to the producer.
 template <int SLOTS_PER_TILE>
 __device__ __forceinline__ void finish_slot(const ScanParams &p, const CtlView &c, int lane, uint32_t s, uint32_t tile,
-                                            uint32_t anym, uint32_t slice0)
+                                            uint32_t anym, uint32_t slice0, const uint8_t *buf)
 {
     anym = __reduce_or_sync(0xffffffffu, anym);   // (a warp barrier: the lanes' candidate stores precede lane 0's atomic)
     uint32_t old = 0;
@@ -675,6 +862,21 @@ __device__ __forceinline__ void finish_slot(const ScanParams &p, const CtlView &
         nc = *reinterpret_cast<volatile uint32_t *>(&c.ncand[s]);
         if (nc > (uint32_t)kCandPerTile) nc = kCandOverflow;   // too many (or the overflow bit is set)
         if (nc != kCandOverflow && (uint32_t)lane < nc) my_cand = *reinterpret_cast<volatile uint16_t *>(&c.cand[s * kCandPerTile + lane]);
+        __syncwarp();
+    }
+    // one or two candidates and a pattern directory: their bytes are taken along (lane l: bytes l and l + 32)
+    const bool by_dir = p.emit.dir != nullptr && nc >= 1u && nc <= (uint32_t)kDirCand;
+    uint32_t key0 = 0xFFFFu, key1 = 0xFFFFu, b0_lo = 0, b0_hi = 0, b1_lo = 0, b1_hi = 0;
+    if (by_dir) {
+        key0 = __shfl_sync(0xffffffffu, my_cand, 0);
+        key1 = __shfl_sync(0xffffffffu, my_cand, 1);
+        if (key1 < key0) { const uint32_t t = key0; key0 = key1; key1 = t; }
+        if ((uint32_t)lane < p.max_pat_len) b0_lo = buf[key0 + lane];
+        if ((uint32_t)lane + 32u < p.max_pat_len) b0_hi = buf[key0 + 32u + lane];
+        if (key1 != 0xFFFFu) {
+            if ((uint32_t)lane < p.max_pat_len) b1_lo = buf[key1 + lane];
+            if ((uint32_t)lane + 32u < p.max_pat_len) b1_hi = buf[key1 + 32u + lane];
+        }
         __syncwarp();
     }
     if (lane == 0) {
@@ -694,7 +896,9 @@ __device__ __forceinline__ void finish_slot(const ScanParams &p, const CtlView &
     // the producer (the walk reads the input and the PHF from global memory: microseconds of dependent
     // loads that must stall one warp, not the ring).
 #ifndef PFAC_EXP_NO_EMIT   // (timing experiment: no walks, no records)
-    if (flags && nc != kCandOverflow) emit_tile(p.emit, tile, my_cand, lane);
+    if (flags && nc != kCandOverflow) {
+        if (!by_dir || !emit_tile_dir(p.emit, tile, key0, key1, b0_lo, b0_hi, b1_lo, b1_hi, lane)) emit_tile(p.emit, tile, my_cand, lane);
+    }
 #endif
 }
 
@@ -980,7 +1184,7 @@ __global__ void __launch_bounds__(kThreads, 1) pfac_scan2_kernel(const ScanParam
                 add_candidate(c.ncand + s, c.cand + s * kCandPerTile, tpos);
             }
         }
-        finish_slot<kSlotsPerTile>(p, c, lane, s, tile, anym, slice0);
+        finish_slot<kSlotsPerTile>(p, c, lane, s, tile, anym, slice0, buf);
     }
 }
 
@@ -1145,7 +1349,7 @@ __global__ void __launch_bounds__(kThreads, 1) pfac_scan_kernel(const ScanParams
                 add_candidate(s_ncand + s, s_cand + s * kCandPerTile, tpos);
             }
         }
-        finish_slot<kSlotsPerTile>(p, c, lane, s, tile, anym, slice0);
+        finish_slot<kSlotsPerTile>(p, c, lane, s, tile, anym, slice0, buf);
     }
 }
 
@@ -1195,7 +1399,11 @@ __host__ inline size_t dense_smem_bytes(uint32_t wc_bytes, uint32_t halo)
 template <bool DIRECT>
 __global__ void __launch_bounds__(kDenseThreads, 1) pfac_dense_kernel(const DenseParams d)
 {
-    if (!DIRECT && *d.n_dense == 0u) return;   // the common case: sparse matches, nothing was handed over
+    if (!DIRECT) {
+        pdl_launch_next();
+        pdl_wait();   // the detector has finished
+        if (*reinterpret_cast<const volatile unsigned int *>(d.n_dense) == 0u) return;   // the common case: sparse matches, nothing was handed over
+    }
     const EmitParams &p = d.e;
     const uint32_t wcb = (d.wc_bytes + 127u) & ~127u;
     const int32_t *s_s0 = reinterpret_cast<const int32_t *>(smem);
@@ -1529,6 +1737,7 @@ __global__ void __launch_bounds__(kFinThreads) pfac_finalize_kernel(const Finali
     __shared__ unsigned int s_big[kFinThreads / 32];
     __shared__ unsigned long long s_run;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    pdl_wait();   // the kernels before this one have finished
     const uint32_t per = f.tiles_per_part;   // CTA b owns tiles [b*per, (b+1)*per); partial[b] = matches in them
     const uint32_t lo = min(f.n_tiles, blockIdx.x * per), hi = min(f.n_tiles, lo + per);
 

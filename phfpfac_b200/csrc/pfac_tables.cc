@@ -787,6 +787,12 @@ int pfac_tables_derive_check(const pfac_tables *t, int part, uint32_t t2_bytes, 
         }
         const int bad = derive_selfcheck(*P, d);
         if (bad) return set_error(PFAC_ERR_INTERNAL, "derived tables violate invariant %d", bad);
+        {   // the pattern directory of the candidate walks must answer like the walk
+            PatDir pd;
+            derive_patdir(*P, pd);
+            const int pbad = patdir_selfcheck(*P, pd);
+            if (pbad) return set_error(PFAC_ERR_INTERNAL, "pattern directory violates invariant %d", pbad);
+        }
         // the dense-match kernel's walk cache must be the PHF's transition function on the levels it covers
         for (uint32_t budget : {131072u, 16384u, 2048u}) {
             WalkCache w;
