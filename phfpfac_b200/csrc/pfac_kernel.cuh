@@ -355,7 +355,7 @@ __device__ __forceinline__ void filter16(const uint4 v, const uint32_t nx, const
 
 // Stage 1 of the global mode (pattern sets whose prefixes do not fit the shared-memory Tm): the
 // hashed 4-byte prefix of each of the 16 starts against T2 (a blocked Bloom filter, pfac_derive.h), which
-// fills shared memory -- one LDS.32 and one mask compare per start.  Same result format as filter16.
+// fills shared memory -- one LDS.32 and one mask compare per start.  Result: bit j = start j of the lane passes.
 __device__ __forceinline__ uint32_t one_hot(uint32_t n) { return __funnelshift_l(0u, 1u, n); }   // 1 << (n & 31): SHF.L.W
 __device__ __forceinline__ bool t2_probe(const uint32_t *__restrict__ t2, uint32_t w4, uint32_t shift)
 {
@@ -365,21 +365,27 @@ __device__ __forceinline__ bool t2_probe(const uint32_t *__restrict__ t2, uint32
     for (int i = 1; i < kT2KeyBits; i++) m |= one_hot(h >> (shift - 5u * i));   // (shared-memory tables have at most 2^21 bits: shift >= 11)
     return (t2[h >> (shift + 5u)] & m) == m;
 }
-__device__ __forceinline__ void filter16_t2(const uint4 v, const uint32_t nx, const uint32_t *__restrict__ t2,
-                                            uint32_t shift, uint32_t &lo, uint32_t &hi)
+__device__ __forceinline__ uint32_t filter16_t2(const uint4 v, const uint32_t nx, const uint32_t *__restrict__ t2, uint32_t shift)
 {
     const uint32_t w[5] = {v.x, v.y, v.z, v.w, nx};
-    uint32_t acc[2] = {0u, 0u};
+    uint32_t acc = 0u;   // bit j: start j passes
 #pragma unroll
     for (int k = 0; k < 4; k++) {
 #pragma unroll
         for (int j = 0; j < 4; j++) {
             const uint32_t w4 = j == 0 ? w[k] : __funnelshift_r(w[k], w[k + 1], 8 * j);
-            if (t2_probe(t2, w4, shift)) acc[k >> 1] |= 1u << (((k & 1) * 4 + j) * 4);
+            if (t2_probe(t2, w4, shift)) acc |= 1u << (k * 4 + j);
         }
     }
-    lo = acc[0];
-    hi = acc[1];
+    return acc;
+}
+// bit 0 of each of the 8 nibbles -> 8 adjacent bits
+__device__ __forceinline__ uint32_t nibble_bits(uint32_t x)
+{
+    x &= 0x11111111u;
+    x = (x | (x >> 3)) & 0x03030303u;
+    x = (x | (x >> 6)) & 0x000F000Fu;
+    return (x | (x >> 12)) & 0xFFu;
 }
 
 // tile-relative bound of what a start at tile-relative tpos may read (master_kernel.cu:141-144 + input end)
@@ -673,7 +679,8 @@ __device__ __noinline__ bool emit_tile_dir(const EmitParams &p, uint32_t tile, u
             if (d <= dmax && ((p.len_mask >> (d - 1u)) & 1ull)) {
                 const uint32_t lo = (uint32_t)hd[r], hi = (uint32_t)(hd[r] >> 32);
                 for (uint32_t sl = dir_slot(hd[r], p.dir_slots);; sl = (sl + 1u) & (p.dir_slots - 1u)) {
-                    const uint4 e = __ldg(&p.dir[sl]);
+                    const int4 ei = ldg_keep(reinterpret_cast<const int4 *>(&p.dir[sl]));   // (evict-last: the directory stays in L2)
+                    const uint4 e = make_uint4((uint32_t)ei.x, (uint32_t)ei.y, (uint32_t)ei.z, (uint32_t)ei.w);
                     if (e.w == 0xFFFFFFFFu) break;
                     if (e.x == lo && e.y == hi && (e.w >> 25) == d) { ew[r] = e.w; ez[r] = e.z; break; }
                 }
@@ -1227,7 +1234,6 @@ __global__ void __launch_bounds__(kThreads, 1) pfac_scan_kernel(const ScanParams
     // k % n_stages, phase k / n_stages.  A warp leaves on a slot of the sentinel tile or, told by
     // s_kend, on one past it.
     uint16_t *wq = reinterpret_cast<uint16_t *>(qbase + warp * kQueueBytes);   // stage-1 survivors of the slot
-    const uint32_t lt_mask = (1u << lane) - 1u;
 
     for (;;) {
         uint32_t s, slot_in_tile, tile;
@@ -1242,27 +1248,32 @@ __global__ void __launch_bounds__(kThreads, 1) pfac_scan_kernel(const ScanParams
         const bool interior = !p.use_ref_bound && a0 >= p.mis && valid_t >= (uint32_t)kTile + p.max_pat_len &&
                               a0 + (uint32_t)kTile <= p.a_start_end;
         uint32_t anym = 0;   // bit h: slice slice0 + h has a start that survived
-        uint32_t nq = 0;
-        // stage 1: T1 over 16 positions per lane and slice, compaction into the warp queue
+        // stage 1 of all the slot's slices: T1 (or, in global mode, T2) over 16 positions per lane and slice ->
+        // one 16-bit mask per slice (bit j: start j of the lane's 16 bytes passed)
+        uint32_t m16[kSlotSlices];
 #pragma unroll
         for (int h = 0; h < kSlotSlices; h++) {
+            m16[h] = 0u;
             const uint32_t off = (slice0 + h) * kSlice + lane * 16;
-            if (a0 + (slice0 + h) * kSlice >= p.a_start_end) break;   // no start positions from here on
+            if (a0 + (slice0 + h) * kSlice >= p.a_start_end) continue;   // (uniform) no start positions from here on
             const uint4 v = *reinterpret_cast<const uint4 *>(buf + off);
             // the 4 bytes after the lane's 16 are the next lane's first word (a strided shared-memory
             // read of them would be a 4-way bank conflict); lane 31 reads its own
             uint32_t nx = __shfl_down_sync(0xffffffffu, v.x, 1);
             if (lane == 31) nx = *reinterpret_cast<const uint32_t *>(buf + off + 16);
-            uint32_t lo = 0, hi = 0;   // one nibble per start, bit 0 = passes stage 1
+            uint32_t m = 0;
             if (!(p.debug & 4u)) {
                 if (MODE == 2) {
-                    filter16_t2(v, nx, s_t2, p.t2_shift, lo, hi);
+                    m = filter16_t2(v, nx, s_t2, p.t2_shift);
+                } else {
+                    uint32_t lo = 0, hi = 0;   // one nibble per start, bit 0 = passes stage 1
+                    filter16(v, nx, lane, lo, hi);
+                    m = nibble_bits(lo) | (nibble_bits(hi) << 8);
                 }
-                else filter16(v, nx, lane, lo, hi);
             }
             if (p.debug & 16u) {   // diagnostics: stage 1 alone (its result is consumed, nothing survives)
-                if ((lo ^ hi) == 0x9e3779b9u) anym |= 1u << h;
-                lo = hi = 0;
+                if (m == 0x9e37u) anym |= 1u << h;
+                m = 0;
             }
             if (!interior) {   // start positions are [mis, a_start_end) in aligned coordinates
                 const uint32_t a = a0 + off;
@@ -1270,30 +1281,28 @@ __global__ void __launch_bounds__(kThreads, 1) pfac_scan_kernel(const ScanParams
                 const uint32_t last = p.a_start_end > a ? p.a_start_end - a : 0u;
                 uint32_t keep = last >= 16u ? 0xffffu : ((1u << last) - 1u);
                 keep &= first >= 16u ? 0u : (0xffffu << first);
-                // spread the 16-bit keep mask to nibbles
-                uint32_t klo = 0, khi = 0;
-#pragma unroll
-                for (int j = 0; j < 8; j++) {
-                    klo |= ((keep >> j) & 1u) << (4 * j);
-                    khi |= ((keep >> (8 + j)) & 1u) << (4 * j);
-                }
-                lo &= klo;
-                hi &= khi;
+                m &= keep;
             }
-            // compaction into the warp queue: every round, each lane that still has survivors hands over
-            // its lowest one (rank by ballot).  Few lanes have any, so this beats a prefix scan; the
-            // order of the queue does not matter (the emit kernel sorts the few candidates).
-            while (true) {
-                const uint32_t bal = __ballot_sync(0xffffffffu, (lo | hi) != 0u);
-                if (!bal) break;
-                if (lo | hi) {
-                    uint32_t pos;
-                    if (lo) { pos = (__ffs(lo) - 1) >> 2; lo &= lo - 1; }
-                    else { pos = 8 + ((__ffs(hi) - 1) >> 2); hi &= hi - 1; }
-                    const uint32_t idx = nq + __popc(bal & lt_mask);
-                    if (idx < (uint32_t)kQ1Cap) wq[idx] = (uint16_t)(off + pos);
-                }
-                nq += __popc(bal);
+            m16[h] = m;
+        }
+        // compaction: the lanes' survivor counts are scanned across the warp and every lane writes its own
+        // into the queue (order irrelevant: the candidates are sorted where it matters)
+        uint32_t cnt = 0;
+#pragma unroll
+        for (int h = 0; h < kSlotSlices; h++) cnt += __popc(m16[h]);
+        uint32_t incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t n = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += n;
+        }
+        uint32_t nq = __shfl_sync(0xffffffffu, incl, 31);
+        if (nq <= (uint32_t)kQ1Cap) {
+            uint16_t *wp = wq + (incl - cnt);
+#pragma unroll
+            for (int h = 0; h < kSlotSlices; h++) {
+                const uint32_t pb = (slice0 + h) * kSlice + lane * 16;
+                for (uint32_t mm = m16[h]; mm; mm &= mm - 1) *wp++ = (uint16_t)(pb + __ffs(mm) - 1);
             }
         }
         if (nq > (uint32_t)kQ1Cap) {   // dense slot: the emit kernel looks at all of it
