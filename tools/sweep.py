@@ -1,6 +1,9 @@
 #!/usr/bin/env python
-"""Input-size / stream-count sweep on one GPU (BASELINE.json configs[4]): device-resident and
-end-to-end GB/s of the config-3 pattern set over 1 MiB .. 4 GiB.  Prints a markdown table."""
+"""Input-size / stream-count / GPU-count sweep (BASELINE.json configs[4]).  Part 1, one GPU: device-resident
+and end-to-end (pfac_scan_host) GB/s of a pattern set over 1 MiB .. 3 GiB at 1-8 streams.  Part 2
+(--job-gib): inputs of several GiB through the product's own scheduler, pfac_job_run, from ONE process over
+1, 2, 4, 8 of the box's GPUs (pinned host input -> H2D -> scan -> D2H, wall clock), and the same input
+device-resident on one GPU in 1 GiB calls.  Prints markdown tables."""
 import argparse, ctypes as C, os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
@@ -14,12 +17,16 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--mib", default="1,4,16,64,256,1024,3072")
 ap.add_argument("--streams", default="1,2,4,8")
 ap.add_argument("--workload", default="config3")
+ap.add_argument("--job-gib", default="", help="part 2: input sizes in GiB, e.g. 1,4,8,16,32")
+ap.add_argument("--job-streams", default="1,4,8")
 a = ap.parse_args()
 pk, cnt, pseed, lo, hi, tk, tseed, nbytes, desc = WORKLOADS[a.workload]
 pats = synth.synth_patterns(pk, cnt, pseed, lo, hi)
 tables = pf.Tables.from_bytes(pats)
-sizes = [int(x) << 20 for x in a.mib.split(",")]
-nmax = max(sizes)
+sizes = [int(x) << 20 for x in a.mib.split(",") if x]
+job_sizes = [int(x) << 30 for x in a.job_gib.split(",") if x]
+nmax = max(sizes + [1 << 20])
+print(f"workload {a.workload}: {desc}; {torch.cuda.device_count()} GPU(s)\n")
 h_text = torch.empty(nmax, dtype=torch.uint8, pin_memory=True)
 synth.synth_text(tk, tseed, nmax, patterns=pats, out=h_text.numpy())
 d_text = h_text.cuda()
@@ -57,3 +64,55 @@ for n in sizes:
         cols.append(n * it2 / (time.perf_counter() - t0) / 1e9)
         m.close()
     print(f"| {n >> 20} MiB | {dev:.1f} | " + " | ".join(f"{x:.1f}" for x in cols) + " |", flush=True)
+
+if job_sizes:
+    del d_text, h_text
+    torch.cuda.empty_cache()
+    ngpu = torch.cuda.device_count()
+    gl = [g for g in (1, 2, 4, 8) if g <= ngpu]
+    streams = [int(x) for x in a.job_streams.split(",")]
+    print()
+    print("| input | device-resident GB/s (1 GPU, 1 GiB calls) | " + " | ".join(f"job e2e GB/s, {g} GPU x {s} streams" for g in gl for s in streams) + " |")
+    print("|---|---|" + "---|" * (len(gl) * len(streams)))
+    base = None
+    for n in job_sizes:
+        try:
+            h = torch.empty(n, dtype=torch.uint8, pin_memory=True)
+        except Exception as e:   # not enough host memory to pin
+            print(f"| {n >> 30} GiB | (cannot pin {n >> 30} GiB of host memory: {type(e).__name__}) |")
+            break
+        hn = h.numpy()
+        if base is None:
+            base = np.empty(1 << 30, dtype=np.uint8)
+            synth.synth_text(tk, tseed, 1 << 30, patterns=pats, out=base)
+        for o in range(0, n, 1 << 30):
+            hn[o:o + (1 << 30)] = base[:min(1 << 30, n - o)]
+        # device-resident: the same bytes in 1 GiB calls on GPU 0
+        m = pf.Matcher(tables, device=0, n_streams=1)
+        d = torch.from_numpy(base).cuda()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        calls = n >> 30
+        for _ in range(2):
+            m.scan_device_raw(d.data_ptr(), 1 << 30, 1 << 30, 0, d_out.data_ptr(), cap, d_cnt.data_ptr(), st.cuda_stream)
+        e0.record()
+        for _ in range(calls):
+            m.scan_device_raw(d.data_ptr(), 1 << 30, 1 << 30, 0, d_out.data_ptr(), cap, d_cnt.data_ptr(), st.cuda_stream)
+        e1.record(); torch.cuda.synchronize()
+        dev = n / (e0.elapsed_time(e1) * 1e-3) / 1e9
+        m.close(); del d
+        cols = []
+        for g in gl:
+            for s_ in streams:
+                job = pf.Job(tables, devices=list(range(g)), streams_per_gpu=s_)
+                nm = C.c_uint64(0)
+                pf.check(pf.lib.pfac_job_run(job._h, h.data_ptr(), n, C.byref(nm)))   # warm-up (allocations)
+                best = 1e9
+                for _ in range(2):
+                    t0 = time.perf_counter()
+                    pf.check(pf.lib.pfac_job_run(job._h, h.data_ptr(), n, C.byref(nm)))
+                    best = min(best, time.perf_counter() - t0)
+                cols.append(n / best / 1e9)
+                job.close()
+        print(f"| {n >> 30} GiB | {dev:.1f} | " + " | ".join(f"{x:.1f}" for x in cols) + f" | ({nm.value} matches)", flush=True)
+        del h, hn
