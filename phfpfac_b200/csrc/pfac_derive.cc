@@ -575,18 +575,8 @@ void derive_patdir(const Partition &P, PatDir &out)
     uint32_t n_slots = 64;
     while (n_slots < 2 * ents.size()) n_slots *= 2;
     out.n_slots = n_slots;
-    out.off_pow = n_slots * 16u;
-    out.off_pool = out.off_pow + (65u + 64u) * 8u + 8u;
+    out.off_pool = n_slots * 16u;
     out.image.assign((size_t)out.off_pool + ((pool.size() + 15) & ~(size_t)15), 0);
-    {
-        uint64_t kinv = 1;   // inverse of the odd K modulo 2^64 (Newton)
-        for (int i = 0; i < 6; i++) kinv *= 2 - kDirMul * kinv;
-        uint64_t *pw = reinterpret_cast<uint64_t *>(out.image.data() + out.off_pow);
-        pw[0] = 1;
-        for (int i = 1; i <= 64; i++) pw[i] = pw[i - 1] * kDirMul;
-        pw[65] = 1;
-        for (int i = 1; i < 64; i++) pw[65 + i] = pw[65 + i - 1] * kinv;
-    }
     uint32_t *dir = reinterpret_cast<uint32_t *>(out.image.data());
     for (uint32_t i = 0; i < n_slots; i++) dir[4 * i + 3] = 0xFFFFFFFFu;
     for (const Ent &e : ents) {

@@ -188,19 +188,34 @@ int32_t walk_cache_lookup(const WalkCache &w, const uint8_t *t, uint32_t depth);
 // answers equal SUBSEG_MATCH's: the automaton is a trie, so text[start, start+d) reaches a final state iff
 // it IS that state's string.
 //   image = dir (n_slots x {h_lo, h_hi, id, len << 25 | pool offset}; open addressing, linear probing,
-//           0xFFFFFFFF in the last word = empty) | powers (K^0..K^64, K^-0..K^-63 as u64) | pool (the strings)
+//           0xFFFFFFFF in the last word = empty) | pool (the strings)
 // Built only for tree-shaped automata with max_len <= 64 and < 32 MiB of strings; otherwise empty and the
 // kernels walk.
 // Hash of a string b_0..b_{d-1}: the polynomial sum of (b_i + 1) K^(d-i) modulo 2^64 (Horner: h = (h + b + 1) K).
 // K is odd, so it has an inverse and the hashes of ALL prefixes of a text follow from one prefix sum:
 // h_d = K^d * sum_{i<d} (b_i + 1) K^-i  -- a warp scan on the device (emit_tile_dir).
 constexpr uint64_t kDirMul = 0x9E3779B97F4A7C15ull;
+PFAC_HD constexpr uint64_t dir_cpow(uint64_t b, uint32_t e)   // b^e modulo 2^64
+{
+    uint64_t r = 1;
+    for (; e; e >>= 1, b *= b)
+        if (e & 1u) r *= b;
+    return r;
+}
+PFAC_HD constexpr uint64_t dir_inverse(uint64_t k)   // of an odd k modulo 2^64 (Newton)
+{
+    uint64_t x = 1;
+    for (int i = 0; i < 6; i++) x *= 2 - k * x;
+    return x;
+}
+constexpr uint64_t kDirMulInv = dir_inverse(kDirMul);
+static_assert(kDirMul * kDirMulInv == 1ull, "K is invertible");
 PFAC_HD inline uint64_t dir_hash_step(uint64_t h, uint32_t byte) { return (h + (uint64_t)byte + 1ull) * kDirMul; }
 PFAC_HD inline uint32_t dir_slot(uint64_t h, uint32_t n_slots) { return (uint32_t)(h >> 24) & (n_slots - 1u); }
 struct PatDir {
     std::vector<uint8_t> image;
     uint32_t n_slots = 0;        // power of two, 0 = no directory
-    uint32_t off_pow = 0, off_pool = 0;
+    uint32_t off_pool = 0;
     uint64_t len_mask = 0;       // bit d-1: some pattern has length d
 };
 void derive_patdir(const Partition &P, PatDir &out);

@@ -271,7 +271,6 @@ int launch_scan(pfac_ctx *ctx, Slot &slot, const void *d_in, uint64_t n_starts, 
     ep.s0r = ctx->d_s0r;
     if (ctx->d_patdir) {
         ep.dir = reinterpret_cast<const uint4 *>(ctx->d_patdir);
-        ep.dir_pow = reinterpret_cast<const unsigned long long *>(ctx->d_patdir + ctx->pd.off_pow);
         ep.pool = ctx->d_patdir + ctx->pd.off_pool;
         ep.dir_slots = ctx->pd.n_slots;
         ep.len_mask = ctx->pd.len_mask;
@@ -303,13 +302,27 @@ int launch_scan(pfac_ctx *ctx, Slot &slot, const void *d_in, uint64_t n_starts, 
     // match at a large share of the start positions of natural text: no filter pays off, the dense-match
     // kernel walks every tile straight away.
     const bool dense_first = ctx->dense_first;
+    // Every kernel of a scan is a programmatic dependent launch: its CTAs are set up (and the detector's filter
+    // image is on its way into shared memory) while the kernel before it -- the ordering pass of the previous
+    // scan on this stream, for the detector -- still runs; each kernel waits (griddepcontrol.wait) before it
+    // touches anything an earlier kernel may write.
+    cudaLaunchAttribute pdl[1];
+    pdl[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    pdl[0].val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchConfig_t lc;
+    memset(&lc, 0, sizeof lc);
+    lc.stream = stream;
+    lc.attrs = pdl;
+    lc.numAttrs = ctx->use_pdl ? 1 : 0;
+    lc.gridDim = dim3(grid);
+    lc.blockDim = dim3(kThreads);
+    lc.dynamicSmemBytes = ctx->smem_bytes;
     if (dense_first) {}
-    else if (ctx->dv.mode == 2) pfac_scan_kernel<2><<<grid, kThreads, ctx->smem_bytes, stream>>>(p);
-    else if (ctx->dv.mode == 1) pfac_scan_kernel<1><<<grid, kThreads, ctx->smem_bytes, stream>>>(p);
-    else if (ctx->dv.has_short) pfac_scan2_kernel<true, true><<<grid, kThreads, ctx->smem_bytes, stream>>>(p);
-    else if (ctx->dv.has_shortc) pfac_scan2_kernel<false, true><<<grid, kThreads, ctx->smem_bytes, stream>>>(p);
-    else pfac_scan2_kernel<false, false><<<grid, kThreads, ctx->smem_bytes, stream>>>(p);
-    CU_TRY(cudaGetLastError());
+    else if (ctx->dv.mode == 2) CU_TRY(cudaLaunchKernelEx(&lc, pfac_scan_kernel<2>, p));
+    else if (ctx->dv.mode == 1) CU_TRY(cudaLaunchKernelEx(&lc, pfac_scan_kernel<1>, p));
+    else if (ctx->dv.has_short) CU_TRY(cudaLaunchKernelEx(&lc, pfac_scan2_kernel<true, true>, p));
+    else if (ctx->dv.has_shortc) CU_TRY(cudaLaunchKernelEx(&lc, pfac_scan2_kernel<false, true>, p));
+    else CU_TRY(cudaLaunchKernelEx(&lc, pfac_scan2_kernel<false, false>, p));
     if (ev_after && !dense_first) CU_TRY(cudaEventRecord(ev_after, stream));
 
 
@@ -343,15 +356,7 @@ int launch_scan(pfac_ctx *ctx, Slot &slot, const void *d_in, uint64_t n_starts, 
         guard.armed = false;
         return PFAC_OK;
     }
-    // dense-match pass and ordering pass: programmatic dependent launches (their set-up overlaps the kernel before)
-    cudaLaunchAttribute pdl[1];
-    pdl[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    pdl[0].val.programmaticStreamSerializationAllowed = 1;
-    cudaLaunchConfig_t lc;
-    memset(&lc, 0, sizeof lc);
-    lc.stream = stream;
-    lc.attrs = pdl;
-    lc.numAttrs = ctx->use_pdl ? 1 : 0;
+    // dense-match pass and ordering pass
     lc.gridDim = dim3(grid);
     lc.blockDim = dim3(kDenseThreads);
     lc.dynamicSmemBytes = ctx->dense_smem;

@@ -65,7 +65,6 @@ struct EmitParams {
     const int2 *s0r;
     // pattern directory (pfac_derive.h PatDir; null: walk instead): the strings of the final states, hashed
     const uint4 *dir;
-    const unsigned long long *dir_pow;   // K^0..K^64, K^-0..K^-63
     const uint8_t *pool;
     uint32_t dir_slots;
     unsigned long long len_mask;
@@ -640,29 +639,42 @@ __device__ __noinline__ void emit_tile(const EmitParams &p, uint32_t tile, uint3
 // foreign string with the same 64-bit hash and length -- the caller then walks.
 constexpr int kDirCand = 2;
 constexpr uint32_t kNoHit = 0xFFFFFFFFu;
+// K^e (or K^-e) for e < 64 from compile-time squares: six predicated 64-bit multiplies, no memory
+template <bool INV>
+__device__ __forceinline__ unsigned long long dir_pow(uint32_t e)
+{
+    unsigned long long r = 1ull;
+#pragma unroll
+    for (int i = 0; i < 6; i++)
+        if ((e >> i) & 1u) r *= dir_cpow(INV ? kDirMulInv : kDirMul, 1u << i);
+    return r;
+}
 __device__ __noinline__ bool emit_tile_dir(const EmitParams &p, uint32_t tile, uint32_t key0, uint32_t key1, uint32_t b0_lo,
                                            uint32_t b0_hi, uint32_t b1_lo, uint32_t b1_hi, int lane)
 {
     const uint32_t a0 = tile * (uint32_t)kTile;
     const uint32_t key[kDirCand] = {key0, key1};   // tile-relative starts in position order, 0xFFFF = none
     const uint32_t blo[kDirCand] = {b0_lo, b1_lo}, bhi[kDirCand] = {b0_hi, b1_hi};
-    const unsigned long long kinv_lo = __ldg(&p.dir_pow[65 + lane]), kinv_hi = __ldg(&p.dir_pow[97 + lane]);
-    const unsigned long long kpow_lo = __ldg(&p.dir_pow[lane + 1]), kpow_hi = __ldg(&p.dir_pow[lane + 33]);
-    uint32_t hit[kDirCand][2], bal[kDirCand][2], total = 0;
-    bool clean = true;
+    const unsigned long long kinv_lo = dir_pow<true>((uint32_t)lane), kinv_hi = kinv_lo * dir_cpow(kDirMulInv, 32u);
+    const unsigned long long kpow_lo = dir_pow<false>((uint32_t)lane + 1u), kpow_hi = kpow_lo * dir_cpow(kDirMul, 32u);
+    // 1. the prefix hashes and the first probe of every (candidate, length): independent loads, all in flight together
+    unsigned long long hd[kDirCand][2];
+    uint32_t sl[kDirCand][2];
+    int4 e[kDirCand][2];
+    bool ask[kDirCand][2];
 #pragma unroll
     for (int c = 0; c < kDirCand; c++) {
-        hit[c][0] = hit[c][1] = kNoHit;
-        bal[c][0] = bal[c][1] = 0u;
-        if (key[c] == 0xFFFFu) continue;   // (uniform)
-        const uint32_t a = a0 + key[c];
-        uint32_t lim_a = p.a_valid_end;
-        if (p.use_ref_bound) {   // reference tiles: 4096 bytes of global positions + 512-byte halo (master_kernel.cu:141-144)
-            const unsigned long long g = p.base_pos + (unsigned long long)(a - p.mis);
-            const unsigned long long lim2 = ((g & ~4095ull) + 4608ull) - p.base_pos + p.mis;
-            if (lim2 < lim_a) lim_a = (uint32_t)lim2;
+        uint32_t dmax = 0;
+        if (key[c] != 0xFFFFu) {   // (uniform)
+            const uint32_t a = a0 + key[c];
+            uint32_t lim_a = p.a_valid_end;
+            if (p.use_ref_bound) {   // reference tiles: 4096 bytes of global positions + 512-byte halo (master_kernel.cu:141-144)
+                const unsigned long long g = p.base_pos + (unsigned long long)(a - p.mis);
+                const unsigned long long lim2 = ((g & ~4095ull) + 4608ull) - p.base_pos + p.mis;
+                if (lim2 < lim_a) lim_a = (uint32_t)lim2;
+            }
+            dmax = min(lim_a - a, p.max_pat_len);   // the deepest state the walk can reach (:50)
         }
-        const uint32_t dmax = min(lim_a - a, p.max_pat_len);   // the deepest state the walk can reach (:50)
         // prefix sums of (byte_i + 1) K^-i over i = 0..63, two elements per lane
         unsigned long long s_lo = (unsigned long long)(blo[c] + 1u) * kinv_lo, s_hi = (unsigned long long)(bhi[c] + 1u) * kinv_hi;
 #pragma unroll
@@ -671,43 +683,57 @@ __device__ __noinline__ bool emit_tile_dir(const EmitParams &p, uint32_t tile, u
             if (lane >= o) { s_lo += u; s_hi += v; }
         }
         s_hi += __shfl_sync(0xffffffffu, s_lo, 31);
-        const unsigned long long hd[2] = {s_lo * kpow_lo, s_hi * kpow_hi};   // hash of text[a, a + d), d = lane + 1 / lane + 33
-        uint32_t ew[2] = {0xFFFFFFFFu, 0xFFFFFFFFu}, ez[2] = {0u, 0u};
+        hd[c][0] = s_lo * kpow_lo;   // hash of text[a, a + d), d = lane + 1
+        hd[c][1] = s_hi * kpow_hi;   //                         d = lane + 33
 #pragma unroll
         for (int r = 0; r < 2; r++) {
             const uint32_t d = (uint32_t)lane + 1u + 32u * r;
-            if (d <= dmax && ((p.len_mask >> (d - 1u)) & 1ull)) {
-                const uint32_t lo = (uint32_t)hd[r], hi = (uint32_t)(hd[r] >> 32);
-                for (uint32_t sl = dir_slot(hd[r], p.dir_slots);; sl = (sl + 1u) & (p.dir_slots - 1u)) {
-                    const int4 ei = ldg_keep(reinterpret_cast<const int4 *>(&p.dir[sl]));   // (evict-last: the directory stays in L2)
-                    const uint4 e = make_uint4((uint32_t)ei.x, (uint32_t)ei.y, (uint32_t)ei.z, (uint32_t)ei.w);
-                    if (e.w == 0xFFFFFFFFu) break;
-                    if (e.x == lo && e.y == hi && (e.w >> 25) == d) { ew[r] = e.w; ez[r] = e.z; break; }
-                }
-            }
+            ask[c][r] = d <= dmax && ((p.len_mask >> (d - 1u)) & 1ull);
+            sl[c][r] = dir_slot(hd[c][r], p.dir_slots);
+            e[c][r] = make_int4(0, 0, 0, -1);
+            if (ask[c][r]) e[c][r] = ldg_keep(reinterpret_cast<const int4 *>(&p.dir[sl[c][r]]));
         }
-        // every hit is verified byte by byte, by the whole warp (lane l compares bytes l and l + 32)
+    }
+    // 2. resolve the probes (open addressing: nearly always the first slot decides)
+    uint32_t hit[kDirCand][2], ew[kDirCand][2], bal[kDirCand][2], total = 0;
+#pragma unroll
+    for (int c = 0; c < kDirCand; c++)
 #pragma unroll
         for (int r = 0; r < 2; r++) {
-            for (uint32_t hits = __ballot_sync(0xffffffffu, ew[r] != 0xFFFFFFFFu); hits; hits &= hits - 1u) {
-                const int src = __ffs(hits) - 1;
-                const uint32_t w = __shfl_sync(0xffffffffu, ew[r], src);
+            hit[c][r] = kNoHit;
+            ew[c][r] = 0xFFFFFFFFu;
+            if (ask[c][r]) {
+                const uint32_t d = (uint32_t)lane + 1u + 32u * r, lo = (uint32_t)hd[c][r], hi = (uint32_t)(hd[c][r] >> 32);
+                int4 x = e[c][r];
+                for (uint32_t q = sl[c][r]; (uint32_t)x.w != 0xFFFFFFFFu;) {
+                    if ((uint32_t)x.x == lo && (uint32_t)x.y == hi && ((uint32_t)x.w >> 25) == d) { ew[c][r] = (uint32_t)x.w; hit[c][r] = (uint32_t)x.z; break; }
+                    q = (q + 1u) & (p.dir_slots - 1u);
+                    x = ldg_keep(reinterpret_cast<const int4 *>(&p.dir[q]));
+                }
+            }
+            bal[c][r] = __ballot_sync(0xffffffffu, hit[c][r] != kNoHit);
+            total += __popc(bal[c][r]);
+        }
+    // 3. the records' place in the scratch is reserved while the hits are verified byte by byte by the whole warp
+    //    (lane l compares bytes l and l + 32 of the stored string)
+    unsigned long long base = 0;
+    if (total && lane == 0) base = atomicAdd(&p.ctrl->alloc, (unsigned long long)total);
+    bool clean = true;
+#pragma unroll
+    for (int c = 0; c < kDirCand; c++)
+#pragma unroll
+        for (int r = 0; r < 2; r++)
+            for (uint32_t hits = bal[c][r]; hits; hits &= hits - 1u) {
+                const uint32_t w = __shfl_sync(0xffffffffu, ew[c][r], __ffs(hits) - 1);
                 const uint32_t d = w >> 25;
                 const uint8_t *pat = p.pool + (w & 0x1FFFFFFu);
                 bool same = true;
                 if ((uint32_t)lane < d) same = (uint32_t)__ldg(&pat[lane]) == blo[c];
                 if ((uint32_t)lane + 32u < d) same = same && (uint32_t)__ldg(&pat[lane + 32]) == bhi[c];
-                if (__all_sync(0xffffffffu, same)) { if (lane == src) hit[c][r] = ez[r]; }
-                else clean = false;   // (uniform)
+                clean = clean && __all_sync(0xffffffffu, same);   // (uniform)
             }
-            bal[c][r] = __ballot_sync(0xffffffffu, hit[c][r] != kNoHit);
-            total += __popc(bal[c][r]);
-        }
-    }
-    if (!clean) return false;
+    if (!clean) return false;   // a foreign string with the same hash and length: the caller walks (the reservation stays unused)
     if (total) {
-        unsigned long long base = 0;
-        if (lane == 0) base = atomicAdd(&p.ctrl->alloc, (unsigned long long)total);
         base = __shfl_sync(0xffffffffu, base, 0);
         uint32_t off = 0;
         const uint32_t lt = (1u << lane) - 1u;
@@ -769,8 +795,6 @@ __device__ __forceinline__ void detector_init(const ScanParams &p, const CtlView
 {
     const int tid = threadIdx.x;
     pdl_launch_next();
-    if (blockIdx.x == 0)
-        for (int i = tid; i < kMaxParts; i += kThreads) p.partial_next[i] = 0ull;   // (nobody touches it during this scan)
     if (tid == 0) {
         for (uint32_t s = 0; s < p.n_stages; s++) {
             mbar_init(&c.full[s], 1);
@@ -788,6 +812,12 @@ __device__ __forceinline__ void detector_init(const ScanParams &p, const CtlView
         for (uint32_t o = 0; o < p.image_bytes; o += 32768u)
             bulk_g2s(smem + o, src + o, min(32768u, p.image_bytes - o), c.imgbar, keep);
     }
+    // up to here nothing was read or written that an earlier kernel on the stream may touch (the image is
+    // constant): the kernels before this one -- the previous scan's ordering pass, whoever produced the input --
+    // must have finished before the rest
+    pdl_wait();
+    if (blockIdx.x == 0)
+        for (int i = tid; i < kMaxParts; i += kThreads) p.partial_next[i] = 0ull;   // (nobody touches it during this scan)
     __syncthreads();
 }
 __device__ __forceinline__ void image_wait(const ScanParams &p, const CtlView &c)
@@ -925,13 +955,16 @@ __device__ __forceinline__ bool take_slot(const ScanParams &p, const CtlView &c,
     const uint32_t round = __umulhi(k, p.stage_magic);   // k / n_stages, exact for k < 2^32 / n_stages
     s = k - round * p.n_stages;
     // the wait suspends the warp in hardware; only when it times out is the end of the work checked
-    for (Watchdog wd; !mbar_try_wait_for(&c.full[s], round & 1u, kWaitNs);) {
+    if (mbar_try_wait(&c.full[s], round & 1u)) goto have_tile;   // the common case: the tile is there already
+    for (Watchdog wd;;) {
         if (*reinterpret_cast<volatile uint32_t *>(c.kend) < k) return false;   // a slot past the end of the work
+        if (mbar_try_wait_for(&c.full[s], round & 1u, kWaitNs)) break;
         if (wd.expired()) {
             atomicExch(&p.ctrl->error_flag, 2u);
             return false;
         }
     }
+have_tile:
     tile = c.tile[s];   // bit 31 = interior flag (producer_role)
     return (tile & 0x7FFFFFFFu) < p.n_tiles;
 }
@@ -1746,7 +1779,8 @@ __global__ void __launch_bounds__(kFinThreads) pfac_finalize_kernel(const Finali
     __shared__ unsigned int s_big[kFinThreads / 32];
     __shared__ unsigned long long s_run;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    pdl_wait();   // the kernels before this one have finished
+    pdl_launch_next();   // (the next scan's detector may set itself up)
+    pdl_wait();          // the kernels before this one have finished
     const uint32_t per = f.tiles_per_part;   // CTA b owns tiles [b*per, (b+1)*per); partial[b] = matches in them
     const uint32_t lo = min(f.n_tiles, blockIdx.x * per), hi = min(f.n_tiles, lo + per);
 

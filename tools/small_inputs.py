@@ -30,4 +30,26 @@ for mib in (1, 4, 16, 64, 128):
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / 20
     kms, kn = m.kernel_time()
-    print(f"{mib} MiB: step {ms*1e3:.1f} us, detector {kms/kn*1e3:.1f} us, emit+finalize+gaps {(ms-kms/kn)*1e3:.1f} us, {n/ms/1e6:.1f} GB/s")
+    # the same without the event pair around the detector (which breaks the chain of dependent launches),
+    # and the host's own time to enqueue a scan
+    m.set_timing(False)
+    import time
+    for _ in range(3):
+        m.scan_device_raw(d.data_ptr(), n, n, 0, out.data_ptr(), cap, cntd.data_ptr(), st.cuda_stream)
+    torch.cuda.synchronize()
+    e0.record()
+    t0 = time.perf_counter()
+    for _ in range(200):
+        m.scan_device_raw(d.data_ptr(), n, n, 0, out.data_ptr(), cap, cntd.data_ptr(), st.cuda_stream)
+    t_enq = (time.perf_counter() - t0) / 200
+    e1.record(); torch.cuda.synchronize()
+    ms2 = e0.elapsed_time(e1) / 200
+    # one scan at a time (host waits for each): latency of a single call
+    t0 = time.perf_counter()
+    for _ in range(50):
+        m.scan_device_raw(d.data_ptr(), n, n, 0, out.data_ptr(), cap, cntd.data_ptr(), st.cuda_stream)
+        st.synchronize()
+    t_one = (time.perf_counter() - t0) / 50
+    m.set_timing(True)
+    print(f"{mib} MiB: step {ms2*1e3:.1f} us back to back ({n/ms2/1e6:.1f} GB/s; host enqueue {t_enq*1e6:.1f} us per scan; one call + sync {t_one*1e6:.1f} us); "
+          f"with event timing: step {ms*1e3:.1f} us, detector {kms/kn*1e3:.1f} us")
