@@ -447,6 +447,23 @@ def main():
     sampler.active.clear()
     kernel_ms_total, kernel_launches = m.kernel_time()
     m.set_timing(False)
+    warm = None
+    if flush:
+        # the same steps back to back with a warm L2 and no event pair around each kernel: NOT the bench value
+        # (the input fits the L2), reported because the reference's own kernel time -- one launch right after
+        # its H2D copy, `reference_gpu` of the reference arm -- is a warm-L2 figure too
+        for _ in range(3):
+            step_dev()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        for _ in range(max(args.steps, 20)):
+            step_dev()
+        ev1.record()
+        torch.cuda.synchronize()
+        warm_ms = ev0.elapsed_time(ev1) / max(args.steps, 20)
+        warm = {"ms_per_step": warm_ms, "value": n / (warm_ms * 1e-3) / 1e9, "unit": "GB/s",
+                "note": "steps back to back, input and tables L2-resident (the input is smaller than the L2): like for like with "
+                        "reference_gpu.kernel_ms of `bench.py --impl reference`, which is one launch right after its H2D copy"}
     dev_records = d_out[:n_matches].cpu().numpy().copy()
     dev_launches_per_step = m.last_info()["launches"]
     if dist:
@@ -574,9 +591,15 @@ def main():
         kernel_name = "pfac_dense_kernel<DIRECT>" if dense_first else \
             ("pfac_scan2_kernel" if dinfo["mode"] == 0 else "pfac_scan_kernel")
         ncu = None   # selected metrics of the committed ncu capture of the dominant kernel (not measured in this run)
-        npath = os.path.join(ROOT, "profiles", "r2_ncu_full_detector_1GiB.json")
+        npath = os.path.join(ROOT, "profiles", "r2_ncu_detector_config3_1GiB.json")   # tools/ncu_summary.py
         if os.path.exists(npath) and args.workload == "config3" and plain:
-            capture = json.load(open(npath))[0]
+            capture = json.load(open(npath))["kernels"][0]
+
+            def _bytes(v):   # "1.074303 Gbyte" -> bytes
+                x, u = str(v).split()[:2]
+                return float(x) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[u]
+            if "dram__bytes_read.sum" in capture and "dram__bytes_write.sum" in capture:
+                traffic = _bytes(capture["dram__bytes_read.sum"]) + _bytes(capture["dram__bytes_write.sum"])
             pick = {"smem_pipe_pct_of_peak": "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed",
                     "issue_active_pct": "smsp__issue_active.avg.pct_of_peak_sustained_active",
                     "alu_pipe_pct": "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active",
@@ -585,7 +608,7 @@ def main():
                     "shared_wavefronts": "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
                     "threads_per_instruction": "smsp__thread_inst_executed_per_inst_executed.ratio"}
             ncu = {k: float(str(capture[v]).split()[0]) for k, v in pick.items() if v in capture}
-            ncu["source"] = "profiles/r2_ncu_full_detector_1GiB.json (ncu --set full, same workload)"
+            ncu["source"] = "profiles/r2_ncu_detector_config3_1GiB.json (ncu --set full, same workload)"
         ms_step = ms_max / args.steps
         alg_bytes = n + 8 * n_matches           # per launch: input bytes + 8 B per match record
         kernel_ms = kernel_ms_total / max(kernel_launches, 1)
@@ -628,6 +651,8 @@ def main():
         }
         if job_leg is not None:
             line["e2e_job"] = job_leg
+        if warm is not None:
+            line["warm_l2"] = warm
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(part, mpl, text[:n])
         print(json.dumps(line))

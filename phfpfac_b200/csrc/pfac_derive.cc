@@ -3,6 +3,7 @@
 // i.e. from what CreateTable + FFDM (reference create_table_reorder.c:277, phf.c:151) emit, so
 // tables handed in through pfac_tables_from_arrays get the same treatment.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <numeric>
 #include <string>
@@ -494,6 +495,36 @@ void derive_tables(const Partition &P, uint32_t t2_bytes, uint32_t t3_bytes, uin
         out.off_t3 = off;
         off = align128(off + t3_bits / 8);
         out.image.assign(off, 0);
+        if (out.mode == 0 && !any_short && !getenv("PFAC_NO_W3")) {
+            // third-window planes: pairs at bytes 4-5 / 5-6 of every path, and the exceptions for the patterns
+            // that end before them (depth-first to depth 7; an automaton with too many paths gets planes that
+            // pass everything)
+            std::vector<uint8_t> w3(65536, 0);
+            uint64_t visits = 0;
+            bool flood = false;
+            struct Node { int32_t state; uint32_t depth; uint8_t byte; };
+            std::vector<Node> stack;
+            uint8_t path[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            for (int b = kCharSet - 1; b >= 0; b--)
+                if (s0(b) >= 0) stack.push_back({s0(b), 1u, (uint8_t)b});
+            while (!stack.empty() && !flood) {
+                const Node nd = stack.back();
+                stack.pop_back();
+                if (++visits > kPathLimit) { flood = true; break; }
+                path[nd.depth - 1] = nd.byte;
+                if (nd.depth == 6) w3[t1_index(path[4], path[5])] |= kT1P45;
+                if (nd.depth == 7) w3[t1_index(path[5], path[6])] |= kT1P56;
+                if (g.is_final(nd.state)) {
+                    if (nd.depth == 4 || nd.depth == 5) w3[t1_index(path[2], path[3])] |= kT1ShX;
+                    if (nd.depth == 5 || nd.depth == 6) w3[t1_index(path[3], path[4])] |= kT1ShX;
+                }
+                if (nd.depth < 7)
+                    for (uint32_t e = g.end(nd.state); e > g.begin(nd.state); e--)
+                        stack.push_back({g.edges[e - 1].next, nd.depth + 1, (uint8_t)g.edges[e - 1].byte});
+            }
+            for (size_t i = 0; i < 65536; i++) t1[i] |= flood ? (uint8_t)(kT1P45 | kT1P56) : w3[i];
+            out.has_w3 = 1;
+        }
         memcpy(out.image.data() + out.off_t1, t1.data(), 65536);
         if (t2_bits) memcpy(out.image.data() + out.off_t2, t2.data(), t2_bits / 8);
         if (out.has_t3) {
@@ -623,11 +654,15 @@ bool stage1_pass(const Derived &d, const uint8_t *t, size_t len, bool odd)
         // mode 0 probes T1 at even offsets of the (16-byte aligned) input stream only.  A start at an
         // even offset sees its bytes 0-1 and 2-3, one at an odd offset its bytes 1-2 and 3-4.
         if (!odd) {
-            const uint32_t v0 = t1[t1_index(at(0), at(1))];
-            return (v0 & kT1P01) && ((v0 & kT1Short) || (t1[t1_index(at(2), at(3))] & kT1P23));
+            const uint32_t v0 = t1[t1_index(at(0), at(1))], v2 = t1[t1_index(at(2), at(3))];
+            if (d.has_w3)   // (no Short plane: its bit is ShX)
+                return (v0 & kT1P01) && (v2 & kT1P23) && ((v2 & kT1ShX) || (t1[t1_index(at(4), at(5))] & kT1P45));
+            return (v0 & kT1P01) && ((v0 & kT1Short) || (v2 & kT1P23));
         }
-        const uint32_t v1 = t1[t1_index(at(1), at(2))];
-        return (v1 & kT1ShortC) || ((v1 & kT1P12) && (t1[t1_index(at(3), at(4))] & kT1P34));
+        const uint32_t v1 = t1[t1_index(at(1), at(2))], v3 = t1[t1_index(at(3), at(4))];
+        if (d.has_w3)
+            return (v1 & kT1ShortC) || ((v1 & kT1P12) && (v3 & kT1P34) && ((v3 & kT1ShX) || (t1[t1_index(at(5), at(6))] & kT1P56)));
+        return (v1 & kT1ShortC) || ((v1 & kT1P12) && (v3 & kT1P34));
     }
     const uint32_t v0 = t1[t1_index(at(0), at(1))];
     if (!(v0 & kT1P01)) return false;

@@ -113,6 +113,11 @@ PFAC_HD inline uint32_t rot2(uint32_t c) { return c; }
 #endif
 PFAC_HD inline uint32_t t1_index(uint32_t c0, uint32_t c1) { return rot2(c0) | (rot2(c1) << 8); }
 constexpr uint8_t kT1P01 = 1, kT1P12 = 2, kT1P23 = 4, kT1Short = 8, kT1P34 = 16, kT1ShortC = 32;
+// Third-window planes of the mode-0 detector (Derived::has_w3; only for sets without patterns of <= 3 bytes,
+// whose Short plane is empty -- ShX takes its bit): an even start also needs its bytes 4-5 (P45) unless its
+// bytes 2-3 end-or-nearly-end a pattern of 4-5 bytes (ShX); an odd start its bytes 5-6 (P56) unless its
+// bytes 3-4 belong to a pattern of 5-6 bytes (ShX again: one plane for both exceptions).
+constexpr uint8_t kT1P45 = 64, kT1P56 = 128, kT1ShX = 8;
 
 // ---- perfect-hash tables of the mode-0 detector (hash-and-displace, one slot per key).
 // bucket = mulhi(x, nb) with x = a mixed hash of the key, d = D[bucket], slot = mulhi(key * c3 + d *
@@ -151,6 +156,7 @@ struct Derived {
     uint32_t t2_shift = 32;      // T2 has 2^(32 - t2_shift) bits (t2_word / t2_mask above); 32: no T2
     uint32_t has_short = 0;      // patterns of length <= 3 exist (T1's Short plane is not empty)
     uint32_t has_shortc = 0;     // patterns of length <= 4 exist (T1's ShortC plane is not empty)
+    uint32_t has_w3 = 0;         // T1 carries the third-window planes P45 / P56 / ShX (mode 0, no short patterns)
     uint32_t has_t3 = 0;         // Tm + T3 present (then no T2)
     uint32_t t3_shift = 32;
     uint32_t tm_bits = 0, tm2_bits = 0;   // log2 buckets of Tm / Tm2 (0: absent; mode 2 only)

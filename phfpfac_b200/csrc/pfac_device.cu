@@ -320,9 +320,11 @@ int launch_scan(pfac_ctx *ctx, Slot &slot, const void *d_in, uint64_t n_starts, 
     if (dense_first) {}
     else if (ctx->dv.mode == 2) CU_TRY(cudaLaunchKernelEx(&lc, pfac_scan_kernel<2>, p));
     else if (ctx->dv.mode == 1) CU_TRY(cudaLaunchKernelEx(&lc, pfac_scan_kernel<1>, p));
-    else if (ctx->dv.has_short) CU_TRY(cudaLaunchKernelEx(&lc, pfac_scan2_kernel<true, true>, p));
-    else if (ctx->dv.has_shortc) CU_TRY(cudaLaunchKernelEx(&lc, pfac_scan2_kernel<false, true>, p));
-    else CU_TRY(cudaLaunchKernelEx(&lc, pfac_scan2_kernel<false, false>, p));
+    else if (ctx->dv.has_short) CU_TRY(cudaLaunchKernelEx(&lc, pfac_scan2_kernel<true, true, false>, p));
+    else if (ctx->dv.has_shortc && ctx->dv.has_w3) CU_TRY(cudaLaunchKernelEx(&lc, pfac_scan2_kernel<false, true, true>, p));
+    else if (ctx->dv.has_shortc) CU_TRY(cudaLaunchKernelEx(&lc, pfac_scan2_kernel<false, true, false>, p));
+    else if (ctx->dv.has_w3) CU_TRY(cudaLaunchKernelEx(&lc, pfac_scan2_kernel<false, false, true>, p));
+    else CU_TRY(cudaLaunchKernelEx(&lc, pfac_scan2_kernel<false, false, false>, p));
     if (ev_after && !dense_first) CU_TRY(cudaEventRecord(ev_after, stream));
 
 
@@ -346,8 +348,10 @@ int launch_scan(pfac_ctx *ctx, Slot &slot, const void *d_in, uint64_t n_starts, 
         dp.epoch = slot.flip % 0xFFFFFEu + 1u;
         dp.result = slot.d_result;
         dp.count_out = (unsigned long long *)d_count;
-        pfac_dense_kernel<true><<<grid, kDenseThreads, ctx->dense_smem, stream>>>(dp);
-        CU_TRY(cudaGetLastError());
+        lc.gridDim = dim3(grid);
+        lc.blockDim = dim3(kDenseThreads);
+        lc.dynamicSmemBytes = ctx->dense_smem;
+        CU_TRY(cudaLaunchKernelEx(&lc, pfac_dense_kernel<true>, dp));
         if (ev_after) CU_TRY(cudaEventRecord(ev_after, stream));
         if (tiles_out) *tiles_out = p.n_tiles;
         if (ctas_out) *ctas_out = grid;
@@ -567,16 +571,18 @@ int pfac_ctx_create(int device, const pfac_tables *t, int part, int n_streams, s
     // the attribute is per function and device, not per context: always allow the device maximum
     CU_TRY(cudaFuncSetAttribute(pfac_scan_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
     CU_TRY(cudaFuncSetAttribute(pfac_scan_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
-    CU_TRY(cudaFuncSetAttribute(pfac_scan2_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
-    CU_TRY(cudaFuncSetAttribute(pfac_scan2_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
-    CU_TRY(cudaFuncSetAttribute(pfac_scan2_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
+    CU_TRY(cudaFuncSetAttribute(pfac_scan2_kernel<true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
+    CU_TRY(cudaFuncSetAttribute(pfac_scan2_kernel<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
+    CU_TRY(cudaFuncSetAttribute(pfac_scan2_kernel<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
+    CU_TRY(cudaFuncSetAttribute(pfac_scan2_kernel<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
+    CU_TRY(cudaFuncSetAttribute(pfac_scan2_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
     int bps = 0;
     if (ctx->dv.mode == 2)
         CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, pfac_scan_kernel<2>, kThreads, ctx->smem_bytes));
     else if (ctx->dv.mode == 1)
         CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, pfac_scan_kernel<1>, kThreads, ctx->smem_bytes));
     else
-        CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, pfac_scan2_kernel<true, true>, kThreads, ctx->smem_bytes));
+        CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, pfac_scan2_kernel<true, true, false>, kThreads, ctx->smem_bytes));
     if (bps < 1) return set_error(PFAC_ERR_CUDA, "scan kernel does not fit on an SM (smem %zu B)", ctx->smem_bytes);
 
     CU_TRY(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));

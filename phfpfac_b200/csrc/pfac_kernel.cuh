@@ -982,9 +982,17 @@ have_tile:
 // Stage 2 (per slot, lane-parallel over the compacted survivors): the 4-byte prefix in the
 // perfect-hash table of level 1 -> m1; the window that ends the shortest pattern below it keys level 2
 // -> m2; the window that ends the shortest pattern of that group in T3.
-template <bool HAS_SHORT, bool HAS_SC>
+template <bool HAS_SHORT, bool HAS_SC, bool W3>
 __device__ __forceinline__ uint32_t s1_combine(uint32_t X, uint32_t Xn)
 {
+    if (W3) {
+        // with the third-window planes (pfac_derive.h; no Short plane then): an even start 2k also needs P45 of
+        // window k+2 unless ShX of window k+1 excuses it, an odd start 2k+1 P56 of window k+3 unless ShX of k+2
+        const uint32_t ev = __funnelshift_r(X, Xn, 10) & (__funnelshift_r(X, Xn, 22) | __funnelshift_r(X, Xn, 11));   // -> bit 0
+        uint32_t od = __funnelshift_r(X, Xn, 8) & __funnelshift_r(X, Xn, 19) & (__funnelshift_r(X, Xn, 30) | __funnelshift_r(X, Xn, 18));   // -> bit 1
+        if (HAS_SC) od |= __funnelshift_r(X, Xn, 12);
+        return (X & ev & 0x01010101u) | (od & 0x02020202u);
+    }
     // X = T1 bytes of windows k..k+3, Xn = of the four after them.  Result: bit 0 of byte k = even
     // start 2k passes, bit 1 = odd start 2k+1 passes.
     uint32_t b = __funnelshift_r(X, Xn, 10);                       // P23 of window k+1 -> bit 0
@@ -1017,7 +1025,7 @@ __device__ __forceinline__ uint32_t load_w4(const uint8_t *buf, uint32_t pos)
 // `above` (HAS_ABOVE): the first T1 register of the slice after the pair, already probed by the caller (the
 // slot's pairs go top down), so that only the slot's last slice pays lane 31's own look-ups; x0_out = this
 // pair's lower slice's, for the pair below.
-template <bool HAS_SHORT, bool HAS_SC, bool HAS_ABOVE>
+template <bool HAS_SHORT, bool HAS_SC, bool W3, bool HAS_ABOVE>
 __device__ __forceinline__ uint32_t s1_pair(const uint8_t *buf, uint32_t pair, int lane, uint32_t next_lane, uint32_t above, uint32_t &x0_out)
 {
     const uint4 v1 = *reinterpret_cast<const uint4 *>(buf + pair + kSlice);
@@ -1034,12 +1042,13 @@ __device__ __forceinline__ uint32_t s1_pair(const uint8_t *buf, uint32_t pair, i
     if (!HAS_ABOVE && lane == 31) {
         const uint32_t r = rot2x4(*reinterpret_cast<const uint32_t *>(buf + pair + kSlice + 16));
         ey = (uint32_t)smem[r & 0xffffu] | ((uint32_t)smem[r >> 16] << 8);
+        if (W3) ey |= (uint32_t)smem[rot2x4(*reinterpret_cast<const uint32_t *>(buf + pair + kSlice + 20)) & 0xffffu] << 16;   // (one window more)
     }
     const uint32_t ex = __shfl_sync(0xffffffffu, lane == 0 ? Y0 : X0, next_lane);
-    const uint32_t q0 = s1_combine<HAS_SHORT, HAS_SC>(X0, X1) * 0x01041040u;
-    const uint32_t q1 = s1_combine<HAS_SHORT, HAS_SC>(X1, ex) * 0x01041040u;
-    const uint32_t q2 = s1_combine<HAS_SHORT, HAS_SC>(Y0, Y1) * 0x01041040u;
-    const uint32_t q3 = s1_combine<HAS_SHORT, HAS_SC>(Y1, ey) * 0x01041040u;
+    const uint32_t q0 = s1_combine<HAS_SHORT, HAS_SC, W3>(X0, X1) * 0x01041040u;
+    const uint32_t q1 = s1_combine<HAS_SHORT, HAS_SC, W3>(X1, ex) * 0x01041040u;
+    const uint32_t q2 = s1_combine<HAS_SHORT, HAS_SC, W3>(Y0, Y1) * 0x01041040u;
+    const uint32_t q3 = s1_combine<HAS_SHORT, HAS_SC, W3>(Y1, ey) * 0x01041040u;
     // byte 3 of each product = the 8 results in start order
     return __byte_perm(__byte_perm(q0, q1, 0x0073), __byte_perm(q2, q3, 0x0073), 0x5410);
 }
@@ -1048,7 +1057,7 @@ constexpr int kSlotSlices2 = slot_slices(0);   // slices per slot of the mode-0 
 static_assert(kSlotSlices2 % 2 == 0 && kSlicesPerTile % kSlotSlices2 == 0, "slots are made of slice pairs");
 constexpr int kQ2Cap = q1_cap(0);              // survivors a slot's queue holds; a slot with more is handed over whole
 
-template <bool HAS_SHORT, bool HAS_SC>
+template <bool HAS_SHORT, bool HAS_SC, bool W3>
 __global__ void __launch_bounds__(kThreads, 1) pfac_scan2_kernel(const ScanParams p)
 {
     constexpr int kSlotSlices = kSlotSlices2, kSlotsPerTile = kSlicesPerTile / kSlotSlices;
@@ -1091,9 +1100,9 @@ __global__ void __launch_bounds__(kThreads, 1) pfac_scan2_kernel(const ScanParam
         const uint32_t base = slice0 * kSlice + lane * 16;   // tile-relative position of the lane's first start
         {
             uint32_t x0 = 0;
-            m[kPairs - 1] = s1_pair<HAS_SHORT, HAS_SC, false>(buf, base + (kPairs - 1) * 2 * kSlice, lane, next_lane, 0u, x0);
+            m[kPairs - 1] = s1_pair<HAS_SHORT, HAS_SC, W3, false>(buf, base + (kPairs - 1) * 2 * kSlice, lane, next_lane, 0u, x0);
 #pragma unroll
-            for (int pr = kPairs - 2; pr >= 0; pr--) m[pr] = s1_pair<HAS_SHORT, HAS_SC, true>(buf, base + pr * 2 * kSlice, lane, next_lane, x0, x0);
+            for (int pr = kPairs - 2; pr >= 0; pr--) m[pr] = s1_pair<HAS_SHORT, HAS_SC, W3, true>(buf, base + pr * 2 * kSlice, lane, next_lane, x0, x0);
         }
         if (!interior) {   // start positions are [mis, a_start_end) in aligned coordinates
 #pragma unroll
@@ -1466,8 +1475,10 @@ __global__ void __launch_bounds__(kDenseThreads, 1) pfac_dense_kernel(const Dens
     uint2 *const dst = DIRECT ? d.out : p.scratch;
     const unsigned long long dst_cap = DIRECT ? d.cap : p.scratch_cap;
 
+    if (DIRECT) pdl_launch_next();
     for (uint32_t i = tid; i < d.wc_bytes / 16; i += kDenseThreads)
         reinterpret_cast<uint4 *>(smem)[i] = __ldg(reinterpret_cast<const uint4 *>(d.wc_image) + i);
+    if (DIRECT) pdl_wait();   // the walk cache (constant) is on its way; everything else waits for the kernels before
 
     // the cached transition: state after (b0 .. b_{depth-1}) or -1
     auto cached = [&](uint32_t key) -> int32_t {
