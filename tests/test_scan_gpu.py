@@ -418,6 +418,46 @@ def test_shallow_ring(monkeypatch):
     assert np.array_equal(want["pos"][:k].astype(np.int64), pos[:k]) and np.array_equal(want["id"][:k].astype(np.int32), ids[:k])
 
 
+@pytest.mark.parametrize("toggle", ["PFAC_NO_PATDIR", "PFAC_NO_W3", "PFAC_NO_PDL"])
+def test_alternative_paths_agree(monkeypatch, toggle):
+    """The candidates of a tile are settled through the pattern directory (all lengths probed in parallel, exact
+    compare) or by the walk; stage 1 runs with or without the third-window planes; the kernels of a scan are
+    programmatic dependent launches or plain ones.  Whatever the path: the oracle's records, bit for bit --
+    sparse planted matches, matches side by side in one tile (two-candidate tiles), nested patterns, a match at
+    the very end of the input, back-to-back scans on one stream."""
+    torch = torch_cuda()
+    pats = synth.synth_patterns(1, 3000, 3, 4, 64) + b"GET /index\nGET /in\nGET /index.html HTTP/1.1\n"
+    text = synth.synth_text(1, 21, 6 << 20, patterns=pats).copy()
+    lines = pats.split(b"\n")[:-1]
+    rng = np.random.default_rng(5)
+    for k in range(400):   # pairs of matches a few bytes apart, nested ones, one ending the input
+        at = int(rng.integers(0, len(text) - 400))
+        for j in range(2):
+            q = lines[int(rng.integers(0, len(lines)))]
+            text[at:at + len(q)] = np.frombuffer(q, dtype=np.uint8)
+            at += len(q) + int(rng.integers(0, 40))
+    last = lines[-1]
+    text[len(text) - len(last):] = np.frombuffer(last, dtype=np.uint8)
+    o = Oracle(pats, 1, 256)
+    pos, ids = o.scan(text)
+    t = pf.Tables.from_bytes(pats, 1, 256)
+    d = torch.from_numpy(text).cuda()
+    got = {}
+    for off in (False, True):
+        if off:
+            monkeypatch.setenv(toggle, "1")
+        m = pf.Matcher(t, device=0, n_streams=3, chunk_bytes=1 << 20)
+        for _ in range(3):   # back to back on one stream
+            r = m.scan_device(d, n_starts=len(text), n_valid=len(text))
+        got[off] = (r, m.scan_host(text))
+        m.close()
+    monkeypatch.delenv(toggle)
+    for off, (rd, rh) in got.items():
+        for r in (rd, rh):
+            assert len(r) == len(pos) and len(pos) > 800, (toggle, off, len(r), len(pos))
+            assert np.array_equal(r["pos"].astype(np.int64), pos) and np.array_equal(r["id"].astype(np.int32), ids), (toggle, off)
+
+
 def test_device_scans_on_two_streams_share_one_context(fixtures):
     """pfac_scan_device calls of one context enqueued on different streams are ordered on the device
     (they share the control block and the tile directory): interleave two inputs on two streams."""
