@@ -114,8 +114,8 @@ int pfac_tables_derive_check(const pfac_tables *t, int part, uint32_t t2_bytes, 
                              uint32_t tm2_bytes, uint64_t stats[10]);
 /* Diagnostics: how many start positions of `text` survive each stage of the detector's filter
  * cascade (a host model that COUNTS; it reports no matches).  counts[0..8] = positions, T1 pass,
- * prefix found (T2/Tm), level-1 window pass, level-2 window pass, bypass, starts left for the
- * emit kernel, 512-byte slices flagged, slices. */
+ * prefix found (T2 / level 1), level-1 window pass, level-2 window pass, bypass, starts left as
+ * candidates, 512-byte slices flagged, slices. */
 int pfac_tables_filter_profile(const pfac_tables *t, int part, uint32_t t2_bytes, uint32_t t3_bytes,
                                uint32_t tm2_bytes, const void *text, uint64_t n, uint64_t counts[12]);
 /* One transition through the PHF exactly as master_kernel.cu:52-64 does it; -1 = none. */
@@ -168,8 +168,7 @@ void pfac_host_unregister(const void *ptr);
 
 /* Counters of the last scan on this context (for bench.py's gpu_launches / roofline):
  * info[0] = kernel launches, info[1] = tiles, info[2] = CTAs, info[3] = dynamic smem bytes,
- * info[4] = h2d bytes, info[5] = d2h bytes, info[6] = sub-chunks, info[7] = tiles the detector
- * flagged for the emit kernel (pfac_scan_device_sync only) */
+ * info[4] = h2d bytes, info[5] = d2h bytes, info[6] = sub-chunks, info[7] = reserved (0) */
 int pfac_ctx_last_scan_info(const pfac_ctx *ctx, uint64_t info[8]);
 
 /* Optional CUDA-event timing of the detector kernel (pfac_scan_kernel) alone, for roofline
