@@ -14,6 +14,10 @@ Workload at N=1 = BASELINE.json configs[2] (the config the metric is quoted on):
 Snort-like patterns over 1 GiB of HTTP-like text, 4 streams per GPU.  For N>1 every rank scans its
 own 1 GiB shard (+ halo from the next shard): weak scaling, no data-path collective; with
 `--scaling strong` the workload's bytes are ONE input cut over the ranks by pfac_job_plan.
+The K timed steps of `value` run with nothing between the kernels of a step; the dominant kernel's own duration
+(`roofline`) comes from K more steps with a CUDA-event pair around that kernel.  Shards smaller than the L2 are
+scanned from rotating device copies (>= 256 MiB in all) so that every step's input comes from HBM; inputs under
+16 MiB get the L2 flushed between steps instead.
 After the timed regions every rank compares its full record arrays (device-resident and end to end)
 with the oracle's scan of the same bytes: `parity` in the line, exit code 1 if they differ.
 """
@@ -402,8 +406,20 @@ def main():
     stream = tstream.cuda_stream
     assert stream != 0
 
+    # Inputs smaller than the 126 MB L2 must not be re-read from it step after step.  From 16 MiB up the step
+    # rotates over copies of the shard that together exceed twice the L2 (the input of every step comes from
+    # HBM, the tables stay warm -- what a GPU sees when it scans fresh data each time); smaller inputs get the
+    # L2 flushed between steps (below).
+    d_copies = [d_text]
+    if (16 << 20) <= n + halo < (192 << 20):
+        while len(d_copies) * (n + halo) < (256 << 20) + (n + halo):
+            d_copies.append(d_text.clone())
+    step_no = [0]
+
     def step_dev():
-        m.scan_device_raw(d_text.data_ptr(), n, n_valid, base_pos, d_out.data_ptr(), cap, d_cnt.data_ptr(), stream)
+        d = d_copies[step_no[0] % len(d_copies)]
+        step_no[0] += 1
+        m.scan_device_raw(d.data_ptr(), n, n_valid, base_pos, d_out.data_ptr(), cap, d_cnt.data_ptr(), stream)
 
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -422,28 +438,35 @@ def main():
     torch.cuda.synchronize()
     # small inputs fit the 126 MB L2: flush it between timed steps (write a buffer larger than L2) and time
     # every step with its own event pair
-    flush = n + 8 * n_matches < (192 << 20)
+    flush = n + 8 * n_matches < (192 << 20) and len(d_copies) == 1
     d_flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda") if flush else None
-    m.set_timing(True)      # event pair around the dominant kernel of every launch sequence, on its stream
     sampler.active.set()
-    if flush:
-        ms = 0.0
-        for _ in range(args.steps):
-            d_flush.fill_(1)
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            step_dev()
-            e1.record()
-            torch.cuda.synchronize()
-            ms += e0.elapsed_time(e1)
-    else:
+
+    def timed_steps():
+        if flush:
+            t = 0.0
+            for _ in range(args.steps):
+                d_flush.fill_(1)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                step_dev()
+                e1.record()
+                torch.cuda.synchronize()
+                t += e0.elapsed_time(e1)
+            return t
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
         for _ in range(args.steps):
             step_dev()
         ev1.record()
         torch.cuda.synchronize()
-        ms = ev0.elapsed_time(ev1)
+        return ev0.elapsed_time(ev1)
+
+    ms = timed_steps()      # the bench value: exactly args.steps steps, nothing between the kernels of a step
+    # the roofline's kernel time: the same steps once more with an event pair around the dominant kernel of every
+    # launch sequence, on its stream (the pair sits between the kernels of a step, so these steps are not the value)
+    m.set_timing(True)
+    timed_steps()
     sampler.active.clear()
     kernel_ms_total, kernel_launches = m.kernel_time()
     m.set_timing(False)
@@ -617,7 +640,9 @@ def main():
         cfg = base_config(args, desc, n)
         cfg.update({"total_bytes": job_bytes, "matches_per_gpu_step": n_matches, "total_matches": total_matches,
                     "tables": dinfo,
-                    "l2": ("input per step exceeds the 126 MB L2; no flush needed" if not flush else
+                    "l2": (f"input smaller than the L2: the steps rotate over {len(d_copies)} device copies of the shard ({len(d_copies) * (n + halo) >> 20} MiB in all), so every step's input comes from HBM"
+                           if len(d_copies) > 1 else
+                           "input per step exceeds the 126 MB L2; no flush needed" if not flush else
                            "input fits the L2: a 256 MiB buffer is written between timed steps, every step timed by its own event pair"),
                     "timed": "value: input resident in HBM; e2e: host buffers, H2D and D2H inside the timed region",
                     "parallelism": f"input sharded x{world} ({args.scaling}), no collective", "numa_node_rank0": numa_node})
