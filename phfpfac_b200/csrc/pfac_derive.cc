@@ -469,7 +469,7 @@ void derive_tables(const Partition &P, uint32_t t2_bytes, uint32_t t3_bytes, uin
     if (t2_bits) out.t2_shift = t2_shift;
 
     // ---- images.  Shared memory: T1 + (Tm, Tm2, T3 | T2) -- or, in global mode, T2 alone; global
-    // memory (mode 2): T1 (for the emit kernel), Tm, Tm2, T3.
+    // memory (mode 2): T1, Tm, Tm2, T3.
     const uint32_t tm_bytes = out.has_t3 ? (uint32_t)tm.size() * 2 : 0, tm2_bytes_used = (uint32_t)tm2.size() * 2;
     uint32_t off = 0;
     if (!global_mode) {
@@ -682,10 +682,10 @@ bool stage2_pass(const Derived &d, const uint8_t *t, size_t len, bool odd, int *
     const uint16_t *tm2 = reinterpret_cast<const uint16_t *>(img + d.off_tm2);
     const uint32_t *t3 = reinterpret_cast<const uint32_t *>(img + d.off_t3);
     if (stage) *stage = 1;
-    if (len < 4) return true;   // fewer than 4 readable bytes: the emit kernel decides
+    if (len < 4) return true;   // fewer than 4 readable bytes: settled as a candidate
     const uint32_t w4 = le32(t);
     if (d.mode == 0) {
-        // short patterns (<= 3 bytes) are not in the prefix tables: their starts go to the emit kernel
+        // short patterns (<= 3 bytes) are not in the prefix tables: their starts become candidates
         if (d.has_short) {
             if (!odd && (t1[t1_index(w4 & 255u, (w4 >> 8) & 255u)] & kT1Short)) return true;
             if (odd && (t1[t1_index((w4 >> 8) & 255u, (w4 >> 16) & 255u)] & kT1ShortC)) return true;
@@ -749,7 +749,7 @@ void derive_profile(const Partition &P, const Derived &d, const uint8_t *text, s
         if (stage >= 4) out[4]++;   // level-2 window passed
         if (!pass) continue;
         if (stage == 1) out[5]++;   // bypass (short patterns / end of input)
-        out[6]++;   // starts handed to the emit kernel
+        out[6]++;   // starts left as candidates
         if (i / 512 != last_slice) {
             last_slice = i / 512;
             slices++;

@@ -2,7 +2,7 @@
 //
 // The canonical PHF arrays r/HT/val (bit-compatible with CreateTable/FFDM, reference phf.c:151)
 // stay the authoritative transition function: they are uploaded unchanged (HT and val
-// interleaved) and the emit kernel walks them exactly as master_kernel.cu:52-64 does.  What is
+// interleaved) and the candidate / dense-match walks follow them exactly as master_kernel.cu:52-64 does.  What is
 // derived here is the shared-memory image of the DETECTOR kernel: prefix filters computed from the
 // first rows of the PHF.  Every one of them is a superset test -- it may pass a start position
 // that cannot match, it never rejects one that can:

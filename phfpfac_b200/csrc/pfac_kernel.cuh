@@ -1,30 +1,29 @@
 // PFAC scan kernels for sm_100a (B200).  Replace TraceTable_kernel + SUBSEG_MATCH
 // (reference master_kernel.cu:37-180).  Design notes: DESIGN.md section 3.
 //
-//   pfac_scan_kernel      the detector: persistent, one CTA per SM, warp specialised.
-//     * producer warp: claims tile tickets and streams tiles of 32 x 512 bytes (+ halo of
-//       max_pat_len-1 bytes) into a shared-memory ring with cp.async.bulk (TMA bulk copy, SASS
-//       UBLKCP), full/empty mbarriers per stage, L2 evict-first hint on the streamed input; it
-//       also publishes every finished tile's result (flag mask, candidate list);
-//     * 31 consumer warps taking slots (2 or 4 consecutive 512-byte slices) of the CTA's tiles
-//       from a shared counter.  Per slice
-//         stage 1  16 start positions per lane against T1 (64 KiB byte table over 2-byte windows,
-//                  four bit-planes: root fan-out + depth-1 rows, bytes 1-2, bytes 2-3, short
-//                  patterns), survivors compacted into the warp queue by ballot rank;
-//       and per slot
-//         stage 2  survivors against Tm/T3/Tm2 (two-point checks on the 4-byte prefix and on
-//                  the bytes that end the shortest pattern below it) or T2.
-//       A start that survives becomes a CANDIDATE of its tile and flags its slice; the detector
-//       decides nothing else.  All its tables are shared-memory resident prefix filters derived
-//       from the first PHF rows.
-//   pfac_emit_kernel      one warp per tile with flagged slices: the plain PFAC walk of
-//                         SUBSEG_MATCH over the tile's candidates (or, when there are too many,
-//                         over every start of the flagged slices), straight from the PHF
-//                         (r[] then {HT,val}, read-only, L2-resident), records written in
-//                         (position, pattern length) order into the arrival-order scratch.
-//   pfac_finalize_kernel  scans the per-tile counts and moves the records from arrival order to
-//                         position order (tile, slice, start, depth) -- the order main.cc:341-349
-//                         prints.  Output is deterministic run to run.
+//   pfac_scan2_kernel / pfac_scan_kernel<MODE>   the detector: persistent, one CTA per SM, warp specialised.
+//     * producer warp (one lane): streams the CTA's tiles of 16 x 512 bytes (+ halo of max_pat_len-1 bytes)
+//       into a shared-memory ring with cp.async.bulk (TMA bulk copy, SASS UBLKCP), full/empty mbarriers per
+//       stage, L2 evict-first hint on the streamed input;
+//     * 31 consumer warps taking slots (4 consecutive 512-byte slices) of the CTA's tiles from a shared
+//       counter.  Per slot
+//         stage 1  16 start positions per lane and slice against T1 (64 KiB byte table over 2-byte windows,
+//                  probed at even offsets only in mode 0; up to eight bit-planes: root fan-out + depth-1 rows,
+//                  bytes 1-2 .. 5-6, short-pattern exceptions) -- or, in global mode, against T2 (a blocked
+//                  Bloom filter of the 4-byte prefixes); survivors compacted into the warp's queue;
+//         stage 2  survivors against the two-point checks (4-byte prefix -> m1 -> window -> m2 -> window -> T3)
+//                  or T2.
+//       A start that survives becomes a CANDIDATE of its tile; the detector's filters decide nothing else.
+//       All of them are shared-memory (global mode: L2) resident prefix filters derived from the first PHF rows.
+//     * the warp that finishes a tile's last slot publishes the tile, hands the stage back and settles the
+//       tile's candidates: through the pattern directory (emit_tile_dir: every pattern length probed in
+//       parallel, exact compare) or by the plain PFAC walk of SUBSEG_MATCH (emit_tile) straight from the PHF;
+//       records go, one (position, pattern length)-ordered run per tile, into the arrival-order scratch.
+//   pfac_dense_kernel     tiles with more candidates than the detector keeps (and, DIRECT, whole scans of sets
+//                         with patterns of <= 3 bytes): every start walked, level-synchronously.
+//   pfac_finalize_kernel  scans the per-tile counts and moves the runs from arrival order to position order --
+//                         the order main.cc:341-349 prints.  Output is deterministic run to run.
+//   All kernels of a scan are programmatic dependent launches (griddepcontrol).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -130,7 +129,7 @@ constexpr int kSlice = 512;           // start positions per stage-1 step of a w
 #ifndef PFAC_TILE_SLICES
 #define PFAC_TILE_SLICES 16
 #endif
-constexpr int kSlicesPerTile = PFAC_TILE_SLICES;    // one bit each in tile_mask (<= 32)
+constexpr int kSlicesPerTile = PFAC_TILE_SLICES;    // (<= 32: one flag bit each in the stage's `done` word)
 constexpr int kTile = kSlicesPerTile * kSlice;   // 16,384 start positions per tile
 // Slices a warp takes at a time (a slot): stage 2 then runs over the survivors of all of them.
 // Shared-memory mode: 2 (more would leave too few slots in flight for the ring to prefetch).  Global
@@ -403,8 +402,8 @@ __device__ __forceinline__ uint32_t walk_limit(const ScanParams &p, uint32_t a0,
     return lim_t < depth ? lim_t : depth;
 }
 
-// A start that survived every filter: remember it for the emit kernel (per tile; past
-// kCandPerTile the counter keeps growing and the tile is handed over slice by slice instead)
+// A start that survived every filter: remember it as a candidate of its tile (past
+// kCandPerTile the counter keeps growing and the tile is handed to the dense-match kernel whole)
 __device__ __forceinline__ void add_candidate(uint32_t *n, uint16_t *list, uint32_t tpos)
 {
     const uint32_t i = atomicAdd(n, 1u);
@@ -1138,7 +1137,7 @@ __global__ void __launch_bounds__(kThreads, 1) pfac_scan2_kernel(const ScanParam
                 }
             }
         }
-        if (nq > (uint32_t)kQ2Cap) {   // dense slot: the emit kernel looks at all of it
+        if (nq > (uint32_t)kQ2Cap) {   // dense slot: the dense-match kernel looks at the whole tile
             anym = (1u << kSlotSlices) - 1u;
             if (lane == 0) atomicOr(c.ncand + s, 0x80000000u);
             nq = 0;
@@ -1199,7 +1198,7 @@ __global__ void __launch_bounds__(kThreads, 1) pfac_scan2_kernel(const ScanParam
             if (e >= nq) continue;
             const uint32_t tpos = wq[e];
             bool keep = true;
-            if (tpos + 4u <= valid_t) {   // else: the emit kernel decides
+            if (tpos + 4u <= valid_t) {   // else: settled as a candidate
                 const uint32_t w4 = load_w4(buf, tpos);
                 bool shortp = false;
                 if (HAS_SHORT) {   // starts of patterns that are not in the prefix tables
@@ -1347,7 +1346,7 @@ __global__ void __launch_bounds__(kThreads, 1) pfac_scan_kernel(const ScanParams
                 for (uint32_t mm = m16[h]; mm; mm &= mm - 1) *wp++ = (uint16_t)(pb + __ffs(mm) - 1);
             }
         }
-        if (nq > (uint32_t)kQ1Cap) {   // dense slot: the emit kernel looks at all of it
+        if (nq > (uint32_t)kQ1Cap) {   // dense slot: the dense-match kernel looks at the whole tile
             anym = (1u << kSlotSlices) - 1u;
             if (lane == 0) atomicOr(s_ncand + s, 0x80000000u);
             nq = 0;
@@ -1418,7 +1417,7 @@ __global__ void __launch_bounds__(kThreads, 1) pfac_scan_kernel(const ScanParams
 //     reserved in the arrival-order scratch with one atomic and written from the stored states
 //     (starts with more than two matches are walked again, writing directly).
 // Records of a tile come out in (position, pattern length) order; the ordering pass moves the run
-// into place like those of the emit kernel.
+// into place like those of the detector.
 struct DenseParams {
     EmitParams e;
     const uint8_t *wc_image;    // walk cache image (global); copied to shared memory per CTA
