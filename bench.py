@@ -596,6 +596,16 @@ def main():
                                         n if not strong else max(65536, (total_bytes // world) & ~65535))
             except Exception as e:   # never lose the main line to this leg
                 job_leg = {"error": str(e)[:300]}
+        # The other ranks wait on the HOST (a key of the rendezvous store) until rank 0's job leg is over: in an
+        # NCCL barrier they would keep a kernel spinning on their GPUs, which rank 0's job uses from its own process
+        try:
+            store = dist.distributed_c10d._get_default_store()
+            if rank == 0:
+                store.set("pfac_job_leg_done", "1")
+            else:
+                store.wait(["pfac_job_leg_done"])
+        except Exception:
+            pass
         dist.barrier()
 
     if rank == 0:
