@@ -379,6 +379,8 @@ int launch_scan(pfac_ctx *ctx, Slot &slot, const void *d_in, uint64_t n_starts, 
     f.ctrl = slot.d_ctrl;
     f.result = slot.d_result;
     f.count_out = (unsigned long long *)d_count;
+    f.debug = ctx->debug;
+    f.trace_ctas = grid;
     lc.gridDim = dim3(fgrid);
     lc.blockDim = dim3(kFinThreads);
     lc.dynamicSmemBytes = 0;

@@ -27,6 +27,9 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#ifdef PFAC_TRACE   // development build (make variant NAME=trace EXTRA=-DPFAC_TRACE): device-side timeline of a scan
+#include <stdio.h>
+#endif
 
 #include "pfac_derive.h"
 
@@ -118,6 +121,7 @@ struct FinalizeParams {
     Ctrl *ctrl;
     Result *result;
     unsigned long long *count_out;    // caller's device counter (may be null)
+    uint32_t debug, trace_ctas;       // PFAC_TRACE builds: PFAC_DEBUG bits, CTAs of the detector
 };
 
 #ifndef PFAC_CONSUMER_WARPS
@@ -753,6 +757,21 @@ __device__ __noinline__ bool emit_tile_dir(const EmitParams &p, uint32_t tile, u
     return true;
 }
 
+// Development timeline (PFAC_TRACE builds, PFAC_DEBUG bit 64): every CTA of the detector stamps %globaltimer at
+// its start (0), when the filter image is in (1), when its last tile is done (2), when that tile's candidates
+// are settled (3) and when its last warp leaves (4) -- atomicMax into the last words of the record scratch;
+// the ordering pass prints the minima / maxima over the CTAs next to its own start, wait and end.
+#ifdef PFAC_TRACE
+#define PFAC_STAMP(p, k)                                                                                                       \
+    do {                                                                                                                       \
+        if ((p).debug & 64u)                                                                                                   \
+            atomicMax(reinterpret_cast<unsigned long long *>((p).emit.scratch + ((p).emit.scratch_cap - 1ull - blockIdx.x * 8ull - (k)))), \
+                      gtime_ns());                                                                                             \
+    } while (0)
+#else
+#define PFAC_STAMP(p, k) do { } while (0)
+#endif
+
 // The control block of the detector kernels (kCtrlBytes of shared memory after the image).
 struct CtlView {
     uint64_t *full, *empty;     // [kMaxStages] mbarriers of the input ring
@@ -793,6 +812,7 @@ __device__ __forceinline__ void bulk_g2s_plain(void *dst, const void *src, uint3
 __device__ __forceinline__ void detector_init(const ScanParams &p, const CtlView &c)
 {
     const int tid = threadIdx.x;
+    if (tid == 0) PFAC_STAMP(p, 0);
     pdl_launch_next();
     if (tid == 0) {
         for (uint32_t s = 0; s < p.n_stages; s++) {
@@ -932,8 +952,10 @@ __device__ __forceinline__ void finish_slot(const ScanParams &p, const CtlView &
     // the producer (the walk reads the input and the PHF from global memory: microseconds of dependent
     // loads that must stall one warp, not the ring).
 #ifndef PFAC_EXP_NO_EMIT   // (timing experiment: no walks, no records)
+    if (lane == 0) PFAC_STAMP(p, 2);
     if (flags && nc != kCandOverflow) {
         if (!by_dir || !emit_tile_dir(p.emit, tile, key0, key1, b0_lo, b0_hi, b1_lo, b1_hi, lane)) emit_tile(p.emit, tile, my_cand, lane);
+        if (lane == 0) PFAC_STAMP(p, 3);
     }
 #endif
 }
@@ -1074,6 +1096,7 @@ __global__ void __launch_bounds__(kThreads, 1) pfac_scan2_kernel(const ScanParam
         return;
     }
     image_wait(p, c);
+    if (tid == 0) PFAC_STAMP(p, 1);
 
     const uint16_t *s_d1 = reinterpret_cast<const uint16_t *>(smem + p.off_d1);
     const uint16_t *s_e1 = reinterpret_cast<const uint16_t *>(smem + p.off_e1);
@@ -1234,6 +1257,7 @@ __global__ void __launch_bounds__(kThreads, 1) pfac_scan2_kernel(const ScanParam
         }
         finish_slot<kSlotsPerTile>(p, c, lane, s, tile, anym, slice0, buf);
     }
+    if (lane == 0) PFAC_STAMP(p, 4);
 }
 
 // The detector of the modes without shared-memory two-point tables.  MODE 0 here: stage 1 = T1 (one
@@ -1790,7 +1814,13 @@ __global__ void __launch_bounds__(kFinThreads) pfac_finalize_kernel(const Finali
     __shared__ unsigned long long s_run;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     pdl_launch_next();   // (the next scan's detector may set itself up)
+#ifdef PFAC_TRACE
+    const unsigned long long t_start = gtime_ns();
+#endif
     pdl_wait();          // the kernels before this one have finished
+#ifdef PFAC_TRACE
+    const unsigned long long t_wait = gtime_ns();
+#endif
     const uint32_t per = f.tiles_per_part;   // CTA b owns tiles [b*per, (b+1)*per); partial[b] = matches in them
     const uint32_t lo = min(f.n_tiles, blockIdx.x * per), hi = min(f.n_tiles, lo + per);
 
@@ -1857,6 +1887,24 @@ __global__ void __launch_bounds__(kFinThreads) pfac_finalize_kernel(const Finali
         if (tid == kFinThreads - 1) s_run = s_base[tid] + c;
         __syncthreads();
     }
+#ifdef PFAC_TRACE
+    if ((f.debug & 64u) && tid == 0 && blockIdx.x == 0) {
+        const unsigned long long t_end = gtime_ns();
+        unsigned long long mn[5] = {~0ull, ~0ull, ~0ull, ~0ull, ~0ull}, mx[5] = {0, 0, 0, 0, 0};
+        for (uint32_t b = 0; b < f.trace_ctas; b++)
+            for (int k = 0; k < 5; k++) {
+                unsigned long long *q = const_cast<unsigned long long *>(reinterpret_cast<const unsigned long long *>(f.scratch + (f.scratch_cap - 1ull - b * 8ull - k)));
+                const unsigned long long v = *q;
+                *q = 0;
+                if (v) { mn[k] = v < mn[k] ? v : mn[k]; mx[k] = v > mx[k] ? v : mx[k]; }
+            }
+        const unsigned long long t0 = mn[0];
+        printf("TRACE ns since the first CTA started: CTA starts ..%llu | image in %llu..%llu | last tile done %llu..%llu | its candidates settled %llu..%llu | "
+               "last warp out %llu..%llu | ordering pass: CTA 0 starts %lld, passes its wait %llu, ends %llu\n",
+               mx[0] - t0, mn[1] - t0, mx[1] - t0, mn[2] - t0, mx[2] - t0, mn[3] - t0, mx[3] - t0, mn[4] - t0, mx[4] - t0,
+               (long long)(t_start - t0), t_wait - t0, t_end - t0);
+    }
+#endif
     if (tid == 0 && lo < hi && hi == f.n_tiles) {   // the CTA whose range ends the input owns the total
         f.result->count = s_run;
         f.result->error_flag = f.ctrl->error_flag;
