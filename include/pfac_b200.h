@@ -226,6 +226,19 @@ int pfac_write_end(void *writer);
 size_t pfac_format_records(uint64_t base_pos, const pfac_match *records, uint64_t count, char *buf,
                            size_t buf_len);
 
+
+/* Optional binary sidecar of the compact records (the reference has none: main.cc:335-350 writes text only).
+ * File = 32-byte header {"PFACREC1", u32 version = 1, u32 record bytes = 8, u64 blocks, u64 records}, then per
+ * pfac_sidecar_records call with count > 0 one block {u64 base_pos, u64 count, count x pfac_match}; little-endian.
+ * The header's totals are written by pfac_sidecar_end.  GPU_match_result.txt is a pure function of the sidecar. */
+int pfac_sidecar_begin(const char *path, void **sidecar);
+int pfac_sidecar_records(void *sidecar, uint64_t base_pos, const pfac_match *records, uint64_t count);
+int pfac_sidecar_end(void *sidecar);
+/* Read a sidecar back: *n_records = the total; with pos / id non-NULL (capacity `cap` records each, either may
+ * be NULL) the absolute 64-bit positions and pattern ids in file order.  PFAC_ERR_OUTPUT_FULL if cap is too
+ * small, PFAC_ERR_IO for a file that is not a complete sidecar. */
+int pfac_sidecar_read(const char *path, uint64_t *pos, uint32_t *id, uint64_t cap, uint64_t *n_records);
+
 #ifdef __cplusplus
 }
 #endif

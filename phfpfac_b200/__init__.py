@@ -24,7 +24,7 @@ from ._lib import PFAC_ERR_OUTPUT_FULL, PfacError, check, lib
 MATCH_DTYPE = np.dtype([("pos", "<u4"), ("id", "<u4")])   # struct pfac_match
 
 __all__ = ["Tables", "Matcher", "Job", "PfacError", "MATCH_DTYPE", "format_records", "write_result",
-           "synth_patterns", "synth_text", "device_count", "plan_shard"]
+           "write_sidecar", "read_sidecar", "pattern_file_hash", "pinned", "device_count", "plan_shard"]
 
 
 def _arr(ptr, n):
@@ -326,3 +326,26 @@ def write_result(path, segments):
             check(lib.pfac_write_records(w, base, rec.ctypes.data if len(rec) else None, len(rec)))
     finally:
         check(lib.pfac_write_end(w))
+
+
+def write_sidecar(path, segments):
+    """segments: iterable of (base_pos, MATCH_DTYPE array).  Writes the binary sidecar of the compact records
+    (include/pfac_b200.h, pfac_sidecar_*): 8 bytes per match; the text file is a pure function of it."""
+    w = C.c_void_p()
+    check(lib.pfac_sidecar_begin(str(path).encode(), C.byref(w)))
+    try:
+        for base, rec in segments:
+            rec = np.ascontiguousarray(rec, dtype=MATCH_DTYPE)
+            check(lib.pfac_sidecar_records(w, base, rec.ctypes.data if len(rec) else None, len(rec)))
+    finally:
+        check(lib.pfac_sidecar_end(w))
+
+
+def read_sidecar(path):
+    """-> (pos: uint64 absolute start positions, id: uint32 pattern ids) in file (= position) order."""
+    n = C.c_uint64(0)
+    check(lib.pfac_sidecar_read(str(path).encode(), None, None, 0, C.byref(n)))
+    pos = np.empty(n.value, dtype=np.uint64)
+    ids = np.empty(n.value, dtype=np.uint32)
+    check(lib.pfac_sidecar_read(str(path).encode(), pos.ctypes.data, ids.ctypes.data, n.value, C.byref(n)))
+    return pos, ids

@@ -25,6 +25,7 @@ ABI_SYMBOLS = [
     "pfac_job_create", "pfac_job_destroy", "pfac_job_run", "pfac_job_run_file", "pfac_job_n_segments", "pfac_job_segment",
     "pfac_job_last_timing", "pfac_job_plan",
     "pfac_write_begin", "pfac_write_records", "pfac_write_end", "pfac_format_records",
+    "pfac_sidecar_begin", "pfac_sidecar_records", "pfac_sidecar_end", "pfac_sidecar_read",
 ]
 
 PFAC_OK = 0
@@ -108,6 +109,10 @@ def _load():
     lib.pfac_write_end.argtypes = [_vp]
     lib.pfac_format_records.argtypes = [C.c_uint64, _vp, C.c_uint64, _vp, C.c_size_t]
     lib.pfac_format_records.restype = C.c_size_t
+    lib.pfac_sidecar_begin.argtypes = [C.c_char_p, C.POINTER(_vp)]
+    lib.pfac_sidecar_records.argtypes = [_vp, C.c_uint64, _vp, C.c_uint64]
+    lib.pfac_sidecar_end.argtypes = [_vp]
+    lib.pfac_sidecar_read.argtypes = [C.c_char_p, _vp, _vp, C.c_uint64, C.POINTER(C.c_uint64)]
     return lib
 
 

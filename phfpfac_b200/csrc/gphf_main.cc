@@ -6,6 +6,7 @@
 // reference.  argv[2] keeps its place but means "pipeline streams per GPU" (input sub-chunks
 // in flight); the result does not depend on it.  Exits 1 with a message on any failure, 255
 // on a usage error (the reference's exit(-1), main.cc:95).
+#include <algorithm>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -28,6 +29,26 @@ static int fail(const char *what)
 {
     fprintf(stderr, "%s: %s\n", what, pfac_last_error());
     return 1;
+}
+
+// main.cc:335-350: the job's position-ordered segments -> GPU_match_result.txt; with GPHF_SIDECAR=<file> also the
+// binary sidecar of the compact records (pfac_sidecar_*; the reference has no such file)
+static int write_results(const pfac_job *job, const char *out_name)
+{
+    const char *side_name = getenv("GPHF_SIDECAR");
+    void *w = nullptr, *sc = nullptr;
+    if (pfac_write_begin(out_name, &w)) return fail("open output");
+    if (side_name && *side_name && pfac_sidecar_begin(side_name, &sc)) return fail("open sidecar");
+    for (int i = 0; i < pfac_job_n_segments(job); i++) {
+        uint64_t base, cnt;
+        const pfac_match *rec;
+        pfac_job_segment(job, i, &base, &rec, &cnt);
+        if (pfac_write_records(w, base, rec, cnt)) return fail("write output");
+        if (sc && pfac_sidecar_records(sc, base, rec, cnt)) return fail("write sidecar");
+    }
+    if (pfac_write_end(w)) return fail("close output");
+    if (sc && pfac_sidecar_end(sc)) return fail("close sidecar");
+    return 0;
 }
 
 int main(int argc, char **argv)
@@ -118,15 +139,7 @@ int main(int argc, char **argv)
         uint64_t n_matches = 0;
         if (pfac_job_run_file(job, argv[4], input_size, &n_matches)) return fail("scan");
         double t3 = now();
-        void *w = nullptr;
-        if (pfac_write_begin(out_name, &w)) return fail("open output");
-        for (int i = 0; i < pfac_job_n_segments(job); i++) {
-            uint64_t base, cnt;
-            const pfac_match *rec;
-            pfac_job_segment(job, i, &base, &rec, &cnt);
-            if (pfac_write_records(w, base, rec, cnt)) return fail("write output");
-        }
-        if (pfac_write_end(w)) return fail("close output");
+        if (write_results(job, out_name)) return 1;
         double t4 = now();
         printf("/////////////////////////////////////////////\n");
         printf("1.Time for  create PFAC + Hashtable : %lf seconds\n", t1 - t0);
@@ -171,15 +184,7 @@ int main(int argc, char **argv)
     if (pfac_job_run(job, input, input_size, &n_matches)) return fail("scan");
     double t3 = now();
 
-    void *w = nullptr;
-    if (pfac_write_begin(out_name, &w)) return fail("open output");
-    for (int i = 0; i < pfac_job_n_segments(job); i++) {
-        uint64_t base, cnt;
-        const pfac_match *rec;
-        pfac_job_segment(job, i, &base, &rec, &cnt);
-        if (pfac_write_records(w, base, rec, cnt)) return fail("write output");
-    }
-    if (pfac_write_end(w)) return fail("close output");
+    if (write_results(job, out_name)) return 1;
     double t4 = now();
 
     printf("/////////////////////////////////////////////\n");

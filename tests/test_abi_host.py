@@ -103,6 +103,65 @@ def test_writer_matches_reference_format(tmp_path, golden):
     assert f.read_bytes() == pf.format_records(many, base_pos=7)
 
 
+def test_binary_sidecar_round_trip(tmp_path, golden):
+    """pfac_sidecar_*: the compact records as a binary file.  The text result is a pure function of
+    it: reading the sidecar back and formatting it gives the golden GPU_match_result.txt of the reference flow."""
+    g = golden["results"]["experimentpattern_x_experimentinput"]
+    rec = np.zeros(g["lines"], dtype=pf.MATCH_DTYPE)
+    for i, line in enumerate(g["text"].splitlines()):
+        m = re.fullmatch(r"At position +(\d+), match pattern (\d+)", line)
+        rec[i] = (int(m.group(1)), int(m.group(2)))
+    f = tmp_path / "records.pfacrec"
+    pf.write_sidecar(f, [(0, rec[:10]), (0, rec[:0]), (0, rec[10:])])   # the empty segment leaves no block
+    raw = f.read_bytes()
+    assert raw[:8] == b"PFACREC1" and np.frombuffer(raw[8:16], dtype="<u4").tolist() == [1, 8]
+    assert np.frombuffer(raw[16:32], dtype="<u8").tolist() == [2, g["lines"]]
+    assert len(raw) == 32 + 2 * 16 + 8 * g["lines"]
+    pos, ids = pf.read_sidecar(f)
+    assert pos.dtype == np.uint64 and np.array_equal(pos, rec["pos"]) and np.array_equal(ids, rec["id"])
+    assert render_result(pos.astype(np.int64), ids.astype(np.int64)).decode() == g["text"]
+    # 64-bit base positions, several blocks
+    rng = np.random.default_rng(2)
+    segs, want_pos, want_id = [], [], []
+    for k in range(5):
+        r = np.zeros(int(rng.integers(1, 3000)), dtype=pf.MATCH_DTYPE)
+        r["pos"] = np.sort(rng.integers(0, 2 ** 32, len(r), dtype=np.uint64)).astype(np.uint32)
+        r["id"] = rng.integers(1, 2 ** 31, len(r))
+        base = k * 2 ** 33 + 5
+        segs.append((base, r))
+        want_pos.append(r["pos"].astype(np.uint64) + np.uint64(base))
+        want_id.append(r["id"])
+    pf.write_sidecar(f, segs)
+    pos, ids = pf.read_sidecar(f)
+    assert np.array_equal(pos, np.concatenate(want_pos)) and np.array_equal(ids, np.concatenate(want_id))
+    # no records at all
+    pf.write_sidecar(f, [])
+    pos, ids = pf.read_sidecar(f)
+    assert len(pos) == 0 and len(ids) == 0 and f.stat().st_size == 32
+    # damaged files are refused: wrong magic, a file cut short, a capacity that is too small
+    pf.write_sidecar(f, segs)
+    raw = f.read_bytes()
+    bad = tmp_path / "bad.pfacrec"
+    bad.write_bytes(b"XFACREC1" + raw[8:])
+    with pytest.raises(pf.PfacError) as e:
+        pf.read_sidecar(bad)
+    assert e.value.code == -1
+    bad.write_bytes(raw[:-4])
+    with pytest.raises(pf.PfacError) as e:
+        pf.read_sidecar(bad)
+    assert e.value.code == -1
+    bad.write_bytes(raw[:32 + 8] + np.array([2 ** 40], dtype="<u8").tobytes() + raw[48:])   # a block count beyond the total
+    with pytest.raises(pf.PfacError) as e:
+        pf.read_sidecar(bad)
+    assert e.value.code == -1
+    n = C.c_uint64(0)
+    buf = np.zeros(4, dtype=np.uint64)
+    assert lib.pfac_sidecar_read(str(f).encode(), buf.ctypes.data, None, 4, C.byref(n)) == -8
+    assert n.value == sum(len(r) for _, r in segs) > 4   # the required capacity is reported
+    with pytest.raises(pf.PfacError):
+        pf.read_sidecar(tmp_path / "nope")
+
+
 def test_synth_is_deterministic_and_shaped():
     p1 = synth.synth_patterns(1, 2000, 3, 4, 64)
     assert p1 == synth.synth_patterns(1, 2000, 3, 4, 64) and p1 != synth.synth_patterns(1, 2000, 4, 4, 64)

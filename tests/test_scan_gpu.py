@@ -517,11 +517,15 @@ def test_cli_byte_identical_result_file(fixtures, golden, tmp_path):
     dic.write_bytes(fixtures["dictionary"])
     for (streams, width), reader in zip(((4, 64), (2, 4096), (3, 256)), ("mmap", "fread", "stream")):
         r = subprocess.run([GPHF, str(dic), str(streams), str(width), str(inp)], cwd=tmp_path, capture_output=True,
-                           text=True, env=dict(os.environ, GPHF_READER=reader))
+                           text=True, env=dict(os.environ, GPHF_READER=reader, GPHF_SIDECAR=str(tmp_path / "records.pfacrec")))
         assert r.returncode == 0, r.stderr
         assert f"input reader: {reader}" in r.stdout
         out = (tmp_path / "GPU_match_result.txt").read_bytes()
         assert hashlib.md5(out).hexdigest() == golden["results"]["dictionary_x_1M"]["md5"]
+        # GPHF_SIDECAR: the compact records as a binary file; the text file is a pure function of it
+        spos, sid = pf.read_sidecar(tmp_path / "records.pfacrec")
+        assert len(spos) == golden["results"]["dictionary_x_1M"]["lines"]
+        assert hashlib.md5(render_result(spos.astype(np.int64), sid.astype(np.int64))).hexdigest() == golden["results"]["dictionary_x_1M"]["md5"]
     # GPHF_TABLE_CACHE: first run builds and writes the cache, second run loads it; same bytes out
     cache = tmp_path / "tables.cache"
     for run in range(2):
