@@ -198,7 +198,12 @@ int pfac_job_run_file(pfac_job *job, const char *path, uint64_t n, uint64_t *n_m
         const size_t buf_bytes = (size_t)(kChunk + halo + 2 * kAlign);
         uint8_t *bufs[kRing] = {};
         for (auto &b : bufs)
-            if (pfac_host_alloc((void **)&b, buf_bytes)) { close(fd0); return fail(PFAC_ERR_NOMEM, pfac_last_error()); }
+            if (pfac_host_alloc((void **)&b, buf_bytes)) {
+                const std::string why = pfac_last_error();
+                for (auto &x : bufs) pfac_host_free(x);   // (null entries are skipped)
+                close(fd0);
+                return fail(PFAC_ERR_NOMEM, why);
+            }
         struct Slot { uint64_t off = 0, len = 0, skip = 0; bool full = false, err = false; } slots[kRing];
         std::mutex mu;
         std::condition_variable cv;
