@@ -235,9 +235,28 @@ def cpu_baseline(part, mpl, text, budget_s=12.0):
             "sample": f"first {sample} bytes of the rank-0 shard, best of 2, {cnt} records written"}
 
 
-def base_config(args, desc, n):
-    return {"workload": desc, "bytes_per_gpu": n, "streams_per_gpu": args.streams, "phf_width": 256,
-            "scaling": args.scaling}
+def shared_config(args, desc, nbytes, fixture, world):
+    """The `config` object of BOTH arms (the driver compares them): a pure function of the command line and
+    the workload.  What a run finds out (match counts, table sizes, the L2 handling it chose) goes into the
+    line's `detail` object instead."""
+    strong = args.scaling == "strong" and fixture is None
+    if strong:
+        total = args.bytes or nbytes
+        per = min(total, (-(-total // world) + 65535) & ~65535)   # pfac_job_plan's rule: shard 0 of `world`
+    else:
+        per = args.bytes or nbytes
+        total = per * world
+    if per >= (192 << 20):
+        l2 = "input per step exceeds the 126 MB L2; no flush needed"
+    elif per >= (16 << 20):
+        l2 = ("input smaller than the L2: the steps rotate over device copies of the shard that together exceed "
+              "256 MiB, so every step's input comes from HBM")
+    else:
+        l2 = "input fits the L2: a 256 MiB buffer is written between timed steps, every step timed by its own event pair"
+    return {"workload": desc, "bytes_per_gpu": per, "streams_per_gpu": args.streams, "phf_width": 256,
+            "scaling": args.scaling, "total_bytes": total, "l2": l2,
+            "timed": "value: input resident in HBM; e2e: host buffers, H2D and D2H inside the timed region",
+            "parallelism": f"input sharded x{world} ({args.scaling}), no collective"}
 
 
 def run_reference(args):
@@ -274,9 +293,7 @@ def run_reference(args):
         n_rec = len(pos)
     dt = time.perf_counter() - t0
     v = sample * args.steps / dt / 1e9
-    cfg = base_config(args, desc, n)
-    cfg["note"] = ("the reference ships no CPU matcher and its kernel does not compile on CUDA 12; this arm is the "
-                   "oracle's OpenMP port of SUBSEG_MATCH over the oracle-built PHF tables, records written")
+    cfg = shared_config(args, desc, nbytes, fixture, int(os.environ.get("WORLD_SIZE", "1")))
     line = {
         "impl": "reference", "metric": "input GB/s matched", "value": v, "unit": "GB/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
@@ -287,6 +304,8 @@ def run_reference(args):
                          "sample": f"{sample} bytes of the rank-0 shard per step, {n_rec} records written"},
         "e2e": {"value": v, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
+        "note": ("the reference ships no CPU matcher and its kernel does not compile on CUDA 12; this arm is the "
+                 "oracle's OpenMP port of SUBSEG_MATCH over the oracle-built PHF tables, records written"),
     }
     line["reference_gpu"] = reference_gpu_leg(args)
     print(json.dumps(line))
@@ -411,7 +430,7 @@ def main():
     # HBM, the tables stay warm -- what a GPU sees when it scans fresh data each time); smaller inputs get the
     # L2 flushed between steps (below).
     d_copies = [d_text]
-    if (16 << 20) <= n + halo < (192 << 20):
+    if (16 << 20) <= n < (192 << 20):
         while len(d_copies) * (n + halo) < (256 << 20) + (n + halo):
             d_copies.append(d_text.clone())
     step_no = [0]
@@ -438,7 +457,7 @@ def main():
     torch.cuda.synchronize()
     # small inputs fit the 126 MB L2: flush it between timed steps (write a buffer larger than L2) and time
     # every step with its own event pair
-    flush = n + 8 * n_matches < (192 << 20) and len(d_copies) == 1
+    flush = n < (16 << 20)
     d_flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda") if flush else None
     sampler.active.set()
 
@@ -647,21 +666,16 @@ def main():
         kernel_ms = kernel_ms_total / max(kernel_launches, 1)
         achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
         job_bytes = total_bytes if strong else world * n
-        cfg = base_config(args, desc, n)
-        cfg.update({"total_bytes": job_bytes, "matches_per_gpu_step": n_matches, "total_matches": total_matches,
-                    "tables": dinfo,
-                    "l2": (f"input smaller than the L2: the steps rotate over {len(d_copies)} device copies of the shard ({len(d_copies) * (n + halo) >> 20} MiB in all), so every step's input comes from HBM"
-                           if len(d_copies) > 1 else
-                           "input per step exceeds the 126 MB L2; no flush needed" if not flush else
-                           "input fits the L2: a 256 MiB buffer is written between timed steps, every step timed by its own event pair"),
-                    "timed": "value: input resident in HBM; e2e: host buffers, H2D and D2H inside the timed region",
-                    "parallelism": f"input sharded x{world} ({args.scaling}), no collective", "numa_node_rank0": numa_node})
+        cfg = shared_config(args, desc, nbytes, fixture, world)
+        detail = {"matches_per_gpu_step": n_matches, "total_matches": total_matches, "tables": dinfo,
+                  "bytes_rank0": n, "device_copies_rotated": len(d_copies), "l2_flushed_between_steps": bool(flush),
+                  "numa_node_rank0": numa_node}
         line = {
             "metric": "input GB/s matched", "value": job_bytes * args.steps / (ms_max * 1e-3) / 1e9,
             "unit": "GB/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
             "dtype": "u8", "data": "synthetic" if fixture is None else "reference fixture",
-            "config": cfg,
+            "config": cfg, "detail": detail,
             "clocks": sampler.summary(),
             "e2e": {"value": job_bytes * e2e_steps / e2e_s / 1e9, "unit": "GB/s", "steps": e2e_steps,
                     "h2d_bytes_per_step": int(info["h2d_bytes"]), "d2h_bytes_per_step": int(info["d2h_bytes"]),
