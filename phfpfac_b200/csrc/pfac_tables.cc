@@ -11,7 +11,7 @@
 //     max-segment-tree (O(R log R));
 //   * the first-fit search (phf.c:188-195) tests 64 candidate slots per step against the row's
 //     columns with word-wide occupancy masks, and skips full regions through a hierarchical bitmap,
-//     instead of trying every offset (100,000 patterns: 1.7 s at width 256, 18 s at width 4096
+//     instead of trying every offset (100,000 patterns: 1.7 s at width 256, 9 s at width 4096
 //     where one offset at a time took 20 minutes).
 // tests/test_tables_*.py pin this against the reference's own code (oracle/_ref) and the
 // plain-C restatement (oracle/pfac_oracle.c).
@@ -324,7 +324,12 @@ struct SlotMap {
     // free for every i (d = the row's other columns relative to its first).  Same answer as trying
     // the free slots one by one; here kFitWords x 64 candidate slots are tested per pass, one
     // column at a time over consecutive occupancy words.
+    // (compiled three times; the loader picks the widest vector unit the host has: the word loops below are
+    // the whole cost of wide tables -- 100,000 patterns at width 4096: 17 s -> 9 s with AVX-512)
     static constexpr int kFitWords = 32;
+#if defined(__x86_64__) && defined(__GNUC__) && !defined(__clang__)
+    __attribute__((target_clones("avx512f", "avx2", "default")))
+#endif
     size_t first_fit(size_t start, const uint32_t *d, int nd)
     {
         size_t s = next_free(start);
