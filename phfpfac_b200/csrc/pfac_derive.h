@@ -6,25 +6,28 @@
 // derived here is the shared-memory image of the DETECTOR kernel: prefix filters computed from the
 // first rows of the PHF.  Every one of them is a superset test -- it may pass a start position
 // that cannot match, it never rejects one that can:
-//   T1    65,536 x u8 : four bit-planes per 2-byte window (x,y), one LDS.U8 per start position:
+//   T1    65,536 x u8 : up to eight bit-planes per 2-byte window (x,y), one LDS.U8 per probe:
 //                         P01   a walk starting with (x,y) matches a 1-byte pattern or has a second
 //                               edge (root fan-out, s0Table of main.cc:200, folded in) -- exact
-//                         P12   (x,y) are bytes 1-2 of some path of the automaton
-//                         P23   (x,y) are bytes 2-3 of some path
-//                         Short (x,y) as bytes 0-1 can complete a pattern of <= 3 bytes
-//                       a start at i passes stage 1 iff P01(i) and (Short(i) or P12(i+1) and
-//                       P23(i+2)) -- the windows of the next two positions are looked up anyway.
+//                         P12 / P23 / P34   (x,y) are bytes 1-2 / 2-3 / 3-4 of some path of the automaton
+//                         Short / ShortC    (x,y) as bytes 0-1 / 1-2 can complete a pattern of <= 3 / <= 4 bytes
+//                         P45 / P56 / ShX   third-window planes (sets without patterns of <= 3 bytes; below)
+//                       Mode 0 probes the windows at EVEN offsets only: an even start 2k is judged by the
+//                       windows at 2k (P01), 2k+2 (P23) and 2k+4 (P45), an odd start 2k+1 by those at 2k+2
+//                       (P12), 2k+4 (P34) and 2k+6 (P56); modes 1 / 2 probe every start (P01, P12, P23).
 //                       Indexed with both bytes rotated left by 2 so that the low, high-entropy
 //                       bits of ASCII text select the shared-memory bank.
-//   Tm    8192 x u16  : COMPLETE cuckoo table (2 buckets x 2 tagged slots) of every 4-byte prefix
-//                       -> m1 = (at most) the shortest pattern length below it.  A miss rejects.
-//   Tm2   2^k x 2 u16 : same structure, (prefix, level-1 window) group -> m2
+//   level 1 / level 2 (mode 0): perfect-hash tables (hash-and-displace D / E, u16) of every 4-byte prefix -> m1
+//                       and of every (prefix, bytes [m1-4, m1)) group -> m2; m = (at most) the shortest pattern
+//                       length below the key.  A word that is no key finds m = 0 or, once in 256, another key's m.
+//   Tm / Tm2 (mode 2) : the same two levels as COMPLETE cuckoo tables (2 buckets x 2 tagged u16 slots), sized
+//                       for the key counts, in global memory
 //   T3    2^k3 bits   : hash of (key, pattern bytes [m-4, m)) for every pattern below a key: a start
 //                       whose text at offset m-4 is not in T3 cannot complete any pattern under
 //                       that key (Wu-Manber style two-point checks; they settle the starts that
 //                       share a long prefix with many patterns without walking it)
 //   T2    2^k2 bits   : blocked Bloom filter (one word, kT2KeyBits bits) of every 4-byte prefix -- only for pattern sets whose
-//                       prefixes do not fit the shared-memory Tm.  Such sets (e.g. 100,000 patterns)
+//                       prefixes do not fit the shared-memory tables.  Such sets (e.g. 100,000 patterns)
 //                       get Tm/Tm2/T3 sized for their key counts in GLOBAL memory (a few MB, L2
 //                       resident) and T2, filling shared memory, becomes stage 1.
 #pragma once
