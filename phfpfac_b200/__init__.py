@@ -27,6 +27,16 @@ __all__ = ["Tables", "Matcher", "Job", "PfacError", "MATCH_DTYPE", "format_recor
            "write_sidecar", "read_sidecar", "pattern_file_hash", "pinned", "device_count", "plan_shard"]
 
 
+def _as_u8(data):
+    """The caller's bytes as a flat uint8 array WITHOUT a copy where they already are one (pinned buffers keep
+    their address); anything that is not made of single bytes is refused rather than reinterpreted."""
+    if isinstance(data, np.ndarray):
+        if data.dtype.itemsize != 1:
+            raise TypeError(f"input must be an array of bytes (uint8), not {data.dtype}")
+        return np.ascontiguousarray(data).view(np.uint8).reshape(-1)
+    return np.frombuffer(bytes(data), dtype=np.uint8)
+
+
 def _arr(ptr, n):
     if n <= 0 or not ptr:
         return np.zeros(0, dtype=np.int32)
@@ -212,7 +222,7 @@ class Matcher:
 
     # -- host input: H2D + kernel + D2H pipeline
     def scan_host(self, data, n_starts=None, base_pos=0, cap=None):
-        buf = data if isinstance(data, np.ndarray) else np.frombuffer(bytes(data), dtype=np.uint8)
+        buf = _as_u8(data)
         n_valid = len(buf)
         n_starts = n_valid if n_starts is None else n_starts
         cap = max(1024, n_starts // 8) if cap is None else cap
@@ -242,19 +252,11 @@ class Job:
         self.tables = tables
 
     def run(self, data):
-        buf = data if isinstance(data, np.ndarray) else np.frombuffer(bytes(data), dtype=np.uint8)
+        """-> (total matches, [(base position, uint32 array [count, 2] of (pos - base, id)), ...] in position order)."""
+        buf = _as_u8(data)
         n = C.c_uint64(0)
         check(lib.pfac_job_run(self._h, buf.ctypes.data if len(buf) else None, len(buf), C.byref(n)))
-        segs = []
-        for i in range(lib.pfac_job_n_segments(self._h)):
-            base, cnt, ptr = C.c_uint64(0), C.c_uint64(0), C.c_void_p()
-            check(lib.pfac_job_segment(self._h, i, C.byref(base), C.byref(ptr), C.byref(cnt)))
-            if cnt.value:
-                a = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_uint32)), shape=(cnt.value, 2)).copy()
-            else:
-                a = np.zeros((0, 2), dtype=np.uint32)
-            segs.append((base.value, a))
-        return n.value, segs
+        return n.value, self._segments()
 
     def _segments(self):
         segs = []

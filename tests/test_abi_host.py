@@ -162,6 +162,20 @@ def test_binary_sidecar_round_trip(tmp_path, golden):
         pf.read_sidecar(tmp_path / "nope")
 
 
+def test_input_buffers_are_passed_without_a_copy():
+    """Matcher.scan_host / Job.run hand the caller's bytes to the library where they lie (a pinned buffer must
+    keep its address); arrays that are not made of bytes are refused."""
+    a = np.arange(4096, dtype=np.uint8)
+    assert pf._as_u8(a).ctypes.data == a.ctypes.data and pf._as_u8(a[16:]).ctypes.data == a.ctypes.data + 16
+    assert pf._as_u8(a.reshape(64, 64)).ctypes.data == a.ctypes.data and pf._as_u8(a.reshape(64, 64)).shape == (4096,)
+    assert pf._as_u8(a.view(np.int8)).dtype == np.uint8
+    assert pf._as_u8(a[::2]).tobytes() == a[::2].tobytes()            # strided: copied, same bytes
+    assert pf._as_u8(b"abc").tobytes() == b"abc" and pf._as_u8(bytearray(b"xy")).tobytes() == b"xy"
+    assert len(pf._as_u8(b"")) == 0
+    with pytest.raises(TypeError):
+        pf._as_u8(np.zeros(4, dtype=np.int32))
+
+
 def test_synth_is_deterministic_and_shaped():
     p1 = synth.synth_patterns(1, 2000, 3, 4, 64)
     assert p1 == synth.synth_patterns(1, 2000, 3, 4, 64) and p1 != synth.synth_patterns(1, 2000, 4, 4, 64)
