@@ -16,9 +16,13 @@
 // tests/test_tables_*.py pin this against the reference's own code (oracle/_ref) and the
 // plain-C restatement (oracle/pfac_oracle.c).
 #include <algorithm>
+#include <atomic>
 #include <cstdio>
 #include <cstring>
 #include <memory>
+#include <string>
+#include <thread>
+#include <vector>
 
 #include "pfac_derive.h"
 #include "pfac_internal.h"
@@ -327,7 +331,7 @@ struct SlotMap {
     // (compiled three times; the loader picks the widest vector unit the host has: the word loops below are
     // the whole cost of wide tables -- 100,000 patterns at width 4096: 17 s -> 9 s with AVX-512)
     static constexpr int kFitWords = 32;
-#if defined(__x86_64__) && defined(__GNUC__) && !defined(__clang__)
+#if defined(__x86_64__) && defined(__GNUC__) && !defined(__clang__) && !defined(__SANITIZE_THREAD__)   // (ifunc resolvers run before TSan is up)
     __attribute__((target_clones("avx512f", "avx2", "default")))
 #endif
     size_t first_fit(size_t start, const uint32_t *d, int nd)
@@ -488,15 +492,42 @@ int build(const unsigned char *buf, size_t len, int n_parts, int width, unsigned
     const int n = (int)pats.size();
     const int k = n / n_parts;            // create_table_reorder.c:220
     const int l = k + n % n_parts;        // create_table_reorder.c:222
-    for (int g = 0; g < n_parts; g++) {
+    // The partitions are independent: trie + FFDM of each on its own thread (the reference runs FFDM per
+    // partition under `omp parallel for`, main.cc:123-126).  Errors are thread-local: the first failing
+    // partition's code and message are handed back to the caller's thread.
+    std::vector<int> rcs((size_t)n_parts, PFAC_OK);
+    std::vector<std::string> errs((size_t)n_parts);
+    auto one = [&](int g) {
         const int cnt = (g == n_parts - 1) ? l : k;   // divide_patterns, :260-272
         Partition &P = t->parts[(size_t)g];
-        if ((int64_t)cnt + 2 + (int64_t)len > (int64_t)(INT32_MAX / kCharSet))
-            return set_error(PFAC_ERR_LIMIT, "automaton too large for 32-bit keys");
+        if ((int64_t)cnt + 2 + (int64_t)len > (int64_t)(INT32_MAX / kCharSet)) {
+            rcs[(size_t)g] = PFAC_ERR_LIMIT;
+            errs[(size_t)g] = "automaton too large for 32-bit keys";
+            return;
+        }
         build_trie(pats.data() + (size_t)g * (size_t)k, cnt, P);
-        if (P.max_len > t->max_pat_len) t->max_pat_len = P.max_len;   // :238
-        e = ffdm(P, width);
-        if (e) return e;
+        const int rc = ffdm(P, width);
+        if (rc) {
+            rcs[(size_t)g] = rc;
+            errs[(size_t)g] = g_last_error;
+        }
+    };
+    const int n_threads = std::max(1, std::min<int>(n_parts, (int)std::thread::hardware_concurrency()));
+    if (n_threads == 1) {
+        for (int g = 0; g < n_parts; g++) one(g);
+    } else {
+        std::atomic<int> next{0};
+        auto worker = [&] {
+            for (int g; (g = next.fetch_add(1)) < n_parts;) one(g);
+        };
+        std::vector<std::thread> th;
+        for (int i = 1; i < n_threads; i++) th.emplace_back(worker);
+        worker();
+        for (auto &x : th) x.join();
+    }
+    for (int g = 0; g < n_parts; g++) {
+        if (rcs[(size_t)g]) return set_error(rcs[(size_t)g], "%s", errs[(size_t)g].c_str());
+        if (t->parts[(size_t)g].max_len > t->max_pat_len) t->max_pat_len = t->parts[(size_t)g].max_len;   // :238
     }
     *out = t.release();
     return PFAC_OK;
