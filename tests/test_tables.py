@@ -344,3 +344,23 @@ def test_table_cache_roundtrip(tmp_path, fixtures):
     assert pf.pattern_file_hash(str(pat)) != u.source_hash()
     p0 = t.part(0)
     assert pf.Tables.from_arrays(p0.s0, p0.r, p0.HT, p0.val, 256, p0.state_num, p0.n_final, p0.idmap, p0.max_len).source_hash() == 0
+
+
+def test_numpy_stage1_model_equals_the_cpp_model():
+    """tools/host_model.py restates the detector's stage 1 in numpy to evaluate other strides / folds.
+    Its restatement of the BUILT rule must count exactly the survivors the C++ model of the shipped tables counts."""
+    import host_model as hm
+    from bench import WORKLOADS
+    for name in ("config3", "config2"):
+        pk, cnt, pseed, lo, hi, tk, tseed, _n, _d = WORKLOADS[name]
+        blob = synth.synth_patterns(pk, cnt, pseed, lo, hi)
+        pats = [np.frombuffer(x, dtype=np.uint8).astype(np.uint32) for x in blob.split(b"\n")[:-1]]
+        text = synth.synth_text(tk, tseed, 2 << 20, patterns=blob)
+        t = pf.Tables.from_bytes(blob)
+        cpp = t.filter_profile(text)
+        got, n = hm.built(text, pats, True)
+        # (the numpy model leaves the last 16 start positions of the text out)
+        assert cpp["positions"] == len(text) == n + 16 and 0 <= cpp["t1_pass"] - got <= 16, (name, cpp["t1_pass"], got)
+        # the generic (phase, window) planes are at least as selective as the built design's shared ShX plane
+        ideal, _ = hm.survivors(text, pats, 2, 3)
+        assert ideal <= got
